@@ -1,0 +1,173 @@
+/*
+ * raider_b200.h -- C ABI of libraider_b200.so: the B200 (sm_100a) slant / zenith tropospheric-delay hot path.
+ *
+ * This is the drop-in boundary.  The reference (dbekaert/RAiDER @ e38c4eb4) has no C ABI of its own for this
+ * path: it exposes CPython extension modules (setup.py:20-40) and Python functions.  Each entry point below
+ * therefore names the reference *Python-level* interface it sits under (path:line relative to the reference
+ * root); the Python shims in raider_b200/ keep those names/signatures and call these symbols through ctypes.
+ * INTEGRATION.md shows the binding a RAiDER maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers + int64 sizes, no C++/torch types; every function returns an rdr_status (0 = OK).
+ *   - `mem` says where the *bulk* arrays of that call live: RDR_MEM_HOST (library stages H2D/D2H itself)
+ *     or RDR_MEM_DEVICE (pointers are CUDA device pointers of the handle's device; no copies).
+ *     Small parameter vectors (axes, layer tables, maxlen) are always host pointers.
+ *   - caller allocates every output; the library never frees caller memory; scratch lives in the handle.
+ *   - one handle = one device + one stream; calls on a handle are serialised by the caller.
+ *   - no exception crosses the boundary; rdr_last_error() gives the message for the last failing call.
+ *   - there is no CPU fallback: without a CUDA device rdr_create() fails with RDR_ERR_CUDA.
+ */
+#ifndef RAIDER_B200_H
+#define RAIDER_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RDR_ABI_VERSION 1
+
+typedef struct rdr_handle_s *rdr_handle_t;
+
+typedef enum {
+    RDR_OK = 0,
+    RDR_ERR_INVALID = 1,   /* bad argument / shape  -> TypeError or ValueError in the shims (module.cpp:36-63) */
+    RDR_ERR_CUDA = 2,      /* CUDA runtime failure   -> RuntimeError */
+    RDR_ERR_STATE = 3,     /* call order (no cube set, integrate before layers, ...) -> RuntimeError */
+    RDR_ERR_NO_LAYERS = 4, /* no model layer contributes (losreader.py:832-833 returns (None, None, None)) */
+    RDR_ERR_ALL_NAN = 5    /* every ray length is NaN (delay.py:279-280 raises ValueError) */
+} rdr_status;
+
+enum { RDR_MEM_HOST = 0, RDR_MEM_DEVICE = 1 };
+enum { RDR_F64 = 0, RDR_F32 = 1 };
+
+/* cube field layout handed to rdr_set_cube */
+enum {
+    RDR_LAYOUT_ZYX = 0, /* (nz, ny, nx) C-order: the on-disk order of the processed weather model (weatherModel.py:676-724) */
+    RDR_LAYOUT_YXZ = 1  /* (ny, nx, nz) C-order: the order getInterpolators hands to scipy (delayFcns.py:40-41) */
+};
+
+/* model CRS of the cube's x/y axes (delay.py:253 ecef_to_model) */
+enum {
+    RDR_CRS_GEOGRAPHIC = 0, /* x = lon deg, y = lat deg (EPSG:4326: ERA5/GMAO/HRES/MERRA2...) */
+    RDR_CRS_LCC_SPHERE = 1  /* Lambert conformal conic on a sphere (HRRR, models/hrrr.py:255-260);
+                               crs_params = {n, c, rho0, lam0_rad, R, x_0, y_0} */
+};
+
+/* where the ground (target) points of a ray-tracing call come from (delay.py:242,262-267) */
+enum {
+    RDR_GEOM_GRID = 0,  /* regular raster: gx = xpts[nx] (lon deg), gy = ypts[ny] (lat deg), one height `ht`; ray r = j*nx + i */
+    RDR_GEOM_POINTS = 1 /* explicit points: gx = lon[n], gy = lat[n] (deg), n = ny*nx, all at height `ht` */
+};
+
+/* line-of-sight source (delay.py:270 los.getLookVectors) */
+enum {
+    RDR_LOS_ARRAY = 0,  /* los = [n][3] ECEF unit vectors ground->sensor (Raytracing.getLookVectors, losreader.py:219-255) */
+    RDR_LOS_ENU_CONST = 1, /* los = {east, north, up}: constant local ENU vector, rotated to ECEF per pixel
+                              (inc_hd_to_enu losreader.py:374-396 + enu2ecef utilFcns.py:91-121) */
+    RDR_LOS_ZENITH = 2  /* los = NULL: local zenith (getZenithLookVecs, losreader.py:302-316) */
+};
+
+/* interval semantics of the sampler */
+enum {
+    RDR_SEM_SCIPY = 0,       /* scipy RegularGridInterpolator(fill_value=nan, bounds_error=False): last node inclusive (delayFcns.py:55-56) */
+    RDR_SEM_RAIDER_FILL = 1, /* RAiDER.interpolate with fill_value: bisect_left, upper edge exclusive (interpolate.cpp:116-125) */
+    RDR_SEM_RAIDER_CLAMP = 2 /* RAiDER.interpolate without fill_value: clamp -> linear extrapolation (interpolate.cpp:127-131) */
+};
+
+/* ---------------------------------------------------------------- lifecycle ---------------------------- */
+int rdr_abi_version(void);
+/* number of CUDA devices visible to the library (0 when there is none); never fails */
+int rdr_device_count(void);
+int rdr_create(int device, rdr_handle_t *out);
+int rdr_destroy(rdr_handle_t h);
+/* message of the last failing call on `h` (or of the last failing handle-less call when h == NULL) */
+const char *rdr_last_error(rdr_handle_t h);
+/* run subsequent calls on an existing cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream); NULL = own stream */
+int rdr_set_stream(rdr_handle_t h, void *cuda_stream);
+int rdr_synchronize(rdr_handle_t h);
+/* number of kernels this handle has launched since creation (bench.py's gpu_launches claim) */
+int64_t rdr_launch_count(rdr_handle_t h);
+
+/* ---------------------------------------------------------------- cube --------------------------------- */
+/* Replaces delayFcns.getInterpolators (delayFcns.py:23-58): stage one weather-model cube (two float32 fields on
+ * one grid: wet+hydro for ray tracing, wet_total+hydro_total for zenith) into HBM, z fastest, the two fields and
+ * the z/z+1 neighbours interleaved so one 16-byte load feeds a bilinear column pair.  Axes are host f64 arrays;
+ * descending axes are flipped on the way in (scipy does the same at construction).  Fields are host or device
+ * by `mem`. */
+int rdr_set_cube(rdr_handle_t h, const double *ys, int64_t ny, const double *xs, int64_t nx, const double *zs, int64_t nz,
+                 const float *wet, const float *hydro, int layout, int crs_kind, const double *crs_params, int mem);
+/* Second epoch for temporal interpolation, blended as cube = w0*cube0 + w1*cube1 (cli/raider.py:817-819)
+ * at staging time, in fp64 then rounded to fp32 exactly like the reference's xarray arithmetic. */
+int rdr_blend_cube(rdr_handle_t h, const float *wet1, const float *hydro1, int layout, double w0, double w1, int mem);
+
+/* ---------------------------------------------------------------- K2: trilinear sample ------------------ */
+/* Replaces scipy RGI __call__ as configured at delayFcns.py:55-56 (call sites delay.py:120-121,214,319):
+ * pts = [n][3] (y, x, z) in cube coordinates, dtype f64 or f32; out_wet/out_hydro = [n] same dtype. */
+int rdr_sample(rdr_handle_t h, const void *pts, int64_t n, void *out_wet, void *out_hydro, int dtype, int semantics, int mem);
+/* Replaces _build_cube (delay.py:196-216) for one height: sample both fields at (ypts[j], xpts[i], ht); out = [ny][nx] f64.
+ * Query axes are in the cube's own CRS (model_crs == pts_crs branch, delay.py:210-211). */
+int rdr_sample_grid(rdr_handle_t h, const double *xpts, int64_t nx, const double *ypts, int64_t ny, double ht,
+                    double *out_wet, double *out_hydro, int mem);
+
+/* ---------------------------------------------------------------- K0 + K3: ray tracing ------------------ */
+/* Scalar layer decisions of build_ray (losreader.py:785-809) for the staged cube: writes up to nz-1 (low, high)
+ * height pairs and their count.  Pure host logic, exposed for tests and the shims. */
+int rdr_ray_plan(rdr_handle_t h, double ht, double zref, int64_t *n_layers, double *low_ht, double *high_ht);
+
+/* K0 -- replaces build_ray + getTopOfAtmosphere (losreader.py:706-733,772-835) over a whole raster: one thread per
+ * ray runs the 10-then-3 Newton schedule for every contributing layer, keeps the along-ray distance of each layer
+ * top in handle scratch, and reduces max_over_raster(ray_length[k]) (delay.py:283) with warp shuffles + atomics.
+ *   maxlen_out[n_layers]  host, this call's (this GPU's) per-layer maxima  -> all-reduce(MAX) across GPUs
+ *   counts_out[4]         host: {n_rays, n_rays_with_nan_length, n_first_sample_below_zmin, n_layers}
+ */
+int rdr_ray_layers(rdr_handle_t h, int geom_kind, const double *gx, const double *gy, int64_t ny, int64_t nx,
+                   int los_kind, const double *los, double ht, double zref,
+                   double *maxlen_out, int64_t *counts_out, int mem);
+
+/* K3 -- replaces the integration loops of _build_cube_ray (delay.py:283-323) for the rays of the last
+ * rdr_ray_layers call: nParts from the (globally reduced) maxlen, sub-step points, ECEF -> model CRS, trilinear
+ * wet+hydro sample, trapezoid weights, fp64 accumulation in layer-then-step order.
+ *   maxlen[n_layers]      host: global per-layer maxima (delay.py:283)
+ *   clamp_low_first       1 if *all* pixels of the very first sample are below min(z) globally (delay.py:306-307)
+ *   out_wet/out_hydro     [n_rays] f64 (or f32 when out_dtype == RDR_F32); accumulate != 0 -> out += (delay.py:245-248,323)
+ *   nparts_out[n_layers]  host, optional: the integer step counts used (bit-exact contract)
+ *   oob_out[2]            host, optional: {samples below min(z), samples above max(z)} that became NaN
+ */
+int rdr_ray_integrate(rdr_handle_t h, const double *maxlen, double max_segment_length, int clamp_low_first,
+                      void *out_wet, void *out_hydro, int out_dtype, int accumulate,
+                      int64_t *nparts_out, int64_t *oob_out, int mem);
+
+/* API-parity pieces of losreader (small problems, tests): */
+/* getTopOfAtmosphere(xyz, look_vecs, toaheight, factor=None) losreader.py:706-733; factor == NULL -> 10 iterations */
+int rdr_top_of_atmosphere(const double *xyz, const double *look, int64_t n, double toaheight, const double *factor,
+                          double *out_xyz, int device);
+/* build_ray(model_zs, ht, xyz, LOS, MAX_TROPO_HEIGHT) losreader.py:772-835: outputs [K][n], [K][n][3], [K][n][3]; K via rdr_ray_plan */
+int rdr_build_ray(const double *model_zs, int64_t nz, double ht, const double *xyz, const double *look, int64_t n, double zref,
+                  int64_t *n_layers, double *ray_lengths, double *low_xyzs, double *high_xyzs, int device);
+/* lla2ecef / ecef2lla (utilFcns.py:77-88); n points, SoA in / SoA out, host pointers */
+int rdr_lla2ecef(const double *lat, const double *lon, const double *hgt, int64_t n, double *x, double *y, double *z, int device);
+int rdr_ecef2lla(const double *x, const double *y, const double *z, int64_t n, double *lon, double *lat, double *hgt, int device);
+
+/* ---------------------------------------------------------------- K1: makePoints ------------------------ */
+/* Npts rule of makePoints.pyx:130-134 */
+int rdr_make_points_count(double max_len, double step, int64_t *npts);
+/* makePoints{0,1,2,3}D (makePoints.pyx:15-148): sp/slv = [n_rays][3]; out = [n_rays][3][npts], out[r][c][k] = sp[r][c] + (k*step)*slv[r][c] */
+int rdr_make_points(double max_len, const double *sp, const double *slv, int64_t n_rays, double step, double *out, int64_t npts,
+                    int device, int mem);
+
+/* ---------------------------------------------------------------- RAiDER.interpolate -------------------- */
+/* interpolate(points, values, interp_points, fill_value, assume_sorted, max_threads) module.cpp:26-294:
+ * ndim grids (host), values f64 C-order, pts = [n][ndim], out = [n].  ndim <= 8. */
+int rdr_interpolate(int ndim, const double *const *grids, const int64_t *sizes, const double *values, const double *pts, int64_t n,
+                    int has_fill, double fill_value, double *out, int device, int mem);
+/* interpolate_along_axis (module.cpp:296-493 -> interpolate.cpp:260-332) on columns made contiguous by the shim:
+ * x, y = [ncol][nin]; xnew, out = [ncol][nout]. */
+int rdr_interp_along_axis(const double *x, const double *y, const double *xnew, int64_t ncol, int64_t nin, int64_t nout,
+                          int has_fill, double fill_value, double *out, int device, int mem);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RAIDER_B200_H */

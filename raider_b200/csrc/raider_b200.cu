@@ -1,0 +1,1304 @@
+// libraider_b200.so -- hand-written sm_100a kernels + C ABI for the RAiDER slant/zenith delay hot path.
+// See include/raider_b200.h for the boundary and DESIGN.md for the kernel inventory:
+//   K0 k_ray_layers     build_ray/getTopOfAtmosphere over a raster + global per-layer max length
+//   K3 k_ray_integrate  fused sub-step point generation + ECEF->model + trilinear wet/hydro + trapezoid
+//   K2 k_sample_*       unfused trilinear sampler (points streamed from HBM) -- the HBM-roofline kernel
+//   K1 k_make_points    makePoints{0..3}D
+//   K4 k_interp_axis    interpolate_along_axis;  k_interp_nd  RAiDER.interpolate.interpolate
+// No CPU fallback lives here: every entry point needs a CUDA device.
+#include "../../include/raider_b200.h"
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "geodesy.cuh"
+#include "sampler.cuh"
+
+using namespace rdr;
+
+#define RDR_API extern "C" __attribute__((visibility("default")))
+
+// ------------------------------------------------------------------------------------------------
+// handle + error plumbing
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+thread_local std::string g_last_error;
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T>
+    T *as() const { return static_cast<T *>(p); }
+};
+
+constexpr int MAX_LAYERS = 1024;
+
+}  // namespace
+
+struct rdr_handle_s {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+    int64_t launches = 0;
+
+    // cube
+    bool has_cube = false;
+    int64_t ny = 0, nx = 0, nz = 0;
+    std::vector<double> ys, xs, zs;  // ascending host copies
+    bool flip_y = false, flip_x = false, flip_z = false;
+    int crs_kind = RDR_CRS_GEOGRAPHIC;
+    double crs[7] = {0, 0, 0, 0, 0, 0, 0};
+    DevBuf d_axes;   // ys | xs | zs
+    DevBuf d_cells;  // float4 [ny][nx][nz-1]
+    DevBuf d_stage;  // staging for field uploads (and packed fp32 pairs for blending)
+    DevBuf d_fields; // float2 [ny][nx][nz] (wet, hydro) kept for blending
+
+    // ray state (between rdr_ray_layers and rdr_ray_integrate)
+    bool has_rays = false;
+    int64_t n_rays = 0, ray_ny = 0, ray_nx = 0;
+    int geom_kind = 0, los_kind = 0;
+    double ht = 0, zref = 0;
+    int n_layers = 0;
+    std::vector<double> low_ht, high_ht;
+    std::vector<int> layer_cell;  // model layer index of each contributing layer (z-cell hint)
+    DevBuf d_gx, d_gy, d_los;     // staged geometry when the caller's arrays are on the host
+    const double *p_gx = nullptr, *p_gy = nullptr, *p_los = nullptr;
+    double los_const[3] = {0, 0, 1};
+    DevBuf d_plan;    // low[K] | high[K]
+    DevBuf d_t;       // [K+1][n_rays] along-ray distances: row 0 = bottom of first layer, row k+1 = top of layer k
+    DevBuf d_red;     // maxlen bits [K] | counters
+    DevBuf d_nparts;  // int [K] + int cell [K]
+    DevBuf d_out;     // staging for host outputs
+    DevBuf d_in;      // staging for host inputs of K2
+};
+
+namespace {
+
+int fail(rdr_handle_t h, int code, const std::string &msg) {
+    g_last_error = msg;
+    if (h) h->err = msg;
+    return code;
+}
+
+#define CUDA_TRY(h, expr)                                                                                         \
+    do {                                                                                                          \
+        cudaError_t _e = (expr);                                                                                  \
+        if (_e != cudaSuccess)                                                                                    \
+            return fail(h, RDR_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" __FILE__ ":" + \
+                                             std::to_string(__LINE__) + ")");                                     \
+    } while (0)
+
+#define CHECK_ARG(h, cond, msg) \
+    do {                        \
+        if (!(cond)) return fail(h, RDR_ERR_INVALID, msg); \
+    } while (0)
+
+inline int grid_for(int64_t n, int block, int sm_count, int per_sm) {
+    int64_t need = (n + block - 1) / block;
+    int64_t cap = (int64_t)sm_count * per_sm;
+    return (int)std::max<int64_t>(1, std::min(need, cap));
+}
+
+__device__ __forceinline__ double qnan() { return __longlong_as_double(0x7ff8000000000000LL); }
+
+// ------------------------------------------------------------------------------------------------
+// cube staging
+// ------------------------------------------------------------------------------------------------
+// src fields in caller layout -> float2 (wet, hydro) [ny][nx][nz] with ascending axes
+__global__ void k_gather_fields(const float *__restrict__ wet, const float *__restrict__ hydro, float2 *__restrict__ dst, int ny,
+                                int nx, int nz, int layout, int flip_y, int flip_x, int flip_z) {
+    const int64_t total = (int64_t)ny * nx * nz;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int iz = (int)(i % nz);
+        const int ix = (int)((i / nz) % nx);
+        const int iy = (int)(i / ((int64_t)nz * nx));
+        const int sy = flip_y ? ny - 1 - iy : iy, sx = flip_x ? nx - 1 - ix : ix, sz = flip_z ? nz - 1 - iz : iz;
+        const int64_t s = layout == RDR_LAYOUT_ZYX ? ((int64_t)sz * ny + sy) * nx + sx : ((int64_t)sy * nx + sx) * nz + sz;
+        dst[i] = make_float2(wet[s], hydro[s]);
+    }
+}
+
+// temporal blend exactly as the reference's float32 xarray arithmetic: fl32(w0)*a + fl32(w1)*b (cli/raider.py:817-819)
+__global__ void k_blend_fields(float2 *__restrict__ a, const float2 *__restrict__ b, int64_t total, float w0, float w1) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const float2 p = a[i], q = b[i];
+        a[i] = make_float2(__fadd_rn(__fmul_rn(w0, p.x), __fmul_rn(w1, q.x)), __fadd_rn(__fmul_rn(w0, p.y), __fmul_rn(w1, q.y)));
+    }
+}
+
+// float2 [ny][nx][nz] -> float4 cells [ny][nx][nz-1] = {f[z], f[z+1]}
+__global__ void k_pack_cells(const float2 *__restrict__ f, float4 *__restrict__ cells, int64_t ncol, int nz) {
+    const int64_t total = ncol * (nz - 1);
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t col = i / (nz - 1);
+        const int iz = (int)(i % (nz - 1));
+        const float2 a = f[col * nz + iz], b = f[col * nz + iz + 1];
+        cells[i] = make_float4(a.x, a.y, b.x, b.y);
+    }
+}
+
+CubeView make_view(rdr_handle_t h) {
+    CubeView c;
+    c.cells = h->d_cells.as<float4>();
+    const double *ax = h->d_axes.as<double>();
+    auto mk = [](const double *g, const std::vector<double> &v) {
+        Axis a;
+        a.g = g;
+        a.n = (int)v.size();
+        a.g0 = v[0];
+        const double d = (v.back() - v[0]) / (double)(v.size() - 1);
+        a.inv_d = 1.0 / d;
+        // "uniform" only needs the floor() guess to land within a couple of cells; the fix-up loops make it exact
+        bool uni = true;
+        for (size_t i = 1; i < v.size(); ++i)
+            if (fabs((v[i] - v[i - 1]) - d) > 0.25 * fabs(d)) uni = false;
+        a.uniform = uni ? 1 : 0;
+        return a;
+    };
+    c.ay = mk(ax, h->ys);
+    c.ax = mk(ax + h->ny, h->xs);
+    c.az = mk(ax + h->ny + h->nx, h->zs);
+    c.crs_kind = h->crs_kind;
+    for (int i = 0; i < 7; ++i) c.crs[i] = h->crs[i];
+    return c;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: unfused trilinear sampler.  One thread per point; the [n][3] AoS points are read with coalesced
+// 16-byte loads through shared memory (3 x 16 B per 2 points), the two outputs are written as plain
+// coalesced fp64/fp32 stores.  Algorithmic traffic: 40 B/point (f64) or 20 B/point (f32).
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ void sample_any(const CubeView &c, int semantics, double y, double x, double z, double &vw, double &vh) {
+    if (semantics == RDR_SEM_SCIPY) {
+        sample_scipy(c, y, x, z, -1, vw, vh);
+        return;
+    }
+    // RAiDER.interpolate rules on the staged fp32 cube (values promoted to fp64)
+    const Axis *ax[3] = {&c.ay, &c.ax, &c.az};
+    const double v[3] = {y, x, z};
+    int hi[3];
+    for (int d = 0; d < 3; ++d) {
+        int k = bisect_left(ax[d]->g, ax[d]->n, v[d]);
+        if (semantics == RDR_SEM_RAIDER_FILL) {
+            if (k < 1 || k > ax[d]->n - 1) {
+                vw = vh = qnan();
+                return;
+            }
+        } else {
+            k = k < 1 ? 1 : (k > ax[d]->n - 1 ? ax[d]->n - 1 : k);
+        }
+        hi[d] = k;
+    }
+    double lo_d[3], hi_d[3], vol = 1.0;
+    for (int d = 0; d < 3; ++d) {
+        const double g0 = __ldg(ax[d]->g + hi[d] - 1), g1 = __ldg(ax[d]->g + hi[d]);
+        lo_d[d] = v[d] - g0;
+        hi_d[d] = g1 - v[d];
+        vol = d == 0 ? (g1 - g0) : __dmul_rn(vol, g1 - g0);
+    }
+    const int nzc = c.az.n - 1;
+    const float4 *p = c.cells + ((size_t)(hi[0] - 1) * c.ax.n + (hi[1] - 1)) * nzc + (hi[2] - 1);
+    const float4 c00 = __ldg(p), c01 = __ldg(p + nzc), c10 = __ldg(p + (size_t)c.ax.n * nzc), c11 = __ldg(p + (size_t)c.ax.n * nzc + nzc);
+    vw = trilinear_raider(c00.x, c00.z, c01.x, c01.z, c10.x, c10.z, c11.x, c11.z, lo_d[0], hi_d[0], lo_d[1], hi_d[1], lo_d[2], hi_d[2], vol);
+    vh = trilinear_raider(c00.y, c00.w, c01.y, c01.w, c10.y, c10.w, c11.y, c11.w, lo_d[0], hi_d[0], lo_d[1], hi_d[1], lo_d[2], hi_d[2], vol);
+}
+
+template <typename T, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_sample_points(const CubeView c, const T *__restrict__ pts, int64_t n, T *__restrict__ out_wet,
+                                                         T *__restrict__ out_hydro, int semantics) {
+    __shared__ __align__(16) T tile[BLOCK * 3];
+    const int64_t ntiles = (n + BLOCK - 1) / BLOCK;
+    for (int64_t tile_i = blockIdx.x; tile_i < ntiles; tile_i += gridDim.x) {
+        const int64_t base = tile_i * BLOCK;
+        const int cnt = (int)min((int64_t)BLOCK, n - base);
+        // coalesced 16-byte loads of this tile's cnt*3 scalars
+        constexpr int VEC = 16 / sizeof(T);
+        const T *src = pts + base * 3;
+        const int nscal = cnt * 3;
+        if (cnt == BLOCK && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+            const float4 *s4 = reinterpret_cast<const float4 *>(src);
+            float4 *d4 = reinterpret_cast<float4 *>(tile);
+            for (int i = threadIdx.x; i < BLOCK * 3 / VEC; i += BLOCK) d4[i] = __ldcs(s4 + i);
+        } else {
+            for (int i = threadIdx.x; i < nscal; i += BLOCK) tile[i] = src[i];
+        }
+        __syncthreads();
+        if ((int)threadIdx.x < cnt) {
+            const double y = (double)tile[threadIdx.x * 3 + 0], x = (double)tile[threadIdx.x * 3 + 1], z = (double)tile[threadIdx.x * 3 + 2];
+            double vw, vh;
+            sample_any<T>(c, semantics, y, x, z, vw, vh);
+            __stcs(out_wet + base + threadIdx.x, (T)vw);
+            __stcs(out_hydro + base + threadIdx.x, (T)vh);
+        }
+        __syncthreads();
+    }
+}
+
+// _build_cube for one height: points generated on device from the query axes (delay.py:211)
+__global__ void k_sample_grid(const CubeView c, const double *__restrict__ xpts, int nx, const double *__restrict__ ypts, int ny, double ht,
+                              double *__restrict__ out_wet, double *__restrict__ out_hydro) {
+    const int64_t n = (int64_t)ny * nx;
+    for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
+        const int j = (int)(r / nx), i = (int)(r % nx);
+        double vw, vh;
+        sample_scipy(c, __ldg(ypts + j), __ldg(xpts + i), ht, -1, vw, vh);
+        out_wet[r] = vw;
+        out_hydro[r] = vh;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// ray geometry shared by K0 and K3
+// ------------------------------------------------------------------------------------------------
+struct RayGeom {
+    int geom_kind, los_kind;
+    const double *gx, *gy;  // GRID: xpts[nx], ypts[ny];  POINTS: lon[n], lat[n]
+    const double *los;      // ARRAY: [n][3]
+    double e, n, u;         // ENU_CONST
+    double ht;
+    int nx;
+};
+
+__device__ __forceinline__ void ray_setup(const RayGeom &G, int64_t r, Vec3 &g, Vec3 &u) {
+    double lat, lon;
+    if (G.geom_kind == RDR_GEOM_GRID) {
+        lon = __ldg(G.gx + (r % G.nx));
+        lat = __ldg(G.gy + (r / G.nx));
+    } else {
+        lon = __ldg(G.gx + r);
+        lat = __ldg(G.gy + r);
+    }
+    double slat, clat, slon, clon;
+    g = lla2ecef(lat, lon, G.ht, slat, clat, slon, clon);
+    if (G.los_kind == RDR_LOS_ARRAY) {
+        u = {__ldg(G.los + 3 * r), __ldg(G.los + 3 * r + 1), __ldg(G.los + 3 * r + 2)};
+    } else if (G.los_kind == RDR_LOS_ENU_CONST) {
+        u = enu2ecef(G.e, G.n, G.u, slat, clat, slon, clon);
+    } else {  // zenith: getZenithLookVecs (losreader.py:312-314)
+        u = {clat * clon, clat * slon, slat};
+    }
+}
+
+// warp max of non-negative doubles via two 32-bit REDUX ops on the IEEE bit pattern (monotone for x >= 0)
+__device__ __forceinline__ unsigned long long warp_max_bits(unsigned long long bits) {
+    const unsigned hi = (unsigned)(bits >> 32), lo = (unsigned)bits;
+    const unsigned mhi = __reduce_max_sync(0xffffffffu, hi);
+    const unsigned mlo = __reduce_max_sync(0xffffffffu, hi == mhi ? lo : 0u);
+    return ((unsigned long long)mhi << 32) | mlo;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K0: layer intersections for every ray + per-layer max length + first-sample-below counter
+//   t_out[0][r]   = along-ray distance of the bottom of the first contributing layer
+//   t_out[k+1][r] = along-ray distance of the top of contributing layer k
+//   red[k]        = bits of max_r |P_hi - P_lo| (atomicMax on the bit pattern), red[K] = #NaN rays, red[K+1] = #first sample below zmin
+// ------------------------------------------------------------------------------------------------
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_ray_layers(const RayGeom G, int64_t n_rays, int K, const double *__restrict__ plan,
+                                                      double *__restrict__ t_out, unsigned long long *__restrict__ red, double zmin) {
+    extern __shared__ unsigned long long smax[];  // [K + 2]
+    for (int i = threadIdx.x; i < K + 2; i += BLOCK) smax[i] = 0ull;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int64_t n_pad = (n_rays + 31) / 32 * 32;
+    for (int64_t r = blockIdx.x * (int64_t)BLOCK + threadIdx.x; r < n_pad; r += (int64_t)gridDim.x * BLOCK) {
+        const bool valid = r < n_rays;
+        Vec3 g, u;
+        ray_setup(G, valid ? r : n_rays - 1, g, u);
+        Vec3 lo, hi;
+        double cosf = 1.0, t;
+        bool any_nan = false;
+        for (int k = 0; k < K; ++k) {
+            const double a = __ldg(plan + k), b = __ldg(plan + K + k);
+            double len;
+            if (k == 0) {
+                lo = top_of_atmosphere<10>(g, u, a, 1.0, t);
+                if (valid) t_out[r] = t;
+                // hint for the whole-raster clamp of delay.py:306-307: height of the very first sample, evaluated on the
+                // same reconstructed point K3 will use
+                const double h0 = ecef2height(ray_point(g, u, t));
+                const unsigned below = __ballot_sync(0xffffffffu, valid && (h0 < zmin));
+                if (lane == 0 && below) atomicAdd(&smax[K + 1], (unsigned long long)__popc(below));
+                hi = top_of_atmosphere<10>(g, u, b, 1.0, t);
+                len = norm3(hi - lo);
+                cosf = (b - a) / len;
+            } else {
+                lo = hi;
+                hi = top_of_atmosphere<3>(g, u, b, cosf, t);
+                len = norm3(hi - lo);
+            }
+            if (valid) t_out[(int64_t)(k + 1) * n_rays + r] = t;
+            const bool isn = !(len == len);
+            any_nan |= isn;
+            const unsigned long long bits = (valid && !isn) ? (unsigned long long)__double_as_longlong(len) : 0ull;
+            const unsigned long long m = warp_max_bits(bits);
+            if (lane == 0 && m > smax[k]) atomicMax(&smax[k], m);
+        }
+        const unsigned nn = __ballot_sync(0xffffffffu, valid && any_nan);
+        if (lane == 0 && nn) atomicAdd(&smax[K], (unsigned long long)__popc(nn));
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < K + 2; i += BLOCK) {
+        const unsigned long long v = smax[i];
+        if (v) {
+            if (i < K) atomicMax(red + i, v); else atomicAdd(red + i, v);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3: fused integrate.  One thread per ray; all lanes of a warp walk the same (layer, step) sequence because the
+// step counts are global (delay.py:283), so there is no divergence and neighbouring rays hit the same cube cells.
+// The sample at a layer interface is evaluated once and used with both layers' end weights (the reference evaluates
+// the same point twice, delay.py:290-323).
+// ------------------------------------------------------------------------------------------------
+template <typename OUT, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_ray_integrate(const CubeView c, const RayGeom G, int64_t n_rays, int K,
+                                                         const double *__restrict__ t_in, const int *__restrict__ nparts,
+                                                         const int *__restrict__ layer_cell, int clamp_low_first, double zmin, double zmax,
+                                                         OUT *__restrict__ out_wet, OUT *__restrict__ out_hydro, int accumulate,
+                                                         unsigned long long *__restrict__ counters) {
+    const int lane = threadIdx.x & 31;
+    const int64_t n_pad = (n_rays + 31) / 32 * 32;
+    unsigned long long n_below = 0, n_above = 0, n_first_below = 0;
+    for (int64_t r = blockIdx.x * (int64_t)BLOCK + threadIdx.x; r < n_pad; r += (int64_t)gridDim.x * BLOCK) {
+        const bool valid = r < n_rays;
+        const int64_t rr = valid ? r : n_rays - 1;
+        Vec3 g, u;
+        ray_setup(G, rr, g, u);
+        double acc_w = 0.0, acc_h = 0.0;
+        double t_lo = __ldcs(t_in + rr);
+        Vec3 lo = ray_point(g, u, t_lo);
+        double vw_prev = 0.0, vh_prev = 0.0;
+        for (int k = 0; k < K; ++k) {
+            const double t_hi = __ldcs(t_in + (int64_t)(k + 1) * n_rays + rr);
+            const Vec3 hi = ray_point(g, u, t_hi);
+            const Vec3 d = hi - lo;
+            const double len = norm3(d);
+            const int np = __ldg(nparts + k);
+            const int cell = __ldg(layer_cell + k);
+            const double step = 1.0 / (double)(np - 1);                 // np.linspace(0, 1, np): j * step, last = 1.0
+            const double wt_full = (len * 1.0e-6) / ((double)np - 1.0);  // delay.py:315
+            const double wt_half = 0.5 * wt_full;
+            for (int j = (k == 0 ? 0 : 1); j < np; ++j) {
+                const double ff = (j == np - 1) ? 1.0 : (double)j * step;
+                const Vec3 p = {lo.x + ff * d.x, lo.y + ff * d.y, lo.z + ff * d.z};  // delay.py:292
+                double lon, lat, h;
+                ecef2lla(p, lon, lat, h);
+                double X = lon, Y = lat;
+                if (c.crs_kind == RDR_CRS_LCC_SPHERE) lcc_forward(c.crs, lon, lat, X, Y);
+                if (k == 0 && j == 0) {
+                    const unsigned b = __ballot_sync(0xffffffffu, valid && (h < zmin));
+                    if (lane == 0) n_first_below += __popc(b);
+                    if (clamp_low_first) h = zmin;  // all pixels below min(z): delay.py:306-307
+                }
+                const unsigned bl = __ballot_sync(0xffffffffu, valid && (h < zmin)), ab = __ballot_sync(0xffffffffu, valid && (h > zmax));
+                if (lane == 0) {
+                    n_below += __popc(bl);
+                    n_above += __popc(ab);
+                }
+                double vw, vh;
+                sample_scipy(c, Y, X, h, cell, vw, vh);
+                if (j == 0) {  // only k == 0
+                    acc_w = __dadd_rn(acc_w, __dmul_rn(wt_half, vw));
+                    acc_h = __dadd_rn(acc_h, __dmul_rn(wt_half, vh));
+                } else {
+                    const double wt = (j == np - 1) ? wt_half : wt_full;
+                    acc_w = __dadd_rn(acc_w, __dmul_rn(wt, vw));
+                    acc_h = __dadd_rn(acc_h, __dmul_rn(wt, vh));
+                }
+                vw_prev = vw;
+                vh_prev = vh;
+            }
+            // next layer's first sample (ff = 0) is this layer's last point: reuse the value with the next end weight
+            if (k + 1 < K) {
+                const double t_nx = __ldcs(t_in + (int64_t)(k + 2) * n_rays + rr);
+                const Vec3 hi2 = ray_point(g, u, t_nx);
+                const double len2 = norm3(hi2 - hi);
+                const int np2 = __ldg(nparts + k + 1);
+                const double wt2 = 0.5 * ((len2 * 1.0e-6) / ((double)np2 - 1.0));
+                acc_w = __dadd_rn(acc_w, __dmul_rn(wt2, vw_prev));
+                acc_h = __dadd_rn(acc_h, __dmul_rn(wt2, vh_prev));
+            }
+            lo = hi;
+            t_lo = t_hi;
+        }
+        if (valid) {
+            if (accumulate) {
+                out_wet[r] = (OUT)((double)out_wet[r] + acc_w);
+                out_hydro[r] = (OUT)((double)out_hydro[r] + acc_h);
+            } else {
+                out_wet[r] = (OUT)acc_w;
+                out_hydro[r] = (OUT)acc_h;
+            }
+        }
+    }
+    if (lane == 0) {
+        if (n_first_below) atomicAdd(counters + 0, n_first_below);
+        if (n_below) atomicAdd(counters + 1, n_below);
+        if (n_above) atomicAdd(counters + 2, n_above);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// small API-parity kernels
+// ------------------------------------------------------------------------------------------------
+__global__ void k_top_of_atmosphere(const double *__restrict__ xyz, const double *__restrict__ look, int64_t n, double toa,
+                                    const double *__restrict__ factor, double *__restrict__ out) {
+    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const Vec3 g = {xyz[3 * r], xyz[3 * r + 1], xyz[3 * r + 2]}, u = {look[3 * r], look[3 * r + 1], look[3 * r + 2]};
+    double t;
+    const Vec3 p = factor ? top_of_atmosphere<3>(g, u, toa, factor[r], t) : top_of_atmosphere<10>(g, u, toa, 1.0, t);
+    out[3 * r] = p.x;
+    out[3 * r + 1] = p.y;
+    out[3 * r + 2] = p.z;
+}
+
+__global__ void k_build_ray(const double *__restrict__ xyz, const double *__restrict__ look, int64_t n, int K, const double *__restrict__ plan,
+                            double *__restrict__ lens, double *__restrict__ lows, double *__restrict__ highs) {
+    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const Vec3 g = {xyz[3 * r], xyz[3 * r + 1], xyz[3 * r + 2]}, u = {look[3 * r], look[3 * r + 1], look[3 * r + 2]};
+    Vec3 lo, hi;
+    double cosf = 1.0, t;
+    for (int k = 0; k < K; ++k) {
+        const double a = plan[k], b = plan[K + k];
+        if (k == 0) {
+            lo = top_of_atmosphere<10>(g, u, a, 1.0, t);
+            hi = top_of_atmosphere<10>(g, u, b, 1.0, t);
+        } else {
+            lo = hi;
+            hi = top_of_atmosphere<3>(g, u, b, cosf, t);
+        }
+        const double len = norm3(hi - lo);
+        if (k == 0) cosf = (b - a) / len;
+        const int64_t o = (int64_t)k * n + r;
+        lens[o] = len;
+        lows[3 * o] = lo.x; lows[3 * o + 1] = lo.y; lows[3 * o + 2] = lo.z;
+        highs[3 * o] = hi.x; highs[3 * o + 1] = hi.y; highs[3 * o + 2] = hi.z;
+    }
+}
+
+__global__ void k_lla2ecef(const double *lat, const double *lon, const double *hgt, int64_t n, double *x, double *y, double *z) {
+    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    double a, b, c2, d;
+    const Vec3 p = lla2ecef(lat[r], lon[r], hgt[r], a, b, c2, d);
+    x[r] = p.x; y[r] = p.y; z[r] = p.z;
+}
+
+__global__ void k_ecef2lla(const double *x, const double *y, const double *z, int64_t n, double *lon, double *lat, double *hgt) {
+    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    double lo, la, h;
+    ecef2lla({x[r], y[r], z[r]}, lo, la, h);
+    lon[r] = lo; lat[r] = la; hgt[r] = h;
+}
+
+// K1: makePoints (makePoints.pyx:142-147): out[r][c][k] = sp[r][c] + (k*step)*slv[r][c]; separate multiply and add, no FMA,
+// because the reference is built without FMA contraction (setup.py:31-37) -- bit-exact against test_result_makePoints3D.txt
+__global__ void k_make_points(const double *__restrict__ sp, const double *__restrict__ slv, int64_t n_rays, double step, int64_t npts,
+                              double *__restrict__ out) {
+    const int64_t total = n_rays * 3 * npts;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t k = i % npts, rc = i / npts;
+        const double base = __dmul_rn((double)k, step);  // np.arange(0, L+step, step)[k]
+        __stcs(out + i, __dadd_rn(__ldg(sp + rc), __dmul_rn(base, __ldg(slv + rc))));
+    }
+}
+
+// K4: interpolate_along_axis (interpolate.h:78-118 per column): one thread per output element
+__global__ void k_interp_axis(const double *__restrict__ x, const double *__restrict__ y, const double *__restrict__ xnew, int64_t ncol,
+                              int nin, int nout, int has_fill, double fill, double *__restrict__ out) {
+    const int64_t total = ncol * nout;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t col = i / nout;
+        const double *gx = x + col * nin, *gy = y + col * nin;
+        const double v = xnew[i];
+        int hi = bisect_left(gx, nin, v);
+        if (has_fill) {
+            if (hi < 1 || hi > nin - 1) {
+                out[i] = fill;
+                continue;
+            }
+        } else {
+            hi = hi < 1 ? 1 : (hi > nin - 1 ? nin - 1 : hi);
+        }
+        const double x0 = gx[hi - 1], x1 = gx[hi], y0 = gy[hi - 1], y1 = gy[hi];
+        const double slope = __ddiv_rn(y1 - y0, x1 - x0);
+        out[i] = __dadd_rn(y0, __dmul_rn(slope, v - x0));
+    }
+}
+
+// RAiDER.interpolate.interpolate for ndim = 1, 2, 3 (dedicated formulas) and N-D (corner bitmask walk)
+struct NdGrid {
+    const double *g[8];
+    int n[8];
+    int ndim;
+};
+
+__global__ void k_interp_nd(const NdGrid G, const double *__restrict__ values, const double *__restrict__ pts, int64_t n, int has_fill,
+                            double fill, double *__restrict__ out) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int nd = G.ndim;
+        int hi[8];
+        double dlo[8], dhi[8], span[8];
+        bool filled = false;
+        for (int d = 0; d < nd; ++d) {
+            const double v = pts[i * nd + d];
+            int k = bisect_left(G.g[d], G.n[d], v);
+            if (has_fill) {
+                if (k < 1 || k > G.n[d] - 1) {
+                    filled = true;
+                    break;
+                }
+            } else {
+                k = k < 1 ? 1 : (k > G.n[d] - 1 ? G.n[d] - 1 : k);
+            }
+            hi[d] = k;
+            const double g0 = G.g[d][k - 1], g1 = G.g[d][k];
+            dlo[d] = v - g0;
+            dhi[d] = g1 - v;
+            span[d] = g1 - g0;
+        }
+        if (filled) {
+            out[i] = fill;
+            continue;
+        }
+        if (nd == 1) {  // interpolate.h:109-116
+            const double y0 = values[hi[0] - 1], y1 = values[hi[0]];
+            const double slope = __ddiv_rn(y1 - y0, span[0]);
+            out[i] = __dadd_rn(y0, __dmul_rn(slope, dlo[0]));
+        } else if (nd == 2) {  // interpolate.cpp:61-81
+            const int64_t n1 = G.n[1];
+            const double z00 = values[(hi[0] - 1) * n1 + hi[1] - 1], z01 = values[(hi[0] - 1) * n1 + hi[1]];
+            const double z10 = values[hi[0] * n1 + hi[1] - 1], z11 = values[hi[0] * n1 + hi[1]];
+            const double a = __dadd_rn(__dmul_rn(z00, dhi[1]), __dmul_rn(z01, dlo[1]));
+            const double b = __dadd_rn(__dmul_rn(z10, dhi[1]), __dmul_rn(z11, dlo[1]));
+            out[i] = __ddiv_rn(__dadd_rn(__dmul_rn(dhi[0], a), __dmul_rn(dlo[0], b)), __dmul_rn(span[0], span[1]));
+        } else if (nd == 3) {  // interpolate.cpp:138-174
+            const int64_t n1 = G.n[1], n2 = G.n[2];
+            const int64_t l0 = (hi[0] - 1) * n1 * n2, h0 = hi[0] * n1 * n2, l1 = (hi[1] - 1) * n2, h1 = hi[1] * n2, l2 = hi[2] - 1, h2 = hi[2];
+            out[i] = trilinear_raider(values[l0 + l1 + l2], values[l0 + l1 + h2], values[l0 + h1 + l2], values[l0 + h1 + h2],
+                                      values[h0 + l1 + l2], values[h0 + l1 + h2], values[h0 + h1 + l2], values[h0 + h1 + h2], dlo[0], dhi[0],
+                                      dlo[1], dhi[1], dlo[2], dhi[2], __dmul_rn(__dmul_rn(span[0], span[1]), span[2]));
+        } else {  // interpolate.cpp:204-256
+            double vol = 1.0;
+            for (int d = 0; d < nd; ++d) vol = __dmul_rn(vol, span[d]);
+            double acc = 0.0;
+            for (unsigned j = 0; j < (1u << nd); ++j) {
+                int64_t index = 0;
+                for (int d = 0; d < nd; ++d) {
+                    index += ((j >> d) & 1) ? hi[d] : hi[d] - 1;
+                    index *= (d + 1 < nd) ? G.n[d + 1] : 1;
+                }
+                double term = values[index];
+                for (int d = 0; d < nd; ++d) term = __dmul_rn(term, ((j >> d) & 1) ? dlo[d] : dhi[d]);
+                acc = __dadd_rn(acc, term);
+            }
+            out[i] = __ddiv_rn(acc, vol);
+        }
+    }
+}
+
+// host-side restatement of the scalar layer decisions of build_ray (losreader.py:785-809)
+void layer_plan(const std::vector<double> &zs, double ht, double zref, std::vector<double> &low, std::vector<double> &high,
+                std::vector<int> &cell) {
+    low.clear();
+    high.clear();
+    cell.clear();
+    const size_t nz = zs.size();
+    for (size_t zz = 0; zz + 1 < nz; ++zz) {
+        double low_ht = zs[zz], high_ht = zs[zz + 1];
+        if (high_ht == zs[nz - 1]) high_ht -= 0.01;
+        if (high_ht < ht || low_ht >= zref) continue;
+        if (low_ht < ht) low_ht = ht;
+        if (high_ht > zref) high_ht = zref;
+        if (fabs(high_ht - low_ht) < 1.0) continue;
+        low.push_back(low_ht);
+        high.push_back(high_ht);
+        cell.push_back((int)zz);
+    }
+}
+
+// The Npts rule of makePoints.pyx:130-134 as Cython compiles it for C doubles: `a // b` is floor(a / b) and `a % b` is
+// fmod with Python's sign convention (__Pyx_mod_double).  Pinned against the compiled reference (tests/golden/makepoints.npz).
+int64_t make_points_npts(double max_len, double step) {
+    double r = fmod(max_len, step);
+    if (r != 0.0 && ((r < 0.0) != (step < 0.0))) r += step;
+    int64_t n = (int64_t)floor(max_len / step);
+    if (r != 0.0) n += 1;
+    return n;
+}
+
+struct ScopedDevice {
+    int prev = -1;
+    explicit ScopedDevice(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+    }
+    ~ScopedDevice() {
+        int cur = -1;
+        cudaGetDevice(&cur);
+        if (prev >= 0 && cur != prev) cudaSetDevice(prev);
+    }
+};
+
+// stage a host array to device scratch (or pass a device pointer through)
+template <typename T>
+int stage_in(rdr_handle_t h, DevBuf &buf, const T *src, size_t count, int mem, const T **out) {
+    if (mem == RDR_MEM_DEVICE) {
+        *out = src;
+        return RDR_OK;
+    }
+    CUDA_TRY(h, buf.reserve(std::max<size_t>(count * sizeof(T), 16)));
+    CUDA_TRY(h, cudaMemcpyAsync(buf.p, src, count * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+    *out = buf.as<T>();
+    return RDR_OK;
+}
+
+}  // namespace
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+RDR_API int rdr_abi_version(void) { return RDR_ABI_VERSION; }
+
+RDR_API int rdr_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+RDR_API const char *rdr_last_error(rdr_handle_t h) { return h ? h->err.c_str() : g_last_error.c_str(); }
+
+RDR_API int rdr_create(int device, rdr_handle_t *out) {
+    if (!out) return fail(nullptr, RDR_ERR_INVALID, "rdr_create: out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(nullptr, RDR_ERR_CUDA, std::string("rdr_create: no CUDA device available (") + cudaGetErrorString(e) +
+                                               "); libraider_b200 has no CPU fallback");
+    }
+    if (device < 0 || device >= n) return fail(nullptr, RDR_ERR_INVALID, "rdr_create: device index out of range");
+    rdr_handle_t h = new rdr_handle_s();
+    h->device = device;
+    ScopedDevice sd(device);
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) {
+        delete h;
+        return fail(nullptr, RDR_ERR_CUDA, std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(e));
+    }
+    h->sm_count = prop.multiProcessorCount;
+    if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        delete h;
+        return fail(nullptr, RDR_ERR_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
+    }
+    h->own_stream = true;
+    *out = h;
+    return RDR_OK;
+}
+
+RDR_API int rdr_destroy(rdr_handle_t h) {
+    if (!h) return RDR_OK;
+    ScopedDevice sd(h->device);
+    cudaStreamSynchronize(h->stream);
+    for (DevBuf *b : {&h->d_axes, &h->d_cells, &h->d_stage, &h->d_fields, &h->d_gx, &h->d_gy, &h->d_los, &h->d_plan, &h->d_t, &h->d_red,
+                      &h->d_nparts, &h->d_out, &h->d_in})
+        b->release();
+    if (h->own_stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return RDR_OK;
+}
+
+RDR_API int rdr_set_stream(rdr_handle_t h, void *cuda_stream) {
+    CHECK_ARG(h, h != nullptr, "rdr_set_stream: NULL handle");
+    ScopedDevice sd(h->device);
+    cudaStreamSynchronize(h->stream);
+    if (cuda_stream == nullptr) {
+        if (!h->own_stream) {
+            CUDA_TRY(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+            h->own_stream = true;
+        }
+    } else {
+        if (h->own_stream) cudaStreamDestroy(h->stream);
+        h->stream = static_cast<cudaStream_t>(cuda_stream);
+        h->own_stream = false;
+    }
+    return RDR_OK;
+}
+
+RDR_API int rdr_synchronize(rdr_handle_t h) {
+    CHECK_ARG(h, h != nullptr, "rdr_synchronize: NULL handle");
+    ScopedDevice sd(h->device);
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return RDR_OK;
+}
+
+RDR_API int64_t rdr_launch_count(rdr_handle_t h) { return h ? h->launches : 0; }
+
+// ------------------------------------------------------------------------------------------------
+static int check_axis(rdr_handle_t h, const double *a, int64_t n, const char *name, std::vector<double> &out, bool &flipped) {
+    CHECK_ARG(h, a != nullptr && n >= 2, std::string("rdr_set_cube: axis ") + name + " needs at least 2 nodes");
+    out.assign(a, a + n);
+    bool asc = true, desc = true;
+    for (int64_t i = 1; i < n; ++i) {
+        if (!(a[i] > a[i - 1])) asc = false;
+        if (!(a[i] < a[i - 1])) desc = false;
+    }
+    CHECK_ARG(h, asc || desc, std::string("rdr_set_cube: axis ") + name + " must be strictly ascending or descending");
+    flipped = !asc;
+    if (flipped) std::reverse(out.begin(), out.end());
+    return RDR_OK;
+}
+
+static int upload_fields(rdr_handle_t h, const float *wet, const float *hydro, int layout, int mem, float2 *dst) {
+    const int64_t total = h->ny * h->nx * h->nz;
+    const float *dw = wet, *dh = hydro;
+    if (mem == RDR_MEM_HOST) {
+        CUDA_TRY(h, h->d_stage.reserve(2 * total * sizeof(float)));
+        float *s = h->d_stage.as<float>();
+        CUDA_TRY(h, cudaMemcpyAsync(s, wet, total * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+        CUDA_TRY(h, cudaMemcpyAsync(s + total, hydro, total * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+        dw = s;
+        dh = s + total;
+    }
+    k_gather_fields<<<grid_for(total, 256, h->sm_count, 16), 256, 0, h->stream>>>(dw, dh, dst, (int)h->ny, (int)h->nx, (int)h->nz, layout,
+                                                                                  h->flip_y, h->flip_x, h->flip_z);
+    h->launches++;
+    CUDA_TRY(h, cudaGetLastError());
+    return RDR_OK;
+}
+
+static int pack_cells(rdr_handle_t h) {
+    const int64_t ncol = h->ny * h->nx;
+    CUDA_TRY(h, h->d_cells.reserve(ncol * (h->nz - 1) * sizeof(float4)));
+    k_pack_cells<<<grid_for(ncol * (h->nz - 1), 256, h->sm_count, 16), 256, 0, h->stream>>>(h->d_fields.as<float2>(), h->d_cells.as<float4>(),
+                                                                                            ncol, (int)h->nz);
+    h->launches++;
+    CUDA_TRY(h, cudaGetLastError());
+    return RDR_OK;
+}
+
+RDR_API int rdr_set_cube(rdr_handle_t h, const double *ys, int64_t ny, const double *xs, int64_t nx, const double *zs, int64_t nz,
+                         const float *wet, const float *hydro, int layout, int crs_kind, const double *crs_params, int mem) {
+    CHECK_ARG(h, h != nullptr, "rdr_set_cube: NULL handle");
+    CHECK_ARG(h, wet && hydro, "rdr_set_cube: NULL field pointer");
+    CHECK_ARG(h, layout == RDR_LAYOUT_ZYX || layout == RDR_LAYOUT_YXZ, "rdr_set_cube: unknown layout");
+    CHECK_ARG(h, crs_kind == RDR_CRS_GEOGRAPHIC || crs_kind == RDR_CRS_LCC_SPHERE, "rdr_set_cube: unknown crs_kind");
+    CHECK_ARG(h, crs_kind == RDR_CRS_GEOGRAPHIC || crs_params, "rdr_set_cube: LCC needs crs_params");
+    CHECK_ARG(h, ny < (1 << 24) && nx < (1 << 24) && nz <= MAX_LAYERS, "rdr_set_cube: cube too large");
+    ScopedDevice sd(h->device);
+    h->has_cube = false;
+    h->has_rays = false;
+    int rc;
+    if ((rc = check_axis(h, ys, ny, "y", h->ys, h->flip_y))) return rc;
+    if ((rc = check_axis(h, xs, nx, "x", h->xs, h->flip_x))) return rc;
+    if ((rc = check_axis(h, zs, nz, "z", h->zs, h->flip_z))) return rc;
+    h->ny = ny; h->nx = nx; h->nz = nz;
+    h->crs_kind = crs_kind;
+    for (int i = 0; i < 7; ++i) h->crs[i] = crs_params ? crs_params[i] : 0.0;
+    std::vector<double> axes;
+    axes.insert(axes.end(), h->ys.begin(), h->ys.end());
+    axes.insert(axes.end(), h->xs.begin(), h->xs.end());
+    axes.insert(axes.end(), h->zs.begin(), h->zs.end());
+    CUDA_TRY(h, h->d_axes.reserve(axes.size() * sizeof(double)));
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_axes.p, axes.data(), axes.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, h->d_fields.reserve(ny * nx * nz * sizeof(float2)));
+    if ((rc = upload_fields(h, wet, hydro, layout, mem, h->d_fields.as<float2>()))) return rc;
+    if ((rc = pack_cells(h))) return rc;
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));  // host staging vectors go out of scope
+    h->has_cube = true;
+    return RDR_OK;
+}
+
+RDR_API int rdr_blend_cube(rdr_handle_t h, const float *wet1, const float *hydro1, int layout, double w0, double w1, int mem) {
+    CHECK_ARG(h, h != nullptr, "rdr_blend_cube: NULL handle");
+    if (!h->has_cube) return fail(h, RDR_ERR_STATE, "rdr_blend_cube: no cube staged (call rdr_set_cube first)");
+    CHECK_ARG(h, wet1 && hydro1, "rdr_blend_cube: NULL field pointer");
+    ScopedDevice sd(h->device);
+    const int64_t total = h->ny * h->nx * h->nz;
+    // second epoch goes behind the (possibly host-staged) raw fields in d_stage
+    DevBuf second;
+    CUDA_TRY(h, second.reserve(total * sizeof(float2)));
+    int rc = upload_fields(h, wet1, hydro1, layout, mem, second.as<float2>());
+    if (rc == RDR_OK) {
+        k_blend_fields<<<grid_for(total, 256, h->sm_count, 16), 256, 0, h->stream>>>(h->d_fields.as<float2>(), second.as<float2>(), total,
+                                                                                     (float)w0, (float)w1);
+        h->launches++;
+        if (cudaGetLastError() != cudaSuccess) rc = fail(h, RDR_ERR_CUDA, "k_blend_fields launch failed");
+    }
+    if (rc == RDR_OK) rc = pack_cells(h);
+    cudaStreamSynchronize(h->stream);
+    second.release();
+    h->has_rays = false;
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+RDR_API int rdr_sample(rdr_handle_t h, const void *pts, int64_t n, void *out_wet, void *out_hydro, int dtype, int semantics, int mem) {
+    CHECK_ARG(h, h != nullptr, "rdr_sample: NULL handle");
+    if (!h->has_cube) return fail(h, RDR_ERR_STATE, "rdr_sample: no cube staged");
+    CHECK_ARG(h, n >= 0 && (n == 0 || (pts && out_wet && out_hydro)), "rdr_sample: NULL pointer");
+    CHECK_ARG(h, dtype == RDR_F64 || dtype == RDR_F32, "rdr_sample: dtype must be RDR_F64 or RDR_F32");
+    CHECK_ARG(h, semantics >= RDR_SEM_SCIPY && semantics <= RDR_SEM_RAIDER_CLAMP, "rdr_sample: unknown semantics");
+    if (n == 0) return RDR_OK;
+    ScopedDevice sd(h->device);
+    const size_t es = dtype == RDR_F64 ? 8 : 4;
+    const void *dpts = pts;
+    void *dw = out_wet, *dh = out_hydro;
+    if (mem == RDR_MEM_HOST) {
+        CUDA_TRY(h, h->d_in.reserve(n * 3 * es));
+        CUDA_TRY(h, h->d_out.reserve(n * 2 * es));
+        CUDA_TRY(h, cudaMemcpyAsync(h->d_in.p, pts, n * 3 * es, cudaMemcpyHostToDevice, h->stream));
+        dpts = h->d_in.p;
+        dw = h->d_out.p;
+        dh = static_cast<char *>(h->d_out.p) + n * es;
+    }
+    const CubeView c = make_view(h);
+    constexpr int BLOCK = 256;
+    const int grid = grid_for(n, BLOCK, h->sm_count, 8);
+    if (dtype == RDR_F64)
+        k_sample_points<double, BLOCK><<<grid, BLOCK, 0, h->stream>>>(c, static_cast<const double *>(dpts), n, static_cast<double *>(dw),
+                                                                      static_cast<double *>(dh), semantics);
+    else
+        k_sample_points<float, BLOCK><<<grid, BLOCK, 0, h->stream>>>(c, static_cast<const float *>(dpts), n, static_cast<float *>(dw),
+                                                                     static_cast<float *>(dh), semantics);
+    h->launches++;
+    CUDA_TRY(h, cudaGetLastError());
+    if (mem == RDR_MEM_HOST) {
+        CUDA_TRY(h, cudaMemcpyAsync(out_wet, dw, n * es, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(h, cudaMemcpyAsync(out_hydro, dh, n * es, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    }
+    return RDR_OK;
+}
+
+RDR_API int rdr_sample_grid(rdr_handle_t h, const double *xpts, int64_t nx, const double *ypts, int64_t ny, double ht, double *out_wet,
+                            double *out_hydro, int mem) {
+    CHECK_ARG(h, h != nullptr, "rdr_sample_grid: NULL handle");
+    if (!h->has_cube) return fail(h, RDR_ERR_STATE, "rdr_sample_grid: no cube staged");
+    CHECK_ARG(h, xpts && ypts && out_wet && out_hydro && nx > 0 && ny > 0, "rdr_sample_grid: bad arguments");
+    ScopedDevice sd(h->device);
+    const int64_t n = nx * ny;
+    const double *dx, *dy;
+    int rc;
+    // query axes are small parameter vectors: always host
+    if ((rc = stage_in(h, h->d_gx, xpts, nx, RDR_MEM_HOST, &dx))) return rc;
+    if ((rc = stage_in(h, h->d_gy, ypts, ny, RDR_MEM_HOST, &dy))) return rc;
+    double *dw = out_wet, *dh = out_hydro;
+    if (mem == RDR_MEM_HOST) {
+        CUDA_TRY(h, h->d_out.reserve(n * 2 * sizeof(double)));
+        dw = h->d_out.as<double>();
+        dh = dw + n;
+    }
+    k_sample_grid<<<grid_for(n, 256, h->sm_count, 8), 256, 0, h->stream>>>(make_view(h), dx, (int)nx, dy, (int)ny, ht, dw, dh);
+    h->launches++;
+    CUDA_TRY(h, cudaGetLastError());
+    if (mem == RDR_MEM_HOST) {
+        CUDA_TRY(h, cudaMemcpyAsync(out_wet, dw, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(h, cudaMemcpyAsync(out_hydro, dh, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    }
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    h->has_rays = false;  // d_gx/d_gy were reused
+    return RDR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+RDR_API int rdr_ray_plan(rdr_handle_t h, double ht, double zref, int64_t *n_layers, double *low_ht, double *high_ht) {
+    CHECK_ARG(h, h != nullptr, "rdr_ray_plan: NULL handle");
+    if (!h->has_cube) return fail(h, RDR_ERR_STATE, "rdr_ray_plan: no cube staged");
+    CHECK_ARG(h, n_layers != nullptr, "rdr_ray_plan: n_layers is NULL");
+    std::vector<double> lo, hi;
+    std::vector<int> cell;
+    layer_plan(h->zs, ht, zref, lo, hi, cell);
+    *n_layers = (int64_t)lo.size();
+    if (low_ht) std::copy(lo.begin(), lo.end(), low_ht);
+    if (high_ht) std::copy(hi.begin(), hi.end(), high_ht);
+    return RDR_OK;
+}
+
+static RayGeom make_geom(rdr_handle_t h) {
+    RayGeom G;
+    G.geom_kind = h->geom_kind;
+    G.los_kind = h->los_kind;
+    G.gx = h->p_gx;
+    G.gy = h->p_gy;
+    G.los = h->p_los;
+    G.e = h->los_const[0];
+    G.n = h->los_const[1];
+    G.u = h->los_const[2];
+    G.ht = h->ht;
+    G.nx = (int)h->ray_nx;
+    return G;
+}
+
+RDR_API int rdr_ray_layers(rdr_handle_t h, int geom_kind, const double *gx, const double *gy, int64_t ny, int64_t nx, int los_kind,
+                           const double *los, double ht, double zref, double *maxlen_out, int64_t *counts_out, int mem) {
+    CHECK_ARG(h, h != nullptr, "rdr_ray_layers: NULL handle");
+    if (!h->has_cube) return fail(h, RDR_ERR_STATE, "rdr_ray_layers: no cube staged");
+    CHECK_ARG(h, geom_kind == RDR_GEOM_GRID || geom_kind == RDR_GEOM_POINTS, "rdr_ray_layers: unknown geom_kind");
+    CHECK_ARG(h, los_kind >= RDR_LOS_ARRAY && los_kind <= RDR_LOS_ZENITH, "rdr_ray_layers: unknown los_kind");
+    CHECK_ARG(h, gx && gy && ny > 0 && nx > 0, "rdr_ray_layers: bad geometry arguments");
+    CHECK_ARG(h, los_kind == RDR_LOS_ZENITH || los != nullptr, "rdr_ray_layers: los is NULL");
+    ScopedDevice sd(h->device);
+    h->has_rays = false;
+    const int64_t n = ny * nx;
+    h->n_rays = n; h->ray_ny = ny; h->ray_nx = nx;
+    h->geom_kind = geom_kind; h->los_kind = los_kind;
+    h->ht = ht; h->zref = zref;
+    layer_plan(h->zs, ht, zref, h->low_ht, h->high_ht, h->layer_cell);
+    const int K = (int)h->low_ht.size();
+    h->n_layers = K;
+    if (counts_out) {
+        counts_out[0] = n; counts_out[1] = 0; counts_out[2] = 0; counts_out[3] = K;
+    }
+    if (K == 0) return fail(h, RDR_ERR_NO_LAYERS, "rdr_ray_layers: no model layer contributes between ht and zref");
+    int rc;
+    // geometry: grid axes are parameter vectors (host); point lists and LOS arrays are bulk (per `mem`)
+    if (geom_kind == RDR_GEOM_GRID) {
+        if ((rc = stage_in(h, h->d_gx, gx, nx, RDR_MEM_HOST, &h->p_gx))) return rc;
+        if ((rc = stage_in(h, h->d_gy, gy, ny, RDR_MEM_HOST, &h->p_gy))) return rc;
+    } else {
+        if ((rc = stage_in(h, h->d_gx, gx, n, mem, &h->p_gx))) return rc;
+        if ((rc = stage_in(h, h->d_gy, gy, n, mem, &h->p_gy))) return rc;
+    }
+    h->p_los = nullptr;
+    if (los_kind == RDR_LOS_ARRAY) {
+        if ((rc = stage_in(h, h->d_los, los, n * 3, mem, &h->p_los))) return rc;
+    } else if (los_kind == RDR_LOS_ENU_CONST) {
+        h->los_const[0] = los[0]; h->los_const[1] = los[1]; h->los_const[2] = los[2];
+    }
+    std::vector<double> plan(h->low_ht);
+    plan.insert(plan.end(), h->high_ht.begin(), h->high_ht.end());
+    CUDA_TRY(h, h->d_plan.reserve(plan.size() * sizeof(double)));
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_plan.p, plan.data(), plan.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, h->d_t.reserve((size_t)(K + 1) * n * sizeof(double)));
+    CUDA_TRY(h, h->d_red.reserve((K + 8) * sizeof(unsigned long long)));
+    CUDA_TRY(h, cudaMemsetAsync(h->d_red.p, 0, (K + 8) * sizeof(unsigned long long), h->stream));
+    constexpr int BLOCK = 128;
+    const int grid = grid_for(n, BLOCK, h->sm_count, 16);
+    k_ray_layers<BLOCK><<<grid, BLOCK, (K + 2) * sizeof(unsigned long long), h->stream>>>(
+        make_geom(h), n, K, h->d_plan.as<double>(), h->d_t.as<double>(), h->d_red.as<unsigned long long>(), h->zs.front());
+    h->launches++;
+    CUDA_TRY(h, cudaGetLastError());
+    std::vector<unsigned long long> red(K + 2);
+    CUDA_TRY(h, cudaMemcpyAsync(red.data(), h->d_red.p, (K + 2) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (maxlen_out)
+        for (int k = 0; k < K; ++k) memcpy(&maxlen_out[k], &red[k], sizeof(double));
+    if (counts_out) {
+        counts_out[1] = (int64_t)red[K];
+        counts_out[2] = (int64_t)red[K + 1];
+    }
+    h->has_rays = true;
+    if ((int64_t)red[K] == n) return fail(h, RDR_ERR_ALL_NAN, "geo2rdr did not converge. Check orbit coverage");
+    return RDR_OK;
+}
+
+RDR_API int rdr_ray_integrate(rdr_handle_t h, const double *maxlen, double max_segment_length, int clamp_low_first, void *out_wet,
+                              void *out_hydro, int out_dtype, int accumulate, int64_t *nparts_out, int64_t *oob_out, int mem) {
+    CHECK_ARG(h, h != nullptr, "rdr_ray_integrate: NULL handle");
+    if (!h->has_cube || !h->has_rays) return fail(h, RDR_ERR_STATE, "rdr_ray_integrate: call rdr_ray_layers first");
+    CHECK_ARG(h, maxlen && out_wet && out_hydro, "rdr_ray_integrate: NULL pointer");
+    CHECK_ARG(h, max_segment_length > 0, "rdr_ray_integrate: max_segment_length must be positive");
+    CHECK_ARG(h, out_dtype == RDR_F64 || out_dtype == RDR_F32, "rdr_ray_integrate: out_dtype must be RDR_F64 or RDR_F32");
+    ScopedDevice sd(h->device);
+    const int K = h->n_layers;
+    const int64_t n = h->n_rays;
+    // nParts = ceil(max / MAX_SEGMENT_LENGTH).astype(int) + 1   (delay.py:283) -- the bit-exact integer contract
+    std::vector<int> np_cell(2 * K);
+    for (int k = 0; k < K; ++k) {
+        const double q = ceil(maxlen[k] / max_segment_length);
+        CHECK_ARG(h, q == q && q < 1e7, "rdr_ray_integrate: per-layer max length is NaN or absurd");
+        int np = (int)q + 1;
+        if (np < 2) np = 2;  // a zero-length layer would divide by zero in the reference (np.linspace(0,1,1)); keep 2
+        np_cell[k] = np;
+        np_cell[K + k] = h->layer_cell[k];
+        if (nparts_out) nparts_out[k] = np;
+    }
+    CUDA_TRY(h, h->d_nparts.reserve(2 * K * sizeof(int)));
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_nparts.p, np_cell.data(), 2 * K * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    unsigned long long *counters = h->d_red.as<unsigned long long>() + K + 2;
+    CUDA_TRY(h, cudaMemsetAsync(counters, 0, 4 * sizeof(unsigned long long), h->stream));
+    const size_t es = out_dtype == RDR_F64 ? 8 : 4;
+    void *dw = out_wet, *dh = out_hydro;
+    if (mem == RDR_MEM_HOST) {
+        CUDA_TRY(h, h->d_out.reserve(2 * n * es));
+        dw = h->d_out.p;
+        dh = static_cast<char *>(h->d_out.p) + n * es;
+        if (accumulate) {
+            CUDA_TRY(h, cudaMemcpyAsync(dw, out_wet, n * es, cudaMemcpyHostToDevice, h->stream));
+            CUDA_TRY(h, cudaMemcpyAsync(dh, out_hydro, n * es, cudaMemcpyHostToDevice, h->stream));
+        }
+    }
+    constexpr int BLOCK = 128;
+    const int grid = grid_for(n, BLOCK, h->sm_count, 16);
+    const CubeView c = make_view(h);
+    const RayGeom G = make_geom(h);
+    const int *d_np = h->d_nparts.as<int>();
+    if (out_dtype == RDR_F64)
+        k_ray_integrate<double, BLOCK><<<grid, BLOCK, 0, h->stream>>>(c, G, n, K, h->d_t.as<double>(), d_np, d_np + K, clamp_low_first,
+                                                                      h->zs.front(), h->zs.back(), static_cast<double *>(dw),
+                                                                      static_cast<double *>(dh), accumulate, counters);
+    else
+        k_ray_integrate<float, BLOCK><<<grid, BLOCK, 0, h->stream>>>(c, G, n, K, h->d_t.as<double>(), d_np, d_np + K, clamp_low_first,
+                                                                     h->zs.front(), h->zs.back(), static_cast<float *>(dw),
+                                                                     static_cast<float *>(dh), accumulate, counters);
+    h->launches++;
+    CUDA_TRY(h, cudaGetLastError());
+    unsigned long long cnt[4] = {0, 0, 0, 0};
+    if (mem == RDR_MEM_HOST) {
+        CUDA_TRY(h, cudaMemcpyAsync(out_wet, dw, n * es, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(h, cudaMemcpyAsync(out_hydro, dh, n * es, cudaMemcpyDeviceToHost, h->stream));
+    }
+    if (oob_out || mem == RDR_MEM_HOST) {
+        CUDA_TRY(h, cudaMemcpyAsync(cnt, counters, sizeof(cnt), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        if (oob_out) {
+            oob_out[0] = (int64_t)cnt[0];  // first sample below min(z) (pre-clamp)
+            oob_out[1] = (int64_t)cnt[1];  // samples below min(z) after the clamp decision
+            oob_out[2] = (int64_t)cnt[2];  // samples above max(z)
+        }
+    }
+    return RDR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// handle-less helpers: create a transient context on `device`
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct Transient {
+    int device;
+    ScopedDevice sd;
+    std::vector<void *> bufs;
+    explicit Transient(int dev) : device(dev), sd(dev) {}
+    ~Transient() {
+        for (void *p : bufs) cudaFree(p);
+    }
+    template <typename T>
+    cudaError_t in(const T *src, size_t count, int mem, const T **out) {
+        if (mem == RDR_MEM_DEVICE) {
+            *out = src;
+            return cudaSuccess;
+        }
+        void *p = nullptr;
+        cudaError_t e = cudaMalloc(&p, std::max<size_t>(count * sizeof(T), 16));
+        if (e != cudaSuccess) return e;
+        bufs.push_back(p);
+        *out = static_cast<const T *>(p);
+        return cudaMemcpy(p, src, count * sizeof(T), cudaMemcpyHostToDevice);
+    }
+    template <typename T>
+    cudaError_t out(T *dst, size_t count, int mem, T **dev) {
+        if (mem == RDR_MEM_DEVICE) {
+            *dev = dst;
+            return cudaSuccess;
+        }
+        void *p = nullptr;
+        cudaError_t e = cudaMalloc(&p, std::max<size_t>(count * sizeof(T), 16));
+        if (e != cudaSuccess) return e;
+        bufs.push_back(p);
+        *dev = static_cast<T *>(p);
+        return cudaSuccess;
+    }
+};
+
+int need_device(int device) {
+    const int n = rdr_device_count();
+    if (n == 0) return fail(nullptr, RDR_ERR_CUDA, "no CUDA device available; libraider_b200 has no CPU fallback");
+    if (device < 0 || device >= n) return fail(nullptr, RDR_ERR_INVALID, "device index out of range");
+    return RDR_OK;
+}
+}  // namespace
+
+#define T_TRY(expr) CUDA_TRY(nullptr, expr)
+
+RDR_API int rdr_top_of_atmosphere(const double *xyz, const double *look, int64_t n, double toaheight, const double *factor, double *out_xyz,
+                                  int device) {
+    CHECK_ARG(nullptr, xyz && look && out_xyz && n >= 0, "rdr_top_of_atmosphere: bad arguments");
+    int rc = need_device(device);
+    if (rc || n == 0) return rc;
+    Transient T(device);
+    const double *dx, *dl, *df = nullptr;
+    double *dout;
+    T_TRY(T.in(xyz, 3 * n, RDR_MEM_HOST, &dx));
+    T_TRY(T.in(look, 3 * n, RDR_MEM_HOST, &dl));
+    if (factor) T_TRY(T.in(factor, n, RDR_MEM_HOST, &df));
+    T_TRY(T.out(out_xyz, 3 * n, RDR_MEM_HOST, &dout));
+    k_top_of_atmosphere<<<(unsigned)((n + 127) / 128), 128>>>(dx, dl, n, toaheight, df, dout);
+    T_TRY(cudaGetLastError());
+    T_TRY(cudaMemcpy(out_xyz, dout, 3 * n * sizeof(double), cudaMemcpyDeviceToHost));
+    return RDR_OK;
+}
+
+RDR_API int rdr_build_ray(const double *model_zs, int64_t nz, double ht, const double *xyz, const double *look, int64_t n, double zref,
+                          int64_t *n_layers, double *ray_lengths, double *low_xyzs, double *high_xyzs, int device) {
+    CHECK_ARG(nullptr, model_zs && nz >= 2 && n_layers, "rdr_build_ray: bad arguments");
+    std::vector<double> zs(model_zs, model_zs + nz), lo, hi;
+    std::vector<int> cell;
+    layer_plan(zs, ht, zref, lo, hi, cell);
+    const int K = (int)lo.size();
+    *n_layers = K;
+    if (K == 0) return RDR_ERR_NO_LAYERS;
+    if (!ray_lengths) return RDR_OK;  // count query
+    CHECK_ARG(nullptr, xyz && look && low_xyzs && high_xyzs && n >= 0, "rdr_build_ray: bad arguments");
+    int rc = need_device(device);
+    if (rc || n == 0) return rc;
+    Transient T(device);
+    std::vector<double> plan(lo);
+    plan.insert(plan.end(), hi.begin(), hi.end());
+    const double *dx, *dl, *dp;
+    double *dlen, *dlo, *dhi;
+    T_TRY(T.in(xyz, 3 * n, RDR_MEM_HOST, &dx));
+    T_TRY(T.in(look, 3 * n, RDR_MEM_HOST, &dl));
+    T_TRY(T.in(plan.data(), plan.size(), RDR_MEM_HOST, &dp));
+    T_TRY(T.out(ray_lengths, (size_t)K * n, RDR_MEM_HOST, &dlen));
+    T_TRY(T.out(low_xyzs, (size_t)K * n * 3, RDR_MEM_HOST, &dlo));
+    T_TRY(T.out(high_xyzs, (size_t)K * n * 3, RDR_MEM_HOST, &dhi));
+    k_build_ray<<<(unsigned)((n + 127) / 128), 128>>>(dx, dl, n, K, dp, dlen, dlo, dhi);
+    T_TRY(cudaGetLastError());
+    T_TRY(cudaMemcpy(ray_lengths, dlen, (size_t)K * n * sizeof(double), cudaMemcpyDeviceToHost));
+    T_TRY(cudaMemcpy(low_xyzs, dlo, (size_t)K * n * 3 * sizeof(double), cudaMemcpyDeviceToHost));
+    T_TRY(cudaMemcpy(high_xyzs, dhi, (size_t)K * n * 3 * sizeof(double), cudaMemcpyDeviceToHost));
+    return RDR_OK;
+}
+
+RDR_API int rdr_lla2ecef(const double *lat, const double *lon, const double *hgt, int64_t n, double *x, double *y, double *z, int device) {
+    CHECK_ARG(nullptr, lat && lon && hgt && x && y && z && n >= 0, "rdr_lla2ecef: bad arguments");
+    int rc = need_device(device);
+    if (rc || n == 0) return rc;
+    Transient T(device);
+    const double *a, *b, *c;
+    double *dx, *dy, *dz;
+    T_TRY(T.in(lat, n, 0, &a)); T_TRY(T.in(lon, n, 0, &b)); T_TRY(T.in(hgt, n, 0, &c));
+    T_TRY(T.out(x, n, 0, &dx)); T_TRY(T.out(y, n, 0, &dy)); T_TRY(T.out(z, n, 0, &dz));
+    k_lla2ecef<<<(unsigned)((n + 255) / 256), 256>>>(a, b, c, n, dx, dy, dz);
+    T_TRY(cudaGetLastError());
+    T_TRY(cudaMemcpy(x, dx, n * 8, cudaMemcpyDeviceToHost)); T_TRY(cudaMemcpy(y, dy, n * 8, cudaMemcpyDeviceToHost));
+    T_TRY(cudaMemcpy(z, dz, n * 8, cudaMemcpyDeviceToHost));
+    return RDR_OK;
+}
+
+RDR_API int rdr_ecef2lla(const double *x, const double *y, const double *z, int64_t n, double *lon, double *lat, double *hgt, int device) {
+    CHECK_ARG(nullptr, lat && lon && hgt && x && y && z && n >= 0, "rdr_ecef2lla: bad arguments");
+    int rc = need_device(device);
+    if (rc || n == 0) return rc;
+    Transient T(device);
+    const double *a, *b, *c;
+    double *dlo, *dla, *dh;
+    T_TRY(T.in(x, n, 0, &a)); T_TRY(T.in(y, n, 0, &b)); T_TRY(T.in(z, n, 0, &c));
+    T_TRY(T.out(lon, n, 0, &dlo)); T_TRY(T.out(lat, n, 0, &dla)); T_TRY(T.out(hgt, n, 0, &dh));
+    k_ecef2lla<<<(unsigned)((n + 255) / 256), 256>>>(a, b, c, n, dlo, dla, dh);
+    T_TRY(cudaGetLastError());
+    T_TRY(cudaMemcpy(lon, dlo, n * 8, cudaMemcpyDeviceToHost)); T_TRY(cudaMemcpy(lat, dla, n * 8, cudaMemcpyDeviceToHost));
+    T_TRY(cudaMemcpy(hgt, dh, n * 8, cudaMemcpyDeviceToHost));
+    return RDR_OK;
+}
+
+RDR_API int rdr_make_points_count(double max_len, double step, int64_t *npts) {
+    CHECK_ARG(nullptr, npts != nullptr, "rdr_make_points_count: npts is NULL");
+    CHECK_ARG(nullptr, step != 0.0, "float modulo");  // Python raises ZeroDivisionError('float modulo')
+    *npts = make_points_npts(max_len, step);
+    return RDR_OK;
+}
+
+RDR_API int rdr_make_points(double max_len, const double *sp, const double *slv, int64_t n_rays, double step, double *out, int64_t npts,
+                            int device, int mem) {
+    CHECK_ARG(nullptr, sp && slv && out && n_rays >= 0 && npts >= 0, "rdr_make_points: bad arguments");
+    int rc = need_device(device);
+    if (rc || n_rays == 0 || npts == 0) return rc;
+    Transient T(device);
+    const double *dsp, *dslv;
+    double *dout;
+    T_TRY(T.in(sp, 3 * n_rays, mem, &dsp));
+    T_TRY(T.in(slv, 3 * n_rays, mem, &dslv));
+    T_TRY(T.out(out, (size_t)3 * n_rays * npts, mem, &dout));
+    const int64_t total = 3 * n_rays * npts;
+    k_make_points<<<(unsigned)std::min<int64_t>((total + 255) / 256, 148 * 32), 256>>>(dsp, dslv, n_rays, step, npts, dout);
+    T_TRY(cudaGetLastError());
+    if (mem == RDR_MEM_HOST) T_TRY(cudaMemcpy(out, dout, total * sizeof(double), cudaMemcpyDeviceToHost));
+    else T_TRY(cudaDeviceSynchronize());
+    (void)max_len;
+    return RDR_OK;
+}
+
+RDR_API int rdr_interpolate(int ndim, const double *const *grids, const int64_t *sizes, const double *values, const double *pts, int64_t n,
+                            int has_fill, double fill_value, double *out, int device, int mem) {
+    CHECK_ARG(nullptr, ndim >= 1 && ndim <= 8, "rdr_interpolate: 1 <= ndim <= 8 supported");
+    CHECK_ARG(nullptr, grids && sizes && values && pts && out && n >= 0, "rdr_interpolate: NULL pointer");
+    int rc = need_device(device);
+    if (rc || n == 0) return rc;
+    Transient T(device);
+    NdGrid G;
+    G.ndim = ndim;
+    size_t nval = 1;
+    for (int d = 0; d < ndim; ++d) {
+        CHECK_ARG(nullptr, sizes[d] >= 1 && sizes[d] < (1ll << 31), "rdr_interpolate: bad grid size");
+        T_TRY(T.in(grids[d], sizes[d], RDR_MEM_HOST, &G.g[d]));
+        G.n[d] = (int)sizes[d];
+        nval *= (size_t)sizes[d];
+    }
+    const double *dv, *dp;
+    double *dout;
+    T_TRY(T.in(values, nval, mem, &dv));
+    T_TRY(T.in(pts, (size_t)n * ndim, mem, &dp));
+    T_TRY(T.out(out, n, mem, &dout));
+    k_interp_nd<<<(unsigned)std::min<int64_t>((n + 255) / 256, 148 * 16), 256>>>(G, dv, dp, n, has_fill, fill_value, dout);
+    T_TRY(cudaGetLastError());
+    if (mem == RDR_MEM_HOST) T_TRY(cudaMemcpy(out, dout, n * sizeof(double), cudaMemcpyDeviceToHost));
+    else T_TRY(cudaDeviceSynchronize());
+    return RDR_OK;
+}
+
+RDR_API int rdr_interp_along_axis(const double *x, const double *y, const double *xnew, int64_t ncol, int64_t nin, int64_t nout, int has_fill,
+                                  double fill_value, double *out, int device, int mem) {
+    CHECK_ARG(nullptr, x && y && xnew && out && ncol >= 0 && nin >= 1 && nout >= 0, "rdr_interp_along_axis: bad arguments");
+    CHECK_ARG(nullptr, nin < (1ll << 31) && nout < (1ll << 31), "rdr_interp_along_axis: axis too long");
+    int rc = need_device(device);
+    if (rc || ncol == 0 || nout == 0) return rc;
+    Transient T(device);
+    const double *dx, *dy, *dq;
+    double *dout;
+    T_TRY(T.in(x, (size_t)ncol * nin, mem, &dx));
+    T_TRY(T.in(y, (size_t)ncol * nin, mem, &dy));
+    T_TRY(T.in(xnew, (size_t)ncol * nout, mem, &dq));
+    T_TRY(T.out(out, (size_t)ncol * nout, mem, &dout));
+    const int64_t total = ncol * nout;
+    k_interp_axis<<<(unsigned)std::min<int64_t>((total + 255) / 256, 148 * 16), 256>>>(dx, dy, dq, ncol, (int)nin, (int)nout, has_fill, fill_value,
+                                                                                      dout);
+    T_TRY(cudaGetLastError());
+    if (mem == RDR_MEM_HOST) T_TRY(cudaMemcpy(out, dout, total * sizeof(double), cudaMemcpyDeviceToHost));
+    else T_TRY(cudaDeviceSynchronize());
+    return RDR_OK;
+}

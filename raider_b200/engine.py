@@ -1,0 +1,165 @@
+"""Host driver of the device delay path: a staged cube + the K0 -> (all-reduce) -> K3 sequence.
+
+This is the layer the Python shims (delay.py, delayFcns.py, losreader.py) sit on.  It owns no numerics: every
+number comes out of libraider_b200.so.  Reference structure it replaces: the per-height body of
+``_build_cube_ray`` (tools/RAiDER/delay.py:256-323) and ``_build_cube`` (:205-214).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _lib
+from ._lib import Handle, NoLayersError, f64, is_device, ptr
+from .crs import Geographic, parse_crs
+
+
+@dataclass
+class TraceInfo:
+    """What one height slice did: the integer contract (nParts) and the whole-raster predicates."""
+    ht: float
+    n_rays: int = 0
+    n_layers: int = 0
+    maxlen: np.ndarray | None = None      # global per-layer max ray length (delay.py:283)
+    nparts: np.ndarray | None = None      # int steps per layer
+    samples_per_ray: int = 0              # sum(nParts): samples the reference evaluates per ray
+    clamp_low_first: bool = False         # delay.py:306-307 fired
+    reruns: int = 0
+    oob_below: int = 0
+    oob_above: int = 0
+    n_nan_rays: int = 0
+    skipped: bool = False                 # no contributing layer at the last output height (delay.py:276-277)
+
+
+class DeviceCube:
+    """A weather-model cube staged in HBM (replaces the pair of scipy RGIs of delayFcns.py:55-56)."""
+
+    def __init__(self, ys, xs, zs, wet, hydro, layout=_lib.LAYOUT_ZYX, crs=None, device: int | None = None) -> None:
+        self.h = Handle(device)
+        self.crs = parse_crs(crs)
+        self.h.set_cube(ys, xs, zs, wet, hydro, layout=layout, crs_kind=self.crs.kind, crs_params=self.crs.params())
+        # ascending copies, as scipy exposes them through .grid (read at delay.py:239)
+        self.grid = tuple(np.sort(f64(a)) for a in (ys, xs, zs))
+        self.shape_zyx = (np.size(zs), np.size(ys), np.size(xs))
+        self.last_info: list[TraceInfo] = []
+
+    @property
+    def device(self) -> int:
+        return self.h.device
+
+    @classmethod
+    def from_dict(cls, cube: dict, kind: str = 'pointwise', crs=None, device=None) -> 'DeviceCube':
+        """``cube`` = {x, y, z, wet, hydro[, wet_total, hydro_total]} with (z, y, x) fields (the processed-file layout)."""
+        w = cube['wet_total' if kind == 'total' else 'wet']
+        hy = cube['hydro_total' if kind == 'total' else 'hydro']
+        return cls(cube['y'], cube['x'], cube['z'], w, hy, layout=_lib.LAYOUT_ZYX, crs=crs if crs is not None else cube.get('crs'),
+                   device=device)
+
+    def blend(self, wet1, hydro1, w0: float, w1: float, layout=_lib.LAYOUT_ZYX) -> None:
+        """Fused two-epoch temporal interpolation (cli/raider.py:817-819) at staging time."""
+        self.h.blend_cube(wet1, hydro1, w0, w1, layout)
+
+    # ------------------------------------------------------------------------------------ K2
+    def sample(self, pts, semantics=_lib.SEM_SCIPY, out=None):
+        """Both fields at ``pts[..., 3]`` = (y, x, z).  numpy in -> numpy out; torch CUDA in -> torch CUDA out."""
+        if is_device(pts):
+            import torch
+            dt = _lib.F32 if pts.dtype == torch.float32 else _lib.F64
+            if dt == _lib.F64 and pts.dtype != torch.float64:
+                raise TypeError('device points must be float32 or float64')
+            p = pts.contiguous()
+            n = p.numel() // 3
+            if out is None:
+                out = (torch.empty(p.shape[:-1], dtype=p.dtype, device=p.device), torch.empty(p.shape[:-1], dtype=p.dtype, device=p.device))
+            self.h.call('rdr_sample', ptr(p), n, ptr(out[0]), ptr(out[1]), dt, semantics, _lib.MEM_DEVICE)
+            return out
+        p = np.asarray(pts)
+        if p.dtype != np.float32:
+            p = p.astype(np.float64, copy=False)
+        p = np.ascontiguousarray(p)
+        if p.shape[-1] != 3:
+            raise ValueError(f'The requested sample points xi have dimension {p.shape[-1]} but this interpolator has dimension 3')
+        n = p.size // 3
+        w = np.empty(p.shape[:-1], dtype=p.dtype)
+        hy = np.empty(p.shape[:-1], dtype=p.dtype)
+        self.h.call('rdr_sample', ptr(p), n, ptr(w), ptr(hy), _lib.F32 if p.dtype == np.float32 else _lib.F64, semantics, _lib.MEM_HOST)
+        return w, hy
+
+    def sample_grid(self, xpts, ypts, ht: float):
+        """One height of ``_build_cube`` (delay.py:205-214) when the query grid is in the cube's own CRS."""
+        xpts, ypts = f64(xpts), f64(ypts)
+        w = np.empty((ypts.size, xpts.size))
+        hy = np.empty((ypts.size, xpts.size))
+        self.h.call('rdr_sample_grid', ptr(xpts), xpts.size, ptr(ypts), ypts.size, float(ht), ptr(w), ptr(hy), _lib.MEM_HOST)
+        return w, hy
+
+    # ------------------------------------------------------------------------------------ K0 + K3
+    def ray_plan(self, ht: float, zref: float):
+        n = C.c_int64(0)
+        nz = self.grid[2].size
+        lo, hi = np.empty(nz), np.empty(nz)
+        self.h.call('rdr_ray_plan', float(ht), float(zref), C.byref(n), ptr(lo), ptr(hi))
+        return lo[: n.value].copy(), hi[: n.value].copy()
+
+    def ray_layers(self, geom_kind, gx, gy, ny, nx, los_kind, los, ht, zref):
+        """K0.  Returns (maxlen[K], counts[4]) for this device's rays; raises NoLayersError when K == 0."""
+        nz = self.grid[2].size
+        maxlen = np.zeros(nz)
+        counts = np.zeros(4, dtype=np.int64)
+        dev = is_device(gx) or is_device(los)
+        self._keep_geom = (gx, gy, los)  # device pointers must outlive rdr_ray_integrate
+        self.h.call('rdr_ray_layers', geom_kind, ptr(gx), ptr(gy), int(ny), int(nx), los_kind, ptr(los), float(ht), float(zref),
+                    ptr(maxlen), ptr(counts), _lib.MEM_DEVICE if dev else _lib.MEM_HOST)
+        return maxlen[: counts[3]].copy(), counts
+
+    def ray_integrate(self, maxlen, max_segment_length, clamp_low_first, out_wet, out_hydro, accumulate=False):
+        """K3 on the rays of the last ray_layers call.  Returns (nparts[K], oob[3])."""
+        maxlen = f64(maxlen)
+        nparts = np.zeros(maxlen.size, dtype=np.int64)
+        oob = np.zeros(3, dtype=np.int64)
+        dev = is_device(out_wet)
+        if dev:
+            import torch
+            dt = _lib.F32 if out_wet.dtype == torch.float32 else _lib.F64
+        else:
+            dt = _lib.F32 if out_wet.dtype == np.float32 else _lib.F64
+        self.h.call('rdr_ray_integrate', ptr(maxlen), float(max_segment_length), int(bool(clamp_low_first)), ptr(out_wet), ptr(out_hydro),
+                    dt, int(bool(accumulate)), ptr(nparts), ptr(oob), _lib.MEM_DEVICE if dev else _lib.MEM_HOST)
+        return nparts, oob
+
+    def trace(self, geom_kind, gx, gy, ny, nx, los_kind, los, ht, zref, max_segment_length, out_wet, out_hydro,
+              reduce_max=None, reduce_sum=None) -> TraceInfo:
+        """One output height: K0 -> global reduction of the per-layer maxima / predicates -> K3.
+
+        ``reduce_max`` / ``reduce_sum`` are the cross-GPU hooks (numpy array in -> reduced numpy array out); they are
+        what keeps ``nParts`` (delay.py:283) and the ``.all()`` clamp (delay.py:306-307) *global* when the raster is
+        sharded over ranks.  Outputs are written (not accumulated) into out_wet/out_hydro.
+        """
+        info = TraceInfo(ht=float(ht))
+        maxlen, counts = self.ray_layers(geom_kind, gx, gy, ny, nx, los_kind, los, ht, zref)
+        if reduce_max is not None:
+            maxlen = reduce_max(maxlen)
+            counts = np.concatenate([reduce_sum(counts[:3]), counts[3:]])
+        info.n_rays, info.n_nan_rays, info.n_layers = int(counts[0]), int(counts[1]), int(counts[3])
+        clamp = bool(counts[2] == counts[0])
+        nparts, oob = self.ray_integrate(maxlen, max_segment_length, clamp, out_wet, out_hydro)
+        first_below = oob[:1] if reduce_sum is None else reduce_sum(oob[:1])
+        if bool(first_below[0] == counts[0]) != clamp:  # K0's hint and K3's own evaluation disagree on a knife edge: K3 rules
+            clamp = not clamp
+            nparts, oob = self.ray_integrate(maxlen, max_segment_length, clamp, out_wet, out_hydro)
+            info.reruns = 1
+        info.maxlen, info.nparts = maxlen, nparts
+        info.samples_per_ray = int(nparts.sum())
+        info.clamp_low_first = clamp
+        info.oob_below, info.oob_above = int(oob[1]), int(oob[2])
+        return info
+
+
+def los_device_spec(los, ny: int, nx: int):
+    """(los_kind, los_payload) for LOS objects that can be generated on the device, else None."""
+    spec = getattr(los, 'device_spec', None)
+    if spec is None:
+        return None
+    return spec()
