@@ -1,0 +1,427 @@
+#!/usr/bin/env python
+"""bench.py -- LOS rays/s of the slant-delay hot path on BASELINE.json config C2, with the roofline and CPU baseline beside it.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A *step* is one pass of the hot path over one batch of synthetic input: the C2 raster (2000 x 2000 rays per GPU, fixed
+30 deg incidence, NZ = 37 cube, 225 m segments => ~296 samples/ray, one output height):  K0 ray_layers -> global
+max/predicate reduction -> K3 ray_integrate (-> all-gather of the two delay maps when N > 1).
+
+One JSON line on stdout (rank 0):
+  value     rays/s, whole job, geometry + cube resident in HBM, outputs left in HBM, CUDA events, max over ranks
+  e2e       rays/s through the reference-facing API (getInterpolators + _build_cube_ray) with HOST buffers: cube H2D,
+            axes H2D, both delay maps D2H inside the timed region
+  roofline  the unfused trilinear-sample kernel K2 on materialised sample points of the same rays (40 B/point fp64),
+            achieved HBM GB/s vs MEASURED_PEAKS.json -- the kernel north_star puts the HBM-roofline claim on
+  fused     the K3 kernel's own byte accounts (it is fp64-issue bound, not HBM bound)
+  cpu_baseline  the oracle port (NumPy + scipy restatement of the reference loops) on a bounded sub-raster, 1 core
+
+--impl reference times that same CPU port on all host cores (row blocks in worker processes, global nParts injected);
+the reference itself is single-process (delay.py:133,178-185) and cannot be imported offline (pyproj/xarray/isce3).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = 'LOS rays/sec, slant delay (ray-traced), C2: 2000x2000 raster, 30deg incidence, NZ=37 cube, ~300 steps/ray'
+UNIT = 'rays/s'
+N_SIDE = 2000
+INC, HEAD = 30.0, -168.0
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def measured_peak_gbs():
+    p = ROOT / 'MEASURED_PEAKS.json'
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+        except Exception:
+            pass
+    return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled every 200 ms during the timed region (B200_PROFILING.md)."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index: int) -> None:
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '200', '-i', str(self.idx)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def __exit__(self, *exc):
+        if self.proc:
+            time.sleep(0.25)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, reasons, smax = [], set(), None
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                smax = float(r[2])
+                for nme, v in zip(names, r[5:9]):
+                    if v.lower().startswith('active'):
+                        reasons.add(nme)
+            except (ValueError, IndexError):
+                continue
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': smax, 'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def global_config(n_gpus: int):
+    """Weak scaling: every GPU owns a 2000 x 2000 block of rows; the global raster is (2000 N) x 2000 at 0.001 deg."""
+    from raider_b200 import synthetic as syn
+    ny = N_SIDE * n_gpus
+    xpts, ypts = syn.raster(34.0, -118.0, ny, N_SIDE, 0.001)
+    xs, ys = syn.cube_axes_around(xpts, ypts)
+    zs = syn.z_levels(37)
+    cube = syn.make_cube(ys, xs, zs, totals=False)
+    return {'cube': cube, 'xpts': xpts, 'ypts': ypts, 'zref': float(zs[-1] - 1.0), 'max_segment_length': 225.0}
+
+
+def enu_const():
+    from raider_b200.losreader import inc_hd_to_enu
+    return np.ascontiguousarray(inc_hd_to_enu(np.float64(INC), np.float64(HEAD)))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# CPU arms (oracle port)
+# ----------------------------------------------------------------------------------------------------------------
+def _cpu_block(args):
+    """One worker: the oracle's _build_cube_ray on a row block with the global per-layer maxima injected."""
+    cube, xpts, ypts, zref, seg, maxlen = args
+    os.environ.setdefault('OMP_NUM_THREADS', '1')
+    from oracle import raytrace as rt
+    crs = rt.GeographicCRS()
+    t0 = time.perf_counter()
+    out = rt.build_cube_ray(xpts, ypts, np.array([0.0]), rt.FixedIncidenceLOS(INC, HEAD), crs, crs, list(rt.get_interpolators(cube)),
+                            MAX_SEGMENT_LENGTH=seg, MAX_TROPO_HEIGHT=zref, layer_maxlen=None if maxlen is None else [maxlen])
+    return time.perf_counter() - t0, float(out[0].sum() + out[1].sum())
+
+
+def cpu_global_maxlen(cfg):
+    """Per-layer maxima of the FULL raster, from its border pixels (the max of a smooth field sits on the border; exactness
+    is checked by the GPU run's own maxima in the `ours` arm -- here it only keeps samples/ray identical to the full job)."""
+    from oracle import geodesy, raytrace as rt
+    xp, yp = cfg['xpts'], cfg['ypts']
+    xx = np.concatenate([xp, xp, np.full(yp.size, xp[0]), np.full(yp.size, xp[-1])])
+    yy = np.concatenate([np.full(xp.size, yp[0]), np.full(xp.size, yp[-1]), yp, yp])
+    xx, yy = xx[None, :], yy[None, :]
+    xyz = np.stack(geodesy.lla2ecef(yy, xx, np.zeros_like(yy)), -1)
+    look = rt.FixedIncidenceLOS(INC, HEAD).getLookVectors(0.0, [xx, yy, 0 * yy], xyz, yy)
+    lens = rt.build_ray(cfg['cube']['z'], 0.0, xyz, look, cfg['zref'])[0]
+    return lens.max((1, 2))
+
+
+def cpu_baseline_single(cfg, maxlen, rows=20):
+    """cpu_baseline leg: 1 core, `rows` x 2000 rays from the middle of the raster."""
+    mid = cfg['ypts'].size // 2
+    dt, _ = _cpu_block((cfg['cube'], cfg['xpts'], cfg['ypts'][mid:mid + rows], cfg['zref'], cfg['max_segment_length'], maxlen))
+    n = rows * cfg['xpts'].size
+    return {'value': n / dt, 'unit': UNIT, 'cores': 1, 'kind': 'port',
+            'sample': f'{rows}x{cfg["xpts"].size} rays (rows {mid}..{mid + rows - 1} of the C2 raster), global nParts injected, {dt:.1f} s'}
+
+
+def run_reference(args):
+    """--impl reference: the CPU port on all host cores; each step = cores x rows_per_proc x 2000 rays of the C2 raster."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cfg = global_config(1)
+    cores = os.cpu_count() or 1
+    maxlen = cpu_global_maxlen(cfg)
+    # calibrate: ~6 s per step so that (steps + warmup) stays within a few minutes
+    t_probe, _ = _cpu_block((cfg['cube'], cfg['xpts'], cfg['ypts'][1000:1002], cfg['zref'], cfg['max_segment_length'], maxlen))
+    budget = min(8.0, 150.0 / max(1, args.steps + args.warmup))
+    rows = int(max(1, min(N_SIDE // cores, round(budget / (t_probe / 2.0)))))
+    blocks = [(cfg['cube'], cfg['xpts'], cfg['ypts'][i * rows:(i + 1) * rows], cfg['zref'], cfg['max_segment_length'], maxlen) for i in range(cores)]
+    n_step = cores * rows * N_SIDE
+    with mp.get_context('fork').Pool(cores) as pool:
+        for _ in range(args.warmup):
+            pool.map(_cpu_block, blocks)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            pool.map(_cpu_block, blocks)
+        dt = time.perf_counter() - t0
+    value = n_step * args.steps / dt
+    sample = f'{cores} processes x {rows} rows x {N_SIDE} rays per step of the C2 raster, global nParts injected'
+    print(json.dumps({
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': 1e3 * dt / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+        'data': 'synthetic', 'config': {'workload': 'C2 slant delay 2000x2000 rays, 30deg, NZ=37, 225 m segments (bounded sample per step)',
+                                        'rays_per_step': n_step},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from raider_b200 import _lib
+    from raider_b200.delay import _build_cube_ray
+    from raider_b200.delayFcns import getInterpolators
+    from raider_b200.dist import Comm, shard_rows
+    from raider_b200.engine import DeviceCube
+    from raider_b200.losreader import Raytracing
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit(f'--gpus {args.gpus} needs torchrun --nproc-per-node {args.gpus}')
+    torch.cuda.set_device(local)
+    comm = None
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+        comm = Comm()
+
+    cfg = global_config(world)
+    ny_g, nx = cfg['ypts'].size, cfg['xpts'].size
+    r0, r1 = shard_rows(ny_g, rank, world)
+    ypts = np.ascontiguousarray(cfg['ypts'][r0:r1])
+    ny = ypts.size
+    n_local, n_global = ny * nx, ny_g * nx
+    enu = enu_const()
+    stream = torch.cuda.current_stream()
+
+    cube = DeviceCube.from_dict(cfg['cube'], device=local)
+    cube.h.set_stream(stream.cuda_stream)
+    out_w = torch.empty((ny, nx), dtype=torch.float64, device='cuda')
+    out_h = torch.empty((ny, nx), dtype=torch.float64, device='cuda')
+    rmax = comm.reduce_max if comm else None
+    rsum = comm.reduce_sum if comm else None
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device='cuda')  # > 126 MB L2
+
+    def step():
+        info = cube.trace(_lib.GEOM_GRID, cfg['xpts'], ypts, ny, nx, _lib.LOS_ENU_CONST, enu, 0.0, cfg['zref'], cfg['max_segment_length'],
+                          out_w, out_h, reduce_max=rmax, reduce_sum=rsum)
+        if comm:
+            full_w = comm.all_gather_rows(out_w, ny_g)
+            full_h = comm.all_gather_rows(out_h, ny_g)
+            return info, full_w, full_h
+        return info, out_w, out_h
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if comm:
+            comm.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        info, _, _ = step()
+    sync_all()
+
+    # ---- timed region: device-resident value -------------------------------------------------------------------
+    l0 = cube.h.launches
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    with ClockSampler(local) as clocks:
+        sync_all()
+        for a, b in ev:
+            flush.zero_()            # L2 flush between timed iterations (the t-buffer alone is > L2, this makes it explicit)
+            a.record(stream)
+            info, fw, fh = step()
+            b.record(stream)
+        sync_all()
+    ms = np.array([a.elapsed_time(b) for a, b in ev])
+    launches = cube.h.launches - l0
+    t_local = float(ms.sum())
+    if comm:
+        t = torch.tensor([t_local], dtype=torch.float64, device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_local = float(t.item())
+    ms_per_step = t_local / args.steps
+    value = n_global / (ms_per_step * 1e-3)
+    checksum = float(fw.sum().item() + fh.sum().item())
+    nan_count = int(torch.isnan(fw).sum().item())
+
+    # ---- e2e through the public API with host buffers ----------------------------------------------------------
+    los = Raytracing(incidence=INC, heading=HEAD)
+    cube_host = {k: (torch.from_numpy(np.ascontiguousarray(v)).pin_memory().numpy() if k in ('wet', 'hydro') else v)
+                 for k, v in cfg['cube'].items()}
+    e2e_steps = max(3, min(args.steps, 10))
+
+    def e2e_step():
+        ifs = getInterpolators(cube_host, device=local)                                   # cube + axes H2D
+        if comm:
+            from raider_b200.dist import build_cube_ray_sharded
+            return build_cube_ray_sharded(cfg['xpts'], cfg['ypts'], np.array([0.0]), los, 4326, 4326, list(ifs), comm,
+                                          MAX_SEGMENT_LENGTH=cfg['max_segment_length'], MAX_TROPO_HEIGHT=cfg['zref'])
+        return _build_cube_ray(cfg['xpts'], ypts, np.array([0.0]), los, 4326, 4326, list(ifs),   # axes H2D, delay maps D2H
+                               MAX_SEGMENT_LENGTH=cfg['max_segment_length'], MAX_TROPO_HEIGHT=cfg['zref'])
+
+    for _ in range(2):
+        res = e2e_step()
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        res = e2e_step()
+    sync_all()
+    t_e2e = time.perf_counter() - t0
+    if comm:
+        t = torch.tensor([t_e2e], dtype=torch.float64, device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_e2e = float(t.item())
+    e2e_value = n_global * e2e_steps / t_e2e
+    cube_bytes = int(cfg['cube']['wet'].nbytes + cfg['cube']['hydro'].nbytes)
+    h2d = cube_bytes + 8 * (cfg['xpts'].size + ny + cfg['cube']['x'].size + cfg['cube']['y'].size + cfg['cube']['z'].size)
+    d2h = 2 * 8 * n_local
+    e2e_dev_diff = float(np.abs(res[0][0][r0:r1] - fw[r0:r1].cpu().numpy()).max()) if comm else float(np.abs(res[0][0] - out_w.cpu().numpy()).max())
+
+    if rank != 0:
+        if comm:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the unfused trilinear-sample kernel K2 (rank 0, N = 1 semantics) ---------------------------
+    peak, peak_src = measured_peak_gbs()
+    nslots = 48
+    maxlen, _ = cube.ray_layers(_lib.GEOM_GRID, cfg['xpts'], ypts, ny, nx, _lib.LOS_ENU_CONST, enu, 0.0, cfg['zref'])
+    if comm:
+        maxlen = info.maxlen
+    pts = torch.empty((nslots, n_local, 3), dtype=torch.float64, device='cuda')
+    cube.ray_points(maxlen, cfg['max_segment_length'], slot0=100, nslots=nslots, out=pts)
+    npts = nslots * n_local
+    sw = torch.empty(npts, dtype=torch.float64, device='cuda')
+    sh = torch.empty(npts, dtype=torch.float64, device='cuda')
+    for _ in range(3):
+        cube.sample(pts.view(-1, 3), out=(sw, sh))
+    torch.cuda.synchronize()
+    k2 = []
+    for _ in range(10):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        cube.sample(pts.view(-1, 3), out=(sw, sh))   # 10.2 GB of points + outputs per launch >> L2
+        b.record(stream)
+        torch.cuda.synchronize()
+        k2.append(a.elapsed_time(b))
+    k2_ms = float(np.mean(k2))
+    k2_bytes = npts * 40 + cube_bytes
+    k2_gbs = k2_bytes / (k2_ms * 1e-3) / 1e9
+    # fp32-I/O tier of the same kernel (20 B/point)
+    pts32 = pts.to(torch.float32)
+    sw32 = torch.empty(npts, dtype=torch.float32, device='cuda')
+    sh32 = torch.empty(npts, dtype=torch.float32, device='cuda')
+    for _ in range(3):
+        cube.sample(pts32.view(-1, 3), out=(sw32, sh32))
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(stream)
+    for _ in range(10):
+        cube.sample(pts32.view(-1, 3), out=(sw32, sh32))
+    b.record(stream)
+    torch.cuda.synchronize()
+    k2_32_gbs = (npts * 20 + cube_bytes) / (a.elapsed_time(b) / 10 * 1e-3) / 1e9
+    del pts, pts32, sw, sh, sw32, sh32
+
+    # ---- K3 alone (events around the integrate launch) for the fused accounts -----------------------------------
+    k3 = []
+    for _ in range(5):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        flush.zero_()
+        a.record(stream)
+        cube.ray_integrate(maxlen, cfg['max_segment_length'], False, out_w, out_h)
+        b.record(stream)
+        torch.cuda.synchronize()
+        k3.append(a.elapsed_time(b))
+    k3_ms = float(np.mean(k3))
+    uniq = int(info.samples_per_ray - info.n_layers + 1)
+    fused = {
+        'kernel': 'k_ray_integrate<double>', 'ms': k3_ms, 'bound': 'fp64 issue (not HBM): see DESIGN.md',
+        'algorithmic_bytes_per_ray': 16 + 8 * (info.n_layers + 1),
+        'hbm_gbs': n_local * (16 + 8 * (info.n_layers + 1)) / (k3_ms * 1e-3) / 1e9,
+        'equivalent_unfused_gbs': n_local * info.samples_per_ray * 40 / (k3_ms * 1e-3) / 1e9,
+        'samples_per_ray_reference': info.samples_per_ray, 'unique_samples_per_ray': uniq,
+        'samples_per_s': n_local * info.samples_per_ray / (k3_ms * 1e-3),
+    }
+
+    # ---- cpu_baseline (N = 1 only): the oracle port on a bounded sample, same inputs, global nParts from the GPU --
+    cpu = None
+    if world == 1:
+        cpu = cpu_baseline_single(cfg, info.maxlen)
+        # parity spot-check on the same sample while we are here
+        from oracle import raytrace as rt
+        crs = rt.GeographicCRS()
+        sl = slice(1000, 1004)
+        want = rt.build_cube_ray(cfg['xpts'], cfg['ypts'][sl], np.array([0.0]), rt.FixedIncidenceLOS(INC, HEAD), crs, crs,
+                                 list(rt.get_interpolators(cfg['cube'])), MAX_SEGMENT_LENGTH=cfg['max_segment_length'],
+                                 MAX_TROPO_HEIGHT=cfg['zref'], layer_maxlen=[info.maxlen])
+        got = out_w[sl].cpu().numpy()
+        cpu['max_abs_diff_vs_gpu_m'] = float(np.abs(got - want[0][0]).max())
+
+    line = {
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
+        'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': f'C2 slant delay: {N_SIDE}x{N_SIDE} rays per GPU ({ny_g}x{nx} global), fixed {INC} deg incidence, heading {HEAD}, '
+                               f'0.001 deg posting, cube {cfg["cube"]["y"].size}x{cfg["cube"]["x"].size}x37 @0.25 deg fp32, 225 m max segment',
+                   'rays_per_step': n_global, 'samples_per_ray': info.samples_per_ray, 'layers': info.n_layers,
+                   'l2': 'flushed with a 256 MB write between timed steps', 'parallelism': f'row-block x{world}' if world > 1 else 'single GPU',
+                   'collectives': 'all-reduce(max K doubles) + all-reduce(sum 3 ints) + all-gather(2 delay maps)' if world > 1 else 'none'},
+        'clocks': clocks.summary(),
+        'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'steps': e2e_steps,
+                'ms_per_step': 1e3 * t_e2e / e2e_steps, 'api': 'getInterpolators(host cube) + _build_cube_ray(host axes) -> host float64 maps',
+                'max_abs_diff_vs_device_path_m': e2e_dev_diff},
+        'gpu_launches': int(launches),
+        'roofline': {'kernel': 'k_sample_points<double> (K2 trilinear_sample, unfused)', 'bound': 'hbm', 'achieved': k2_gbs, 'peak': peak,
+                     'unit': 'GB/s', 'frac': k2_gbs / peak, 'traffic': None, 'peak_source': peak_src, 'bytes_per_point': 40,
+                     'points_per_launch': npts, 'ms_per_launch': k2_ms, 'fp32_io_tier_gbs': k2_32_gbs, 'fp32_io_tier_frac': k2_32_gbs / peak},
+        'fused': fused,
+        'cpu_baseline': cpu,
+        'check': {'checksum': checksum, 'nan': nan_count, 'nparts_sum': int(info.samples_per_ray)},
+    }
+    print(json.dumps(line))
+    if comm:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -139,6 +139,13 @@ int rdr_ray_integrate(rdr_handle_t h, const double *maxlen, double max_segment_l
                       void *out_wet, void *out_hydro, int out_dtype, int accumulate,
                       int64_t *nparts_out, int64_t *oob_out, int mem);
 
+/* K1b -- north_star (a): generate the 3-D sample points along each ray of the last rdr_ray_layers call, in model
+ * coordinates, i.e. the per-sub-step `pts` arrays of delay.py:292-298 (replaces the role of tools/bindings makePoints3D in
+ * the unfused dataflow).  Unique samples are numbered in layer-then-step order ("slots"); pts = [nslots][n_rays][3] (y, x, z)
+ * for slots slot0 .. slot0+nslots-1.  pts == NULL only reports total_slots. */
+int rdr_ray_points(rdr_handle_t h, const double *maxlen, double max_segment_length, int64_t slot0, int64_t nslots, void *pts, int dtype,
+                   int64_t *total_slots, int mem);
+
 /* API-parity pieces of losreader (small problems, tests): */
 /* getTopOfAtmosphere(xyz, look_vecs, toaheight, factor=None) losreader.py:706-733; factor == NULL -> 10 iterations */
 int rdr_top_of_atmosphere(const double *xyz, const double *look, int64_t n, double toaheight, const double *factor,

@@ -60,9 +60,9 @@ def interpolate(points, values, interp_points, fill_value=None, assume_sorted=Fa
     ``assume_sorted`` only changes *how* the interval is searched (find_left from the previous
     interval); for inputs that honour the promise the result is identical, so it is ignored here.
     """
-    points = [np.ascontiguousarray(p, dtype=np.float64) for p in points]
-    values = np.ascontiguousarray(values, dtype=np.float64)
-    interp_points = np.ascontiguousarray(interp_points, dtype=np.float64)
+    points = [np.asarray(p, dtype=np.float64, order='C') for p in points]
+    values = np.asarray(values, dtype=np.float64, order='C')
+    interp_points = np.asarray(interp_points, dtype=np.float64, order='C')
     ndim = len(points)
     if values.ndim == 0 or interp_points.ndim == 0:
         raise TypeError('Only arrays are supported, not scalar values!')
@@ -143,9 +143,9 @@ def interpolate(points, values, interp_points, fill_value=None, assume_sorted=Fa
 
 def interpolate_along_axis(points, values, interp_points, axis=-1, fill_value=None, assume_sorted=False, max_threads=8):
     """RAiDER.interpolate.interpolate_along_axis (module.cpp:296-493 -> interpolate.cpp:260-332)."""
-    points = np.ascontiguousarray(points, dtype=np.float64)
-    values = np.ascontiguousarray(values, dtype=np.float64)
-    interp_points = np.ascontiguousarray(interp_points, dtype=np.float64)
+    points = np.asarray(points, dtype=np.float64, order='C')
+    values = np.asarray(values, dtype=np.float64, order='C')
+    interp_points = np.asarray(interp_points, dtype=np.float64, order='C')
     if values.ndim == 0 or interp_points.ndim == 0:
         raise TypeError('Only arrays are supported, not scalar values!')
     if points.ndim != values.ndim or points.ndim != interp_points.ndim:

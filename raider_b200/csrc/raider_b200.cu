@@ -465,6 +465,42 @@ __global__ void __launch_bounds__(BLOCK) k_ray_integrate(const CubeView c, const
 }
 
 // ------------------------------------------------------------------------------------------------
+// K1b: materialise the model-coordinate sample points of the rays (the per-sub-step `pts` arrays of delay.py:292-298)
+// for the unfused pipeline / the K2 roofline measurement: pts[(slot - slot0) * n_rays + r] = (y, x, z), slots counted
+// over the unique samples in layer-then-step order.  Each warp writes 32 x 24 contiguous bytes per slot.
+// ------------------------------------------------------------------------------------------------
+template <typename T, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_ray_points(const CubeView c, const RayGeom G, int64_t n_rays, int K, const double *__restrict__ t_in,
+                                                      const int *__restrict__ nparts, int slot0, int nslots, T *__restrict__ pts) {
+    for (int64_t r = blockIdx.x * (int64_t)BLOCK + threadIdx.x; r < n_rays; r += (int64_t)gridDim.x * BLOCK) {
+        Vec3 g, u;
+        ray_setup(G, r, g, u);
+        Vec3 lo = ray_point(g, u, __ldg(t_in + r));
+        int slot = 0;
+        for (int k = 0; k < K && slot < slot0 + nslots; ++k) {
+            const Vec3 hi = ray_point(g, u, __ldg(t_in + (int64_t)(k + 1) * n_rays + r));
+            const Vec3 d = hi - lo;
+            const int np = __ldg(nparts + k);
+            const double step = 1.0 / (double)(np - 1);
+            for (int j = (k == 0 ? 0 : 1); j < np; ++j, ++slot) {
+                if (slot < slot0) continue;
+                if (slot >= slot0 + nslots) break;
+                const double ff = (j == np - 1) ? 1.0 : (double)j * step;
+                double lon, lat, h;
+                ecef2lla({lo.x + ff * d.x, lo.y + ff * d.y, lo.z + ff * d.z}, lon, lat, h);
+                double X = lon, Y = lat;
+                if (c.crs_kind == RDR_CRS_LCC_SPHERE) lcc_forward(c.crs, lon, lat, X, Y);
+                T *o = pts + ((int64_t)(slot - slot0) * n_rays + r) * 3;
+                o[0] = (T)Y;
+                o[1] = (T)X;
+                o[2] = (T)h;
+            }
+            lo = hi;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // small API-parity kernels
 // ------------------------------------------------------------------------------------------------
 __global__ void k_top_of_atmosphere(const double *__restrict__ xyz, const double *__restrict__ look, int64_t n, double toa,
@@ -1091,6 +1127,49 @@ RDR_API int rdr_ray_integrate(rdr_handle_t h, const double *maxlen, double max_s
             oob_out[2] = (int64_t)cnt[2];  // samples above max(z)
         }
     }
+    return RDR_OK;
+}
+
+RDR_API int rdr_ray_points(rdr_handle_t h, const double *maxlen, double max_segment_length, int64_t slot0, int64_t nslots, void *pts, int dtype,
+                           int64_t *total_slots, int mem) {
+    CHECK_ARG(h, h != nullptr, "rdr_ray_points: NULL handle");
+    if (!h->has_cube || !h->has_rays) return fail(h, RDR_ERR_STATE, "rdr_ray_points: call rdr_ray_layers first");
+    CHECK_ARG(h, maxlen && max_segment_length > 0, "rdr_ray_points: bad arguments");
+    CHECK_ARG(h, dtype == RDR_F64 || dtype == RDR_F32, "rdr_ray_points: dtype must be RDR_F64 or RDR_F32");
+    ScopedDevice sd(h->device);
+    const int K = h->n_layers;
+    const int64_t n = h->n_rays;
+    std::vector<int> np(K);
+    int64_t total = 1;
+    for (int k = 0; k < K; ++k) {
+        const double q = ceil(maxlen[k] / max_segment_length);
+        CHECK_ARG(h, q == q && q < 1e7, "rdr_ray_points: per-layer max length is NaN or absurd");
+        np[k] = std::max(2, (int)q + 1);
+        total += np[k] - 1;
+    }
+    if (total_slots) *total_slots = total;
+    if (!pts || nslots <= 0) return RDR_OK;  // count query
+    CHECK_ARG(h, slot0 >= 0 && slot0 + nslots <= total, "rdr_ray_points: slot range out of bounds");
+    CUDA_TRY(h, h->d_nparts.reserve(2 * K * sizeof(int)));
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_nparts.p, np.data(), K * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    const size_t es = dtype == RDR_F64 ? 8 : 4;
+    void *dp = pts;
+    if (mem == RDR_MEM_HOST) {
+        CUDA_TRY(h, h->d_in.reserve((size_t)nslots * n * 3 * es));
+        dp = h->d_in.p;
+    }
+    constexpr int BLOCK = 128;
+    const int grid = grid_for(n, BLOCK, h->sm_count, 16);
+    if (dtype == RDR_F64)
+        k_ray_points<double, BLOCK><<<grid, BLOCK, 0, h->stream>>>(make_view(h), make_geom(h), n, K, h->d_t.as<double>(), h->d_nparts.as<int>(),
+                                                                   (int)slot0, (int)nslots, static_cast<double *>(dp));
+    else
+        k_ray_points<float, BLOCK><<<grid, BLOCK, 0, h->stream>>>(make_view(h), make_geom(h), n, K, h->d_t.as<double>(), h->d_nparts.as<int>(),
+                                                                  (int)slot0, (int)nslots, static_cast<float *>(dp));
+    h->launches++;
+    CUDA_TRY(h, cudaGetLastError());
+    if (mem == RDR_MEM_HOST) CUDA_TRY(h, cudaMemcpyAsync(pts, dp, (size_t)nslots * n * 3 * es, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     return RDR_OK;
 }
 

@@ -99,7 +99,7 @@ def write_cube(path, cube: dict, proj4: str = '+proj=longlat +datum=WGS84 +no_de
                 v = nc.createVariable(k, 'f4', ('z', 'y', 'x'))
                 v[:] = np.asarray(cube[k], dtype=np.float32)
         p = nc.createVariable('proj', 'i4', ())
-        p.assignValue(0)
+        p.data[()] = 0  # (netcdf_variable.assignValue indexes [:], which a 0-d array rejects)
         p.proj4 = proj4
         p.crs_wkt = 'GEOGCRS["WGS 84"]' if 'longlat' in proj4 else 'PROJCRS["custom"]'
     return path

@@ -204,21 +204,26 @@ def _build_cube_ray(
     if cube.crs != model_crs:
         raise ValueError(f'model_crs {model_crs} does not match the CRS the cube was staged with ({cube.crs})')
 
+    ny, nx = ypts.size, xpts.size
     output_created_here = False
     if outputArrs is None:
+        # np.zeros((nz, ny, nx)) in the reference (:248); here each slice is written straight from the device (0 + x == x),
+        # so the arrays start uninitialised and only skipped slices are zero-filled
         output_created_here = True
-        outputArrs = [np.zeros((zpts.size, ypts.size, xpts.size)) for mm in range(2)]
+        outputArrs = [np.empty((zpts.size, ny, nx)) for mm in range(2)]
+    else:
+        wet = np.empty((ny, nx))
+        hydro = np.empty((ny, nx))
 
-    ny, nx = ypts.size, xpts.size
     spec = los_device_spec(los, ny, nx)
     geographic_pts = isinstance(pts_crs, Geographic)
     hooks = _reduce_hooks or (None, None)
-    wet = np.empty((ny, nx))
-    hydro = np.empty((ny, nx))
     cube.last_info = []
 
     for hh, ht in enumerate(zpts):
         logger.info(f'Processing slice {hh+1} / {len(zpts)}: {ht}')
+        if output_created_here:
+            wet, hydro = outputArrs[0][hh], outputArrs[1][hh]
         # Step 1 + 2: ground points and look vectors.  Regular geographic rasters with a device-generated LOS never
         # leave the GPU; anything else goes through the host geometry layer exactly like the reference (:262-270).
         if geographic_pts and spec is not None:
@@ -246,12 +251,16 @@ def _build_cube_ray(
             # if the top most height layer doesnt contribute to the integral, skip it (:276-277)
             if ht == zpts[-1]:
                 cube.last_info.append(TraceInfo(ht=float(ht), skipped=True))
+                if output_created_here:
+                    wet[...] = 0.0
+                    hydro[...] = 0.0
                 continue
             # the reference evaluates np.isnan(None) here and dies with a TypeError (:279); say why instead
             raise TypeError(f'no weather-model layer contributes between height {ht} and MAX_TROPO_HEIGHT={MAX_TROPO_HEIGHT}')
         cube.last_info.append(info)
-        outputArrs[0][hh, ...] += wet
-        outputArrs[1][hh, ...] += hydro
+        if not output_created_here:
+            outputArrs[0][hh, ...] += wet
+            outputArrs[1][hh, ...] += hydro
 
     if output_created_here:
         return outputArrs
@@ -311,7 +320,7 @@ class SimpleDataset:
                 if v.dims:
                     var[:] = v.data
                 else:
-                    var.assignValue(v.data)
+                    var.data[()] = v.data
                 for ak, av in v.attrs.items():
                     setattr(var, ak, av)
         return path

@@ -110,6 +110,7 @@ class DeviceCube:
         counts = np.zeros(4, dtype=np.int64)
         dev = is_device(gx) or is_device(los)
         self._keep_geom = (gx, gy, los)  # device pointers must outlive rdr_ray_integrate
+        self._n_rays = int(ny) * int(nx)
         self.h.call('rdr_ray_layers', geom_kind, ptr(gx), ptr(gy), int(ny), int(nx), los_kind, ptr(los), float(ht), float(zref),
                     ptr(maxlen), ptr(counts), _lib.MEM_DEVICE if dev else _lib.MEM_HOST)
         return maxlen[: counts[3]].copy(), counts
@@ -128,6 +129,26 @@ class DeviceCube:
         self.h.call('rdr_ray_integrate', ptr(maxlen), float(max_segment_length), int(bool(clamp_low_first)), ptr(out_wet), ptr(out_hydro),
                     dt, int(bool(accumulate)), ptr(nparts), ptr(oob), _lib.MEM_DEVICE if dev else _lib.MEM_HOST)
         return nparts, oob
+
+    def ray_points(self, maxlen, max_segment_length, slot0=0, nslots=None, out=None, dtype=np.float64):
+        """K1b: sample points (y, x, z) of the last ray_layers call, shape (nslots, n_rays, 3); out may be a torch CUDA tensor."""
+        maxlen = f64(maxlen)
+        total = C.c_int64(0)
+        self.h.call('rdr_ray_points', ptr(maxlen), float(max_segment_length), 0, 0, None, _lib.F64, C.byref(total), _lib.MEM_HOST)
+        if nslots is None:
+            nslots = total.value - slot0
+        if out is None:
+            n_rays = int(self._n_rays)
+            out = np.empty((nslots, n_rays, 3), dtype=dtype)
+        dev = is_device(out)
+        if dev:
+            import torch
+            dt = _lib.F32 if out.dtype == torch.float32 else _lib.F64
+        else:
+            dt = _lib.F32 if out.dtype == np.float32 else _lib.F64
+        self.h.call('rdr_ray_points', ptr(maxlen), float(max_segment_length), int(slot0), int(nslots), ptr(out), dt, C.byref(total),
+                    _lib.MEM_DEVICE if dev else _lib.MEM_HOST)
+        return out, total.value
 
     def trace(self, geom_kind, gx, gy, ny, nx, los_kind, los, ht, zref, max_segment_length, out_wet, out_hydro,
               reduce_max=None, reduce_sum=None) -> TraceInfo:

@@ -17,7 +17,7 @@ from ._lib import check, ptr
 
 
 def _c64(a):
-    return np.ascontiguousarray(a, dtype=np.float64)
+    return np.asarray(a, dtype=np.float64, order='C')  # (ascontiguousarray would promote 0-d to 1-d)
 
 
 def interpolate(points, values, interp_points, fill_value=None, assume_sorted=False, max_threads=8):

@@ -1,0 +1,473 @@
+"""GPU parity tests proper: CUDA path (through the C ABI / the RAiDER-shaped shims) vs the oracle and the golden vectors.
+
+Tolerances (BASELINE.json north_star): bit-exact for the integer ray-step counts (nParts) and for the kernels whose
+arithmetic is pinned op-for-op (makePoints, RAiDER.interpolate, interpolate_along_axis, the scipy-order trilinear
+sampler); |delta| <= 1e-6 m for fp64 integrated delays (observed ~1e-12); 1e-3 m for the fp32 output tier.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TOL_F64_M = 1e-6
+TOL_F32_M = 1e-3
+
+
+@pytest.fixture(scope='module')
+def gpu(lib):
+    if lib.rdr_device_count() < 1:
+        pytest.fail('no CUDA device visible to libraider_b200.so on a box that runs -m gpu tests')
+    return lib
+
+
+def _c2_small(n, posting, **kw):
+    from raider_b200 import synthetic as syn
+    cfg = syn.config_c2(n=n, **kw)
+    cfg['xpts'], cfg['ypts'] = syn.raster(34.0, -118.0, n, n, posting)
+    return cfg
+
+
+# ---------------------------------------------------------------------------------------- K1
+def test_makepoints_bit_exact(gpu, golden):
+    from raider_b200.makePoints import makePoints0D, makePoints1D, makePoints2D, makePoints3D
+    g = golden('makepoints')
+    out = makePoints3D(100.0, g['sp3'], g['slv3'], 5)
+    assert out.ndim == 5 and np.array_equal(out, g['out3'])           # test_result_makePoints3D.txt, bit for bit
+    assert np.array_equal(makePoints2D(5000.0, g['sp2'], g['slv2'], 15.0), g['out2'])
+    for L, s, n in g['counts']:
+        assert makePoints0D(L, np.zeros(3), np.ones(3), s).shape == (3, int(n))
+    # fixtures of test/test_util.py:49-89
+    ray = makePoints0D(1000.0, np.array([0.0, 0.0, 0.0]), np.array([0.0, 0.0, 1.0]), 5.0)
+    assert np.allclose(ray, np.stack([np.zeros(200), np.zeros(200), np.arange(0, 1000, 5)], axis=-1).T)
+    sp = np.zeros((2, 3)); slv = np.array([[0.0, 0, 1], [0, 1.0, 0]])
+    r1 = makePoints1D(1000.0, sp, slv, 5.0)
+    assert r1.shape == (2, 3, 200) and np.allclose(r1[1, 1], np.arange(0, 1000, 5)) and np.all(r1[1, 2] == 0)
+    with pytest.raises(ValueError):
+        makePoints1D(10.0, sp.astype(np.float32), slv, 5.0)
+
+
+# ---------------------------------------------------------------------------------------- RAiDER.interpolate
+def test_interpolate_bit_exact_vs_reference_natives(gpu, golden):
+    from raider_b200.interpolate import interpolate, interpolate_along_axis
+    g = golden('interpolate')
+    for nd in (1, 2, 3, 4):
+        grids = [g[f'nd{nd}_g{d}'] for d in range(nd)]
+        vals, pts = g[f'nd{nd}_vals'], g[f'nd{nd}_pts']
+        assert np.array_equal(interpolate(grids, vals, pts, fill_value=np.nan), g[f'nd{nd}_fill'], equal_nan=True), nd
+        assert np.array_equal(interpolate(grids, vals, pts), g[f'nd{nd}_clamp'], equal_nan=True), nd
+        assert np.array_equal(interpolate(grids, vals, pts, assume_sorted=False, max_threads=1), g[f'nd{nd}_clamp'], equal_nan=True)
+    assert np.array_equal(interpolate_along_axis(g['ax_x'], g['ax_y'], g['ax_new'], axis=2, fill_value=np.nan), g['ax_fill'], equal_nan=True)
+    assert np.array_equal(interpolate_along_axis(g['ax_x'], g['ax_y'], g['ax_new'], axis=2), g['ax_clamp'], equal_nan=True)
+    x1, y1, n1 = (np.ascontiguousarray(np.moveaxis(g[k], 2, 1)) for k in ('ax_x', 'ax_y', 'ax_new'))
+    assert np.array_equal(interpolate_along_axis(x1, y1, n1, axis=1, fill_value=np.nan), g['ax1_fill'], equal_nan=True)
+
+
+def test_interpolate_error_conventions(gpu):
+    """module.cpp:36-63,309-347: TypeError for shape problems, RuntimeError for axis 0 with threads."""
+    from raider_b200.interpolate import interpolate, interpolate_along_axis
+    with pytest.raises(TypeError):
+        interpolate(points=(np.zeros((10,)), np.zeros((5,))), values=np.zeros((1,)), interp_points=np.zeros((1,)))
+    with pytest.raises(TypeError):
+        interpolate_along_axis(np.array(0), np.array(0), np.array(0))
+    with pytest.raises(TypeError):
+        interpolate_along_axis(np.zeros(1), np.zeros(1), np.zeros((1, 1)))
+    with pytest.raises(TypeError):
+        interpolate_along_axis(np.zeros(1), np.zeros(2), np.zeros(1))
+    with pytest.raises(TypeError):
+        interpolate_along_axis(np.zeros(1), np.zeros(1), np.zeros(1), axis=1)
+    with pytest.raises(TypeError):
+        interpolate_along_axis(np.zeros((2, 2)), np.zeros((2, 2)), np.zeros((3, 2)))
+    with pytest.raises(RuntimeError):
+        interpolate_along_axis(np.zeros((2, 2)), np.zeros((2, 2)), np.zeros((2, 2)), axis=0)
+
+
+def test_interpolate_reference_cases(gpu):
+    """Numeric cases of test/test_interpolator.py (test_small, test_exact_points, *_out_of_bounds, *_fill_value, wrapper)."""
+    from scipy.interpolate import RegularGridInterpolator as RGI
+    from raider_b200.interpolate import interpolate, interpolate_along_axis
+    from raider_b200.interpolator import RegularGridInterpolator as Interpolator, interp_along_axis, interpVector
+    xs = np.array([1, 2, 3, 4, 5, 6]); ys = np.array([10, 9, 30, 10, 6, 1])
+    ans = interpolate(points=(xs,), values=ys, interp_points=np.array([1.25, 2.9, 3.01, 5.7]).reshape(-1, 1))
+    assert ans.shape == (4,) and np.allclose(ans, [9.75, 27.9, 29.8, 2.5], atol=1e-15)
+    assert np.allclose(interpolate((xs,), ys, xs.reshape(-1, 1)), ys, atol=1e-15)
+    assert interpolate((np.array([0, 1]),), np.array([0, 1]), np.array([[100]]), max_threads=1, assume_sorted=True) == np.array([100])
+    assert np.all(np.isnan(interpolate((np.array([0, 1]),), np.array([0, 1]), np.array([[100]]), fill_value=np.nan)))
+    g2 = (np.array([0, 1]), np.array([0, 1]))
+    v2 = np.add.outer([0, 1], [0, 1])
+    assert interpolate(g2, v2, np.array([[0.5, 0.5]])) == np.array([1])
+    assert interpolate(g2, v2, np.array([[100, 100]])) == np.array([200])
+    g4 = (np.array([0, 1]),) * 4
+    v4 = np.add.outer(np.add.outer(v2, [0, 1]), [0, 1])
+    assert interpolate(g4, v4, np.array([[0.5, 0.5, 0.5, 0.5]])) == np.array([2])
+    assert interpolate(g4, v4, np.array([[100, 100, 100, 100]])) == np.array([400])
+    # test_3d_cube_large-style: 2e5 points vs scipy
+    f = lambda x, y, z: x ** 2 + 3 * y - z
+    ax = np.linspace(0, 1000, 100)
+    values = f(*np.meshgrid(ax, ax, ax, indexing='ij', sparse=True))
+    n = 200_000
+    pts = np.stack((np.linspace(10, 990, n), np.linspace(10, 890, n), np.linspace(10, 780, n)), axis=-1)
+    assert np.allclose(interpolate((ax, ax, ax), values, pts, assume_sorted=True), RGI((ax, ax, ax), values)(pts), 1e-15)
+    # wrapper (test_interpolate_wrapper): tuple-of-arrays and (N,3) forms, fill beyond the grid
+    px, py, pz = np.linspace(10, 1090, 5), np.linspace(10, 890, 5), np.linspace(10, 890, 5)
+    interp = Interpolator((ax, ax, ax), values, fill_value=np.nan)
+    want = RGI((ax, ax, ax), values, bounds_error=False)(np.stack((px, py, pz), axis=-1))
+    assert np.allclose(interp(np.stack((px, py, pz), axis=-1)), want, 1e-15, equal_nan=True)
+    assert np.allclose(interp((px, py, pz)), want, 1e-15, equal_nan=True)
+    # along-axis family (test_interp_along_axis*, test_interpVector)
+    z2 = np.tile(np.arange(100)[..., np.newaxis], (5, 1, 5)).swapaxes(1, 2).astype(float)
+    newz = np.tile(np.array([1.5, 9.9, 15, 23.278, 39.99, 50.1])[..., np.newaxis], (5, 1, 5)).swapaxes(1, 2)
+    assert np.allclose(interp_along_axis(z2, newz, 0.3 * z2 - 12.75, axis=2), 0.3 * newz - 12.75)
+    assert np.allclose(interpolate_along_axis(z2, 0.3 * z2 - 12.75, newz, axis=2), 0.3 * newz - 12.75)
+    x1 = np.array([1, 2, 3, 4.0])
+    assert np.allclose(interp_along_axis(x1, np.array([1.5, 3.1]), 2 * x1, axis=0), [3.0, 6.2])
+    assert np.allclose(interp_along_axis(x1, np.array([0, 5.0]), 2 * x1, axis=0), [np.nan, np.nan], equal_nan=True)
+    assert np.allclose(interpVector(np.array([0, 1, 2, 3, 4, 5, 0, 0.84147098, 0.90929743, 0.14112001, -0.7568025, -0.95892427,
+                                              0.5, 1.5, 2.5, 3.5, 4.5]), 6),
+                       [0.42073549, 0.87538421, 0.52520872, -0.30784124, -0.85786338])
+    # threads edge case + large 3-D along-axis with scale (test_interp_along_axis_3d_large)
+    scale = np.arange(1, 31).reshape((30, 1, 1))
+    a2 = np.repeat(np.array([np.arange(100.0)]), 30, axis=0)
+    xs3 = np.repeat(np.array([a2]), 30, axis=0) * scale
+    p3 = np.repeat(np.array([np.array([np.linspace(0, 99, num=200)]).repeat(30, axis=0)]), 30, axis=0) * scale
+    assert np.allclose(interpolate_along_axis(xs3, 2 * xs3, p3, axis=2, assume_sorted=True), 2 * p3)
+
+
+# ---------------------------------------------------------------------------------------- K2
+def test_sampler_bit_exact_vs_scipy(gpu, golden):
+    """scipy RGI as delayFcns.py:55-56 configures it, incl. edges, OOB and NaN coordinates (Appendix A)."""
+    from raider_b200 import _lib
+    from raider_b200.delayFcns import getInterpolators
+    g = golden('scipy_sample')
+    ifW, ifH = getInterpolators({k: g[k[0] + 's'] if k in 'xyz' else g[k] for k in ('x', 'y', 'z', 'wet', 'hydro')})
+    assert [a.size for a in ifW.grid] == [g['ys'].size, g['xs'].size, g['zs'].size]
+    w, h = ifW(g['pts']), ifH(g['pts'])
+    assert np.array_equal(w, g['out_wet'], equal_nan=True)
+    assert np.array_equal(h, g['out_hydro'], equal_nan=True)
+    assert np.isnan(w[4]) and np.isnan(w[5]) and np.isnan(w[6]) and not np.isnan(w[1])
+    # shape handling like scipy: (..., 3) in -> (...) out
+    assert ifW(g['pts'].reshape(30, 100, 3)).shape == (30, 100)
+    # fp32 tier of the sampler (20 B/point): same cells, fp32 I/O
+    w32, _ = ifW.cube.sample(g['pts'].astype(np.float32))
+    ok = ~np.isnan(g['out_wet']) & ~np.isnan(w32)
+    assert ok.sum() > 2500 and np.abs(w32[ok] - g['out_wet'][ok]).max() < 2e-2  # fp32 coordinates move the point by ~1e-3 m in z
+    # C++ interval rules on the staged cube == oracle restatement of interpolate.cpp on the promoted values
+    from oracle import interp as ointerp
+    vals = g['wet'].transpose(1, 2, 0).astype(np.float64)
+    for sem, fill in ((_lib.SEM_RAIDER_FILL, np.nan), (_lib.SEM_RAIDER_CLAMP, None)):
+        got = ifW.cube.sample(g['pts'], semantics=sem)[0]
+        want = ointerp.interpolate((g['ys'], g['xs'], g['zs']), vals, g['pts'], fill_value=fill)
+        assert np.array_equal(got, want, equal_nan=True)
+
+
+def test_sampler_descending_axes_and_layouts(gpu, golden):
+    """Descending y (AOI grids, llreader.py:191) is flipped on staging like scipy does; (y,x,z) and (z,y,x) layouts agree."""
+    from raider_b200 import _lib
+    from raider_b200.engine import DeviceCube
+    g = golden('scipy_sample')
+    a = DeviceCube(g['ys'], g['xs'], g['zs'], g['wet'], g['hydro'], layout=_lib.LAYOUT_ZYX)
+    b = DeviceCube(g['ys'][::-1].copy(), g['xs'], g['zs'], np.ascontiguousarray(g['wet'][:, ::-1]), np.ascontiguousarray(g['hydro'][:, ::-1]))
+    c = DeviceCube(g['ys'], g['xs'], g['zs'], np.ascontiguousarray(g['wet'].transpose(1, 2, 0)),
+                   np.ascontiguousarray(g['hydro'].transpose(1, 2, 0)), layout=_lib.LAYOUT_YXZ)
+    ra = a.sample(g['pts'])
+    for other in (b, c):
+        ro = other.sample(g['pts'])
+        assert np.array_equal(ra[0], ro[0], equal_nan=True) and np.array_equal(ra[1], ro[1], equal_nan=True)
+    assert np.array_equal(b.grid[0], g['ys'])
+    with pytest.raises(TypeError):
+        DeviceCube(np.array([0.0, 1.0, 1.0]), g['xs'], g['zs'], g['wet'][:, :3], g['hydro'][:, :3])
+
+
+def test_zenith_cube_matches_golden(gpu, golden):
+    """_build_cube (delay.py:196-216) on the C1 cube: bit-exact vs scipy on wet_total/hydro_total."""
+    from raider_b200 import synthetic as syn
+    from raider_b200.delay import _build_cube
+    from raider_b200.delayFcns import getInterpolators
+    g = golden('raytrace')
+    c1 = syn.config_c1()
+    ifs = getInterpolators(c1['cube'], 'total')
+    out = _build_cube(g['e_xpts'], g['e_ypts'], g['e_zpts'], 4326, 4326, list(ifs))
+    assert out[0].shape == (5, 20, 20)
+    assert np.array_equal(out[0], g['e_wet']) and np.array_equal(out[1], g['e_hydro'])
+
+
+# ---------------------------------------------------------------------------------------- geodesy / build_ray
+def test_geodesy_and_build_ray_vs_oracle(gpu, golden):
+    from raider_b200.losreader import build_ray, getTopOfAtmosphere
+    from raider_b200.utilFcns import ecef2lla, lla2ecef
+    g = golden('geodesy')
+    x, y, z = lla2ecef(g['lat'], g['lon'], g['h'])
+    assert max(np.abs(x - g['x']).max(), np.abs(y - g['y']).max(), np.abs(z - g['z']).max()) < 5e-9  # ulp-level (sincos vs libm)
+    lo, la, hh = ecef2lla(g['x'], g['y'], g['z'])
+    assert np.abs(la - g['lat_back']).max() < 1e-13 and np.abs(hh - g['h_back']).max() < 5e-9
+    dlon = np.abs(lo - g['lon_back'])
+    assert dlon[np.abs(g['lat']) < 89.99].max() < 1e-13
+    assert lla2ecef(0.0, 0.0, 0.0) == pytest.approx((6378137.0, 0.0, 0.0), abs=1e-9)   # test_delayFcns.py:86-99
+    # Newton schedule: 10 iterations without factor, 3 with (losreader.py:720-733)
+    assert np.abs(getTopOfAtmosphere(g['g0'], g['look'], 30000.0) - g['toa10']).max() < 1e-7
+    assert np.abs(getTopOfAtmosphere(g['g0'], g['look'], 30000.0, factor=g['cosf']) - g['toa3']).max() < 1e-7
+    lens, lows, highs = build_ray(g['zs'], 0.0, g['g0'], g['look'], g['zs'][-1] - 1)
+    assert lens.shape == g['lens'].shape and lows.shape == g['lows'].shape
+    assert np.abs(lens - g['lens']).max() < 1e-7 and np.abs(highs - g['highs']).max() < 1e-7 and np.abs(lows - g['lows']).max() < 1e-7
+    assert build_ray(g['zs'], g['zs'][-1] - 0.5, g['g0'], g['look'], g['zs'][-1] - 1) == (None, None, None)  # losreader.py:832-833
+
+
+# ---------------------------------------------------------------------------------------- K0 + K3
+def _run_gpu(cfg, los, **kw):
+    from raider_b200.delay import _build_cube_ray
+    from raider_b200.delayFcns import getInterpolators
+    ifs = getInterpolators(cfg['cube'])
+    out = _build_cube_ray(cfg['xpts'], cfg['ypts'], cfg['zpts'], los, 4326, 4326, list(ifs), MAX_SEGMENT_LENGTH=cfg['max_segment_length'],
+                          MAX_TROPO_HEIGHT=cfg['zref'], **kw)
+    return out, ifs[0].cube.last_info
+
+
+def test_slant_fixed_incidence_golden_a(gpu, golden):
+    """C2 shape: 30 deg incidence, NZ=37, 225 m segments; nParts bit-exact, delays within 1e-6 m of the oracle golden."""
+    from raider_b200.losreader import Raytracing
+    g = golden('raytrace')
+    cfg = _c2_small(24, 0.08)
+    out, info = _run_gpu(cfg, Raytracing(incidence=30.0, heading=-168.0))
+    assert np.array_equal(info[0].nparts, g['a_nparts'])
+    assert info[0].samples_per_ray == 296 and info[0].n_layers == 33 and info[0].reruns == 0
+    assert np.abs(info[0].maxlen - g['a_maxlen']).max() < 1e-7
+    assert np.abs(out[0] - g['a_wet']).max() < TOL_F64_M and np.abs(out[1] - g['a_hydro']).max() < TOL_F64_M
+    assert np.abs(out[1] - g['a_hydro']).max() < 1e-10  # what the arithmetic really achieves
+    assert not np.isnan(out[0]).any()
+
+
+def test_slant_ml145_two_heights_golden_b(gpu, golden):
+    from raider_b200.losreader import Raytracing
+    g = golden('raytrace')
+    cfg = _c2_small(12, 0.15, table='ml145')
+    cfg['zpts'] = np.array([0.0, 1500.0])
+    out, info = _run_gpu(cfg, Raytracing(incidence=45.0, heading=12.0))
+    assert np.array_equal(info[0].nparts, g['b_nparts']) and np.array_equal(info[1].nparts, g['b_nparts1'])
+    assert out[0].shape == (2, 12, 12)
+    assert np.abs(out[0] - g['b_wet']).max() < TOL_F64_M and np.abs(out[1] - g['b_hydro']).max() < TOL_F64_M
+
+
+def test_slant_zenith_rays_golden_c(gpu, golden):
+    from raider_b200.losreader import ZenithRaytracing
+    g = golden('raytrace')
+    cfg = _c2_small(10, 0.2)
+    out, info = _run_gpu(cfg, ZenithRaytracing())
+    assert np.array_equal(info[0].nparts, g['c_nparts'])
+    assert np.abs(out[0] - g['c_wet']).max() < TOL_F64_M and np.abs(out[1] - g['c_hydro']).max() < TOL_F64_M
+
+
+def test_slant_explicit_los_array_golden_d(gpu, golden):
+    """Per-pixel look vectors handed over as an array (the contract of Raytracing.getLookVectors, losreader.py:219-255)."""
+    from raider_b200.losreader import Raytracing
+    g = golden('raytrace')
+    cfg = _c2_small(16, 0.1)
+    out, info = _run_gpu(cfg, Raytracing(look_vecs=g['d_los']))
+    assert np.array_equal(info[0].nparts, g['d_nparts'])
+    assert np.abs(out[0] - g['d_wet']).max() < TOL_F64_M and np.abs(out[1] - g['d_hydro']).max() < TOL_F64_M
+    # a duck-typed third-party LOS object (only getLookVectors) takes the host geometry path and must agree
+    class Duck:
+        def getLookVectors(self, ht, llh, xyz, yy):
+            assert xyz.shape == yy.shape + (3,)
+            return g['d_los']
+    out2, _ = _run_gpu(cfg, Duck())
+    assert np.array_equal(out2[0], out[0]) and np.array_equal(out2[1], out[1])
+
+
+def test_slant_hrrr_lcc_golden_f(gpu, golden):
+    """HRRR-like cube: spherical LCC model CRS (models/hrrr.py:255-260), geographic query raster."""
+    from raider_b200.crs import LambertConformalSphere
+    from raider_b200.delay import _build_cube_ray
+    from raider_b200.delayFcns import getInterpolators
+    from raider_b200.losreader import Raytracing
+    from raider_b200 import synthetic as syn
+    g = golden('raytrace')
+    lcc = LambertConformalSphere()
+    assert np.allclose(lcc.params(), g['f_lcc'], rtol=1e-15)
+    cube = {'x': g['f_xs'], 'y': g['f_ys'], 'z': syn.z_levels_table('hrrr57'), 'wet': g['f_wet_cube'], 'hydro': g['f_hydro_cube'], 'crs': lcc}
+    ifs = getInterpolators(cube)
+    out = _build_cube_ray(g['f_xpts'], g['f_ypts'], np.array([200.0]), Raytracing(incidence=35.0, heading=-12.0), lcc, 4326, list(ifs),
+                          MAX_TROPO_HEIGHT=float(cube['z'][-1] - 1))
+    assert np.array_equal(ifs[0].cube.last_info[0].nparts, g['f_nparts'])
+    assert np.abs(out[0] - g['f_wet']).max() < TOL_F64_M and np.abs(out[1] - g['f_hydro']).max() < TOL_F64_M
+
+
+def test_slant_vs_oracle_live_and_accumulate(gpu):
+    """Same seeded inputs through the oracle here and now (not a stored vector), plus outputArrs accumulation (delay.py:245-248)."""
+    from oracle import raytrace as rt
+    from raider_b200.losreader import Raytracing
+    cfg = _c2_small(20, 0.09, nz=50)
+    cfg['zpts'] = np.array([0.0, 300.0, 2500.0])
+    crs = rt.GeographicCRS()
+    st = {}
+    want = rt.build_cube_ray(cfg['xpts'], cfg['ypts'], cfg['zpts'], rt.FixedIncidenceLOS(38.0, 191.0), crs, crs,
+                             list(rt.get_interpolators(cfg['cube'])), MAX_SEGMENT_LENGTH=400.0, MAX_TROPO_HEIGHT=cfg['zref'], stats=st)
+    cfg['max_segment_length'] = 400.0
+    out, info = _run_gpu(cfg, Raytracing(incidence=38.0, heading=191.0))
+    for hh in range(3):
+        assert np.array_equal(info[hh].nparts, st['nParts'][hh])
+    assert np.abs(out[0] - want[0]).max() < TOL_F64_M and np.abs(out[1] - want[1]).max() < TOL_F64_M
+    pre = [np.full_like(out[0], 1.0), np.full_like(out[1], -2.0)]
+    ret, _ = _run_gpu(cfg, Raytracing(incidence=38.0, heading=191.0), outputArrs=pre)
+    assert ret is None and np.allclose(pre[0], 1.0 + out[0], atol=1e-15) and np.allclose(pre[1], out[1] - 2.0, atol=1e-15)
+
+
+def test_constant_refractivity_identity_on_device(gpu):
+    """test/test_synthetic.py:217-274 on the GPU: delay * 1e6 == k * sum_k L_k, ray lengths recomputed independently with build_ray."""
+    from raider_b200 import synthetic as syn
+    from raider_b200.losreader import Raytracing, build_ray
+    from raider_b200.utilFcns import lla2ecef
+    cfg = _c2_small(32, 0.06, table='ml145')
+    cube = syn.constant_cube(cfg['cube']['y'], cfg['cube']['x'], cfg['cube']['z'], 77.6, 71.6)
+    los = Raytracing(incidence=41.0, heading=-168.0)
+    out, info = _run_gpu(dict(cfg, cube=cube), los)
+    xx, yy = np.meshgrid(cfg['xpts'], cfg['ypts'])
+    xyz = np.stack(lla2ecef(yy, xx, np.zeros_like(yy)), -1)
+    L = build_ray(cube['z'], 0.0, xyz, los.getLookVectors(0.0, [xx, yy, 0 * yy], xyz, yy), cfg['zref'])[0].sum(0)
+    assert np.all(L > 1)
+    for arr, k in ((out[0][0], np.float32(77.6)), (out[1][0], np.float32(71.6))):
+        resid = (float(k) * L - arr * 1e6) / (float(k) * L)
+        np.testing.assert_almost_equal(0, resid, decimal=9)   # the reference asks for 6 decimals
+
+
+def test_whole_raster_predicates(gpu):
+    """delay.py:276-277 (top slice skipped), :306-307 (all pixels below min(z) -> clamp), partial OOB -> NaN pixels, no error."""
+    from oracle import raytrace as rt
+    from raider_b200.losreader import Raytracing
+    from raider_b200 import synthetic as syn
+    cfg = _c2_small(8, 0.2)
+    zs = cfg['cube']['z']
+    # (1) default height_levels = model levels: the last level contributes nothing and is skipped, zeros stay
+    cfg['zpts'] = np.array([zs[3], zs[-1]])
+    out, info = _run_gpu(cfg, Raytracing(incidence=30.0, heading=-168.0))
+    assert info[1].skipped and np.all(out[0][1] == 0) and np.all(out[0][0] > 0)
+    # (2) ... but a non-final height without layers is the reference's latent TypeError
+    cfg['zpts'] = np.array([zs[-1], zs[3]])
+    with pytest.raises(TypeError):
+        _run_gpu(cfg, Raytracing(incidence=30.0, heading=-168.0))
+    # (3) ht == min(z): the first sample sits within ~1e-9 m of the cube floor; whatever the knife edge decides,
+    #     the device must take the same branch as its own evaluation of the predicate and stay NaN-consistent
+    cfg['zpts'] = np.array([zs[0]])
+    out, info = _run_gpu(cfg, Raytracing(incidence=30.0, heading=-168.0))
+    n_nan = int(np.isnan(out[0]).sum())
+    assert (n_nan == 0) if info[0].clamp_low_first else (n_nan == info[0].oob_below)
+    crs = rt.GeographicCRS()
+    want = rt.build_cube_ray(cfg['xpts'], cfg['ypts'], cfg['zpts'], rt.FixedIncidenceLOS(30.0, -168.0), crs, crs,
+                             list(rt.get_interpolators(cfg['cube'])), MAX_SEGMENT_LENGTH=cfg['max_segment_length'], MAX_TROPO_HEIGHT=cfg['zref'])
+    both = ~np.isnan(out[0]) & ~np.isnan(want[0])
+    assert both.sum() > 0 and np.abs(out[0][both] - want[0][both]).max() < TOL_F64_M
+    # (4) raster hanging over the edge of the cube: those pixels are NaN (delay.py:187-188 only logs), the rest are right
+    xp = np.linspace(cfg['cube']['x'][-1] - 0.3, cfg['cube']['x'][-1] + 0.2, 9)
+    cfg2 = dict(cfg, xpts=xp, zpts=np.array([0.0]))
+    out, _ = _run_gpu(cfg2, Raytracing(incidence=30.0, heading=-168.0))
+    want = rt.build_cube_ray(xp, cfg['ypts'], np.array([0.0]), rt.FixedIncidenceLOS(30.0, -168.0), crs, crs,
+                             list(rt.get_interpolators(cfg['cube'])), MAX_SEGMENT_LENGTH=cfg['max_segment_length'], MAX_TROPO_HEIGHT=cfg['zref'])
+    assert np.array_equal(np.isnan(out[0]), np.isnan(want[0])) and np.isnan(out[0]).any() and not np.isnan(out[0]).all()
+    ok = ~np.isnan(want[0])
+    assert np.abs(out[0][ok] - want[0][ok]).max() < TOL_F64_M
+
+
+def test_two_epoch_blend(gpu):
+    """Temporal interpolation fused at staging (cli/raider.py:817-819) == blend cubes first, then trace."""
+    from raider_b200 import synthetic as syn
+    from raider_b200.delayFcns import getInterpolators
+    from raider_b200.delay import _build_cube_ray
+    from raider_b200.losreader import Raytracing
+    cfg = _c2_small(10, 0.18)
+    c0 = cfg['cube']
+    c1 = syn.make_cube(c0['y'], c0['x'], c0['z'], seed=20200131)
+    w0, w1 = 1 - 5 / 180, 5 / 180   # 12:05 between 12:00 and 15:00 (get_weights_time_interp, cli/raider.py:877-888)
+    los = Raytracing(incidence=30.0, heading=-168.0)
+    kw = dict(MAX_SEGMENT_LENGTH=cfg['max_segment_length'], MAX_TROPO_HEIGHT=cfg['zref'])
+    ifs = getInterpolators(c0)
+    ifs[0].cube.blend(c1['wet'], c1['hydro'], w0, w1)
+    fused = _build_cube_ray(cfg['xpts'], cfg['ypts'], cfg['zpts'], los, 4326, 4326, list(ifs), **kw)
+    pre = _build_cube_ray(cfg['xpts'], cfg['ypts'], cfg['zpts'], los, 4326, 4326, list(getInterpolators(syn.blend_cubes(c0, c1, w0, w1))), **kw)
+    assert np.abs(fused[0] - pre[0]).max() < 1e-7 and np.abs(fused[1] - pre[1]).max() < 1e-7  # fp32 (xarray) vs fp64 blend rounding
+
+
+def test_tropo_delay_entry_points(gpu, tmp_path):
+    """tropo_delay (delay.py:35-130): cube AOI -> Dataset; point AOI -> arrays; zenith, projected and ray-traced."""
+    import datetime as dt
+    from oracle import raytrace as rt
+    from raider_b200 import synthetic as syn
+    from raider_b200.cube_io import write_cube
+    from raider_b200.delay import tropo_delay
+    from raider_b200.llreader import BoundingBox, Points
+    from raider_b200.losreader import Conventional, Raytracing, Zenith
+    cfg = _c2_small(8, 0.2)
+    path = write_cube(tmp_path / 'ERA5_synth.nc', cfg['cube'])
+    t = dt.datetime(2020, 1, 30, 13, 52, 45)
+    aoi = BoundingBox([33.2, 34.8, -118.8, -117.2], spacing=0.2)
+    hts = [0.0, 500.0, 4000.0]
+    crs = rt.GeographicCRS()
+    # zenith cube
+    ds, _ = tropo_delay(t, path, aoi, Zenith(), height_levels=hts)
+    want = rt.build_cube(aoi.xpts, aoi.ypts, np.array(hts), crs, crs, list(rt.get_interpolators(cfg['cube'], 'total')))
+    assert np.array_equal(np.asarray(ds['wet'].values), want[0]) and np.array_equal(np.asarray(ds['hydro'].values), want[1])
+    assert ds['wet'].attrs['units'] == 'm' and 'zenith' in ds['wet'].attrs['description']
+    # ray-traced cube, zref defaulting to top-of-model - 1 (delay.py:78-93)
+    ds, _ = tropo_delay(t, path, aoi, Raytracing(incidence=30.0, heading=-168.0), height_levels=hts)
+    want = rt.build_cube_ray(aoi.xpts, aoi.ypts, np.array(hts), rt.FixedIncidenceLOS(30.0, -168.0), crs, crs,
+                             list(rt.get_interpolators(cfg['cube'])), MAX_TROPO_HEIGHT=cfg['cube']['z'].max() - 1)
+    assert np.abs(np.asarray(ds['wet'].values) - want[0]).max() < TOL_F64_M
+    assert np.abs(np.asarray(ds['hydro'].values) - want[1]).max() < TOL_F64_M
+    # point mode: cube first, then scipy-style interpolation at (lat, lon, hgt), then projection (delay.py:98-128)
+    rng = np.random.default_rng(7)
+    lats, lons, hgts = rng.uniform(33.3, 34.7, 50), rng.uniform(-118.7, -117.3, 50), rng.uniform(10, 3000, 50)
+    pts_aoi = Points(lats, lons, hgts)
+    pts_aoi.xpts, pts_aoi.ypts = aoi.xpts, aoi.ypts
+    from scipy.interpolate import RegularGridInterpolator as RGI
+    wz, hz = tropo_delay(t, path, pts_aoi, Zenith(), height_levels=hts)
+    wantz = rt.build_cube(aoi.xpts, aoi.ypts, np.array(hts), crs, crs, list(rt.get_interpolators(cfg['cube'], 'total')))
+    ref_w = RGI((aoi.ypts, aoi.xpts, np.array(hts)), wantz[0].transpose(1, 2, 0), fill_value=np.nan, bounds_error=False)(np.stack([lats, lons, hgts], -1))
+    assert np.abs(wz - ref_w).max() < 1e-12
+    wp, hp = tropo_delay(t, path, pts_aoi, Conventional(incidence=35.0), height_levels=hts)
+    assert np.allclose(wp, wz / np.cos(np.radians(35.0)), rtol=1e-14) and np.allclose(hp, hz / np.cos(np.radians(35.0)), rtol=1e-14)
+
+
+def test_fp32_output_tier(gpu):
+    """fp32 outputs (16 -> 8 B/ray of writes): within 1e-3 m of the fp64 oracle as north_star states for the fp32 tier."""
+    import ctypes as C
+    from raider_b200 import _lib
+    from raider_b200.delayFcns import getInterpolators
+    g = np.load(__import__('pathlib').Path(__file__).parent / 'golden' / 'raytrace.npz')
+    cfg = _c2_small(24, 0.08)
+    cube = getInterpolators(cfg['cube'])[0].cube
+    enu = np.array([np.sin(np.radians(30)) * np.cos(np.radians(-168 + 90)), np.sin(np.radians(30)) * np.sin(np.radians(-168 + 90)), np.cos(np.radians(30))])
+    maxlen, counts = cube.ray_layers(_lib.GEOM_GRID, cfg['xpts'], cfg['ypts'], 24, 24, _lib.LOS_ENU_CONST, enu, 0.0, cfg['zref'])
+    w, h = np.empty((24, 24), np.float32), np.empty((24, 24), np.float32)
+    nparts, oob = cube.ray_integrate(maxlen, cfg['max_segment_length'], False, w, h)
+    assert np.array_equal(nparts, g['a_nparts'])
+    assert np.abs(w - g['a_wet'][0]).max() < TOL_F32_M and np.abs(h - g['a_hydro'][0]).max() < TOL_F32_M
+
+
+def test_full_size_properties(gpu):
+    """BASELINE C2 at full size (2000 x 2000 rays) through size-independent properties: tiling invariance (sub-raster ==
+    crop of the full raster when the global maxima are shared), linearity in the cube values, and the constant-N identity."""
+    from raider_b200 import _lib, synthetic as syn
+    from raider_b200.delayFcns import getInterpolators
+    cfg = syn.config_c2()
+    cube = getInterpolators(cfg['cube'])[0].cube
+    enu = np.array([np.sin(np.radians(30)) * np.cos(np.radians(-78)), np.sin(np.radians(30)) * np.sin(np.radians(-78)), np.cos(np.radians(30))])
+    ny = nx = 2000
+    w, h = np.empty((ny, nx)), np.empty((ny, nx))
+    info = cube.trace(_lib.GEOM_GRID, cfg['xpts'], cfg['ypts'], ny, nx, _lib.LOS_ENU_CONST, enu, 0.0, cfg['zref'], cfg['max_segment_length'], w, h)
+    assert info.samples_per_ray in range(280, 320) and not np.isnan(w).any() and w.min() > 0.05 and h.min() > 2.0
+    # tiling invariance: rows 700..899 alone, with the full raster's maxima injected
+    ws, hs = np.empty((200, nx)), np.empty((200, nx))
+    cube.ray_layers(_lib.GEOM_GRID, cfg['xpts'], cfg['ypts'][700:900], 200, nx, _lib.LOS_ENU_CONST, enu, 0.0, cfg['zref'])
+    nparts, _ = cube.ray_integrate(info.maxlen, cfg['max_segment_length'], False, ws, hs)
+    assert np.array_equal(nparts, info.nparts) and np.array_equal(ws, w[700:900]) and np.array_equal(hs, h[700:900])
+    # linearity: doubling the cube doubles the delays (power-of-two scaling is exact in fp32 and fp64)
+    c2 = dict(cfg['cube'], wet=cfg['cube']['wet'] * 2, hydro=cfg['cube']['hydro'] * 2)
+    cube2 = getInterpolators(c2)[0].cube
+    w2, h2 = np.empty((ny, nx)), np.empty((ny, nx))
+    cube2.trace(_lib.GEOM_GRID, cfg['xpts'], cfg['ypts'], ny, nx, _lib.LOS_ENU_CONST, enu, 0.0, cfg['zref'], cfg['max_segment_length'], w2, h2)
+    assert np.array_equal(w2, 2 * w) and np.array_equal(h2, 2 * h)
+    # oracle on a 40 x 40 crop with the global maxima injected: the crop must reproduce the device within 1e-6 m
+    from oracle import raytrace as rt
+    crs = rt.GeographicCRS()
+    sl = slice(980, 1020)
+    want = rt.build_cube_ray(cfg['xpts'][sl], cfg['ypts'][sl], cfg['zpts'], rt.FixedIncidenceLOS(30.0, -168.0), crs, crs,
+                             list(rt.get_interpolators(cfg['cube'])), MAX_SEGMENT_LENGTH=cfg['max_segment_length'],
+                             MAX_TROPO_HEIGHT=cfg['zref'], layer_maxlen=[info.maxlen])
+    assert np.abs(w[sl, sl] - want[0][0]).max() < TOL_F64_M and np.abs(h[sl, sl] - want[1][0]).max() < TOL_F64_M
