@@ -143,7 +143,7 @@ def cpu_global_maxlen(cfg):
     return lens.max((1, 2))
 
 
-def cpu_baseline_single(cfg, maxlen, rows=20):
+def cpu_baseline_single(cfg, maxlen, rows=100):
     """cpu_baseline leg: 1 core, `rows` x 2000 rays from the middle of the raster."""
     mid = cfg['ypts'].size // 2
     dt, _ = _cpu_block((cfg['cube'], cfg['xpts'], cfg['ypts'][mid:mid + rows], cfg['zref'], cfg['max_segment_length'], maxlen))
@@ -219,7 +219,8 @@ def run_ours(args):
     ny = ypts.size
     n_local, n_global = ny * nx, ny_g * nx
     enu = enu_const()
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()          # the handle launches on this stream, and the events below are recorded on it
+    torch.cuda.set_stream(stream)
 
     cube = DeviceCube.from_dict(cfg['cube'], device=local)
     cube.h.set_stream(stream.cuda_stream)

@@ -14,6 +14,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -31,20 +32,77 @@ namespace {
 
 thread_local std::string g_last_error;
 
+// Freed device blocks are parked in a small per-process pool instead of going back to the driver: the reference-shaped
+// API creates a fresh cube (handle) per weather-model file, and re-allocating GB-sized ray scratch with cudaMalloc/cudaFree
+// on every call would cost more than the kernels.
+struct BlockPool {
+    struct Block {
+        int device;
+        void *p;
+        size_t cap;
+    };
+    std::mutex mu;
+    std::vector<Block> free_blocks;
+    size_t cached = 0;
+    static constexpr size_t MAX_CACHED = 48ull << 30;
+
+    void *take(int device, size_t bytes, size_t &cap) {
+        std::lock_guard<std::mutex> lk(mu);
+        int best = -1;
+        for (int i = 0; i < (int)free_blocks.size(); ++i) {
+            const Block &b = free_blocks[i];
+            if (b.device == device && b.cap >= bytes && b.cap <= 2 * bytes + (1 << 20) && (best < 0 || b.cap < free_blocks[best].cap)) best = i;
+        }
+        if (best < 0) return nullptr;
+        Block b = free_blocks[best];
+        free_blocks.erase(free_blocks.begin() + best);
+        cached -= b.cap;
+        cap = b.cap;
+        return b.p;
+    }
+    void give(int device, void *p, size_t cap) {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            if (cached + cap <= MAX_CACHED) {
+                free_blocks.push_back({device, p, cap});
+                cached += cap;
+                return;
+            }
+        }
+        cudaFree(p);
+    }
+    void trim(int device) {  // out of memory: hand everything cached on this device back to the driver
+        std::lock_guard<std::mutex> lk(mu);
+        for (int i = (int)free_blocks.size() - 1; i >= 0; --i)
+            if (free_blocks[i].device == device) {
+                cudaFree(free_blocks[i].p);
+                cached -= free_blocks[i].cap;
+                free_blocks.erase(free_blocks.begin() + i);
+            }
+    }
+};
+BlockPool g_pool;
+
 struct DevBuf {
     void *p = nullptr;
     size_t cap = 0;
+    int device = -1;
     cudaError_t reserve(size_t bytes) {
         if (bytes <= cap) return cudaSuccess;
-        if (p) cudaFree(p);
-        p = nullptr;
-        cap = 0;
+        release();
+        cudaGetDevice(&device);
+        if ((p = g_pool.take(device, bytes, cap))) return cudaSuccess;
         cudaError_t e = cudaMalloc(&p, bytes);
-        if (e == cudaSuccess) cap = bytes;
+        if (e == cudaErrorMemoryAllocation) {
+            cudaGetLastError();
+            g_pool.trim(device);
+            e = cudaMalloc(&p, bytes);
+        }
+        if (e == cudaSuccess) cap = bytes; else p = nullptr;
         return e;
     }
     void release() {
-        if (p) cudaFree(p);
+        if (p) g_pool.give(device, p, cap);
         p = nullptr;
         cap = 0;
     }
@@ -71,7 +129,10 @@ struct rdr_handle_s {
     bool flip_y = false, flip_x = false, flip_z = false;
     int crs_kind = RDR_CRS_GEOGRAPHIC;
     double crs[7] = {0, 0, 0, 0, 0, 0, 0};
-    DevBuf d_axes;   // ys | xs | zs
+    DevBuf d_axes;   // ys | xs | zs (nodes)
+    DevBuf d_tabs;   // per axis: interval records (double4) then first-guess bins (uint16)
+    size_t tab_cell_off[3] = {0, 0, 0}, tab_bin_off[3] = {0, 0, 0};
+    int tab_nbin[3] = {0, 0, 0};
     DevBuf d_cells;  // float4 [ny][nx][nz-1]
     DevBuf d_stage;  // staging for field uploads (and packed fp32 pairs for blending)
     DevBuf d_fields; // float2 [ny][nx][nz] (wet, hydro) kept for blending
@@ -163,27 +224,60 @@ __global__ void k_pack_cells(const float2 *__restrict__ f, float4 *__restrict__ 
 CubeView make_view(rdr_handle_t h) {
     CubeView c;
     c.cells = h->d_cells.as<float4>();
-    const double *ax = h->d_axes.as<double>();
-    auto mk = [](const double *g, const std::vector<double> &v) {
-        Axis a;
-        a.g = g;
-        a.n = (int)v.size();
-        a.g0 = v[0];
-        const double d = (v.back() - v[0]) / (double)(v.size() - 1);
-        a.inv_d = 1.0 / d;
-        // "uniform" only needs the floor() guess to land within a couple of cells; the fix-up loops make it exact
-        bool uni = true;
-        for (size_t i = 1; i < v.size(); ++i)
-            if (fabs((v[i] - v[i - 1]) - d) > 0.25 * fabs(d)) uni = false;
-        a.uniform = uni ? 1 : 0;
-        return a;
-    };
-    c.ay = mk(ax, h->ys);
-    c.ax = mk(ax + h->ny, h->xs);
-    c.az = mk(ax + h->ny + h->nx, h->zs);
+    const double *nodes = h->d_axes.as<double>();
+    const char *tabs = h->d_tabs.as<char>();
+    const std::vector<double> *v[3] = {&h->ys, &h->xs, &h->zs};
+    Axis *ax[3] = {&c.ay, &c.ax, &c.az};
+    size_t off = 0;
+    for (int d = 0; d < 3; ++d) {
+        Axis &a = *ax[d];
+        a.g = nodes + off;
+        off += v[d]->size();
+        a.cell = reinterpret_cast<const double4 *>(tabs + h->tab_cell_off[d]);
+        a.bin = reinterpret_cast<const unsigned short *>(tabs + h->tab_bin_off[d]);
+        a.n = (int)v[d]->size();
+        a.nbin = h->tab_nbin[d];
+        a.g_first = v[d]->front();
+        a.g_last = v[d]->back();
+        a.inv_bw = (double)a.nbin / (a.g_last - a.g_first);
+    }
     c.crs_kind = h->crs_kind;
-    for (int i = 0; i < 7; ++i) c.crs[i] = h->crs[i];
+    c.lcc = {h->crs[0], h->crs[1], h->crs[2], h->crs[3], h->crs[4], h->crs[5], h->crs[6]};
     return c;
+}
+
+// interval records + first-guess bins for the three axes (see sampler.cuh)
+int build_axis_tables(rdr_handle_t h) {
+    const std::vector<double> *v[3] = {&h->ys, &h->xs, &h->zs};
+    std::vector<char> blob;
+    for (int d = 0; d < 3; ++d) {
+        const std::vector<double> &g = *v[d];
+        const int n = (int)g.size();
+        h->tab_cell_off[d] = blob.size();
+        std::vector<double> rec(4 * (size_t)(n - 1));
+        for (int i = 0; i + 1 < n; ++i) {
+            const double dd = g[i + 1] - g[i];
+            rec[4 * i] = g[i]; rec[4 * i + 1] = g[i + 1]; rec[4 * i + 2] = dd; rec[4 * i + 3] = 1.0 / dd;
+        }
+        blob.insert(blob.end(), reinterpret_cast<char *>(rec.data()), reinterpret_cast<char *>(rec.data() + rec.size()));
+        const int nbin = std::min(8192, std::max(64, 8 * n));
+        h->tab_nbin[d] = nbin;
+        h->tab_bin_off[d] = blob.size();
+        std::vector<unsigned short> bins(nbin);
+        const double bw = (g.back() - g.front()) / nbin;
+        int i = 0;
+        for (int b = 0; b < nbin; ++b) {
+            const double start = g.front() + b * bw;
+            while (i < n - 2 && g[i + 1] <= start) ++i;
+            bins[b] = (unsigned short)(i > 0 ? i - 1 : 0);  // one interval of slack: the device rounds (v - g0) * inv_bw its own way
+        }
+        blob.insert(blob.end(), reinterpret_cast<char *>(bins.data()), reinterpret_cast<char *>(bins.data() + bins.size()));
+        while (blob.size() % 32) blob.push_back(0);
+    }
+    CUDA_TRY(h, h->d_tabs.reserve(blob.size()));
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_tabs.p, blob.data(), blob.size(), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return RDR_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -194,7 +288,8 @@ CubeView make_view(rdr_handle_t h) {
 template <typename T>
 __device__ __forceinline__ void sample_any(const CubeView &c, int semantics, double y, double x, double z, double &vw, double &vh) {
     if (semantics == RDR_SEM_SCIPY) {
-        sample_scipy(c, y, x, z, -1, vw, vh);
+        int iy = -1, ix = -1, iz = -1;
+        sample_scipy(c, y, x, z, iy, ix, iz, vw, vh);
         return;
     }
     // RAiDER.interpolate rules on the staged fp32 cube (values promoted to fp64)
@@ -265,7 +360,8 @@ __global__ void k_sample_grid(const CubeView c, const double *__restrict__ xpts,
     for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
         const int j = (int)(r / nx), i = (int)(r % nx);
         double vw, vh;
-        sample_scipy(c, __ldg(ypts + j), __ldg(xpts + i), ht, -1, vw, vh);
+        int iy = -1, ix = -1, iz = -1;
+        sample_scipy(c, __ldg(ypts + j), __ldg(xpts + i), ht, iy, ix, iz, vw, vh);
         out_wet[r] = vw;
         out_hydro[r] = vh;
     }
@@ -283,7 +379,7 @@ struct RayGeom {
     int nx;
 };
 
-__device__ __forceinline__ void ray_setup(const RayGeom &G, int64_t r, Vec3 &g, Vec3 &u) {
+__device__ __forceinline__ void ray_setup(const RayGeom &G, int64_t r, Vec3 &g, Vec3 &u, RayRef &R) {
     double lat, lon;
     if (G.geom_kind == RDR_GEOM_GRID) {
         lon = __ldg(G.gx + (r % G.nx));
@@ -294,6 +390,8 @@ __device__ __forceinline__ void ray_setup(const RayGeom &G, int64_t r, Vec3 &g, 
     }
     double slat, clat, slon, clon;
     g = lla2ecef(lat, lon, G.ht, slat, clat, slon, clon);
+    R.lat0_rad = lat * DEG_TO_RAD; R.lon0_rad = lon * DEG_TO_RAD;
+    R.slat = slat; R.clat = clat; R.slon = slon; R.clon = clon;
     if (G.los_kind == RDR_LOS_ARRAY) {
         u = {__ldg(G.los + 3 * r), __ldg(G.los + 3 * r + 1), __ldg(G.los + 3 * r + 2)};
     } else if (G.los_kind == RDR_LOS_ENU_CONST) {
@@ -328,30 +426,32 @@ __global__ void __launch_bounds__(BLOCK) k_ray_layers(const RayGeom G, int64_t n
     for (int64_t r = blockIdx.x * (int64_t)BLOCK + threadIdx.x; r < n_pad; r += (int64_t)gridDim.x * BLOCK) {
         const bool valid = r < n_rays;
         Vec3 g, u;
-        ray_setup(G, valid ? r : n_rays - 1, g, u);
+        RayRef R;
+        ray_setup(G, valid ? r : n_rays - 1, g, u, R);
         Vec3 lo, hi;
-        double cosf = 1.0, t;
+        double rcosf = 1.0, t;
         bool any_nan = false;
         for (int k = 0; k < K; ++k) {
             const double a = __ldg(plan + k), b = __ldg(plan + K + k);
             double len;
             if (k == 0) {
                 lo = top_of_atmosphere<10>(g, u, a, 1.0, t);
-                if (valid) t_out[r] = t;
+                if (valid) __stcs(t_out + r, t);
                 // hint for the whole-raster clamp of delay.py:306-307: height of the very first sample, evaluated on the
-                // same reconstructed point K3 will use
-                const double h0 = ecef2height(ray_point(g, u, t));
+                // same reconstructed point K3 will use (K3 re-evaluates the predicate itself and has the last word)
+                double lon0, lat0, h0;
+                ecef2lla_fast(ray_point(g, u, t), R, lon0, lat0, h0);
                 const unsigned below = __ballot_sync(0xffffffffu, valid && (h0 < zmin));
                 if (lane == 0 && below) atomicAdd(&smax[K + 1], (unsigned long long)__popc(below));
                 hi = top_of_atmosphere<10>(g, u, b, 1.0, t);
                 len = norm3(hi - lo);
-                cosf = (b - a) / len;
+                rcosf = len / (b - a);  // 1 / cos_factor of losreader.py:824-825
             } else {
                 lo = hi;
-                hi = top_of_atmosphere<3>(g, u, b, cosf, t);
+                hi = top_of_atmosphere<3>(g, u, b, rcosf, t);
                 len = norm3(hi - lo);
             }
-            if (valid) t_out[(int64_t)(k + 1) * n_rays + r] = t;
+            if (valid) __stcs(t_out + (int64_t)(k + 1) * n_rays + r, t);
             const bool isn = !(len == len);
             any_nan |= isn;
             const unsigned long long bits = (valid && !isn) ? (unsigned long long)__double_as_longlong(len) : 0ull;
@@ -384,83 +484,78 @@ __global__ void __launch_bounds__(BLOCK) k_ray_integrate(const CubeView c, const
                                                          unsigned long long *__restrict__ counters) {
     const int lane = threadIdx.x & 31;
     const int64_t n_pad = (n_rays + 31) / 32 * 32;
-    unsigned long long n_below = 0, n_above = 0, n_first_below = 0;
+    unsigned n_below = 0, n_above = 0, n_first_below = 0;
     for (int64_t r = blockIdx.x * (int64_t)BLOCK + threadIdx.x; r < n_pad; r += (int64_t)gridDim.x * BLOCK) {
         const bool valid = r < n_rays;
         const int64_t rr = valid ? r : n_rays - 1;
         Vec3 g, u;
-        ray_setup(G, rr, g, u);
+        RayRef R;
+        ray_setup(G, rr, g, u, R);
         double acc_w = 0.0, acc_h = 0.0;
-        double t_lo = __ldcs(t_in + rr);
-        Vec3 lo = ray_point(g, u, t_lo);
-        double vw_prev = 0.0, vh_prev = 0.0;
+        Vec3 lo = ray_point(g, u, __ldcs(t_in + rr));
+        Vec3 hi = ray_point(g, u, __ldcs(t_in + n_rays + rr));
+        double len = norm3(hi - lo);
+        double vw = 0.0, vh = 0.0;
+        int iy = -1, ix = -1;
         for (int k = 0; k < K; ++k) {
-            const double t_hi = __ldcs(t_in + (int64_t)(k + 1) * n_rays + rr);
-            const Vec3 hi = ray_point(g, u, t_hi);
             const Vec3 d = hi - lo;
-            const double len = norm3(d);
             const int np = __ldg(nparts + k);
-            const int cell = __ldg(layer_cell + k);
+            int iz = __ldg(layer_cell + k);
             const double step = 1.0 / (double)(np - 1);                 // np.linspace(0, 1, np): j * step, last = 1.0
             const double wt_full = (len * 1.0e-6) / ((double)np - 1.0);  // delay.py:315
             const double wt_half = 0.5 * wt_full;
+            if (k > 0) {  // first sample of this layer == last sample of the previous one (evaluated once, both end weights)
+                acc_w = __dadd_rn(acc_w, __dmul_rn(wt_half, vw));
+                acc_h = __dadd_rn(acc_h, __dmul_rn(wt_half, vh));
+            }
             for (int j = (k == 0 ? 0 : 1); j < np; ++j) {
                 const double ff = (j == np - 1) ? 1.0 : (double)j * step;
-                const Vec3 p = {lo.x + ff * d.x, lo.y + ff * d.y, lo.z + ff * d.z};  // delay.py:292
+                const Vec3 p = {fma(ff, d.x, lo.x), fma(ff, d.y, lo.y), fma(ff, d.z, lo.z)};  // delay.py:292
                 double lon, lat, h;
-                ecef2lla(p, lon, lat, h);
+                ecef2lla_fast(p, R, lon, lat, h);
                 double X = lon, Y = lat;
-                if (c.crs_kind == RDR_CRS_LCC_SPHERE) lcc_forward(c.crs, lon, lat, X, Y);
+                if (c.crs_kind == RDR_CRS_LCC_SPHERE) {
+                    const double2 xy = lcc_forward(c.lcc, lon, lat);
+                    X = xy.x;
+                    Y = xy.y;
+                }
                 if (k == 0 && j == 0) {
                     const unsigned b = __ballot_sync(0xffffffffu, valid && (h < zmin));
-                    if (lane == 0) n_first_below += __popc(b);
+                    n_first_below += __popc(b);
                     if (clamp_low_first) h = zmin;  // all pixels below min(z): delay.py:306-307
                 }
-                const unsigned bl = __ballot_sync(0xffffffffu, valid && (h < zmin)), ab = __ballot_sync(0xffffffffu, valid && (h > zmax));
-                if (lane == 0) {
-                    n_below += __popc(bl);
-                    n_above += __popc(ab);
+                if (!(h >= zmin && h <= zmax)) {  // rare: counts feed the whole-raster predicate checks on the host
+                    n_below += valid && (h < zmin);
+                    n_above += valid && (h > zmax);
                 }
-                double vw, vh;
-                sample_scipy(c, Y, X, h, cell, vw, vh);
-                if (j == 0) {  // only k == 0
-                    acc_w = __dadd_rn(acc_w, __dmul_rn(wt_half, vw));
-                    acc_h = __dadd_rn(acc_h, __dmul_rn(wt_half, vh));
-                } else {
-                    const double wt = (j == np - 1) ? wt_half : wt_full;
-                    acc_w = __dadd_rn(acc_w, __dmul_rn(wt, vw));
-                    acc_h = __dadd_rn(acc_h, __dmul_rn(wt, vh));
-                }
-                vw_prev = vw;
-                vh_prev = vh;
-            }
-            // next layer's first sample (ff = 0) is this layer's last point: reuse the value with the next end weight
-            if (k + 1 < K) {
-                const double t_nx = __ldcs(t_in + (int64_t)(k + 2) * n_rays + rr);
-                const Vec3 hi2 = ray_point(g, u, t_nx);
-                const double len2 = norm3(hi2 - hi);
-                const int np2 = __ldg(nparts + k + 1);
-                const double wt2 = 0.5 * ((len2 * 1.0e-6) / ((double)np2 - 1.0));
-                acc_w = __dadd_rn(acc_w, __dmul_rn(wt2, vw_prev));
-                acc_h = __dadd_rn(acc_h, __dmul_rn(wt2, vh_prev));
+                sample_scipy(c, Y, X, h, iy, ix, iz, vw, vh);
+                const double wt = (j == 0 || j == np - 1) ? wt_half : wt_full;
+                acc_w = __dadd_rn(acc_w, __dmul_rn(wt, vw));
+                acc_h = __dadd_rn(acc_h, __dmul_rn(wt, vh));
             }
             lo = hi;
-            t_lo = t_hi;
+            if (k + 1 < K) {
+                hi = ray_point(g, u, __ldcs(t_in + (int64_t)(k + 2) * n_rays + rr));
+                len = norm3(hi - lo);
+            }
         }
         if (valid) {
             if (accumulate) {
                 out_wet[r] = (OUT)((double)out_wet[r] + acc_w);
                 out_hydro[r] = (OUT)((double)out_hydro[r] + acc_h);
             } else {
-                out_wet[r] = (OUT)acc_w;
-                out_hydro[r] = (OUT)acc_h;
+                __stcs(out_wet + r, (OUT)acc_w);
+                __stcs(out_hydro + r, (OUT)acc_h);
             }
         }
     }
+    // per-thread OOB counters -> warp sums -> three atomics per warp at most
+    n_below = __reduce_add_sync(0xffffffffu, n_below);
+    n_above = __reduce_add_sync(0xffffffffu, n_above);
     if (lane == 0) {
-        if (n_first_below) atomicAdd(counters + 0, n_first_below);
-        if (n_below) atomicAdd(counters + 1, n_below);
-        if (n_above) atomicAdd(counters + 2, n_above);
+        if (n_first_below) atomicAdd(counters + 0, (unsigned long long)n_first_below);
+        if (n_below) atomicAdd(counters + 1, (unsigned long long)n_below);
+        if (n_above) atomicAdd(counters + 2, (unsigned long long)n_above);
     }
 }
 
@@ -474,7 +569,8 @@ __global__ void __launch_bounds__(BLOCK) k_ray_points(const CubeView c, const Ra
                                                       const int *__restrict__ nparts, int slot0, int nslots, T *__restrict__ pts) {
     for (int64_t r = blockIdx.x * (int64_t)BLOCK + threadIdx.x; r < n_rays; r += (int64_t)gridDim.x * BLOCK) {
         Vec3 g, u;
-        ray_setup(G, r, g, u);
+        RayRef R;
+        ray_setup(G, r, g, u, R);
         Vec3 lo = ray_point(g, u, __ldg(t_in + r));
         int slot = 0;
         for (int k = 0; k < K && slot < slot0 + nslots; ++k) {
@@ -487,9 +583,13 @@ __global__ void __launch_bounds__(BLOCK) k_ray_points(const CubeView c, const Ra
                 if (slot >= slot0 + nslots) break;
                 const double ff = (j == np - 1) ? 1.0 : (double)j * step;
                 double lon, lat, h;
-                ecef2lla({lo.x + ff * d.x, lo.y + ff * d.y, lo.z + ff * d.z}, lon, lat, h);
+                ecef2lla_fast({fma(ff, d.x, lo.x), fma(ff, d.y, lo.y), fma(ff, d.z, lo.z)}, R, lon, lat, h);
                 double X = lon, Y = lat;
-                if (c.crs_kind == RDR_CRS_LCC_SPHERE) lcc_forward(c.crs, lon, lat, X, Y);
+                if (c.crs_kind == RDR_CRS_LCC_SPHERE) {
+                    const double2 xy = lcc_forward(c.lcc, lon, lat);
+                    X = xy.x;
+                    Y = xy.y;
+                }
                 T *o = pts + ((int64_t)(slot - slot0) * n_rays + r) * 3;
                 o[0] = (T)Y;
                 o[1] = (T)X;
@@ -509,7 +609,7 @@ __global__ void k_top_of_atmosphere(const double *__restrict__ xyz, const double
     if (r >= n) return;
     const Vec3 g = {xyz[3 * r], xyz[3 * r + 1], xyz[3 * r + 2]}, u = {look[3 * r], look[3 * r + 1], look[3 * r + 2]};
     double t;
-    const Vec3 p = factor ? top_of_atmosphere<3>(g, u, toa, factor[r], t) : top_of_atmosphere<10>(g, u, toa, 1.0, t);
+    const Vec3 p = factor ? top_of_atmosphere<3>(g, u, toa, 1.0 / factor[r], t) : top_of_atmosphere<10>(g, u, toa, 1.0, t);
     out[3 * r] = p.x;
     out[3 * r + 1] = p.y;
     out[3 * r + 2] = p.z;
@@ -521,7 +621,7 @@ __global__ void k_build_ray(const double *__restrict__ xyz, const double *__rest
     if (r >= n) return;
     const Vec3 g = {xyz[3 * r], xyz[3 * r + 1], xyz[3 * r + 2]}, u = {look[3 * r], look[3 * r + 1], look[3 * r + 2]};
     Vec3 lo, hi;
-    double cosf = 1.0, t;
+    double rcosf = 1.0, t;
     for (int k = 0; k < K; ++k) {
         const double a = plan[k], b = plan[K + k];
         if (k == 0) {
@@ -529,10 +629,10 @@ __global__ void k_build_ray(const double *__restrict__ xyz, const double *__rest
             hi = top_of_atmosphere<10>(g, u, b, 1.0, t);
         } else {
             lo = hi;
-            hi = top_of_atmosphere<3>(g, u, b, cosf, t);
+            hi = top_of_atmosphere<3>(g, u, b, rcosf, t);
         }
         const double len = norm3(hi - lo);
-        if (k == 0) cosf = (b - a) / len;
+        if (k == 0) rcosf = len / (b - a);
         const int64_t o = (int64_t)k * n + r;
         lens[o] = len;
         lows[3 * o] = lo.x; lows[3 * o + 1] = lo.y; lows[3 * o + 2] = lo.z;
@@ -750,12 +850,10 @@ RDR_API int rdr_create(int device, rdr_handle_t *out) {
     rdr_handle_t h = new rdr_handle_s();
     h->device = device;
     ScopedDevice sd(device);
-    cudaDeviceProp prop;
-    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) {
+    if ((e = cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess) {
         delete h;
-        return fail(nullptr, RDR_ERR_CUDA, std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(e));
+        return fail(nullptr, RDR_ERR_CUDA, std::string("cudaDeviceGetAttribute: ") + cudaGetErrorString(e));
     }
-    h->sm_count = prop.multiProcessorCount;
     if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) {
         delete h;
         return fail(nullptr, RDR_ERR_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
@@ -769,7 +867,7 @@ RDR_API int rdr_destroy(rdr_handle_t h) {
     if (!h) return RDR_OK;
     ScopedDevice sd(h->device);
     cudaStreamSynchronize(h->stream);
-    for (DevBuf *b : {&h->d_axes, &h->d_cells, &h->d_stage, &h->d_fields, &h->d_gx, &h->d_gy, &h->d_los, &h->d_plan, &h->d_t, &h->d_red,
+    for (DevBuf *b : {&h->d_axes, &h->d_tabs, &h->d_cells, &h->d_stage, &h->d_fields, &h->d_gx, &h->d_gy, &h->d_los, &h->d_plan, &h->d_t, &h->d_red,
                       &h->d_nparts, &h->d_out, &h->d_in})
         b->release();
     if (h->own_stream) cudaStreamDestroy(h->stream);
@@ -853,7 +951,7 @@ RDR_API int rdr_set_cube(rdr_handle_t h, const double *ys, int64_t ny, const dou
     CHECK_ARG(h, layout == RDR_LAYOUT_ZYX || layout == RDR_LAYOUT_YXZ, "rdr_set_cube: unknown layout");
     CHECK_ARG(h, crs_kind == RDR_CRS_GEOGRAPHIC || crs_kind == RDR_CRS_LCC_SPHERE, "rdr_set_cube: unknown crs_kind");
     CHECK_ARG(h, crs_kind == RDR_CRS_GEOGRAPHIC || crs_params, "rdr_set_cube: LCC needs crs_params");
-    CHECK_ARG(h, ny < (1 << 24) && nx < (1 << 24) && nz <= MAX_LAYERS, "rdr_set_cube: cube too large");
+    CHECK_ARG(h, ny < 65536 && nx < 65536 && nz <= MAX_LAYERS, "rdr_set_cube: cube too large (axes are limited to 65535 nodes, z to 1024)");
     ScopedDevice sd(h->device);
     h->has_cube = false;
     h->has_rays = false;
@@ -870,6 +968,7 @@ RDR_API int rdr_set_cube(rdr_handle_t h, const double *ys, int64_t ny, const dou
     axes.insert(axes.end(), h->zs.begin(), h->zs.end());
     CUDA_TRY(h, h->d_axes.reserve(axes.size() * sizeof(double)));
     CUDA_TRY(h, cudaMemcpyAsync(h->d_axes.p, axes.data(), axes.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    if ((rc = build_axis_tables(h))) return rc;
     CUDA_TRY(h, h->d_fields.reserve(ny * nx * nz * sizeof(float2)));
     if ((rc = upload_fields(h, wet, hydro, layout, mem, h->d_fields.as<float2>()))) return rc;
     if ((rc = pack_cells(h))) return rc;

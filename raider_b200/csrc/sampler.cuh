@@ -2,20 +2,31 @@
 //
 // Reproduces scipy.interpolate.RegularGridInterpolator(method='linear', fill_value=nan, bounds_error=False) as the
 // reference configures it (tools/RAiDER/delayFcns.py:55-56): interval grid[i] <= x < grid[i+1] with the last node
-// inclusive, normalised distances, 8-corner sum in scipy's vertex order with separate (unfused) multiplies and adds
-// so the result is bit-identical to scipy's for identical coordinates; fp32 values promoted to fp64.
-// The RAiDER.interpolate interval rules (tools/bindings/interpolate/src/interpolate.cpp:106-135) are selectable.
+// inclusive, normalised distances t = (x - g[i]) / (g[i+1] - g[i]), 8-corner sum in scipy's vertex order with separate
+// (unfused) multiplies and adds so the result is bit-identical to scipy's for identical coordinates; fp32 values
+// promoted to fp64.  The RAiDER.interpolate interval rules (tools/bindings/interpolate/src/interpolate.cpp:106-135) are
+// selectable in the K2 entry point.
+//
+// Per-axis acceleration tables (built at rdr_set_cube):
+//   cell[i] = {g[i], g[i+1], d = fl(g[i+1] - g[i]), inv = fl(1/d)}   one 32-byte record per interval
+//   bin[b]  = interval containing the start of uniform bin b          first guess for irregular axes (model z levels)
+// The interval found from the guess is always verified against the real nodes, and the division is the two-step
+// Markstein refinement of n * inv (correctly rounded n / d), so none of this changes a single bit of the result.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "geodesy.cuh"
+
 namespace rdr {
 
 struct Axis {
-    const double *g;  // nodes (device), strictly ascending
-    int n;
-    int uniform;      // 1: i = floor((v - g0) * inv_d) is a valid first guess
-    double g0, inv_d;
+    const double *g;           // nodes (device), strictly ascending
+    const double4 *cell;       // n-1 interval records
+    const unsigned short *bin; // nbin first-guess table
+    int n, nbin;
+    double g_first, g_last;    // g[0], g[n-1]: bounds tests read these from the kernel-parameter bank
+    double inv_bw;             // nbin / (g_last - g_first)
 };
 
 struct CubeView {
@@ -23,30 +34,36 @@ struct CubeView {
     const float4 *cells;
     Axis ay, ax, az;
     int crs_kind;
-    double crs[7];
+    LccParams lcc;
 };
 
-// largest i in [0, n-2] with g[i] <= v (0 if v < g[0]): scipy find_interval_ascending with extrapolate=True
-__device__ __forceinline__ int cell_scipy(const Axis &a, double v, int guess) {
+// correctly rounded n / d given inv = RN(1/d): q0 = n*inv, two residual corrections (Markstein)
+__device__ __forceinline__ double div_exact(double n, double d, double inv) {
+    double q = n * inv;
+    double r = fma(-d, q, n);
+    q = fma(r, inv, q);
+    r = fma(-d, q, n);
+    return fma(r, inv, q);
+}
+
+__device__ __forceinline__ double4 ld_cell(const double4 *p) {
+    const double2 a = __ldg(reinterpret_cast<const double2 *>(p)), b = __ldg(reinterpret_cast<const double2 *>(p) + 1);
+    return make_double4(a.x, a.y, b.x, b.y);
+}
+
+// interval of an in-bounds coordinate v: largest i in [0, n-2] with g[i] <= v, found from `guess` (or the bin table when
+// guess < 0) and verified against the nodes; returns t = (v - g[i]) / (g[i+1] - g[i])
+__device__ __forceinline__ double locate(const Axis &a, double v, int &i) {
     const int last = a.n - 2;
-    int i;
-    if (guess >= 0) {
-        i = guess;
-    } else if (a.uniform) {
-        const double f = floor((v - a.g0) * a.inv_d);
-        i = f < 0.0 ? 0 : (f > (double)last ? last : (int)f);  // NaN -> comparisons false -> (int)NaN = 0
-    } else {
-        int lo = 0, hi = a.n - 1;  // invariant: g[lo] <= v (or lo == 0), v < g[hi] (or hi == n-1)
-        while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (v >= __ldg(a.g + mid)) lo = mid; else hi = mid;
-        }
-        return lo;
+    if (i < 0) {
+        int b = (int)((v - a.g_first) * a.inv_bw);
+        b = b < 0 ? 0 : (b >= a.nbin ? a.nbin - 1 : b);
+        i = __ldg(a.bin + b);
     }
-    i = i < 0 ? 0 : (i > last ? last : i);
-    while (i > 0 && v < __ldg(a.g + i)) --i;
-    while (i < last && v >= __ldg(a.g + i + 1)) ++i;
-    return i;
+    double4 c = ld_cell(a.cell + i);
+    while (v < c.x && i > 0) c = ld_cell(a.cell + --i);
+    while (v >= c.y && i < last) c = ld_cell(a.cell + ++i);
+    return div_exact(v - c.x, c.z, c.w);
 }
 
 // bisect_left of interpolate.h:23-38 (first i with v < g[i]); returns hi in [0, n]
@@ -77,26 +94,21 @@ __device__ __forceinline__ void trilinear_scipy(float4 c00, float4 c01, float4 c
     vh = b;
 }
 
-// One scipy-semantics sample of both fields at cube coordinates (y, x, z).  zguess >= 0: cell index hint for z.
-__device__ __forceinline__ void sample_scipy(const CubeView &c, double y, double x, double z, int zguess, double &vw, double &vh) {
-    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
-    const Axis &ay = c.ay, &ax = c.ax, &az = c.az;
+// One scipy-semantics sample of both fields at cube coordinates (y, x, z).  iy/ix/iz: interval hints in (negative = none),
+// intervals used out -- a ray marching through the cube hands each sample's cells to the next one.
+__device__ __forceinline__ void sample_scipy(const CubeView &c, double y, double x, double z, int &iy, int &ix, int &iz, double &vw,
+                                             double &vh) {
     // out of bounds (strictly outside [g0, g_last]) or NaN coordinate -> NaN  (_find_out_of_bounds + nans mask)
-    const bool inb = (y >= __ldg(ay.g)) && (y <= __ldg(ay.g + ay.n - 1)) && (x >= __ldg(ax.g)) && (x <= __ldg(ax.g + ax.n - 1)) &&
-                     (z >= __ldg(az.g)) && (z <= __ldg(az.g + az.n - 1));
+    const bool inb = (y >= c.ay.g_first) && (y <= c.ay.g_last) && (x >= c.ax.g_first) && (x <= c.ax.g_last) && (z >= c.az.g_first) &&
+                     (z <= c.az.g_last);
     if (!inb) {
-        vw = qnan;
-        vh = qnan;
+        vw = vh = __longlong_as_double(0x7ff8000000000000LL);
         return;
     }
-    const int iy = cell_scipy(ay, y, -1), ix = cell_scipy(ax, x, -1), iz = cell_scipy(az, z, zguess);
-    const double y0 = __ldg(ay.g + iy), x0 = __ldg(ax.g + ix), z0 = __ldg(az.g + iz);
-    const double ty = (y - y0) / (__ldg(ay.g + iy + 1) - y0);
-    const double tx = (x - x0) / (__ldg(ax.g + ix + 1) - x0);
-    const double tz = (z - z0) / (__ldg(az.g + iz + 1) - z0);
-    const int nzc = az.n - 1;
-    const float4 *p = c.cells + ((size_t)iy * ax.n + ix) * nzc + iz;
-    const float4 c00 = __ldg(p), c01 = __ldg(p + nzc), c10 = __ldg(p + (size_t)ax.n * nzc), c11 = __ldg(p + (size_t)ax.n * nzc + nzc);
+    const double ty = locate(c.ay, y, iy), tx = locate(c.ax, x, ix), tz = locate(c.az, z, iz);
+    const int nzc = c.az.n - 1;
+    const float4 *p = c.cells + ((size_t)iy * c.ax.n + ix) * nzc + iz;
+    const float4 c00 = __ldg(p), c01 = __ldg(p + nzc), c10 = __ldg(p + (size_t)c.ax.n * nzc), c11 = __ldg(p + (size_t)c.ax.n * nzc + nzc);
     trilinear_scipy(c00, c01, c10, c11, ty, tx, tz, vw, vh);
 }
 
