@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -177,6 +178,13 @@ int fail(rdr_handle_t h, int code, const std::string &msg) {
         if (!(cond)) return fail(h, RDR_ERR_INVALID, msg); \
     } while (0)
 
+// occupancy variant of the ray kernels: __launch_bounds__(128, minb); overridable for tuning runs
+inline int tune_minb(const char *env, int dflt) {
+    const char *v = getenv(env);
+    const int m = v ? atoi(v) : dflt;
+    return (m == 4 || m == 5 || m == 6 || m == 8) ? m : dflt;
+}
+
 inline int grid_for(int64_t n, int block, int sm_count, int per_sm) {
     int64_t need = (n + block - 1) / block;
     int64_t cap = (int64_t)sm_count * per_sm;
@@ -240,6 +248,11 @@ CubeView make_view(rdr_handle_t h) {
         a.g_first = v[d]->front();
         a.g_last = v[d]->back();
         a.inv_bw = (double)a.nbin / (a.g_last - a.g_first);
+        const double dmean = (a.g_last - a.g_first) / (double)(a.n - 1);
+        a.inv_d = 1.0 / dmean;
+        a.uniform = 1;
+        for (size_t i = 0; i < v[d]->size(); ++i)  // every node within a quarter cell of its uniform position: the guess is off by <= 1
+            if (fabs((*v[d])[i] - (a.g_first + dmean * (double)i)) > 0.25 * dmean) a.uniform = 0;
     }
     c.crs_kind = h->crs_kind;
     c.lcc = {h->crs[0], h->crs[1], h->crs[2], h->crs[3], h->crs[4], h->crs[5], h->crs[6]};
@@ -320,6 +333,99 @@ __device__ __forceinline__ void sample_any(const CubeView &c, int semantics, dou
     const float4 c00 = __ldg(p), c01 = __ldg(p + nzc), c10 = __ldg(p + (size_t)c.ax.n * nzc), c11 = __ldg(p + (size_t)c.ax.n * nzc + nzc);
     vw = trilinear_raider(c00.x, c00.z, c01.x, c01.z, c10.x, c10.z, c11.x, c11.z, lo_d[0], hi_d[0], lo_d[1], hi_d[1], lo_d[2], hi_d[2], vol);
     vh = trilinear_raider(c00.y, c00.w, c01.y, c01.w, c10.y, c10.w, c11.y, c11.w, lo_d[0], hi_d[0], lo_d[1], hi_d[1], lo_d[2], hi_d[2], vol);
+}
+
+// ---- mbarrier / TMA-bulk helpers (sm_90+ PTX; on sm_100a these become SYNCS.* and UBLKCP) -------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// 1-D bulk async copy global -> shared, completion counted in bytes on `bar` (cp.async.bulk = the TMA engine without a tensor map)
+__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)), "l"(gsrc),
+                 "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// K2, scipy semantics, streaming form: the [n][3] point stream is pulled into a 4-deep shared-memory ring by TMA bulk copies
+// (one elected thread issues, an mbarrier per stage counts the bytes), so the HBM reads of tile i+3 overlap the arithmetic of
+// tile i; each thread samples two points of a tile (two independent dependency chains), outputs are plain coalesced stores.
+constexpr int K2_THREADS = 128, K2_TILE = 256, K2_STAGES = 4;
+
+template <typename T>
+__global__ void __launch_bounds__(K2_THREADS) k_sample_stream(const CubeView c, const T *__restrict__ pts, int64_t n, T *__restrict__ out_wet,
+                                                            T *__restrict__ out_hydro) {
+    constexpr uint32_t TILE_BYTES = K2_TILE * 3 * sizeof(T);
+    extern __shared__ __align__(128) unsigned char k2_smem[];
+    uint64_t *full = reinterpret_cast<uint64_t *>(k2_smem + K2_STAGES * TILE_BYTES);
+    const int64_t ntiles = n / K2_TILE;  // full tiles go through the ring; the ragged tail is handled below with plain loads
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < K2_STAGES; ++s) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < K2_STAGES; ++s) {
+            const int64_t tile = blockIdx.x + (int64_t)s * gridDim.x;
+            if (tile < ntiles) {
+                mbar_expect_tx(&full[s], TILE_BYTES);
+                tma_load_1d(k2_smem + s * TILE_BYTES, pts + tile * K2_TILE * 3, TILE_BYTES, &full[s]);
+            }
+        }
+    }
+    int it = 0;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const int s = it % K2_STAGES;
+        mbar_wait(&full[s], (uint32_t)(it / K2_STAGES) & 1u);
+        const T *tp = reinterpret_cast<const T *>(k2_smem + s * TILE_BYTES);
+        const int p0 = threadIdx.x, p1 = threadIdx.x + K2_THREADS;
+        const double y0 = (double)tp[3 * p0], x0 = (double)tp[3 * p0 + 1], z0 = (double)tp[3 * p0 + 2];
+        const double y1 = (double)tp[3 * p1], x1 = (double)tp[3 * p1 + 1], z1 = (double)tp[3 * p1 + 2];
+        double w0, h0, w1, h1;
+        int iy = -1, ix = -1, iz = -1, jy = -1, jx = -1, jz = -1;
+        sample_scipy(c, y0, x0, z0, iy, ix, iz, w0, h0);
+        sample_scipy(c, y1, x1, z1, jy, jx, jz, w1, h1);
+        const int64_t base = tile * K2_TILE;
+        __stcs(out_wet + base + p0, (T)w0);
+        __stcs(out_hydro + base + p0, (T)h0);
+        __stcs(out_wet + base + p1, (T)w1);
+        __stcs(out_hydro + base + p1, (T)h1);
+        __syncthreads();  // every thread has read stage s: it can be refilled
+        if (threadIdx.x == 0) {
+            const int64_t next = tile + (int64_t)K2_STAGES * gridDim.x;
+            if (next < ntiles) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_expect_tx(&full[s], TILE_BYTES);
+                tma_load_1d(k2_smem + s * TILE_BYTES, pts + next * K2_TILE * 3, TILE_BYTES, &full[s]);
+            }
+        }
+    }
+    // ragged tail (< K2_TILE points): plain loads, first block only
+    if (blockIdx.x == 0) {
+        for (int64_t i = ntiles * K2_TILE + threadIdx.x; i < n; i += K2_THREADS) {
+            double w, hh;
+            int iy = -1, ix = -1, iz = -1;
+            sample_scipy(c, (double)pts[3 * i], (double)pts[3 * i + 1], (double)pts[3 * i + 2], iy, ix, iz, w, hh);
+            out_wet[i] = (T)w;
+            out_hydro[i] = (T)hh;
+        }
+    }
 }
 
 template <typename T, int BLOCK>
@@ -415,8 +521,8 @@ __device__ __forceinline__ unsigned long long warp_max_bits(unsigned long long b
 //   t_out[k+1][r] = along-ray distance of the top of contributing layer k
 //   red[k]        = bits of max_r |P_hi - P_lo| (atomicMax on the bit pattern), red[K] = #NaN rays, red[K+1] = #first sample below zmin
 // ------------------------------------------------------------------------------------------------
-template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK) k_ray_layers(const RayGeom G, int64_t n_rays, int K, const double *__restrict__ plan,
+template <int BLOCK, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB) k_ray_layers(const RayGeom G, int64_t n_rays, int K, const double *__restrict__ plan,
                                                       double *__restrict__ t_out, unsigned long long *__restrict__ red, double zmin) {
     extern __shared__ unsigned long long smax[];  // [K + 2]
     for (int i = threadIdx.x; i < K + 2; i += BLOCK) smax[i] = 0ull;
@@ -476,8 +582,8 @@ __global__ void __launch_bounds__(BLOCK) k_ray_layers(const RayGeom G, int64_t n
 // The sample at a layer interface is evaluated once and used with both layers' end weights (the reference evaluates
 // the same point twice, delay.py:290-323).
 // ------------------------------------------------------------------------------------------------
-template <typename OUT, int BLOCK>
-__global__ void __launch_bounds__(BLOCK) k_ray_integrate(const CubeView c, const RayGeom G, int64_t n_rays, int K,
+template <typename OUT, int BLOCK, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB) k_ray_integrate(const CubeView c, const RayGeom G, int64_t n_rays, int K,
                                                          const double *__restrict__ t_in, const int *__restrict__ nparts,
                                                          const int *__restrict__ layer_cell, int clamp_low_first, double zmin, double zmax,
                                                          OUT *__restrict__ out_wet, OUT *__restrict__ out_hydro, int accumulate,
@@ -1021,14 +1127,29 @@ RDR_API int rdr_sample(rdr_handle_t h, const void *pts, int64_t n, void *out_wet
         dh = static_cast<char *>(h->d_out.p) + n * es;
     }
     const CubeView c = make_view(h);
-    constexpr int BLOCK = 256;
-    const int grid = grid_for(n, BLOCK, h->sm_count, 8);
-    if (dtype == RDR_F64)
-        k_sample_points<double, BLOCK><<<grid, BLOCK, 0, h->stream>>>(c, static_cast<const double *>(dpts), n, static_cast<double *>(dw),
-                                                                      static_cast<double *>(dh), semantics);
-    else
-        k_sample_points<float, BLOCK><<<grid, BLOCK, 0, h->stream>>>(c, static_cast<const float *>(dpts), n, static_cast<float *>(dw),
-                                                                     static_cast<float *>(dh), semantics);
+    if (semantics == RDR_SEM_SCIPY && (reinterpret_cast<uintptr_t>(dpts) & 15) == 0) {
+        const size_t smem = K2_STAGES * K2_TILE * 3 * es + K2_STAGES * sizeof(uint64_t);
+        const int64_t ntiles = std::max<int64_t>(1, n / K2_TILE);
+        const int grid = (int)std::min<int64_t>(ntiles, (int64_t)h->sm_count * 8);
+        if (dtype == RDR_F64) {
+            CUDA_TRY(h, cudaFuncSetAttribute(k_sample_stream<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_sample_stream<double><<<grid, K2_THREADS, smem, h->stream>>>(c, static_cast<const double *>(dpts), n, static_cast<double *>(dw),
+                                                                           static_cast<double *>(dh));
+        } else {
+            CUDA_TRY(h, cudaFuncSetAttribute(k_sample_stream<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_sample_stream<float><<<grid, K2_THREADS, smem, h->stream>>>(c, static_cast<const float *>(dpts), n, static_cast<float *>(dw),
+                                                                          static_cast<float *>(dh));
+        }
+    } else {
+        constexpr int BLOCK = 256;
+        const int grid = grid_for(n, BLOCK, h->sm_count, 8);
+        if (dtype == RDR_F64)
+            k_sample_points<double, BLOCK><<<grid, BLOCK, 0, h->stream>>>(c, static_cast<const double *>(dpts), n, static_cast<double *>(dw),
+                                                                          static_cast<double *>(dh), semantics);
+        else
+            k_sample_points<float, BLOCK><<<grid, BLOCK, 0, h->stream>>>(c, static_cast<const float *>(dpts), n, static_cast<float *>(dw),
+                                                                         static_cast<float *>(dh), semantics);
+    }
     h->launches++;
     CUDA_TRY(h, cudaGetLastError());
     if (mem == RDR_MEM_HOST) {
@@ -1142,9 +1263,19 @@ RDR_API int rdr_ray_layers(rdr_handle_t h, int geom_kind, const double *gx, cons
     CUDA_TRY(h, h->d_red.reserve((K + 8) * sizeof(unsigned long long)));
     CUDA_TRY(h, cudaMemsetAsync(h->d_red.p, 0, (K + 8) * sizeof(unsigned long long), h->stream));
     constexpr int BLOCK = 128;
-    const int grid = grid_for(n, BLOCK, h->sm_count, 16);
-    k_ray_layers<BLOCK><<<grid, BLOCK, (K + 2) * sizeof(unsigned long long), h->stream>>>(
-        make_geom(h), n, K, h->d_plan.as<double>(), h->d_t.as<double>(), h->d_red.as<unsigned long long>(), h->zs.front());
+    const int minb = tune_minb("RDR_K0_MINB", 6);
+    const int grid = grid_for(n, BLOCK, h->sm_count, 4 * minb);
+    const size_t smem = (K + 2) * sizeof(unsigned long long);
+#define RDR_LAUNCH_K0(M)                                                                                                              \
+    k_ray_layers<BLOCK, M><<<grid, BLOCK, smem, h->stream>>>(make_geom(h), n, K, h->d_plan.as<double>(), h->d_t.as<double>(),          \
+                                                            h->d_red.as<unsigned long long>(), h->zs.front())
+    switch (minb) {
+        case 4: RDR_LAUNCH_K0(4); break;
+        case 5: RDR_LAUNCH_K0(5); break;
+        case 8: RDR_LAUNCH_K0(8); break;
+        default: RDR_LAUNCH_K0(6); break;
+    }
+#undef RDR_LAUNCH_K0
     h->launches++;
     CUDA_TRY(h, cudaGetLastError());
     std::vector<unsigned long long> red(K + 2);
@@ -1198,18 +1329,26 @@ RDR_API int rdr_ray_integrate(rdr_handle_t h, const double *maxlen, double max_s
         }
     }
     constexpr int BLOCK = 128;
-    const int grid = grid_for(n, BLOCK, h->sm_count, 16);
+    const int minb = tune_minb("RDR_K3_MINB", 6);
+    const int grid = grid_for(n, BLOCK, h->sm_count, 4 * minb);
     const CubeView c = make_view(h);
     const RayGeom G = make_geom(h);
     const int *d_np = h->d_nparts.as<int>();
-    if (out_dtype == RDR_F64)
-        k_ray_integrate<double, BLOCK><<<grid, BLOCK, 0, h->stream>>>(c, G, n, K, h->d_t.as<double>(), d_np, d_np + K, clamp_low_first,
-                                                                      h->zs.front(), h->zs.back(), static_cast<double *>(dw),
-                                                                      static_cast<double *>(dh), accumulate, counters);
-    else
-        k_ray_integrate<float, BLOCK><<<grid, BLOCK, 0, h->stream>>>(c, G, n, K, h->d_t.as<double>(), d_np, d_np + K, clamp_low_first,
-                                                                     h->zs.front(), h->zs.back(), static_cast<float *>(dw),
-                                                                     static_cast<float *>(dh), accumulate, counters);
+#define RDR_LAUNCH_K3(T, M)                                                                                                             \
+    k_ray_integrate<T, BLOCK, M><<<grid, BLOCK, 0, h->stream>>>(c, G, n, K, h->d_t.as<double>(), d_np, d_np + K, clamp_low_first,       \
+                                                                h->zs.front(), h->zs.back(), static_cast<T *>(dw), static_cast<T *>(dh), \
+                                                                accumulate, counters)
+    if (out_dtype == RDR_F64) {
+        switch (minb) {
+            case 4: RDR_LAUNCH_K3(double, 4); break;
+            case 5: RDR_LAUNCH_K3(double, 5); break;
+            case 8: RDR_LAUNCH_K3(double, 8); break;
+            default: RDR_LAUNCH_K3(double, 6); break;
+        }
+    } else {
+        RDR_LAUNCH_K3(float, 6);
+    }
+#undef RDR_LAUNCH_K3
     h->launches++;
     CUDA_TRY(h, cudaGetLastError());
     unsigned long long cnt[4] = {0, 0, 0, 0};

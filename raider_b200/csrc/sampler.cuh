@@ -25,6 +25,8 @@ struct Axis {
     const double4 *cell;       // n-1 interval records
     const unsigned short *bin; // nbin first-guess table
     int n, nbin;
+    int uniform;               // nodes are (numerically) equally spaced: first guess = (v - g_first) * inv_d, no bin lookup
+    double inv_d;              // (n - 1) / (g_last - g_first)
     double g_first, g_last;    // g[0], g[n-1]: bounds tests read these from the kernel-parameter bank
     double inv_bw;             // nbin / (g_last - g_first)
 };
@@ -56,9 +58,14 @@ __device__ __forceinline__ double4 ld_cell(const double4 *p) {
 __device__ __forceinline__ double locate(const Axis &a, double v, int &i) {
     const int last = a.n - 2;
     if (i < 0) {
-        int b = (int)((v - a.g_first) * a.inv_bw);
-        b = b < 0 ? 0 : (b >= a.nbin ? a.nbin - 1 : b);
-        i = __ldg(a.bin + b);
+        if (a.uniform) {
+            i = (int)((v - a.g_first) * a.inv_d);
+            i = i < 0 ? 0 : (i > last ? last : i);
+        } else {
+            int b = (int)((v - a.g_first) * a.inv_bw);
+            b = b < 0 ? 0 : (b >= a.nbin ? a.nbin - 1 : b);
+            i = __ldg(a.bin + b);
+        }
     }
     double4 c = ld_cell(a.cell + i);
     while (v < c.x && i > 0) c = ld_cell(a.cell + --i);
