@@ -134,7 +134,7 @@ struct rdr_handle_s {
     DevBuf d_tabs;   // per axis: interval records (double4) then first-guess bins (uint16)
     size_t tab_cell_off[3] = {0, 0, 0}, tab_bin_off[3] = {0, 0, 0};
     int tab_nbin[3] = {0, 0, 0};
-    DevBuf d_cells;  // float4 [ny][nx][nz-1]
+    DevBuf d_cells;  // double4 [ny][nx][nz-1]
     DevBuf d_stage;  // staging for field uploads (and packed fp32 pairs for blending)
     DevBuf d_fields; // float2 [ny][nx][nz] (wet, hydro) kept for blending
 
@@ -218,20 +218,20 @@ __global__ void k_blend_fields(float2 *__restrict__ a, const float2 *__restrict_
     }
 }
 
-// float2 [ny][nx][nz] -> float4 cells [ny][nx][nz-1] = {f[z], f[z+1]}
-__global__ void k_pack_cells(const float2 *__restrict__ f, float4 *__restrict__ cells, int64_t ncol, int nz) {
+// float2 [ny][nx][nz] -> double4 cells [ny][nx][nz-1] = {f[z], f[z+1]} (exact promotion)
+__global__ void k_pack_cells(const float2 *__restrict__ f, double4 *__restrict__ cells, int64_t ncol, int nz) {
     const int64_t total = ncol * (nz - 1);
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t col = i / (nz - 1);
         const int iz = (int)(i % (nz - 1));
         const float2 a = f[col * nz + iz], b = f[col * nz + iz + 1];
-        cells[i] = make_float4(a.x, a.y, b.x, b.y);
+        cells[i] = make_double4((double)a.x, (double)a.y, (double)b.x, (double)b.y);
     }
 }
 
 CubeView make_view(rdr_handle_t h) {
     CubeView c;
-    c.cells = h->d_cells.as<float4>();
+    c.cells = h->d_cells.as<double4>();
     const double *nodes = h->d_axes.as<double>();
     const char *tabs = h->d_tabs.as<char>();
     const std::vector<double> *v[3] = {&h->ys, &h->xs, &h->zs};
@@ -273,7 +273,10 @@ int build_axis_tables(rdr_handle_t h) {
             rec[4 * i] = g[i]; rec[4 * i + 1] = g[i + 1]; rec[4 * i + 2] = dd; rec[4 * i + 3] = 1.0 / dd;
         }
         blob.insert(blob.end(), reinterpret_cast<char *>(rec.data()), reinterpret_cast<char *>(rec.data() + rec.size()));
-        const int nbin = std::min(8192, std::max(64, 8 * n));
+        double dmin = g[1] - g[0];
+        for (int i = 1; i + 1 < n; ++i) dmin = std::min(dmin, g[i + 1] - g[i]);
+        // bin width <= the narrowest interval: a bin contains at most one node, so the guess is at most one step short
+        const int nbin = (int)std::min(65536.0, std::max(64.0, ceil((g.back() - g.front()) / dmin) + 1.0));
         h->tab_nbin[d] = nbin;
         h->tab_bin_off[d] = blob.size();
         std::vector<unsigned short> bins(nbin);
@@ -282,7 +285,7 @@ int build_axis_tables(rdr_handle_t h) {
         for (int b = 0; b < nbin; ++b) {
             const double start = g.front() + b * bw;
             while (i < n - 2 && g[i + 1] <= start) ++i;
-            bins[b] = (unsigned short)(i > 0 ? i - 1 : 0);  // one interval of slack: the device rounds (v - g0) * inv_bw its own way
+            bins[b] = (unsigned short)i;  // interval holding the start of bin b; the device verifies against the nodes either way
         }
         blob.insert(blob.end(), reinterpret_cast<char *>(bins.data()), reinterpret_cast<char *>(bins.data() + bins.size()));
         while (blob.size() % 32) blob.push_back(0);
@@ -329,8 +332,8 @@ __device__ __forceinline__ void sample_any(const CubeView &c, int semantics, dou
         vol = d == 0 ? (g1 - g0) : __dmul_rn(vol, g1 - g0);
     }
     const int nzc = c.az.n - 1;
-    const float4 *p = c.cells + ((size_t)(hi[0] - 1) * c.ax.n + (hi[1] - 1)) * nzc + (hi[2] - 1);
-    const float4 c00 = __ldg(p), c01 = __ldg(p + nzc), c10 = __ldg(p + (size_t)c.ax.n * nzc), c11 = __ldg(p + (size_t)c.ax.n * nzc + nzc);
+    const double4 *p = c.cells + ((size_t)(hi[0] - 1) * c.ax.n + (hi[1] - 1)) * nzc + (hi[2] - 1);
+    const double4 c00 = ld_cell(p), c01 = ld_cell(p + nzc), c10 = ld_cell(p + (size_t)c.ax.n * nzc), c11 = ld_cell(p + (size_t)c.ax.n * nzc + nzc);
     vw = trilinear_raider(c00.x, c00.z, c01.x, c01.z, c10.x, c10.z, c11.x, c11.z, lo_d[0], hi_d[0], lo_d[1], hi_d[1], lo_d[2], hi_d[2], vol);
     vh = trilinear_raider(c00.y, c00.w, c01.y, c01.w, c10.y, c10.w, c11.y, c11.w, lo_d[0], hi_d[0], lo_d[1], hi_d[1], lo_d[2], hi_d[2], vol);
 }
@@ -363,10 +366,10 @@ __device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gsrc, ui
                  : "memory");
 }
 
-// K2, scipy semantics, streaming form: the [n][3] point stream is pulled into a 4-deep shared-memory ring by TMA bulk copies
-// (one elected thread issues, an mbarrier per stage counts the bytes), so the HBM reads of tile i+3 overlap the arithmetic of
+// K2, scipy semantics, streaming form: the [n][3] point stream is pulled into a 3-deep shared-memory ring by TMA bulk copies
+// (one elected thread issues, an mbarrier per stage counts the bytes), so the HBM reads of tile i+2 overlap the arithmetic of
 // tile i; each thread samples two points of a tile (two independent dependency chains), outputs are plain coalesced stores.
-constexpr int K2_THREADS = 128, K2_TILE = 256, K2_STAGES = 4;
+constexpr int K2_THREADS = 128, K2_TILE = 256, K2_STAGES = 3;
 
 template <typename T>
 __global__ void __launch_bounds__(K2_THREADS) k_sample_stream(const CubeView c, const T *__restrict__ pts, int64_t n, T *__restrict__ out_wet,
@@ -1042,8 +1045,8 @@ static int upload_fields(rdr_handle_t h, const float *wet, const float *hydro, i
 
 static int pack_cells(rdr_handle_t h) {
     const int64_t ncol = h->ny * h->nx;
-    CUDA_TRY(h, h->d_cells.reserve(ncol * (h->nz - 1) * sizeof(float4)));
-    k_pack_cells<<<grid_for(ncol * (h->nz - 1), 256, h->sm_count, 16), 256, 0, h->stream>>>(h->d_fields.as<float2>(), h->d_cells.as<float4>(),
+    CUDA_TRY(h, h->d_cells.reserve(ncol * (h->nz - 1) * sizeof(double4)));
+    k_pack_cells<<<grid_for(ncol * (h->nz - 1), 256, h->sm_count, 16), 256, 0, h->stream>>>(h->d_fields.as<float2>(), h->d_cells.as<double4>(),
                                                                                             ncol, (int)h->nz);
     h->launches++;
     CUDA_TRY(h, cudaGetLastError());
@@ -1057,7 +1060,8 @@ RDR_API int rdr_set_cube(rdr_handle_t h, const double *ys, int64_t ny, const dou
     CHECK_ARG(h, layout == RDR_LAYOUT_ZYX || layout == RDR_LAYOUT_YXZ, "rdr_set_cube: unknown layout");
     CHECK_ARG(h, crs_kind == RDR_CRS_GEOGRAPHIC || crs_kind == RDR_CRS_LCC_SPHERE, "rdr_set_cube: unknown crs_kind");
     CHECK_ARG(h, crs_kind == RDR_CRS_GEOGRAPHIC || crs_params, "rdr_set_cube: LCC needs crs_params");
-    CHECK_ARG(h, ny < 65536 && nx < 65536 && nz <= MAX_LAYERS, "rdr_set_cube: cube too large (axes are limited to 65535 nodes, z to 1024)");
+    CHECK_ARG(h, ny < 65536 && nx < 65536 && nz <= MAX_LAYERS && ny * nx * nz < (1ll << 31),
+              "rdr_set_cube: cube too large (axes are limited to 65535 nodes, z to 1024, 2^31 cells in total)");
     ScopedDevice sd(h->device);
     h->has_cube = false;
     h->has_rays = false;
@@ -1130,7 +1134,7 @@ RDR_API int rdr_sample(rdr_handle_t h, const void *pts, int64_t n, void *out_wet
     if (semantics == RDR_SEM_SCIPY && (reinterpret_cast<uintptr_t>(dpts) & 15) == 0) {
         const size_t smem = K2_STAGES * K2_TILE * 3 * es + K2_STAGES * sizeof(uint64_t);
         const int64_t ntiles = std::max<int64_t>(1, n / K2_TILE);
-        const int grid = (int)std::min<int64_t>(ntiles, (int64_t)h->sm_count * 8);
+        const int grid = (int)std::min<int64_t>(ntiles, (int64_t)h->sm_count * (dtype == RDR_F64 ? 12 : 16));
         if (dtype == RDR_F64) {
             CUDA_TRY(h, cudaFuncSetAttribute(k_sample_stream<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             k_sample_stream<double><<<grid, K2_THREADS, smem, h->stream>>>(c, static_cast<const double *>(dpts), n, static_cast<double *>(dw),

@@ -32,8 +32,10 @@ struct Axis {
 };
 
 struct CubeView {
-    // cells[(iy*nx + ix)*(nz-1) + iz] = {wet[iz], hydro[iz], wet[iz+1], hydro[iz+1]} of column (iy, ix): 16-byte aligned pair
-    const float4 *cells;
+    // cells[(iy*nx + ix)*(nz-1) + iz] = {wet[iz], hydro[iz], wet[iz+1], hydro[iz+1]} of column (iy, ix), promoted to fp64 once
+    // at staging (the promotion float -> double is exact, and it keeps 8 F2F conversions per sample off the quarter-rate XU
+    // pipe): one 32-byte record feeds the z-pair of both fields
+    const double4 *cells;
     Axis ay, ax, az;
     int crs_kind;
     LccParams lcc;
@@ -68,8 +70,10 @@ __device__ __forceinline__ double locate(const Axis &a, double v, int &i) {
         }
     }
     double4 c = ld_cell(a.cell + i);
-    while (v < c.x && i > 0) c = ld_cell(a.cell + --i);
-    while (v >= c.y && i < last) c = ld_cell(a.cell + ++i);
+    if (v < c.x || v >= c.y) {  // first guess off (node hit, rounding of the guess, or the inclusive last node): walk to the interval
+        while (v < c.x && i > 0) c = ld_cell(a.cell + --i);
+        while (v >= c.y && i < last) c = ld_cell(a.cell + ++i);
+    }
     return div_exact(v - c.x, c.z, c.w);
 }
 
@@ -84,19 +88,19 @@ __device__ __forceinline__ int bisect_left(const double *g, int n, double v) {
 }
 
 // scipy's _evaluate_linear for ndim = 3 and two fields; vertex order (y,x,z) = 000,001,010,011,100,101,110,111
-__device__ __forceinline__ void trilinear_scipy(float4 c00, float4 c01, float4 c10, float4 c11, double ty, double tx, double tz,
+__device__ __forceinline__ void trilinear_scipy(double4 c00, double4 c01, double4 c10, double4 c11, double ty, double tx, double tz,
                                                 double &vw, double &vh) {
     const double uy = 1.0 - ty, ux = 1.0 - tx, uz = 1.0 - tz;
     const double w00 = __dmul_rn(uy, ux), w01 = __dmul_rn(uy, tx), w10 = __dmul_rn(ty, ux), w11 = __dmul_rn(ty, tx);
     double w, a, b;
-    w = __dmul_rn(w00, uz); a = __dmul_rn((double)c00.x, w);                 b = __dmul_rn((double)c00.y, w);
-    w = __dmul_rn(w00, tz); a = __dadd_rn(a, __dmul_rn((double)c00.z, w));   b = __dadd_rn(b, __dmul_rn((double)c00.w, w));
-    w = __dmul_rn(w01, uz); a = __dadd_rn(a, __dmul_rn((double)c01.x, w));   b = __dadd_rn(b, __dmul_rn((double)c01.y, w));
-    w = __dmul_rn(w01, tz); a = __dadd_rn(a, __dmul_rn((double)c01.z, w));   b = __dadd_rn(b, __dmul_rn((double)c01.w, w));
-    w = __dmul_rn(w10, uz); a = __dadd_rn(a, __dmul_rn((double)c10.x, w));   b = __dadd_rn(b, __dmul_rn((double)c10.y, w));
-    w = __dmul_rn(w10, tz); a = __dadd_rn(a, __dmul_rn((double)c10.z, w));   b = __dadd_rn(b, __dmul_rn((double)c10.w, w));
-    w = __dmul_rn(w11, uz); a = __dadd_rn(a, __dmul_rn((double)c11.x, w));   b = __dadd_rn(b, __dmul_rn((double)c11.y, w));
-    w = __dmul_rn(w11, tz); a = __dadd_rn(a, __dmul_rn((double)c11.z, w));   b = __dadd_rn(b, __dmul_rn((double)c11.w, w));
+    w = __dmul_rn(w00, uz); a = __dmul_rn(c00.x, w);                 b = __dmul_rn(c00.y, w);
+    w = __dmul_rn(w00, tz); a = __dadd_rn(a, __dmul_rn(c00.z, w));   b = __dadd_rn(b, __dmul_rn(c00.w, w));
+    w = __dmul_rn(w01, uz); a = __dadd_rn(a, __dmul_rn(c01.x, w));   b = __dadd_rn(b, __dmul_rn(c01.y, w));
+    w = __dmul_rn(w01, tz); a = __dadd_rn(a, __dmul_rn(c01.z, w));   b = __dadd_rn(b, __dmul_rn(c01.w, w));
+    w = __dmul_rn(w10, uz); a = __dadd_rn(a, __dmul_rn(c10.x, w));   b = __dadd_rn(b, __dmul_rn(c10.y, w));
+    w = __dmul_rn(w10, tz); a = __dadd_rn(a, __dmul_rn(c10.z, w));   b = __dadd_rn(b, __dmul_rn(c10.w, w));
+    w = __dmul_rn(w11, uz); a = __dadd_rn(a, __dmul_rn(c11.x, w));   b = __dadd_rn(b, __dmul_rn(c11.y, w));
+    w = __dmul_rn(w11, tz); a = __dadd_rn(a, __dmul_rn(c11.z, w));   b = __dadd_rn(b, __dmul_rn(c11.w, w));
     vw = a;
     vh = b;
 }
@@ -114,8 +118,9 @@ __device__ __forceinline__ void sample_scipy(const CubeView &c, double y, double
     }
     const double ty = locate(c.ay, y, iy), tx = locate(c.ax, x, ix), tz = locate(c.az, z, iz);
     const int nzc = c.az.n - 1;
-    const float4 *p = c.cells + ((size_t)iy * c.ax.n + ix) * nzc + iz;
-    const float4 c00 = __ldg(p), c01 = __ldg(p + nzc), c10 = __ldg(p + (size_t)c.ax.n * nzc), c11 = __ldg(p + (size_t)c.ax.n * nzc + nzc);
+    const unsigned row = (unsigned)c.ax.n * (unsigned)nzc;  // cells per y-row; the whole cube has < 2^31 cells (checked at staging)
+    const double4 *p = c.cells + ((unsigned)iy * row + (unsigned)ix * (unsigned)nzc + (unsigned)iz);
+    const double4 c00 = ld_cell(p), c01 = ld_cell(p + nzc), c10 = ld_cell(p + row), c11 = ld_cell(p + row + nzc);
     trilinear_scipy(c00, c01, c10, c11, ty, tx, tz, vw, vh);
 }
 
