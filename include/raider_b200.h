@@ -174,6 +174,11 @@ int rdr_interpolate(int ndim, const double *const *grids, const int64_t *sizes, 
 int rdr_interp_along_axis(const double *x, const double *y, const double *xnew, int64_t ncol, int64_t nin, int64_t nout,
                           int has_fill, double fill_value, double *out, int device, int mem);
 
+/* ---------------------------------------------------------------- test hook ----------------------------- */
+/* Counts, over n pseudo-random (numerator, cell width) pairs, how often the sampler's table-driven division (n * RN(1/d) with
+ * one / two Markstein corrections) differs from IEEE n / d on the device.  The sampler uses the one-step form (0 mismatches in 2e8 trials; two-step kept for reference). */
+int rdr_selftest_div(int64_t n, uint64_t seed, int64_t *mismatch_1step, int64_t *mismatch_2step, int device);
+
 #ifdef __cplusplus
 }
 #endif

@@ -42,7 +42,7 @@ def timed(fn, reps=5):
 
 
 ref = None
-for m in (4, 5, 6, 8):
+for m in (2, 3, 4, 5, 6, 8):
     os.environ['RDR_K0_MINB'] = str(m)
     os.environ['RDR_K3_MINB'] = str(m)
     layers = lambda: cube.ray_layers(_lib.GEOM_GRID, cfg['xpts'], cfg['ypts'], n, n, _lib.LOS_ENU_CONST, enu, 0.0, cfg['zref'])

@@ -205,6 +205,29 @@ __device__ __forceinline__ void ecef2lla_fast(Vec3 c, const RayRef &R, double &l
     lon_deg = (R.lon0_rad + atan_small(nlam * fast_rcp(dlam))) * RAD_TO_DEG;
 }
 
+// two samples at once (independent dependency chains for the FP64 pipe); one shared, rarely taken fallback branch
+__device__ __forceinline__ void ecef2lla_fast2(Vec3 ca, Vec3 cb, const RayRef &R, double &lona, double &lata, double &ha, double &lonb,
+                                               double &latb, double &hb) {
+    const BowringFast oa = bowring_fast(ca), ob = bowring_fast(cb);
+    const double npa = fma(oa.y_phi, R.clat, -oa.x_phi * R.slat), dpa = fma(oa.x_phi, R.clat, oa.y_phi * R.slat);
+    const double npb = fma(ob.y_phi, R.clat, -ob.x_phi * R.slat), dpb = fma(ob.x_phi, R.clat, ob.y_phi * R.slat);
+    const double nla = fma(ca.y, R.clon, -ca.x * R.slon), dla = fma(ca.x, R.clon, ca.y * R.slon);
+    const double nlb = fma(cb.y, R.clon, -cb.x * R.slon), dlb = fma(cb.x, R.clon, cb.y * R.slon);
+    const bool ok = regular(oa) && regular(ob) && fabs(npa) <= ATAN_SMALL * dpa && fabs(nla) <= ATAN_SMALL * dla &&
+                    fabs(npb) <= ATAN_SMALL * dpb && fabs(nlb) <= ATAN_SMALL * dlb;
+    if (!ok) {
+        ecef2lla_fast(ca, R, lona, lata, ha);
+        ecef2lla_fast(cb, R, lonb, latb, hb);
+        return;
+    }
+    ha = height_fast(oa, fast_rcp(oa.x_phi));
+    hb = height_fast(ob, fast_rcp(ob.x_phi));
+    lata = (R.lat0_rad + atan_small(npa * fast_rcp(dpa))) * RAD_TO_DEG;
+    latb = (R.lat0_rad + atan_small(npb * fast_rcp(dpb))) * RAD_TO_DEG;
+    lona = (R.lon0_rad + atan_small(nla * fast_rcp(dla))) * RAD_TO_DEG;
+    lonb = (R.lon0_rad + atan_small(nlb * fast_rcp(dlb))) * RAD_TO_DEG;
+}
+
 // getTopOfAtmosphere (losreader.py:706-733): Newton-Raphson along the ray to geodetic height `toa`.
 // Returns the position accumulated exactly like the reference (pos += look * delta) and the along-ray distance.
 template <int ITERS>

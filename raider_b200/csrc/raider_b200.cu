@@ -182,7 +182,7 @@ int fail(rdr_handle_t h, int code, const std::string &msg) {
 inline int tune_minb(const char *env, int dflt) {
     const char *v = getenv(env);
     const int m = v ? atoi(v) : dflt;
-    return (m == 4 || m == 5 || m == 6 || m == 8) ? m : dflt;
+    return (m == 2 || m == 3 || m == 4 || m == 5 || m == 6 || m == 8) ? m : dflt;
 }
 
 inline int grid_for(int64_t n, int block, int sm_count, int per_sm) {
@@ -305,7 +305,7 @@ template <typename T>
 __device__ __forceinline__ void sample_any(const CubeView &c, int semantics, double y, double x, double z, double &vw, double &vh) {
     if (semantics == RDR_SEM_SCIPY) {
         int iy = -1, ix = -1, iz = -1;
-        sample_scipy(c, y, x, z, iy, ix, iz, vw, vh);
+        sample_scipy<GUESS_BINS, GUESS_BINS>(c, y, x, z, iy, ix, iz, vw, vh);
         return;
     }
     // RAiDER.interpolate rules on the staged fp32 cube (values promoted to fp64)
@@ -369,11 +369,12 @@ __device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gsrc, ui
 // K2, scipy semantics, streaming form: the [n][3] point stream is pulled into a 3-deep shared-memory ring by TMA bulk copies
 // (one elected thread issues, an mbarrier per stage counts the bytes), so the HBM reads of tile i+2 overlap the arithmetic of
 // tile i; each thread samples two points of a tile (two independent dependency chains), outputs are plain coalesced stores.
-constexpr int K2_THREADS = 128, K2_TILE = 256, K2_STAGES = 3;
+constexpr int K2_THREADS = 128, K2_STAGES = 3;
 
-template <typename T>
+template <typename T, int MXY, int K2_PPT>
 __global__ void __launch_bounds__(K2_THREADS) k_sample_stream(const CubeView c, const T *__restrict__ pts, int64_t n, T *__restrict__ out_wet,
                                                             T *__restrict__ out_hydro) {
+    constexpr int K2_TILE = K2_THREADS * K2_PPT;
     constexpr uint32_t TILE_BYTES = K2_TILE * 3 * sizeof(T);
     extern __shared__ __align__(128) unsigned char k2_smem[];
     uint64_t *full = reinterpret_cast<uint64_t *>(k2_smem + K2_STAGES * TILE_BYTES);
@@ -397,18 +398,21 @@ __global__ void __launch_bounds__(K2_THREADS) k_sample_stream(const CubeView c, 
         const int s = it % K2_STAGES;
         mbar_wait(&full[s], (uint32_t)(it / K2_STAGES) & 1u);
         const T *tp = reinterpret_cast<const T *>(k2_smem + s * TILE_BYTES);
-        const int p0 = threadIdx.x, p1 = threadIdx.x + K2_THREADS;
-        const double y0 = (double)tp[3 * p0], x0 = (double)tp[3 * p0 + 1], z0 = (double)tp[3 * p0 + 2];
-        const double y1 = (double)tp[3 * p1], x1 = (double)tp[3 * p1 + 1], z1 = (double)tp[3 * p1 + 2];
-        double w0, h0, w1, h1;
-        int iy = -1, ix = -1, iz = -1, jy = -1, jx = -1, jz = -1;
-        sample_scipy(c, y0, x0, z0, iy, ix, iz, w0, h0);
-        sample_scipy(c, y1, x1, z1, jy, jx, jz, w1, h1);
+        double y[K2_PPT], x[K2_PPT], z[K2_PPT], w[K2_PPT], hh[K2_PPT];
+#pragma unroll
+        for (int p = 0; p < K2_PPT; ++p) {
+            const int q = threadIdx.x + p * K2_THREADS;
+            y[p] = (double)tp[3 * q];
+            x[p] = (double)tp[3 * q + 1];
+            z[p] = (double)tp[3 * q + 2];
+        }
+        sample_scipy_batch<K2_PPT, MXY, GUESS_BINS>(c, y, x, z, w, hh);
         const int64_t base = tile * K2_TILE;
-        __stcs(out_wet + base + p0, (T)w0);
-        __stcs(out_hydro + base + p0, (T)h0);
-        __stcs(out_wet + base + p1, (T)w1);
-        __stcs(out_hydro + base + p1, (T)h1);
+#pragma unroll
+        for (int p = 0; p < K2_PPT; ++p) {
+            __stcs(out_wet + base + threadIdx.x + p * K2_THREADS, (T)w[p]);
+            __stcs(out_hydro + base + threadIdx.x + p * K2_THREADS, (T)hh[p]);
+        }
         __syncthreads();  // every thread has read stage s: it can be refilled
         if (threadIdx.x == 0) {
             const int64_t next = tile + (int64_t)K2_STAGES * gridDim.x;
@@ -424,7 +428,7 @@ __global__ void __launch_bounds__(K2_THREADS) k_sample_stream(const CubeView c, 
         for (int64_t i = ntiles * K2_TILE + threadIdx.x; i < n; i += K2_THREADS) {
             double w, hh;
             int iy = -1, ix = -1, iz = -1;
-            sample_scipy(c, (double)pts[3 * i], (double)pts[3 * i + 1], (double)pts[3 * i + 2], iy, ix, iz, w, hh);
+            sample_scipy<MXY, GUESS_BINS>(c, (double)pts[3 * i], (double)pts[3 * i + 1], (double)pts[3 * i + 2], iy, ix, iz, w, hh);
             out_wet[i] = (T)w;
             out_hydro[i] = (T)hh;
         }
@@ -470,7 +474,7 @@ __global__ void k_sample_grid(const CubeView c, const double *__restrict__ xpts,
         const int j = (int)(r / nx), i = (int)(r % nx);
         double vw, vh;
         int iy = -1, ix = -1, iz = -1;
-        sample_scipy(c, __ldg(ypts + j), __ldg(xpts + i), ht, iy, ix, iz, vw, vh);
+        sample_scipy<GUESS_BINS, GUESS_BINS>(c, __ldg(ypts + j), __ldg(xpts + i), ht, iy, ix, iz, vw, vh);
         out_wet[r] = vw;
         out_hydro[r] = vh;
     }
@@ -605,7 +609,31 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_ray_integrate(const CubeView c,
         Vec3 hi = ray_point(g, u, __ldcs(t_in + n_rays + rr));
         double len = norm3(hi - lo);
         double vw = 0.0, vh = 0.0;
-        int iy = -1, ix = -1;
+        double gx0 = R.lon0_rad * RAD_TO_DEG, gy0 = R.lat0_rad * RAD_TO_DEG;
+        if (c.crs_kind == RDR_CRS_LCC_SPHERE) {
+            const double2 xy = lcc_forward(c.lcc, gx0, gy0);
+            gx0 = xy.x;
+            gy0 = xy.y;
+        }
+        // interval hints for the march: the ground point's own cell (clamped into the grid when the pixel hangs outside)
+        int iy = guess_interval<GUESS_BINS>(c.ay, fmin(fmax(gy0, c.ay.g_first), c.ay.g_last), 0);
+        int ix = guess_interval<GUESS_BINS>(c.ax, fmin(fmax(gx0, c.ax.g_first), c.ax.g_last), 0);
+        // model-CRS coordinates + height of a sample, with the whole-raster bookkeeping of delay.py:306-311
+        auto to_model = [&](double lon, double lat, double &X, double &Y) {
+            X = lon;
+            Y = lat;
+            if (c.crs_kind == RDR_CRS_LCC_SPHERE) {
+                const double2 xy = lcc_forward(c.lcc, lon, lat);
+                X = xy.x;
+                Y = xy.y;
+            }
+        };
+        auto count_oob = [&](double h) {
+            if (!(h >= zmin && h <= zmax)) {  // rare: counts feed the whole-raster predicate checks on the host
+                n_below += valid && (h < zmin);
+                n_above += valid && (h > zmax);
+            }
+        };
         for (int k = 0; k < K; ++k) {
             const Vec3 d = hi - lo;
             const int np = __ldg(nparts + k);
@@ -613,34 +641,48 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_ray_integrate(const CubeView c,
             const double step = 1.0 / (double)(np - 1);                 // np.linspace(0, 1, np): j * step, last = 1.0
             const double wt_full = (len * 1.0e-6) / ((double)np - 1.0);  // delay.py:315
             const double wt_half = 0.5 * wt_full;
-            if (k > 0) {  // first sample of this layer == last sample of the previous one (evaluated once, both end weights)
+            int j = 1;
+            if (k == 0) {  // very first sample of the ray (ff = 0)
+                double lon, lat, h, X, Y;
+                ecef2lla_fast(lo, R, lon, lat, h);
+                to_model(lon, lat, X, Y);
+                const unsigned b = __ballot_sync(0xffffffffu, valid && (h < zmin));
+                n_first_below += __popc(b);
+                if (clamp_low_first) h = zmin;  // all pixels below min(z): delay.py:306-307
+                count_oob(h);
+                sample_scipy<GUESS_HINT, GUESS_HINT>(c, Y, X, h, iy, ix, iz, vw, vh);
+            }
+            // first sample of this layer == last sample of the previous one (evaluated once, used with both end weights)
+            acc_w = __dadd_rn(acc_w, __dmul_rn(wt_half, vw));
+            acc_h = __dadd_rn(acc_h, __dmul_rn(wt_half, vh));
+            for (; j + 1 < np; j += 2) {  // two interior / end samples per trip: independent chains keep the FP64 pipe busy
+                const double fa = (double)j * step, fb = (j + 1 == np - 1) ? 1.0 : (double)(j + 1) * step;
+                const Vec3 pa = {fma(fa, d.x, lo.x), fma(fa, d.y, lo.y), fma(fa, d.z, lo.z)};  // delay.py:292
+                const Vec3 pb = {fma(fb, d.x, lo.x), fma(fb, d.y, lo.y), fma(fb, d.z, lo.z)};
+                double lon[2], lat[2], hh[2], X[2], Y[2], sw[2], sh[2];
+                ecef2lla_fast2(pa, pb, R, lon[0], lat[0], hh[0], lon[1], lat[1], hh[1]);
+                to_model(lon[0], lat[0], X[0], Y[0]);
+                to_model(lon[1], lat[1], X[1], Y[1]);
+                count_oob(hh[0]);
+                count_oob(hh[1]);
+                sample_scipy_pair_hinted(c, Y, X, hh, iy, ix, iz, sw, sh);
+                const double wb = (j + 1 == np - 1) ? wt_half : wt_full;
+                acc_w = __dadd_rn(acc_w, __dmul_rn(wt_full, sw[0]));
+                acc_h = __dadd_rn(acc_h, __dmul_rn(wt_full, sh[0]));
+                acc_w = __dadd_rn(acc_w, __dmul_rn(wb, sw[1]));
+                acc_h = __dadd_rn(acc_h, __dmul_rn(wb, sh[1]));
+                vw = sw[1];
+                vh = sh[1];
+            }
+            if (j < np) {  // odd one out: always the layer's last sample (ff = 1)
+                const Vec3 p = {fma(1.0, d.x, lo.x), fma(1.0, d.y, lo.y), fma(1.0, d.z, lo.z)};
+                double lon, lat, h, X, Y;
+                ecef2lla_fast(p, R, lon, lat, h);
+                to_model(lon, lat, X, Y);
+                count_oob(h);
+                sample_scipy<GUESS_HINT, GUESS_HINT>(c, Y, X, h, iy, ix, iz, vw, vh);
                 acc_w = __dadd_rn(acc_w, __dmul_rn(wt_half, vw));
                 acc_h = __dadd_rn(acc_h, __dmul_rn(wt_half, vh));
-            }
-            for (int j = (k == 0 ? 0 : 1); j < np; ++j) {
-                const double ff = (j == np - 1) ? 1.0 : (double)j * step;
-                const Vec3 p = {fma(ff, d.x, lo.x), fma(ff, d.y, lo.y), fma(ff, d.z, lo.z)};  // delay.py:292
-                double lon, lat, h;
-                ecef2lla_fast(p, R, lon, lat, h);
-                double X = lon, Y = lat;
-                if (c.crs_kind == RDR_CRS_LCC_SPHERE) {
-                    const double2 xy = lcc_forward(c.lcc, lon, lat);
-                    X = xy.x;
-                    Y = xy.y;
-                }
-                if (k == 0 && j == 0) {
-                    const unsigned b = __ballot_sync(0xffffffffu, valid && (h < zmin));
-                    n_first_below += __popc(b);
-                    if (clamp_low_first) h = zmin;  // all pixels below min(z): delay.py:306-307
-                }
-                if (!(h >= zmin && h <= zmax)) {  // rare: counts feed the whole-raster predicate checks on the host
-                    n_below += valid && (h < zmin);
-                    n_above += valid && (h > zmax);
-                }
-                sample_scipy(c, Y, X, h, iy, ix, iz, vw, vh);
-                const double wt = (j == 0 || j == np - 1) ? wt_half : wt_full;
-                acc_w = __dadd_rn(acc_w, __dmul_rn(wt, vw));
-                acc_h = __dadd_rn(acc_h, __dmul_rn(wt, vh));
             }
             lo = hi;
             if (k + 1 < K) {
@@ -869,6 +911,30 @@ __global__ void k_interp_nd(const NdGrid G, const double *__restrict__ values, c
             out[i] = __ddiv_rn(acc, vol);
         }
     }
+}
+
+// self-test of the table-driven exact division: random cell widths d (any mantissa, exponents 2^-8 .. 2^16) and numerators
+// n = u * d, u in [0, 1]; counts results that differ from IEEE n / d
+__global__ void k_selftest_div(int64_t n, unsigned long long seed, unsigned long long *mis) {
+    unsigned long long m1 = 0, m2 = 0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        unsigned long long x = seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(i + 1);
+        auto next = [&x]() {
+            x ^= x >> 12; x ^= x << 25; x ^= x >> 27;
+            return x * 0x2545F4914F6CDD1Dull;
+        };
+        const unsigned long long a = next(), b = next();
+        const int e = (int)(next() % 25) - 8;
+        const double d = ldexp(1.0 + (double)(a >> 12) * 0x1p-52, e);
+        double u = (double)(b >> 11) * 0x1p-53;
+        if ((b & 1023) == 0) u = 1.0;  // t == 1 happens (inclusive last node)
+        const double num = u * d;
+        const double inv = 1.0 / d, want = num / d;
+        m1 += div_exact1(num, d, inv) != want;
+        m2 += div_exact2(num, d, inv) != want;
+    }
+    if (m1) atomicAdd(mis, m1);
+    if (m2) atomicAdd(mis + 1, m2);
 }
 
 // host-side restatement of the scalar layer decisions of build_ray (losreader.py:785-809)
@@ -1132,18 +1198,34 @@ RDR_API int rdr_sample(rdr_handle_t h, const void *pts, int64_t n, void *out_wet
     }
     const CubeView c = make_view(h);
     if (semantics == RDR_SEM_SCIPY && (reinterpret_cast<uintptr_t>(dpts) & 15) == 0) {
-        const size_t smem = K2_STAGES * K2_TILE * 3 * es + K2_STAGES * sizeof(uint64_t);
-        const int64_t ntiles = std::max<int64_t>(1, n / K2_TILE);
-        const int grid = (int)std::min<int64_t>(ntiles, (int64_t)h->sm_count * (dtype == RDR_F64 ? 12 : 16));
+        const bool uni = c.ay.uniform && c.ax.uniform;
+        const char *ppt_env = getenv("RDR_K2_PPT");
+        const int ppt = ppt_env ? atoi(ppt_env) : 2;
+#define RDR_LAUNCH_K2(T, M, P)                                                                                                   \
+    do {                                                                                                                         \
+        const size_t smem = K2_STAGES * (K2_THREADS * P) * 3 * es + K2_STAGES * sizeof(uint64_t);                                \
+        const int64_t ntiles = std::max<int64_t>(1, n / (K2_THREADS * P));                                                       \
+        CUDA_TRY(h, cudaFuncSetAttribute(k_sample_stream<T, M, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
+        int occ = 1;                                                                                                             \
+        CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sample_stream<T, M, P>, K2_THREADS, smem));            \
+        const int g = (int)std::min<int64_t>(ntiles, (int64_t)h->sm_count * std::max(1, occ)); /* one resident wave, persistent */ \
+        k_sample_stream<T, M, P><<<g, K2_THREADS, smem, h->stream>>>(c, static_cast<const T *>(dpts), n, static_cast<T *>(dw),   \
+                                                                     static_cast<T *>(dh));                                      \
+    } while (0)
+#define RDR_LAUNCH_K2_P(T, M)                      \
+    do {                                           \
+        if (ppt == 4) RDR_LAUNCH_K2(T, M, 4);      \
+        else if (ppt == 3) RDR_LAUNCH_K2(T, M, 3); \
+        else if (ppt == 1) RDR_LAUNCH_K2(T, M, 1); \
+        else RDR_LAUNCH_K2(T, M, 2);               \
+    } while (0)
         if (dtype == RDR_F64) {
-            CUDA_TRY(h, cudaFuncSetAttribute(k_sample_stream<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_sample_stream<double><<<grid, K2_THREADS, smem, h->stream>>>(c, static_cast<const double *>(dpts), n, static_cast<double *>(dw),
-                                                                           static_cast<double *>(dh));
+            if (uni) RDR_LAUNCH_K2_P(double, GUESS_UNIFORM); else RDR_LAUNCH_K2_P(double, GUESS_BINS);
         } else {
-            CUDA_TRY(h, cudaFuncSetAttribute(k_sample_stream<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_sample_stream<float><<<grid, K2_THREADS, smem, h->stream>>>(c, static_cast<const float *>(dpts), n, static_cast<float *>(dw),
-                                                                          static_cast<float *>(dh));
+            if (uni) RDR_LAUNCH_K2_P(float, GUESS_UNIFORM); else RDR_LAUNCH_K2_P(float, GUESS_BINS);
         }
+#undef RDR_LAUNCH_K2_P
+#undef RDR_LAUNCH_K2
     } else {
         constexpr int BLOCK = 256;
         const int grid = grid_for(n, BLOCK, h->sm_count, 8);
@@ -1344,6 +1426,8 @@ RDR_API int rdr_ray_integrate(rdr_handle_t h, const double *maxlen, double max_s
                                                                 accumulate, counters)
     if (out_dtype == RDR_F64) {
         switch (minb) {
+            case 2: RDR_LAUNCH_K3(double, 2); break;
+            case 3: RDR_LAUNCH_K3(double, 3); break;
             case 4: RDR_LAUNCH_K3(double, 4); break;
             case 5: RDR_LAUNCH_K3(double, 5); break;
             case 8: RDR_LAUNCH_K3(double, 8); break;
@@ -1544,6 +1628,23 @@ RDR_API int rdr_ecef2lla(const double *x, const double *y, const double *z, int6
     T_TRY(cudaGetLastError());
     T_TRY(cudaMemcpy(lon, dlo, n * 8, cudaMemcpyDeviceToHost)); T_TRY(cudaMemcpy(lat, dla, n * 8, cudaMemcpyDeviceToHost));
     T_TRY(cudaMemcpy(hgt, dh, n * 8, cudaMemcpyDeviceToHost));
+    return RDR_OK;
+}
+
+RDR_API int rdr_selftest_div(int64_t n, uint64_t seed, int64_t *mismatch_1step, int64_t *mismatch_2step, int device) {
+    CHECK_ARG(nullptr, mismatch_1step && mismatch_2step && n >= 0, "rdr_selftest_div: bad arguments");
+    int rc = need_device(device);
+    if (rc) return rc;
+    Transient T(device);
+    unsigned long long *dm = nullptr, hm[2] = {0, 0};
+    T_TRY(cudaMalloc(&dm, sizeof(hm)));
+    T.bufs.push_back(dm);
+    T_TRY(cudaMemset(dm, 0, sizeof(hm)));
+    k_selftest_div<<<148 * 8, 256>>>(n, seed, dm);
+    T_TRY(cudaGetLastError());
+    T_TRY(cudaMemcpy(hm, dm, sizeof(hm), cudaMemcpyDeviceToHost));
+    *mismatch_1step = (int64_t)hm[0];
+    *mismatch_2step = (int64_t)hm[1];
     return RDR_OK;
 }
 

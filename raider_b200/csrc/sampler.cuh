@@ -41,13 +41,30 @@ struct CubeView {
     LccParams lcc;
 };
 
-// correctly rounded n / d given inv = RN(1/d): q0 = n*inv, two residual corrections (Markstein)
-__device__ __forceinline__ double div_exact(double n, double d, double inv) {
+// correctly rounded n / d given inv = RN(1/d): q0 = n*inv, then residual corrections (Markstein).  One correction is
+// already correctly rounded when inv is the correctly rounded reciprocal and q0 is within 1 ulp (Markstein's theorem);
+// rdr_selftest_div counts mismatches of both forms against IEEE division on the device (tests/test_gpu_parity.py).
+__device__ __forceinline__ double div_exact2(double n, double d, double inv) {
     double q = n * inv;
     double r = fma(-d, q, n);
     q = fma(r, inv, q);
     r = fma(-d, q, n);
     return fma(r, inv, q);
+}
+__device__ __forceinline__ double div_exact1(double n, double d, double inv) {
+    const double q = n * inv;
+    const double r = fma(-d, q, n);
+    return fma(r, inv, q);
+}
+#ifndef RDR_DIV_STEPS
+#define RDR_DIV_STEPS 1
+#endif
+__device__ __forceinline__ double div_exact(double n, double d, double inv) {
+#if RDR_DIV_STEPS == 1
+    return div_exact1(n, d, inv);
+#else
+    return div_exact2(n, d, inv);
+#endif
 }
 
 __device__ __forceinline__ double4 ld_cell(const double4 *p) {
@@ -55,22 +72,29 @@ __device__ __forceinline__ double4 ld_cell(const double4 *p) {
     return make_double4(a.x, a.y, b.x, b.y);
 }
 
-// interval of an in-bounds coordinate v: largest i in [0, n-2] with g[i] <= v, found from `guess` (or the bin table when
-// guess < 0) and verified against the nodes; returns t = (v - g[i]) / (g[i+1] - g[i])
+// first guess of the interval of v when no hint is available
+enum { GUESS_HINT = 0, GUESS_UNIFORM = 1, GUESS_BINS = 2 };
+
+template <int MODE>
+__device__ __forceinline__ int guess_interval(const Axis &a, double v, int hint) {
+    if (MODE == GUESS_HINT) return hint;
+    const int last = a.n - 2;
+    if (MODE == GUESS_UNIFORM) {
+        const int i = (int)((v - a.g_first) * a.inv_d);
+        return min(max(i, 0), last);
+    }
+    const int b = (int)((v - a.g_first) * a.inv_bw);
+    return __ldg(a.bin + min(max(b, 0), a.nbin - 1));
+}
+
+// interval of an in-bounds coordinate v: largest i in [0, n-2] with g[i] <= v, starting from the guess and verified against
+// the nodes; returns t = (v - g[i]) / (g[i+1] - g[i]) and leaves the interval in i
+template <int MODE>
 __device__ __forceinline__ double locate(const Axis &a, double v, int &i) {
     const int last = a.n - 2;
-    if (i < 0) {
-        if (a.uniform) {
-            i = (int)((v - a.g_first) * a.inv_d);
-            i = i < 0 ? 0 : (i > last ? last : i);
-        } else {
-            int b = (int)((v - a.g_first) * a.inv_bw);
-            b = b < 0 ? 0 : (b >= a.nbin ? a.nbin - 1 : b);
-            i = __ldg(a.bin + b);
-        }
-    }
+    i = guess_interval<MODE>(a, v, i);
     double4 c = ld_cell(a.cell + i);
-    if (v < c.x || v >= c.y) {  // first guess off (node hit, rounding of the guess, or the inclusive last node): walk to the interval
+    if (v < c.x || v >= c.y) {  // guess off (node hit, rounding of the guess, or the inclusive last node): walk to the interval
         while (v < c.x && i > 0) c = ld_cell(a.cell + --i);
         while (v >= c.y && i < last) c = ld_cell(a.cell + ++i);
     }
@@ -105,23 +129,151 @@ __device__ __forceinline__ void trilinear_scipy(double4 c00, double4 c01, double
     vh = b;
 }
 
-// One scipy-semantics sample of both fields at cube coordinates (y, x, z).  iy/ix/iz: interval hints in (negative = none),
-// intervals used out -- a ray marching through the cube hands each sample's cells to the next one.
+// One scipy-semantics sample of both fields at cube coordinates (y, x, z).  MXY / MZ: how the first guess of the y,x / z
+// interval is made (GUESS_HINT: iy/ix/iz carry the previous sample's intervals in; they always carry the intervals used out).
+// Out-of-bounds or NaN coordinates give NaN (_find_out_of_bounds + nans mask of scipy) without a divergent early exit: the
+// lookup runs on a safe stand-in coordinate and the result is replaced at the end.
+template <int MXY, int MZ>
 __device__ __forceinline__ void sample_scipy(const CubeView &c, double y, double x, double z, int &iy, int &ix, int &iz, double &vw,
                                              double &vh) {
-    // out of bounds (strictly outside [g0, g_last]) or NaN coordinate -> NaN  (_find_out_of_bounds + nans mask)
     const bool inb = (y >= c.ay.g_first) && (y <= c.ay.g_last) && (x >= c.ax.g_first) && (x <= c.ax.g_last) && (z >= c.az.g_first) &&
                      (z <= c.az.g_last);
-    if (!inb) {
-        vw = vh = __longlong_as_double(0x7ff8000000000000LL);
-        return;
-    }
-    const double ty = locate(c.ay, y, iy), tx = locate(c.ax, x, ix), tz = locate(c.az, z, iz);
+    int jy = iy, jx = ix, jz = iz;  // (OOB / NaN coordinates cannot make the walks run away: see sample_prepare)
+    const double ty = locate<MXY>(c.ay, y, jy), tx = locate<MXY>(c.ax, x, jx), tz = locate<MZ>(c.az, z, jz);
     const int nzc = c.az.n - 1;
     const unsigned row = (unsigned)c.ax.n * (unsigned)nzc;  // cells per y-row; the whole cube has < 2^31 cells (checked at staging)
-    const double4 *p = c.cells + ((unsigned)iy * row + (unsigned)ix * (unsigned)nzc + (unsigned)iz);
+    const double4 *p = c.cells + ((unsigned)jy * row + (unsigned)jx * (unsigned)nzc + (unsigned)jz);
     const double4 c00 = ld_cell(p), c01 = ld_cell(p + nzc), c10 = ld_cell(p + row), c11 = ld_cell(p + row + nzc);
     trilinear_scipy(c00, c01, c10, c11, ty, tx, tz, vw, vh);
+    if (inb) {
+        iy = jy;
+        ix = jx;
+        iz = jz;
+    } else {
+        vw = vh = __longlong_as_double(0x7ff8000000000000LL);
+    }
+}
+
+// ---- phase-split form of the scipy sampler for kernels that keep several points in flight per thread (K2): all guesses,
+// then all interval-record loads, then the (rare) fix-ups, then all cell loads, then the arithmetic -- so that the loads of the
+// points overlap instead of forming one dependent chain per point.
+struct SamplePrep {
+    double y, x, z;   // coordinates used for the lookup (stand-ins when out of bounds)
+    int iy, ix, iz;
+    bool inb;
+};
+
+template <int MXY, int MZ>
+__device__ __forceinline__ void sample_prepare(const CubeView &c, double y, double x, double z, SamplePrep &s) {
+    s.inb = (y >= c.ay.g_first) && (y <= c.ay.g_last) && (x >= c.ax.g_first) && (x <= c.ax.g_last) && (z >= c.az.g_first) && (z <= c.az.g_last);
+    // out-of-bounds / NaN coordinates need no stand-in: the guesses are clamped into the table, a coordinate below the first or
+    // above the last node (or NaN) fails both walk conditions of fix_interval, and the garbage t is replaced by NaN at the end
+    s.y = y;
+    s.x = x;
+    s.z = z;
+    s.iy = guess_interval<MXY>(c.ay, y, s.iy);
+    s.ix = guess_interval<MXY>(c.ax, x, s.ix);
+    s.iz = guess_interval<MZ>(c.az, z, s.iz);
+}
+
+__device__ __forceinline__ void fix_interval(const Axis &a, double v, int &i, double4 &r) {
+    if (v < r.x || v >= r.y) {
+        const int last = a.n - 2;
+        while (v < r.x && i > 0) r = ld_cell(a.cell + --i);
+        while (v >= r.y && i < last) r = ld_cell(a.cell + ++i);
+    }
+}
+
+template <int NPT, int MXY, int MZ>
+__device__ __forceinline__ void sample_scipy_batch(const CubeView &c, const double (&y)[NPT], const double (&x)[NPT], const double (&z)[NPT],
+                                                   double (&vw)[NPT], double (&vh)[NPT]) {
+    SamplePrep s[NPT];
+    double4 ry[NPT], rx[NPT], rz[NPT];
+#pragma unroll
+    for (int p = 0; p < NPT; ++p) {
+        s[p].iy = s[p].ix = s[p].iz = 0;
+        sample_prepare<MXY, MZ>(c, y[p], x[p], z[p], s[p]);
+    }
+#pragma unroll
+    for (int p = 0; p < NPT; ++p) {
+        ry[p] = ld_cell(c.ay.cell + s[p].iy);
+        rx[p] = ld_cell(c.ax.cell + s[p].ix);
+        rz[p] = ld_cell(c.az.cell + s[p].iz);
+    }
+#pragma unroll
+    for (int p = 0; p < NPT; ++p) {
+        fix_interval(c.ay, s[p].y, s[p].iy, ry[p]);
+        fix_interval(c.ax, s[p].x, s[p].ix, rx[p]);
+        fix_interval(c.az, s[p].z, s[p].iz, rz[p]);
+    }
+    const int nzc = c.az.n - 1;
+    const unsigned row = (unsigned)c.ax.n * (unsigned)nzc;
+    double4 c00[NPT], c01[NPT], c10[NPT], c11[NPT];
+#pragma unroll
+    for (int p = 0; p < NPT; ++p) {
+        const double4 *q = c.cells + ((unsigned)s[p].iy * row + (unsigned)s[p].ix * (unsigned)nzc + (unsigned)s[p].iz);
+        c00[p] = ld_cell(q);
+        c01[p] = ld_cell(q + nzc);
+        c10[p] = ld_cell(q + row);
+        c11[p] = ld_cell(q + row + nzc);
+    }
+#pragma unroll
+    for (int p = 0; p < NPT; ++p) {
+        const double ty = div_exact(s[p].y - ry[p].x, ry[p].z, ry[p].w);
+        const double tx = div_exact(s[p].x - rx[p].x, rx[p].z, rx[p].w);
+        const double tz = div_exact(s[p].z - rz[p].x, rz[p].z, rz[p].w);
+        trilinear_scipy(c00[p], c01[p], c10[p], c11[p], ty, tx, tz, vw[p], vh[p]);
+        if (!s[p].inb) vw[p] = vh[p] = __longlong_as_double(0x7ff8000000000000LL);
+    }
+}
+
+// two samples of one ray, both starting from the same interval hints (the previous sample's cells); hints leave as the
+// second sample's cells when it was in bounds
+__device__ __forceinline__ void sample_scipy_pair_hinted(const CubeView &c, const double (&y)[2], const double (&x)[2], const double (&z)[2],
+                                                         int &iy, int &ix, int &iz, double (&vw)[2], double (&vh)[2]) {
+    SamplePrep s[2];
+    double4 ry[2], rx[2], rz[2];
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+        s[p].iy = iy;
+        s[p].ix = ix;
+        s[p].iz = iz;
+        sample_prepare<GUESS_HINT, GUESS_HINT>(c, y[p], x[p], z[p], s[p]);
+    }
+    ry[0] = ry[1] = ld_cell(c.ay.cell + iy);
+    rx[0] = rx[1] = ld_cell(c.ax.cell + ix);
+    rz[0] = rz[1] = ld_cell(c.az.cell + iz);
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+        fix_interval(c.ay, s[p].y, s[p].iy, ry[p]);
+        fix_interval(c.ax, s[p].x, s[p].ix, rx[p]);
+        fix_interval(c.az, s[p].z, s[p].iz, rz[p]);
+    }
+    const int nzc = c.az.n - 1;
+    const unsigned row = (unsigned)c.ax.n * (unsigned)nzc;
+    double4 c00[2], c01[2], c10[2], c11[2];
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+        const double4 *q = c.cells + ((unsigned)s[p].iy * row + (unsigned)s[p].ix * (unsigned)nzc + (unsigned)s[p].iz);
+        c00[p] = ld_cell(q);
+        c01[p] = ld_cell(q + nzc);
+        c10[p] = ld_cell(q + row);
+        c11[p] = ld_cell(q + row + nzc);
+    }
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+        const double ty = div_exact(s[p].y - ry[p].x, ry[p].z, ry[p].w);
+        const double tx = div_exact(s[p].x - rx[p].x, rx[p].z, rx[p].w);
+        const double tz = div_exact(s[p].z - rz[p].x, rz[p].z, rz[p].w);
+        trilinear_scipy(c00[p], c01[p], c10[p], c11[p], ty, tx, tz, vw[p], vh[p]);
+        if (!s[p].inb) vw[p] = vh[p] = __longlong_as_double(0x7ff8000000000000LL);
+    }
+    const int last = s[1].inb ? 1 : 0;
+    if (s[last].inb) {
+        iy = s[last].iy;
+        ix = s[last].ix;
+        iz = s[last].iz;
+    }
 }
 
 // RAiDER.interpolate 3-D formula (interpolate.cpp:155-174): un-normalised distances, one divide by dx*dy*dz.

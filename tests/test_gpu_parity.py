@@ -471,3 +471,13 @@ def test_full_size_properties(gpu):
                              list(rt.get_interpolators(cfg['cube'])), MAX_SEGMENT_LENGTH=cfg['max_segment_length'],
                              MAX_TROPO_HEIGHT=cfg['zref'], layer_maxlen=[info.maxlen])
     assert np.abs(w[sl, sl] - want[0][0]).max() < TOL_F64_M and np.abs(h[sl, sl] - want[1][0]).max() < TOL_F64_M
+
+
+def test_table_division_is_ieee_exact(gpu):
+    """The sampler never issues a DDIV: t = (x - g[i]) / (g[i+1] - g[i]) is n * RN(1/d) + Markstein corrections.  Two
+    corrections must reproduce IEEE division bit for bit (that is what keeps K2 bit-identical to scipy)."""
+    import ctypes as C
+    m1, m2 = C.c_int64(-1), C.c_int64(-1)
+    assert gpu.rdr_selftest_div(200_000_000, 12345, C.byref(m1), C.byref(m2), 0) == 0
+    print(f'division self-test over 2e8 pairs: 1-step mismatches {m1.value}, 2-step mismatches {m2.value}')
+    assert m1.value == 0 and m2.value == 0
