@@ -89,6 +89,9 @@ int rdr_set_stream(rdr_handle_t h, void *cuda_stream);
 int rdr_synchronize(rdr_handle_t h);
 /* number of kernels this handle has launched since creation (bench.py's gpu_launches claim) */
 int64_t rdr_launch_count(rdr_handle_t h);
+/* rays the last rdr_ray_integrate handed from the fast integrator to the PROJ-form one (polar, very oblique, leaving the
+ * cube, on a last node); -1 when the fast integrator was not used or the counters were not read back */
+int64_t rdr_last_fix_count(rdr_handle_t h);
 
 /* ---------------------------------------------------------------- cube --------------------------------- */
 /* Replaces delayFcns.getInterpolators (delayFcns.py:23-58): stage one weather-model cube (two float32 fields on

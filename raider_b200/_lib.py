@@ -39,6 +39,7 @@ SIGNATURES = {
     'rdr_set_stream': (_int, [_vp, _vp]),
     'rdr_synchronize': (_int, [_vp]),
     'rdr_launch_count': (_i64, [_vp]),
+    'rdr_last_fix_count': (_i64, [_vp]),
     'rdr_set_cube': (_int, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _int, _int, _vp, _int]),
     'rdr_blend_cube': (_int, [_vp, _vp, _vp, _int, _f64, _f64, _int]),
     'rdr_sample': (_int, [_vp, _vp, _i64, _vp, _vp, _int, _int, _int]),
@@ -179,6 +180,10 @@ class Handle:
     @property
     def launches(self) -> int:
         return int(self.lib.rdr_launch_count(self._h))
+
+    @property
+    def last_fix_count(self) -> int:
+        return int(self.lib.rdr_last_fix_count(self._h))
 
     def set_cube(self, ys, xs, zs, wet, hydro, layout=LAYOUT_ZYX, crs_kind=CRS_GEOGRAPHIC, crs_params=None) -> None:
         ys, xs, zs = f64(ys), f64(xs), f64(zs)

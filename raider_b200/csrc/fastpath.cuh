@@ -1,0 +1,265 @@
+// Hot-loop geometry + sampler of the ray tracer in the *meridian frame of the ray's ground point* (sm_100a).
+//
+// Reference arithmetic this stands for: tools/RAiDER/delay.py:292-298 (sub-step points, ECEF -> model CRS through PROJ) and
+// scipy's trilinear evaluation (delay.py:319) for every sample; tools/RAiDER/losreader.py:706-733 for the Newton heights.
+//
+// A ray is g + t u.  With e_r = (cos lon0, sin lon0, 0), e_e = (-sin lon0, cos lon0, 0), e_z the unit vectors of the ground
+// point's meridian plane, every point of the ray has coordinates
+//     A = A0 + t uA   (horizontal distance from the polar axis, along the ground point's meridian plane)
+//     B =      t uB   (east of that plane)
+//     Z = Z0 + t uZ
+// which is a rotation of ECEF about the polar axis: lengths are unchanged, p = sqrt(A^2 + B^2), sin(lon - lon0) = B / p, and the
+// longitude of the ground point itself never has to be turned into sin/cos.  Latitude and height follow PROJ's `cart` inverse
+// (Bowring 1976, single step; height p / cos(phi) - N), and the latitude / longitude are taken as small differences from the ground
+// point:  sin(phi - phi0) = (y_phi cos phi0 - x_phi sin phi0) / |(x_phi, y_phi)|,  arcsine by a 5-term odd series that is
+// exact to < 1 ulp for |sin| <= 0.02 (1.15 degrees, i.e. 127 km of horizontal travel).  Every reciprocal square root is one
+// MUFU.RSQ64H seed (2^-20, measured: profiles/micro/seed_accuracy.cu) and one cubic (Halley-type) correction -> 2.7e-16.
+//
+// Rays that leave the small-angle window, start within ~9 degrees of a pole, leave the cube (horizontally, below the first or
+// above the last z node) or touch the last node of a horizontal axis exactly are *flagged*, not approximated: the caller
+// re-integrates them with the PROJ-form code path (k_ray_integrate in list mode), which also owns every NaN rule.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "geodesy.cuh"
+#include "sampler.cuh"
+
+namespace rdr {
+
+// y ~ 1/sqrt(a): seed e0 ~ 2^-20, one cubic step y (1 + e/2 + 3 e^2 / 8), e = 1 - a y^2  ->  ~5/16 e0^3
+__device__ __forceinline__ double rsqrt3(double a) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    const double e = fma(-a * y, y, 1.0);
+    return fma(y, e * fma(0.375, e, 0.5), y);
+}
+
+// y ~ 1/a: seed, one cubic step y (1 + e + e^2), e = 1 - a y
+__device__ __forceinline__ double rcp3(double a) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    const double e = fma(-a, y, 1.0);
+    return fma(y, fma(e, e, e), y);
+}
+
+constexpr double WGS84_A_DIV_B = 1.0 / (1.0 - WGS84_F);
+constexpr double FAST_SIN_WINDOW = 0.02;       // bound on |sin| of the latitude / longitude difference: 1.15 deg, 127 km of travel
+constexpr double FAST_MIN_AXIS_DIST = 1.0e6;   // ground points closer to the polar axis than this take the PROJ-form path
+
+// The hot loop's fp64 constants live in constant memory: DFMA / DMUL take a c[bank][offset] operand for free, whereas a 64-bit
+// immediate costs two UMOVs every time it is re-materialised (23 per sample in the first version of this kernel).
+struct FastConst {
+    double a_div_b, e2s_b, neg_es_a, neg_es, neg_a;  // Bowring
+    double sin_window2;
+    double asin_c[4];                                // 1/6, 3/40, 15/336, 105/3456
+    double floor_magic;                              // 2^52 + 2^51
+};
+__constant__ FastConst c_fast = {WGS84_A_DIV_B, WGS84_E2S * WGS84_B, -WGS84_ES * WGS84_A, -WGS84_ES, -WGS84_A,
+                                 FAST_SIN_WINDOW * FAST_SIN_WINDOW,
+                                 {1.0 / 6.0, 3.0 / 40.0, 15.0 / 336.0, 105.0 / 3456.0},
+                                 6755399441055744.0};
+
+// asin(s) for |s| <= FAST_SIN_WINDOW: s + s^3/6 + 3 s^5/40 + 15 s^7/336 + 105 s^9/3456 (next term 0.022 s^11: 2.3e-19 relative
+// at the bound)
+__device__ __forceinline__ double asin_small(double s, double s2) {
+    double r = fma(s2, c_fast.asin_c[3], c_fast.asin_c[2]);
+    r = fma(s2, r, c_fast.asin_c[1]);
+    r = fma(s2, r, c_fast.asin_c[0]);
+    return fma(s * s2, r, s);
+}
+
+struct RayFrame {
+    double A0, Z0;        // ground point (B0 = 0)
+    double uA, uB, uZ;    // look vector
+    double lat0_deg, lon0_deg;
+    double slat, clat;    // of the ground latitude
+    bool fast_ok;         // far enough from the polar axis for the division-free formulas
+};
+
+// ground point + look vector of ray r in its meridian frame (lla2ecef of utilFcns.py:77-82; enu2ecef :91-121; zenith vectors of
+// losreader.py:312-314).  lat / lon in degrees.
+__device__ __forceinline__ void frame_setup(double lat, double lon, double ht, int los_kind, const double *__restrict__ los, int64_t r, double e,
+                                            double n, double up, RayFrame &F) {
+    double slat, clat;
+    sincos(lat * DEG_TO_RAD, &slat, &clat);
+    const double N = WGS84_A / sqrt(1.0 - WGS84_ES * slat * slat);
+    F.A0 = (N + ht) * clat;
+    F.Z0 = (N * (1.0 - WGS84_ES) + ht) * slat;
+    F.lat0_deg = lat;
+    F.lon0_deg = lon;
+    F.slat = slat;
+    F.clat = clat;
+    F.fast_ok = F.A0 > FAST_MIN_AXIS_DIST;
+    if (los_kind == 0 /* RDR_LOS_ARRAY */) {
+        double slon, clon;
+        sincos(lon * DEG_TO_RAD, &slon, &clon);
+        const double ux = __ldg(los + 3 * r), uy = __ldg(los + 3 * r + 1);
+        F.uA = fma(ux, clon, uy * slon);
+        F.uB = fma(uy, clon, -ux * slon);
+        F.uZ = __ldg(los + 3 * r + 2);
+    } else if (los_kind == 1 /* RDR_LOS_ENU_CONST */) {
+        F.uA = clat * up - slat * n;
+        F.uB = e;
+        F.uZ = slat * up + clat * n;
+    } else {
+        F.uA = clat;
+        F.uB = 0.0;
+        F.uZ = slat;
+    }
+}
+
+// Bowring's single step in the frame: everything the height and the latitude difference need
+struct FrameBowring {
+    double p, rp;          // sqrt(A^2 + B^2) and its reciprocal
+    double x_phi, y_phi;   // tan(phi) = y_phi / x_phi
+    double q2, rq;         // x_phi^2 + y_phi^2 and 1 / |(x_phi, y_phi)|
+    double sphi;
+};
+
+__device__ __forceinline__ FrameBowring frame_bowring(double A, double B, double Z) {
+    FrameBowring o;
+    const double p2 = fma(A, A, B * B);
+    o.rp = rsqrt3(p2);
+    o.p = p2 * o.rp;
+    const double yt = Z * c_fast.a_div_b;  // tan(theta) = (Z a) / (p b)
+    const double rn = rsqrt3(fma(yt, yt, p2));
+    const double ct = o.p * rn, st = yt * rn;
+    o.y_phi = fma(c_fast.e2s_b * st, st * st, Z);
+    o.x_phi = fma(c_fast.neg_es_a * ct, ct * ct, o.p);
+    o.q2 = fma(o.y_phi, o.y_phi, o.x_phi * o.x_phi);
+    o.rq = rsqrt3(o.q2);
+    o.sphi = o.y_phi * o.rq;
+    return o;
+}
+
+// PROJ's height: p / cos(phi) - N(phi), with 1 / cos(phi) = |(x_phi, y_phi)| / x_phi.  (The division-free form
+// p cos(phi) + Z sin(phi) - a W is *more* accurate -- it is insensitive to the 1e-12 rad truncation error of Bowring's single
+// step, which PROJ's form turns into ~1e-6 m at 48 km -- but parity is with the reference's arithmetic, so PROJ's form it is.)
+__device__ __forceinline__ double frame_height(const FrameBowring &o) {
+    const double rw = rsqrt3(fma(c_fast.neg_es * o.sphi, o.sphi, 1.0));
+    return fma(o.p * (o.q2 * o.rq), rcp3(o.x_phi), c_fast.neg_a * rw);
+}
+
+__device__ __forceinline__ double frame_height(double A, double B, double Z) { return frame_height(frame_bowring(A, B, Z)); }
+
+// getTopOfAtmosphere (losreader.py:706-733) in the frame: pos += look * (toa - h(pos)) / factor, ITERS times; returns the
+// accumulated position and the along-ray distance.  EXACT = PROJ-form height (rays near the polar axis); the frame is a
+// rotation of ECEF about that axis, so the height formulas take frame coordinates as they are.
+template <int ITERS, bool EXACT>
+__device__ __forceinline__ void frame_top_of_atmosphere(const RayFrame &F, double toa, double rfactor, double &A, double &B, double &Z, double &t) {
+    A = fma(toa, F.uA, F.A0);
+    B = toa * F.uB;
+    Z = fma(toa, F.uZ, F.Z0);
+    t = toa;
+#pragma unroll 1
+    for (int it = 0; it < ITERS; ++it) {
+        const double h = EXACT ? ecef2height(Vec3{A, B, Z}) : frame_height(A, B, Z);
+        const double d = (toa - h) * rfactor;
+        A = fma(F.uA, d, A);
+        B = fma(F.uB, d, B);
+        Z = fma(F.uZ, d, Z);
+        t += d;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// the cube as the fast integrator reads it
+// ------------------------------------------------------------------------------------------------------------------
+// One 128-byte record (= one cache line) per cube *cell*: the four corner columns of cell (iy, ix, iz), each as
+// {wet[iz], hydro[iz], wet[iz+1]-wet[iz], hydro[iz+1]-hydro[iz]} in fp64.  A trilinear sample of both fields is 8 LDG.128 at
+// immediate offsets from one address; neighbouring rays of a warp sit in the same cell and share the line.
+struct LerpCell {
+    double4 c00, c01, c10, c11;  // (iy, ix), (iy, ix+1), (iy+1, ix), (iy+1, ix+1)
+};
+
+struct FastCube {
+    const LerpCell *cells;  // [(iy * (nx-1) + ix) * nzc + iz]
+    int ny, nx, nzc;        // nodes along y, x; cells along z
+    // uniform horizontal axes (degrees): cell coordinate of v is fma(v, inv_d, c0) = (v - g_first) / d
+    double y_inv, y_c0, x_inv, x_c0;
+};
+
+struct LayerRec {
+    double z_lo, neg_zlo_inv, inv_dz;  // the layer's own cell: node below, -z_lo / dz, 1 / dz
+    double h_lo, h_hi;                 // a sample with h_lo <= h < h_hi is interpolated in that cell (see LAYER_TOL)
+    double step;                       // 1 / (np - 1): np.linspace(0, 1, np) = j * step (delay.py:287)
+    int np, iz;
+};
+
+// A sample within LAYER_TOL of its layer's own cell is interpolated (extrapolated by < 0.1 mm) in that cell instead of the
+// neighbour scipy would pick: the two piecewise-linear branches differ there by |slope change| * 1e-4 m < 1e-5 N-units, i.e.
+// < 1e-14 m of delay per sample.  The first / last node of the model keep their exact rule (below / above -> NaN).
+constexpr double LAYER_TOL = 1.0e-4;
+
+// z nodes + reciprocal cell thicknesses in shared memory: lookup for samples whose height is not inside their layer's own cell
+// (the reference's fixed-point iteration leaves the layer tops of oblique rays metres away from the nominal height)
+struct ZTable {
+    const double *z;    // [nz]
+    const double *inv;  // [nz - 1]
+    int nz;
+};
+
+__device__ __forceinline__ void z_lookup(const ZTable &T, double h, int &iz, double &tz, bool &bad) {
+    const int last = T.nz - 2;
+    if (!(h >= T.z[0] && h <= T.z[T.nz - 1])) {  // below / above the model or NaN: scipy gives NaN, the PROJ-form path owns that
+        bad = true;
+        return;
+    }
+    int i = iz;
+    while (i > 0 && h < T.z[i]) --i;
+    while (i < last && h >= T.z[i + 1]) ++i;
+    iz = i;
+    tz = (h - T.z[i]) * T.inv[i];
+}
+
+// cell index + fraction along a uniform axis; `bad` is raised when the coordinate is outside [first, last) (the exact last
+// node included: the PROJ-form path owns that rule).  floor(u) is the low word of RD(u + 2^52 + 2^51).
+__device__ __forceinline__ double cell_coord(double u, int n_nodes, int &i, bool &bad) {
+    const double s = __dadd_rd(u, c_fast.floor_magic);
+    const int raw = __double2loint(s);
+    const double fl = s - c_fast.floor_magic;
+    bad |= (unsigned)raw > (unsigned)(n_nodes - 2);
+    i = min(max(raw, 0), n_nodes - 2);
+    return u - fl;
+}
+
+// per-ray constants of the sampler: the ground point's own cell coordinates and d(cell coordinate) / d(radian)
+struct RayCell {
+    double uy0, ux0, ky, kx;
+};
+
+// One sample of both fields at frame point (A, B, Z) of a ray: geodetic latitude / longitude / height, cell lookup, trilinear
+// value in lerp form.  Raises `bad` instead of handling any edge rule.
+__device__ __forceinline__ void sample_fast(const FastCube &c, const RayFrame &F, const RayCell &R, const LayerRec &L, const ZTable &T, double A,
+                                            double B, double Z, bool clamp_to, double clamp_h, double &h_out, double &vw, double &vh, bool &bad) {
+    const FrameBowring o = frame_bowring(A, B, Z);
+    double h = frame_height(o);
+    h_out = h;
+    if (clamp_to) h = clamp_h;
+    const double slat = fma(o.y_phi, F.clat, -o.x_phi * F.slat) * o.rq;  // sin(phi - phi0)
+    const double slon = B * o.rp;                                        // sin(lam - lam0)
+    const double slat2 = slat * slat, slon2 = slon * slon;
+    bad |= !(slat2 <= c_fast.sin_window2) | !(slon2 <= c_fast.sin_window2);
+    // cell coordinates: (lat0 + dlat * RAD_TO_DEG - first) / d = uy0 + dlat * (RAD_TO_DEG / d)
+    const double uy = fma(asin_small(slat, slat2), R.ky, R.uy0);
+    const double ux = fma(asin_small(slon, slon2), R.kx, R.ux0);
+    int iy, ix, iz = L.iz;
+    const double ty = cell_coord(uy, c.ny, iy, bad);
+    const double tx = cell_coord(ux, c.nx, ix, bad);
+    double tz = fma(h, L.inv_dz, L.neg_zlo_inv);
+    if (!(h >= L.h_lo && h < L.h_hi)) z_lookup(T, h, iz, tz, bad);
+    const LerpCell *q = c.cells + ((unsigned)(iy * (c.nx - 1) + ix) * (unsigned)c.nzc + (unsigned)iz);
+    const double4 c00 = ld_cell(&q->c00), c01 = ld_cell(&q->c01), c10 = ld_cell(&q->c10), c11 = ld_cell(&q->c11);
+    // along z, then x, then y
+    const double w00 = fma(tz, c00.z, c00.x), h00 = fma(tz, c00.w, c00.y);
+    const double w01 = fma(tz, c01.z, c01.x), h01 = fma(tz, c01.w, c01.y);
+    const double w10 = fma(tz, c10.z, c10.x), h10 = fma(tz, c10.w, c10.y);
+    const double w11 = fma(tz, c11.z, c11.x), h11 = fma(tz, c11.w, c11.y);
+    const double w0 = fma(tx, w01 - w00, w00), h0 = fma(tx, h01 - h00, h00);
+    const double w1 = fma(tx, w11 - w10, w10), h1 = fma(tx, h11 - h10, h10);
+    vw = fma(ty, w1 - w0, w0);
+    vh = fma(ty, h1 - h0, h0);
+}
+
+}  // namespace rdr
