@@ -335,6 +335,16 @@ def run_ours(args):
     k2_ms = float(np.mean(k2))
     k2_bytes = npts * 40 + cube_bytes
     k2_gbs = k2_bytes / (k2_ms * 1e-3) / 1e9
+    # DRAM traffic of that launch from the committed ncu --set full capture (dram__bytes_read.sum + dram__bytes_write.sum)
+    k2_traffic, k2_traffic_src = None, None
+    tp = ROOT / 'profiles' / 'k2_traffic.json'
+    if tp.exists():
+        try:
+            tj = json.loads(tp.read_text())
+            if int(tj['points_per_launch']) == npts:
+                k2_traffic, k2_traffic_src = float(tj['dram_bytes_read'] + tj['dram_bytes_write']), tj['source']
+        except Exception:
+            pass
     # fp32-I/O tier of the same kernel (20 B/point)
     pts32 = pts.to(torch.float32)
     sw32 = torch.empty(npts, dtype=torch.float32, device='cuda')
@@ -399,8 +409,9 @@ def run_ours(args):
                 'ms_per_step': 1e3 * t_e2e / e2e_steps, 'api': 'getInterpolators(host cube) + _build_cube_ray(host axes) -> host float64 maps',
                 'max_abs_diff_vs_device_path_m': e2e_dev_diff},
         'gpu_launches': int(launches),
-        'roofline': {'kernel': 'k_sample_points<double> (K2 trilinear_sample, unfused)', 'bound': 'hbm', 'achieved': k2_gbs, 'peak': peak,
-                     'unit': 'GB/s', 'frac': k2_gbs / peak, 'traffic': None, 'peak_source': peak_src, 'bytes_per_point': 40,
+        'roofline': {'kernel': 'k_sample_stream<double> (K2 trilinear_sample, unfused, TMA-bulk point stream)', 'bound': 'hbm', 'achieved': k2_gbs,
+                     'peak': peak, 'unit': 'GB/s', 'frac': k2_gbs / peak, 'traffic': k2_traffic, 'traffic_source': k2_traffic_src,
+                     'algorithmic_bytes_per_launch': k2_bytes, 'peak_source': peak_src, 'bytes_per_point': 40,
                      'points_per_launch': npts, 'ms_per_launch': k2_ms, 'fp32_io_tier_gbs': k2_32_gbs, 'fp32_io_tier_frac': k2_32_gbs / peak},
         'fused': fused,
         'cpu_baseline': cpu,

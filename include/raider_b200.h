@@ -87,6 +87,11 @@ const char *rdr_last_error(rdr_handle_t h);
 /* run subsequent calls on an existing cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream); NULL = own stream */
 int rdr_set_stream(rdr_handle_t h, void *cuda_stream);
 int rdr_synchronize(rdr_handle_t h);
+/* Page-locked host memory for result arrays (pooled: freed blocks are reused).  rdr_ray_integrate writes its outputs straight
+ * into such arrays from the kernel (posted PCIe writes that overlap the integration) instead of staging + copying; any other
+ * host pointer still works, through a staged copy.  The reference allocates its outputs with np.zeros (delay.py:248). */
+int rdr_host_alloc(int64_t bytes, void **out);
+int rdr_host_free(void *p);
 /* number of kernels this handle has launched since creation (bench.py's gpu_launches claim) */
 int64_t rdr_launch_count(rdr_handle_t h);
 /* rays the last rdr_ray_integrate handed from the fast integrator to the PROJ-form one (polar, very oblique, leaving the

@@ -23,7 +23,7 @@ ow = torch.empty((n, n), dtype=torch.float64, device='cuda')
 oh = torch.empty((n, n), dtype=torch.float64, device='cuda')
 for _ in range(2):
     info = cube.trace(_lib.GEOM_GRID, xpts, ypts, n, n, _lib.LOS_ENU_CONST, enu_const(), 0.0, cfg['zref'], cfg['max_segment_length'], ow, oh)
-nslots = 16
+nslots = int(sys.argv[2]) if len(sys.argv) > 2 else 16   # bench.py launches K2 on 48 slots (192 M points)
 pts = torch.empty((nslots, n * n, 3), dtype=torch.float64, device='cuda')
 cube.ray_points(info.maxlen, cfg['max_segment_length'], slot0=100, nslots=nslots, out=pts)
 sw = torch.empty(nslots * n * n, dtype=torch.float64, device='cuda')

@@ -42,17 +42,26 @@ def timed(fn, reps=5):
 
 
 ref = None
-for m in (2, 3, 4, 5, 6, 8):
+layers = lambda: cube.ray_layers(_lib.GEOM_GRID, cfg['xpts'], cfg['ypts'], n, n, _lib.LOS_ENU_CONST, enu, 0.0, cfg['zref'])
+for m in (4, 5, 6, 8):
     os.environ['RDR_K0_MINB'] = str(m)
-    os.environ['RDR_K3_MINB'] = str(m)
-    layers = lambda: cube.ray_layers(_lib.GEOM_GRID, cfg['xpts'], cfg['ypts'], n, n, _lib.LOS_ENU_CONST, enu, 0.0, cfg['zref'])
     maxlen, _ = layers()
-    integ = lambda: cube.ray_integrate(maxlen, cfg['max_segment_length'], False, ow, oh)
-    integ()
-    t0, t3 = timed(layers), timed(integ)
-    chk = float(ow.sum() + oh.sum())
-    ref = ref or chk
-    print(f'minBlocks={m}: K0 {t0:.3f} ms  K3 {t3:.3f} ms  -> {n * n / (t0 + t3) * 1e3:.4g} rays/s  checksum diff {chk - ref:.3e}')
+    print(f'K0 minBlocks={m}: {timed(layers):.3f} ms')
+integ = lambda: cube.ray_integrate(maxlen, cfg['max_segment_length'], False, ow, oh)
+for general in (0, 1):
+    os.environ['RDR_K3_GENERAL'] = str(general)
+    for npt in ((1, 2) if not general else (2,)):
+        os.environ['RDR_K3_NPT'] = str(npt)
+        for m in (3, 4, 5, 6, 8):
+            os.environ['RDR_K3_MINB'] = str(m)
+            integ()
+            t3 = timed(integ)
+            chk = float(ow.sum() + oh.sum())
+            ref = ref or chk
+            print(f'K3 {"general" if general else "fast"} npt={npt} minBlocks={m}: {t3:.3f} ms  checksum diff {chk - ref:.3e}')
+os.environ['RDR_K3_GENERAL'] = '0'
+for k in ('RDR_K3_NPT', 'RDR_K3_MINB', 'RDR_K0_MINB'):
+    os.environ.pop(k, None)
 
 nslots = 48
 pts = torch.empty((nslots, n * n, 3), dtype=torch.float64, device='cuda')

@@ -38,6 +38,8 @@ SIGNATURES = {
     'rdr_last_error': (C.c_char_p, [_vp]),
     'rdr_set_stream': (_int, [_vp, _vp]),
     'rdr_synchronize': (_int, [_vp]),
+    'rdr_host_alloc': (_int, [_i64, C.POINTER(_vp)]),
+    'rdr_host_free': (_int, [_vp]),
     'rdr_launch_count': (_i64, [_vp]),
     'rdr_last_fix_count': (_i64, [_vp]),
     'rdr_set_cube': (_int, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _int, _int, _vp, _int]),
@@ -122,6 +124,23 @@ def ptr(a):
             raise ValueError('tensor must be contiguous')
         return a.data_ptr()
     raise TypeError(f'cannot take the address of {type(a)}')
+
+
+def pinned_empty(shape, dtype=np.float64) -> np.ndarray:
+    """An uninitialised ndarray in page-locked host memory from the library's pool (rdr_host_alloc).
+
+    The block goes back to the pool when the last view of the array dies.  Result arrays allocated this way are written by
+    the integration kernel directly (no staging copy); to every other consumer they are ordinary NumPy arrays.
+    """
+    import weakref
+    lib = load()
+    dtype = np.dtype(dtype)
+    nbytes = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
+    p = _vp()
+    check(lib.rdr_host_alloc(nbytes, C.byref(p)))
+    buf = (C.c_char * max(nbytes, 1)).from_address(p.value)
+    weakref.finalize(buf, lib.rdr_host_free, p.value)
+    return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape, dtype=np.int64))).reshape(shape)
 
 
 def is_device(a) -> bool:

@@ -85,6 +85,70 @@ struct BlockPool {
 };
 BlockPool g_pool;
 
+// Page-locked host blocks for result arrays (rdr_host_alloc): cudaHostAlloc costs ~0.3 ms per MB, so freed blocks are parked
+// and handed out again.  Kernels write results straight into such blocks (they are device-mapped under UVA), which turns the
+// device->host copy of the delay maps into posted PCIe writes that overlap the integration.
+struct PinnedPool {
+    struct Block {
+        void *p;
+        size_t cap;
+    };
+    std::mutex mu;
+    std::vector<Block> free_blocks, live;
+    size_t cached = 0;
+    static constexpr size_t MAX_CACHED = 8ull << 30;
+
+    void *take(size_t bytes) {
+        std::lock_guard<std::mutex> lk(mu);
+        int best = -1;
+        for (int i = 0; i < (int)free_blocks.size(); ++i) {
+            const Block &b = free_blocks[i];
+            if (b.cap >= bytes && b.cap <= 2 * bytes + (1 << 16) && (best < 0 || b.cap < free_blocks[best].cap)) best = i;
+        }
+        if (best < 0) return nullptr;
+        Block b = free_blocks[best];
+        free_blocks.erase(free_blocks.begin() + best);
+        cached -= b.cap;
+        live.push_back(b);
+        return b.p;
+    }
+    void add_live(void *p, size_t cap) {
+        std::lock_guard<std::mutex> lk(mu);
+        live.push_back({p, cap});
+    }
+    bool give(void *p) {  // false: not one of ours
+        Block b{nullptr, 0};
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            for (size_t i = 0; i < live.size(); ++i)
+                if (live[i].p == p) {
+                    b = live[i];
+                    live.erase(live.begin() + i);
+                    break;
+                }
+            if (!b.p) return false;
+            if (cached + b.cap <= MAX_CACHED) {
+                free_blocks.push_back(b);
+                cached += b.cap;
+                return true;
+            }
+        }
+        cudaFreeHost(b.p);
+        return true;
+    }
+};
+PinnedPool g_pinned;
+
+// is `p` page-locked host memory the device can address directly (UVA)?  Returns the device-side alias or nullptr.
+void *device_alias_of_host(const void *p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
+}
+
 struct DevBuf {
     void *p = nullptr;
     size_t cap = 0;
@@ -785,7 +849,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_ray_integrate(const CubeView c,
 // cube, on the last node) into `fix_list`; k_ray_integrate re-does exactly those rays in list mode, with all the NaN rules.
 // Dynamic shared memory: LayerRec[K] | z nodes [nz] | 1/dz [nz-1].
 // ------------------------------------------------------------------------------------------------
-template <typename OUT, int BLOCK, int MINB>
+template <typename OUT, int BLOCK, int MINB, int NPT>
 __global__ void __launch_bounds__(BLOCK, MINB) k_ray_integrate_fast(const FastCube c, const RayGeom G, int64_t n_rays, int K,
                                                               const double *__restrict__ t_in, const LayerRec *__restrict__ layers,
                                                               const double *__restrict__ znodes, int nz, int clamp_low_first, double zmin,
@@ -811,45 +875,49 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_ray_integrate_fast(const FastCu
         RayFrame F;
         frame_setup(lat, lon, G.ht, G.los_kind, G.los, rr, G.e, G.n, G.u, F);
         const RayCell R = {fma(lat, c.y_inv, c.y_c0), fma(lon, c.x_inv, c.x_c0), ky, kx};
+        const double unorm = norm3(Vec3{F.uA, F.uB, F.uZ});  // |P_hi - P_lo| = |t_hi - t_lo| |u|  (losreader.py:821)
         bool bad = !F.fast_ok;
         double acc_w = 0.0, acc_h = 0.0, vw, vh, h;
-        double t = __ldcs(t_in + rr);
-        double Alo = fma(t, F.uA, F.A0), Blo = t * F.uB, Zlo = fma(t, F.uZ, F.Z0);
+        // a sample is the point g + t u of the frame, t = t_lo + ff (t_hi - t_lo): the reference's low + ff (high - low) (delay.py:292)
+        auto sample_at = [&](const LayerRec &L, double t, bool clamp, double &w_out, double &h_out) {
+            sample_fast(c, F, R, L, T, fma(t, F.uA, F.A0), t * F.uB, fma(t, F.uZ, F.Z0), clamp, zmin, h, w_out, h_out, bad);
+        };
+        double t_lo = __ldcs(t_in + rr);
         // very first sample of the ray (ff = 0 of the first layer); all pixels below min(z) -> clamp (delay.py:306-307)
-        sample_fast(c, F, R, s_layers[0], T, Alo, Blo, Zlo, clamp_low_first != 0, zmin, h, vw, vh, bad);
+        sample_at(s_layers[0], t_lo, clamp_low_first != 0, vw, vh);
         n_first_below += __popc(__ballot_sync(0xffffffffu, valid && (h < zmin)));
         for (int k = 0; k < K; ++k) {
             const LayerRec L = s_layers[k];
-            t = __ldcs(t_in + (int64_t)(k + 1) * n_rays + rr);
-            const double Ahi = fma(t, F.uA, F.A0), Bhi = t * F.uB, Zhi = fma(t, F.uZ, F.Z0);
-            const double dA = Ahi - Alo, dB = Bhi - Blo, dZ = Zhi - Zlo;
-            const double len2 = fma(dA, dA, fma(dB, dB, dZ * dZ));
-            const double len = len2 > 0.0 ? len2 * rsqrt3(len2) : len2;     // |P_hi - P_lo| (losreader.py:821)
+            const double t_hi = __ldcs(t_in + (int64_t)(k + 1) * n_rays + rr);
+            const double dt = t_hi - t_lo;
+            const double len = fabs(dt) * unorm;
             const double wt_full = (len * 1.0e-6) / ((double)L.np - 1.0);   // delay.py:315
             const double wt_half = 0.5 * wt_full;
             // first sample of this layer == last sample of the previous one (evaluated once, used with both end weights)
             acc_w = fma(wt_half, vw, acc_w);
             acc_h = fma(wt_half, vh, acc_h);
             int j = 1;
-            for (; j + 1 < L.np; j += 2) {  // two samples per trip: independent chains for the FP64 pipe
-                const double fa = (double)j * L.step, fb = (j + 1 == L.np - 1) ? 1.0 : (double)(j + 1) * L.step;
-                double wa, ha, wb, hb;
-                sample_fast(c, F, R, L, T, fma(fa, dA, Alo), fma(fa, dB, Blo), fma(fa, dZ, Zlo), false, 0.0, h, wa, ha, bad);
-                sample_fast(c, F, R, L, T, fma(fb, dA, Alo), fma(fb, dB, Blo), fma(fb, dZ, Zlo), false, 0.0, h, wb, hb, bad);
-                const double wtb = (j + 1 == L.np - 1) ? wt_half : wt_full;
+            if (NPT == 2) {
+                for (; j + 1 < L.np - 1; j += 2) {  // two interior samples per trip: independent chains for the FP64 pipe
+                    double wa, ha, wb, hb;
+                    sample_at(L, fma((double)j * L.step, dt, t_lo), false, wa, ha);
+                    sample_at(L, fma((double)(j + 1) * L.step, dt, t_lo), false, wb, hb);
+                    acc_w = fma(wt_full, wa, acc_w);
+                    acc_h = fma(wt_full, ha, acc_h);
+                    acc_w = fma(wt_full, wb, acc_w);
+                    acc_h = fma(wt_full, hb, acc_h);
+                }
+            }
+            for (; j < L.np - 1; ++j) {
+                double wa, ha;
+                sample_at(L, fma((double)j * L.step, dt, t_lo), false, wa, ha);
                 acc_w = fma(wt_full, wa, acc_w);
                 acc_h = fma(wt_full, ha, acc_h);
-                acc_w = fma(wtb, wb, acc_w);
-                acc_h = fma(wtb, hb, acc_h);
-                vw = wb;
-                vh = hb;
             }
-            if (j < L.np) {  // odd one out: always the layer's last sample (ff = 1)
-                sample_fast(c, F, R, L, T, Alo + dA, Blo + dB, Zlo + dZ, false, 0.0, h, vw, vh, bad);
-                acc_w = fma(wt_half, vw, acc_w);
-                acc_h = fma(wt_half, vh, acc_h);
-            }
-            Alo = Ahi; Blo = Bhi; Zlo = Zhi;
+            sample_at(L, t_hi, false, vw, vh);  // the layer's last sample (ff = 1)
+            acc_w = fma(wt_half, vw, acc_w);
+            acc_h = fma(wt_half, vh, acc_h);
+            t_lo = t_hi;
         }
         if (valid) {
             if (bad) {
@@ -1230,6 +1298,29 @@ RDR_API int rdr_synchronize(rdr_handle_t h) {
     return RDR_OK;
 }
 
+RDR_API int rdr_host_alloc(int64_t bytes, void **out) {
+    CHECK_ARG(nullptr, out != nullptr && bytes >= 0, "rdr_host_alloc: bad arguments");
+    *out = nullptr;
+    if (rdr_device_count() == 0) return fail(nullptr, RDR_ERR_CUDA, "rdr_host_alloc: no CUDA device available; libraider_b200 has no CPU fallback");
+    const size_t want = std::max<size_t>((size_t)bytes, 64);
+    if ((*out = g_pinned.take(want))) return RDR_OK;
+    void *p = nullptr;
+    cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocPortable | cudaHostAllocMapped);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(nullptr, RDR_ERR_CUDA, std::string("cudaHostAlloc: ") + cudaGetErrorString(e));
+    }
+    g_pinned.add_live(p, want);
+    *out = p;
+    return RDR_OK;
+}
+
+RDR_API int rdr_host_free(void *p) {
+    if (!p) return RDR_OK;
+    if (!g_pinned.give(p)) return fail(nullptr, RDR_ERR_INVALID, "rdr_host_free: pointer was not returned by rdr_host_alloc");
+    return RDR_OK;
+}
+
 RDR_API int64_t rdr_launch_count(rdr_handle_t h) { return h ? h->launches : 0; }
 
 RDR_API int64_t rdr_last_fix_count(rdr_handle_t h) { return h ? h->last_fix_count : -1; }
@@ -1512,7 +1603,7 @@ RDR_API int rdr_ray_layers(rdr_handle_t h, int geom_kind, const double *gx, cons
     CUDA_TRY(h, h->d_red.reserve((K + 8) * sizeof(unsigned long long)));
     CUDA_TRY(h, cudaMemsetAsync(h->d_red.p, 0, (K + 8) * sizeof(unsigned long long), h->stream));
     constexpr int BLOCK = 128;
-    const int minb = tune_minb("RDR_K0_MINB", 6);
+    const int minb = tune_minb("RDR_K0_MINB", 8);
     const int grid = grid_for(n, BLOCK, h->sm_count, 4 * minb);
     const size_t smem = (K + 2) * sizeof(unsigned long long);
 #define RDR_LAUNCH_K0(M)                                                                                                              \
@@ -1521,8 +1612,8 @@ RDR_API int rdr_ray_layers(rdr_handle_t h, int geom_kind, const double *gx, cons
     switch (minb) {
         case 4: RDR_LAUNCH_K0(4); break;
         case 5: RDR_LAUNCH_K0(5); break;
-        case 8: RDR_LAUNCH_K0(8); break;
-        default: RDR_LAUNCH_K0(6); break;
+        case 6: RDR_LAUNCH_K0(6); break;
+        default: RDR_LAUNCH_K0(8); break;
     }
 #undef RDR_LAUNCH_K0
     h->launches++;
@@ -1568,13 +1659,23 @@ RDR_API int rdr_ray_integrate(rdr_handle_t h, const double *maxlen, double max_s
     CUDA_TRY(h, cudaMemsetAsync(counters, 0, 4 * sizeof(unsigned long long), h->stream));
     const size_t es = out_dtype == RDR_F64 ? 8 : 4;
     void *dw = out_wet, *dh = out_hydro;
+    bool staged_out = false;
     if (mem == RDR_MEM_HOST) {
-        CUDA_TRY(h, h->d_out.reserve(2 * n * es));
-        dw = h->d_out.p;
-        dh = static_cast<char *>(h->d_out.p) + n * es;
-        if (accumulate) {
-            CUDA_TRY(h, cudaMemcpyAsync(dw, out_wet, n * es, cudaMemcpyHostToDevice, h->stream));
-            CUDA_TRY(h, cudaMemcpyAsync(dh, out_hydro, n * es, cudaMemcpyHostToDevice, h->stream));
+        // page-locked result arrays (rdr_host_alloc) are written by the kernel itself: 16 B per ray of posted PCIe writes spread
+        // over the whole integration instead of a 2 x n x 8 B copy after it
+        void *aw = accumulate ? nullptr : device_alias_of_host(out_wet), *ah = accumulate ? nullptr : device_alias_of_host(out_hydro);
+        if (aw && ah) {
+            dw = aw;
+            dh = ah;
+        } else {
+            staged_out = true;
+            CUDA_TRY(h, h->d_out.reserve(2 * n * es));
+            dw = h->d_out.p;
+            dh = static_cast<char *>(h->d_out.p) + n * es;
+            if (accumulate) {
+                CUDA_TRY(h, cudaMemcpyAsync(dw, out_wet, n * es, cudaMemcpyHostToDevice, h->stream));
+                CUDA_TRY(h, cudaMemcpyAsync(dh, out_hydro, n * es, cudaMemcpyHostToDevice, h->stream));
+            }
         }
     }
     constexpr int BLOCK = 128;
@@ -1607,27 +1708,31 @@ RDR_API int rdr_ray_integrate(rdr_handle_t h, const double *maxlen, double max_s
         CUDA_TRY(h, h->d_layers.reserve(K * sizeof(LayerRec)));
         CUDA_TRY(h, cudaMemcpyAsync(h->d_layers.p, recs.data(), K * sizeof(LayerRec), cudaMemcpyHostToDevice, h->stream));
         CUDA_TRY(h, h->d_fix.reserve(std::max<size_t>(n * sizeof(int), 16)));
-        const int minb = tune_minb("RDR_K3_MINB", 4);
+        const int minb = tune_minb("RDR_K3_MINB", 5);
         const int grid = grid_for(n, BLOCK, h->sm_count, 4 * minb);
         const size_t smem = K * sizeof(LayerRec) + (2 * (size_t)h->nz - 1) * sizeof(double);
         const double *znodes = h->d_axes.as<double>() + h->ny + h->nx;
-#define RDR_LAUNCH_K3F(T, M)                                                                                                           \
-    k_ray_integrate_fast<T, BLOCK, M><<<grid, BLOCK, smem, h->stream>>>(fc, G, n, K, h->d_t.as<double>(), h->d_layers.as<LayerRec>(),  \
-                                                                        znodes, (int)h->nz, clamp_low_first, h->zs.front(),           \
-                                                                        static_cast<T *>(dw), static_cast<T *>(dh), accumulate,        \
-                                                                        counters, h->d_fix.as<int>())
+        const char *npt_env = getenv("RDR_K3_NPT");
+        const int npt = npt_env ? atoi(npt_env) : 1;
+#define RDR_LAUNCH_K3F(T, M, P)                                                                                                            \
+    k_ray_integrate_fast<T, BLOCK, M, P><<<grid, BLOCK, smem, h->stream>>>(fc, G, n, K, h->d_t.as<double>(), h->d_layers.as<LayerRec>(),   \
+                                                                           znodes, (int)h->nz, clamp_low_first, h->zs.front(),            \
+                                                                           static_cast<T *>(dw), static_cast<T *>(dh), accumulate,         \
+                                                                           counters, h->d_fix.as<int>())
+#define RDR_LAUNCH_K3F_M(T, P)                        \
+    switch (minb) {                                   \
+        case 3: RDR_LAUNCH_K3F(T, 3, P); break;       \
+        case 4: RDR_LAUNCH_K3F(T, 4, P); break;       \
+        case 6: RDR_LAUNCH_K3F(T, 6, P); break;       \
+        case 8: RDR_LAUNCH_K3F(T, 8, P); break;       \
+        default: RDR_LAUNCH_K3F(T, 5, P); break;      \
+    }
         if (out_dtype == RDR_F64) {
-            switch (minb) {
-                case 2: RDR_LAUNCH_K3F(double, 2); break;
-                case 3: RDR_LAUNCH_K3F(double, 3); break;
-                case 5: RDR_LAUNCH_K3F(double, 5); break;
-                case 6: RDR_LAUNCH_K3F(double, 6); break;
-                case 8: RDR_LAUNCH_K3F(double, 8); break;
-                default: RDR_LAUNCH_K3F(double, 4); break;
-            }
+            if (npt == 1) { RDR_LAUNCH_K3F_M(double, 1) } else { RDR_LAUNCH_K3F_M(double, 2) }
         } else {
-            RDR_LAUNCH_K3F(float, 4);
+            RDR_LAUNCH_K3F(float, 5, 1);
         }
+#undef RDR_LAUNCH_K3F_M
 #undef RDR_LAUNCH_K3F
         h->launches++;
         CUDA_TRY(h, cudaGetLastError());
@@ -1660,7 +1765,7 @@ RDR_API int rdr_ray_integrate(rdr_handle_t h, const double *maxlen, double max_s
     }
 #undef RDR_LAUNCH_K3
     unsigned long long cnt[4] = {0, 0, 0, 0};
-    if (mem == RDR_MEM_HOST) {
+    if (staged_out) {
         CUDA_TRY(h, cudaMemcpyAsync(out_wet, dw, n * es, cudaMemcpyDeviceToHost, h->stream));
         CUDA_TRY(h, cudaMemcpyAsync(out_hydro, dh, n * es, cudaMemcpyDeviceToHost, h->stream));
     }

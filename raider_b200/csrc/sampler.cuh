@@ -89,14 +89,18 @@ __device__ __forceinline__ int guess_interval(const Axis &a, double v, int hint)
 
 // interval of an in-bounds coordinate v: largest i in [0, n-2] with g[i] <= v, starting from the guess and verified against
 // the nodes; returns t = (v - g[i]) / (g[i+1] - g[i]) and leaves the interval in i
+// `inb` is cleared when v lies outside [g[0], g[n-1]]: only the walk can find that out, so the common case (guess right, v
+// inside its interval) pays no bounds test at all.  A NaN coordinate fails both walk conditions, keeps `inb`, and poisons t --
+// which is scipy's answer for it (NaN in, NaN out).
 template <int MODE>
-__device__ __forceinline__ double locate(const Axis &a, double v, int &i) {
+__device__ __forceinline__ double locate(const Axis &a, double v, int &i, bool &inb) {
     const int last = a.n - 2;
     i = guess_interval<MODE>(a, v, i);
     double4 c = ld_cell(a.cell + i);
-    if (v < c.x || v >= c.y) {  // guess off (node hit, rounding of the guess, or the inclusive last node): walk to the interval
+    if (v < c.x || v >= c.y) {  // guess off (node hit, rounding of the guess, the inclusive last node) or out of bounds: walk
         while (v < c.x && i > 0) c = ld_cell(a.cell + --i);
         while (v >= c.y && i < last) c = ld_cell(a.cell + ++i);
+        inb &= (v >= c.x) && (v <= c.y);
     }
     return div_exact(v - c.x, c.z, c.w);
 }
@@ -136,10 +140,9 @@ __device__ __forceinline__ void trilinear_scipy(double4 c00, double4 c01, double
 template <int MXY, int MZ>
 __device__ __forceinline__ void sample_scipy(const CubeView &c, double y, double x, double z, int &iy, int &ix, int &iz, double &vw,
                                              double &vh) {
-    const bool inb = (y >= c.ay.g_first) && (y <= c.ay.g_last) && (x >= c.ax.g_first) && (x <= c.ax.g_last) && (z >= c.az.g_first) &&
-                     (z <= c.az.g_last);
+    bool inb = true;
     int jy = iy, jx = ix, jz = iz;  // (OOB / NaN coordinates cannot make the walks run away: see sample_prepare)
-    const double ty = locate<MXY>(c.ay, y, jy), tx = locate<MXY>(c.ax, x, jx), tz = locate<MZ>(c.az, z, jz);
+    const double ty = locate<MXY>(c.ay, y, jy, inb), tx = locate<MXY>(c.ax, x, jx, inb), tz = locate<MZ>(c.az, z, jz, inb);
     const int nzc = c.az.n - 1;
     const unsigned row = (unsigned)c.ax.n * (unsigned)nzc;  // cells per y-row; the whole cube has < 2^31 cells (checked at staging)
     const double4 *p = c.cells + ((unsigned)jy * row + (unsigned)jx * (unsigned)nzc + (unsigned)jz);
@@ -165,9 +168,10 @@ struct SamplePrep {
 
 template <int MXY, int MZ>
 __device__ __forceinline__ void sample_prepare(const CubeView &c, double y, double x, double z, SamplePrep &s) {
-    s.inb = (y >= c.ay.g_first) && (y <= c.ay.g_last) && (x >= c.ax.g_first) && (x <= c.ax.g_last) && (z >= c.az.g_first) && (z <= c.az.g_last);
+    s.inb = true;  // cleared by fix_interval when a walk ends outside the grid
     // out-of-bounds / NaN coordinates need no stand-in: the guesses are clamped into the table, a coordinate below the first or
-    // above the last node (or NaN) fails both walk conditions of fix_interval, and the garbage t is replaced by NaN at the end
+    // above the last node stops the walk of fix_interval at the end interval (and the garbage t is replaced by NaN at the end), a
+    // NaN fails every comparison and poisons t by itself
     s.y = y;
     s.x = x;
     s.z = z;
@@ -176,11 +180,12 @@ __device__ __forceinline__ void sample_prepare(const CubeView &c, double y, doub
     s.iz = guess_interval<MZ>(c.az, z, s.iz);
 }
 
-__device__ __forceinline__ void fix_interval(const Axis &a, double v, int &i, double4 &r) {
+__device__ __forceinline__ void fix_interval(const Axis &a, double v, int &i, double4 &r, bool &inb) {
     if (v < r.x || v >= r.y) {
         const int last = a.n - 2;
         while (v < r.x && i > 0) r = ld_cell(a.cell + --i);
         while (v >= r.y && i < last) r = ld_cell(a.cell + ++i);
+        inb &= (v >= r.x) && (v <= r.y);
     }
 }
 
@@ -202,9 +207,9 @@ __device__ __forceinline__ void sample_scipy_batch(const CubeView &c, const doub
     }
 #pragma unroll
     for (int p = 0; p < NPT; ++p) {
-        fix_interval(c.ay, s[p].y, s[p].iy, ry[p]);
-        fix_interval(c.ax, s[p].x, s[p].ix, rx[p]);
-        fix_interval(c.az, s[p].z, s[p].iz, rz[p]);
+        fix_interval(c.ay, s[p].y, s[p].iy, ry[p], s[p].inb);
+        fix_interval(c.ax, s[p].x, s[p].ix, rx[p], s[p].inb);
+        fix_interval(c.az, s[p].z, s[p].iz, rz[p], s[p].inb);
     }
     const int nzc = c.az.n - 1;
     const unsigned row = (unsigned)c.ax.n * (unsigned)nzc;
@@ -245,9 +250,9 @@ __device__ __forceinline__ void sample_scipy_pair_hinted(const CubeView &c, cons
     rz[0] = rz[1] = ld_cell(c.az.cell + iz);
 #pragma unroll
     for (int p = 0; p < 2; ++p) {
-        fix_interval(c.ay, s[p].y, s[p].iy, ry[p]);
-        fix_interval(c.ax, s[p].x, s[p].ix, rx[p]);
-        fix_interval(c.az, s[p].z, s[p].iz, rz[p]);
+        fix_interval(c.ay, s[p].y, s[p].iy, ry[p], s[p].inb);
+        fix_interval(c.ax, s[p].x, s[p].ix, rx[p], s[p].inb);
+        fix_interval(c.az, s[p].z, s[p].iz, rz[p], s[p].inb);
     }
     const int nzc = c.az.n - 1;
     const unsigned row = (unsigned)c.ax.n * (unsigned)nzc;

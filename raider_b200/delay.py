@@ -210,7 +210,7 @@ def _build_cube_ray(
         # np.zeros((nz, ny, nx)) in the reference (:248); here each slice is written straight from the device (0 + x == x),
         # so the arrays start uninitialised and only skipped slices are zero-filled
         output_created_here = True
-        outputArrs = [np.empty((zpts.size, ny, nx)) for mm in range(2)]
+        outputArrs = [_lib.pinned_empty((zpts.size, ny, nx)) for mm in range(2)]   # page-locked: the kernel writes them directly
     else:
         wet = np.empty((ny, nx))
         hydro = np.empty((ny, nx))
