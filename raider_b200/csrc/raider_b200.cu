@@ -200,6 +200,7 @@ struct rdr_handle_s {
     size_t tab_cell_off[3] = {0, 0, 0}, tab_bin_off[3] = {0, 0, 0};
     int tab_nbin[3] = {0, 0, 0};
     DevBuf d_cells;  // double4 [ny][nx][nz-1]  {wet[z], hydro[z], wet[z+1], hydro[z+1]}
+    DevBuf d_cells32;  // float4 [ny][nx][nz-1]: the same records in fp32 for the streaming sampler K2
     DevBuf d_lerp;   // LerpCell [ny-1][nx-1][nz-1]: 128-byte cell records of the fast integrator (fastpath.cuh)
     DevBuf d_stage;  // staging for field uploads (and packed fp32 pairs for blending)
     DevBuf d_fields; // float2 [ny][nx][nz] (wet, hydro) kept for blending
@@ -288,13 +289,14 @@ __global__ void k_blend_fields(float2 *__restrict__ a, const float2 *__restrict_
 }
 
 // float2 [ny][nx][nz] -> double4 cells [ny][nx][nz-1] = {f[z], f[z+1]} (exact promotion)
-__global__ void k_pack_cells(const float2 *__restrict__ f, double4 *__restrict__ cells, int64_t ncol, int nz) {
+__global__ void k_pack_cells(const float2 *__restrict__ f, double4 *__restrict__ cells, float4 *__restrict__ cells32, int64_t ncol, int nz) {
     const int64_t total = ncol * (nz - 1);
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t col = i / (nz - 1);
         const int iz = (int)(i % (nz - 1));
         const float2 a = f[col * nz + iz], b = f[col * nz + iz + 1];
         cells[i] = make_double4((double)a.x, (double)a.y, (double)b.x, (double)b.y);
+        cells32[i] = make_float4(a.x, a.y, b.x, b.y);
     }
 }
 
@@ -317,6 +319,7 @@ __global__ void k_pack_lerp(const float2 *__restrict__ f, double4 *__restrict__ 
 CubeView make_view(rdr_handle_t h) {
     CubeView c;
     c.cells = h->d_cells.as<double4>();
+    c.cells32 = h->d_cells32.as<float4>();
     const double *nodes = h->d_axes.as<double>();
     const char *tabs = h->d_tabs.as<char>();
     const std::vector<double> *v[3] = {&h->ys, &h->xs, &h->zs};
@@ -338,6 +341,13 @@ CubeView make_view(rdr_handle_t h) {
         a.uniform = 1;
         for (size_t i = 0; i < v[d]->size(); ++i)  // every node within a quarter cell of its uniform position: the guess is off by <= 1
             if (fabs((*v[d])[i] - (a.g_first + dmean * (double)i)) > 0.25 * dmean) a.uniform = 0;
+        a.d = (*v[d])[1] - (*v[d])[0];
+        a.inv_dx = 1.0 / a.d;
+        a.exact_uniform = a.uniform;
+        for (size_t i = 0; i < v[d]->size() && a.exact_uniform; ++i)  // bit-for-bit: the kernel recomputes the nodes with this very fma
+            if (fma((double)i, a.d, a.g_first) != (*v[d])[i]) a.exact_uniform = 0;
+        for (size_t i = 0; i + 1 < v[d]->size() && a.exact_uniform; ++i)
+            if ((*v[d])[i] + a.d != (*v[d])[i + 1] || (*v[d])[i + 1] - (*v[d])[i] != a.d) a.exact_uniform = 0;
     }
     c.crs_kind = h->crs_kind;
     c.lcc = {h->crs[0], h->crs[1], h->crs[2], h->crs[3], h->crs[4], h->crs[5], h->crs[6]};
@@ -1267,7 +1277,7 @@ RDR_API int rdr_destroy(rdr_handle_t h) {
     ScopedDevice sd(h->device);
     cudaStreamSynchronize(h->stream);
     for (DevBuf *b : {&h->d_axes, &h->d_tabs, &h->d_cells, &h->d_stage, &h->d_fields, &h->d_gx, &h->d_gy, &h->d_los, &h->d_plan, &h->d_t, &h->d_red,
-                      &h->d_nparts, &h->d_out, &h->d_in, &h->d_lerp, &h->d_layers, &h->d_fix})
+                      &h->d_nparts, &h->d_out, &h->d_in, &h->d_lerp, &h->d_layers, &h->d_fix, &h->d_cells32})
         b->release();
     if (h->own_stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -1361,8 +1371,9 @@ static int upload_fields(rdr_handle_t h, const float *wet, const float *hydro, i
 static int pack_cells(rdr_handle_t h) {
     const int64_t ncol = h->ny * h->nx;
     CUDA_TRY(h, h->d_cells.reserve(ncol * (h->nz - 1) * sizeof(double4)));
+    CUDA_TRY(h, h->d_cells32.reserve(ncol * (h->nz - 1) * sizeof(float4)));
     k_pack_cells<<<grid_for(ncol * (h->nz - 1), 256, h->sm_count, 16), 256, 0, h->stream>>>(h->d_fields.as<float2>(), h->d_cells.as<double4>(),
-                                                                                            ncol, (int)h->nz);
+                                                                                            h->d_cells32.as<float4>(), ncol, (int)h->nz);
     h->launches++;
     const int64_t nlerp = (h->ny - 1) * (h->nx - 1) * (h->nz - 1) * 4;
     CUDA_TRY(h, h->d_lerp.reserve(nlerp * sizeof(double4)));
@@ -1453,6 +1464,8 @@ RDR_API int rdr_sample(rdr_handle_t h, const void *pts, int64_t n, void *out_wet
     const CubeView c = make_view(h);
     if (semantics == RDR_SEM_SCIPY && (reinterpret_cast<uintptr_t>(dpts) & 15) == 0) {
         const bool uni = c.ay.uniform && c.ax.uniform;
+        const char *noexact = getenv("RDR_K2_NO_EXACT_UNIFORM");
+        const bool exact_uni = c.ay.exact_uniform && c.ax.exact_uniform && !(noexact && atoi(noexact) != 0);
         const char *ppt_env = getenv("RDR_K2_PPT");
         const int ppt = ppt_env ? atoi(ppt_env) : 2;
 #define RDR_LAUNCH_K2(T, M, P)                                                                                                   \
@@ -1474,9 +1487,9 @@ RDR_API int rdr_sample(rdr_handle_t h, const void *pts, int64_t n, void *out_wet
         else RDR_LAUNCH_K2(T, M, 2);               \
     } while (0)
         if (dtype == RDR_F64) {
-            if (uni) RDR_LAUNCH_K2_P(double, GUESS_UNIFORM); else RDR_LAUNCH_K2_P(double, GUESS_BINS);
+            if (exact_uni) RDR_LAUNCH_K2_P(double, GUESS_EXACT_UNIFORM); else if (uni) RDR_LAUNCH_K2_P(double, GUESS_UNIFORM); else RDR_LAUNCH_K2_P(double, GUESS_BINS);
         } else {
-            if (uni) RDR_LAUNCH_K2_P(float, GUESS_UNIFORM); else RDR_LAUNCH_K2_P(float, GUESS_BINS);
+            if (exact_uni) RDR_LAUNCH_K2_P(float, GUESS_EXACT_UNIFORM); else if (uni) RDR_LAUNCH_K2_P(float, GUESS_UNIFORM); else RDR_LAUNCH_K2_P(float, GUESS_BINS);
         }
 #undef RDR_LAUNCH_K2_P
 #undef RDR_LAUNCH_K2

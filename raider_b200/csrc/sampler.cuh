@@ -29,9 +29,17 @@ struct Axis {
     double inv_d;              // (n - 1) / (g_last - g_first)
     double g_first, g_last;    // g[0], g[n-1]: bounds tests read these from the kernel-parameter bank
     double inv_bw;             // nbin / (g_last - g_first)
+    // "exact-uniform" axis: every node is bit-for-bit fma(i, d, g_first) with d = g[1] - g[0] (regular grids whose origin and
+    // spacing are short binary fractions: 0.25, 0.3125, 0.5, 0.625 degrees ...).  Then the nodes of an interval are recomputed
+    // in registers instead of loaded, every interval has the same width d, and only inv_dx = RN(1 / d) is needed.
+    int exact_uniform;
+    double d, inv_dx;
 };
 
 struct CubeView {
+    // cells32[(iy*nx + ix)*(nz-1) + iz] = the same z-pair record in fp32 (16 bytes): what the streaming sampler K2 loads -- its
+    // limiter is L1 wavefronts (bytes delivered per lane), and 8 F2F conversions on the XU pipe are cheaper than 64 more bytes
+    const float4 *cells32;
     // cells[(iy*nx + ix)*(nz-1) + iz] = {wet[iz], hydro[iz], wet[iz+1], hydro[iz+1]} of column (iy, ix), promoted to fp64 once
     // at staging (the promotion float -> double is exact, and it keeps 8 F2F conversions per sample off the quarter-rate XU
     // pipe): one 32-byte record feeds the z-pair of both fields
@@ -73,7 +81,38 @@ __device__ __forceinline__ double4 ld_cell(const double4 *p) {
 }
 
 // first guess of the interval of v when no hint is available
-enum { GUESS_HINT = 0, GUESS_UNIFORM = 1, GUESS_BINS = 2 };
+enum { GUESS_HINT = 0, GUESS_UNIFORM = 1, GUESS_BINS = 2, GUESS_EXACT_UNIFORM = 3 };
+
+constexpr double SAMPLER_FLOOR_MAGIC = 6755399441055744.0;  // 2^52 + 2^51
+
+// interval record {g[i], g[i+1], d, inv} of an exact-uniform axis, rebuilt in registers: floor((v - g0) / d) by directed rounding
+// against 2^52 + 2^51 (its low word is the integer, the difference is the same integer as a double -- no F2I / I2F)
+__device__ __forceinline__ double4 exact_uniform_record(const Axis &a, double v, int &i) {
+    const double u = (v - a.g_first) * a.inv_d;
+    const double s = __dadd_rd(u, SAMPLER_FLOOR_MAGIC);
+    const int raw = __double2loint(s);
+    i = min(max(raw, 0), a.n - 2);
+    const double fi = (raw == i) ? s - SAMPLER_FLOOR_MAGIC : (double)i;  // clamped (out of bounds / NaN): rare
+    const double lo = fma(fi, a.d, a.g_first);
+    return make_double4(lo, lo + a.d, a.d, a.inv_dx);
+}
+
+__device__ __forceinline__ void fix_interval_exact_uniform(const Axis &a, double v, int &i, double4 &r, bool &inb) {
+    if (v < r.x || v >= r.y) {
+        const int last = a.n - 2;
+        while (v < r.x && i > 0) {
+            --i;
+            r.x = fma((double)i, a.d, a.g_first);
+            r.y = r.x + a.d;
+        }
+        while (v >= r.y && i < last) {
+            ++i;
+            r.x = fma((double)i, a.d, a.g_first);
+            r.y = r.x + a.d;
+        }
+        inb &= (v >= r.x) && (v <= r.y);
+    }
+}
 
 template <int MODE>
 __device__ __forceinline__ int guess_interval(const Axis &a, double v, int hint) {
@@ -189,26 +228,49 @@ __device__ __forceinline__ void fix_interval(const Axis &a, double v, int &i, do
     }
 }
 
+__device__ __forceinline__ double4 ld_cell32(const float4 *p) {
+    const float4 a = __ldg(p);
+    return make_double4((double)a.x, (double)a.y, (double)a.z, (double)a.w);  // exact promotions
+}
+
 template <int NPT, int MXY, int MZ>
 __device__ __forceinline__ void sample_scipy_batch(const CubeView &c, const double (&y)[NPT], const double (&x)[NPT], const double (&z)[NPT],
                                                    double (&vw)[NPT], double (&vh)[NPT]) {
     SamplePrep s[NPT];
     double4 ry[NPT], rx[NPT], rz[NPT];
+    constexpr bool XY_EXACT = MXY == GUESS_EXACT_UNIFORM;
 #pragma unroll
     for (int p = 0; p < NPT; ++p) {
         s[p].iy = s[p].ix = s[p].iz = 0;
-        sample_prepare<MXY, MZ>(c, y[p], x[p], z[p], s[p]);
+        if (XY_EXACT) {
+            s[p].inb = true;
+            s[p].y = y[p];
+            s[p].x = x[p];
+            s[p].z = z[p];
+            ry[p] = exact_uniform_record(c.ay, y[p], s[p].iy);
+            rx[p] = exact_uniform_record(c.ax, x[p], s[p].ix);
+            s[p].iz = guess_interval<MZ>(c.az, z[p], 0);
+        } else {
+            sample_prepare<MXY, MZ>(c, y[p], x[p], z[p], s[p]);
+        }
     }
 #pragma unroll
     for (int p = 0; p < NPT; ++p) {
-        ry[p] = ld_cell(c.ay.cell + s[p].iy);
-        rx[p] = ld_cell(c.ax.cell + s[p].ix);
+        if (!XY_EXACT) {
+            ry[p] = ld_cell(c.ay.cell + s[p].iy);
+            rx[p] = ld_cell(c.ax.cell + s[p].ix);
+        }
         rz[p] = ld_cell(c.az.cell + s[p].iz);
     }
 #pragma unroll
     for (int p = 0; p < NPT; ++p) {
-        fix_interval(c.ay, s[p].y, s[p].iy, ry[p], s[p].inb);
-        fix_interval(c.ax, s[p].x, s[p].ix, rx[p], s[p].inb);
+        if (XY_EXACT) {
+            fix_interval_exact_uniform(c.ay, s[p].y, s[p].iy, ry[p], s[p].inb);
+            fix_interval_exact_uniform(c.ax, s[p].x, s[p].ix, rx[p], s[p].inb);
+        } else {
+            fix_interval(c.ay, s[p].y, s[p].iy, ry[p], s[p].inb);
+            fix_interval(c.ax, s[p].x, s[p].ix, rx[p], s[p].inb);
+        }
         fix_interval(c.az, s[p].z, s[p].iz, rz[p], s[p].inb);
     }
     const int nzc = c.az.n - 1;
@@ -216,11 +278,11 @@ __device__ __forceinline__ void sample_scipy_batch(const CubeView &c, const doub
     double4 c00[NPT], c01[NPT], c10[NPT], c11[NPT];
 #pragma unroll
     for (int p = 0; p < NPT; ++p) {
-        const double4 *q = c.cells + ((unsigned)s[p].iy * row + (unsigned)s[p].ix * (unsigned)nzc + (unsigned)s[p].iz);
-        c00[p] = ld_cell(q);
-        c01[p] = ld_cell(q + nzc);
-        c10[p] = ld_cell(q + row);
-        c11[p] = ld_cell(q + row + nzc);
+        const float4 *q = c.cells32 + ((unsigned)s[p].iy * row + (unsigned)s[p].ix * (unsigned)nzc + (unsigned)s[p].iz);
+        c00[p] = ld_cell32(q);
+        c01[p] = ld_cell32(q + nzc);
+        c10[p] = ld_cell32(q + row);
+        c11[p] = ld_cell32(q + row + nzc);
     }
 #pragma unroll
     for (int p = 0; p < NPT; ++p) {

@@ -481,3 +481,47 @@ def test_table_division_is_ieee_exact(gpu):
     assert gpu.rdr_selftest_div(200_000_000, 12345, C.byref(m1), C.byref(m2), 0) == 0
     print(f'division self-test over 2e8 pairs: 1-step mismatches {m1.value}, 2-step mismatches {m2.value}')
     assert m1.value == 0 and m2.value == 0
+
+
+def test_sampler_stream_variants_bit_exact_vs_scipy_live(gpu):
+    """Every interval-lookup variant of the streaming sampler K2 against the installed scipy (the code the reference calls,
+    delayFcns.py:55-56): exact-uniform axes (nodes rebuilt in registers), uniform axes (direct index + node table), irregular
+    axes (bin table); node hits, the inclusive last node, out-of-bounds and NaN coordinates; host and device point streams."""
+    import torch
+    from scipy.interpolate import RegularGridInterpolator as RGI
+    from raider_b200.engine import DeviceCube
+    rng = np.random.default_rng(5)
+    zs = np.concatenate([[-500.0, -120.0, 0.0, 35.5], 100.0 + 48000.0 * (np.arange(1, 30) / 29.0) ** 2])
+    axes = {
+        'exact-uniform 0.25 deg': (31.5 + 0.25 * np.arange(23), -121.25 + 0.3125 * np.arange(19)),
+        'uniform, not exact': (np.linspace(31.5, 37.1, 23), -121.2 + 0.1 * np.arange(19)),
+        'irregular': (np.sort(rng.uniform(31.5, 37.0, 23)), np.sort(rng.uniform(-121.0, -115.0, 19))),
+    }
+    for name, (ys, xs) in axes.items():
+        wet = rng.normal(50.0, 20.0, (zs.size, ys.size, xs.size)).astype(np.float32)
+        hydro = rng.normal(250.0, 30.0, wet.shape).astype(np.float32)
+        n = 40000 + 77  # ragged tail after the 256-point tiles
+        pts = np.stack([rng.uniform(ys[0] - 0.2, ys[-1] + 0.2, n), rng.uniform(xs[0] - 0.2, xs[-1] + 0.2, n),
+                        rng.uniform(zs[0] - 50.0, zs[-1] + 50.0, n)], axis=-1)
+        k = np.arange(0, 6000, 3)  # exact node hits on every axis (first and last node included)
+        pts[k, 0] = ys[rng.integers(0, ys.size, k.size)]
+        pts[k + 1, 1] = xs[rng.integers(0, xs.size, k.size)]
+        pts[k + 2, 2] = zs[rng.integers(0, zs.size, k.size)]
+        pts[6000] = (ys[-1], xs[-1], zs[-1])
+        pts[6001] = (ys[0], xs[0], zs[0])
+        pts[6002] = (np.nan, xs[3], zs[3])
+        pts[6003] = (ys[3], np.nan, zs[3])
+        pts[6004] = (ys[3], xs[3], np.nan)
+        pts[6005] = (np.nextafter(ys[-1], np.inf), xs[3], zs[3])
+        pts[6006] = (ys[3], np.nextafter(xs[0], -np.inf), zs[3])
+        want_w = RGI((ys, xs, zs), wet.transpose(1, 2, 0), method='linear', bounds_error=False, fill_value=np.nan)(pts)
+        want_h = RGI((ys, xs, zs), hydro.transpose(1, 2, 0), method='linear', bounds_error=False, fill_value=np.nan)(pts)
+        cube = DeviceCube(ys, xs, zs, wet, hydro)
+        got_w, got_h = cube.sample(pts)  # host stream (staged), fp64
+        assert np.array_equal(got_w, want_w, equal_nan=True), name
+        assert np.array_equal(got_h, want_h, equal_nan=True), name
+        assert np.isnan(want_w).sum() > 100 and np.isfinite(want_w).sum() > 20000
+        dw, dh = cube.sample(torch.from_numpy(pts).cuda())  # device stream
+        torch.cuda.synchronize()
+        assert np.array_equal(dw.cpu().numpy(), want_w, equal_nan=True), name
+        assert np.array_equal(dh.cpu().numpy(), want_h, equal_nan=True), name
