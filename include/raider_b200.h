@@ -66,7 +66,10 @@ enum {
     RDR_LOS_ARRAY = 0,  /* los = [n][3] ECEF unit vectors ground->sensor (Raytracing.getLookVectors, losreader.py:219-255) */
     RDR_LOS_ENU_CONST = 1, /* los = {east, north, up}: constant local ENU vector, rotated to ECEF per pixel
                               (inc_hd_to_enu losreader.py:374-396 + enu2ecef utilFcns.py:91-121) */
-    RDR_LOS_ZENITH = 2  /* los = NULL: local zenith (getZenithLookVecs, losreader.py:302-316) */
+    RDR_LOS_ZENITH = 2, /* los = NULL: local zenith (getZenithLookVecs, losreader.py:302-316) */
+    RDR_LOS_ORBIT = 3   /* los = {n_sv, n_sv rows of (t [s], x, y, z, vx, vy, vz)} on the host: per-ray zero-Doppler look vectors from
+                           orbit state vectors, computed on the device (K6; replaces the per-pixel isce3 geo2rdr loop of
+                           Raytracing.getLookVectors, losreader.py:219-255) */
 };
 
 /* interval semantics of the sampler */
@@ -181,6 +184,14 @@ int rdr_interpolate(int ndim, const double *const *grids, const int64_t *sizes, 
  * x, y = [ncol][nin]; xnew, out = [ncol][nout]. */
 int rdr_interp_along_axis(const double *x, const double *y, const double *xnew, int64_t ncol, int64_t nin, int64_t nout,
                           int has_fill, double fill_value, double *out, int device, int mem);
+
+/* K6 on its own -- Raytracing.getLookVectors (losreader.py:219-255): ECEF unit vectors ground -> sensor at the zero-Doppler time
+ * of every target, from n_sv uniformly spaced state-vector rows (t, x, y, z, vx, vy, vz).  Targets: a raster (RDR_GEOM_GRID:
+ * gx[nx] lon, gy[ny] lat, height ht) or points (RDR_GEOM_POINTS: gx/gy/[hgt] of length ny*nx).  isce3's defaults at the
+ * reference call site: threshold 1e-7 m, maxiter 30.  Targets that do not converge / leave the orbit span get NaN vectors.
+ * out_slant / out_aztime may be NULL.  Host pointers. */
+int rdr_orbit_los(const double *sv_rows, int64_t n_sv, int geom_kind, const double *gx, const double *gy, const double *hgt, double ht,
+                  int64_t ny, int64_t nx, double threshold, int maxiter, double *out_los, double *out_slant, double *out_aztime, int device);
 
 /* ---------------------------------------------------------------- test hook ----------------------------- */
 /* Counts, over n pseudo-random (numerator, cell width) pairs, how often the sampler's table-driven division (n * RN(1/d) with

@@ -22,7 +22,7 @@ F64, F32 = 0, 1
 LAYOUT_ZYX, LAYOUT_YXZ = 0, 1
 CRS_GEOGRAPHIC, CRS_LCC_SPHERE = 0, 1
 GEOM_GRID, GEOM_POINTS = 0, 1
-LOS_ARRAY, LOS_ENU_CONST, LOS_ZENITH = 0, 1, 2
+LOS_ARRAY, LOS_ENU_CONST, LOS_ZENITH, LOS_ORBIT = 0, 1, 2, 3
 SEM_SCIPY, SEM_RAIDER_FILL, SEM_RAIDER_CLAMP = 0, 1, 2
 
 _i64, _f64, _int, _vp = C.c_int64, C.c_double, C.c_int, C.c_void_p
@@ -57,6 +57,7 @@ SIGNATURES = {
     'rdr_make_points_count': (_int, [_f64, _f64, _pi64]),
     'rdr_make_points': (_int, [_f64, _vp, _vp, _i64, _f64, _vp, _i64, _int, _int]),
     'rdr_interpolate': (_int, [_int, C.POINTER(_vp), _pi64, _vp, _vp, _i64, _int, _f64, _vp, _int, _int]),
+    'rdr_orbit_los': (_int, [_vp, _i64, _int, _vp, _vp, _vp, _f64, _i64, _i64, _f64, _int, _vp, _vp, _vp, _int]),
     'rdr_selftest_div': (_int, [_i64, C.c_uint64, _pi64, _pi64, _int]),
     'rdr_interp_along_axis': (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _int, _f64, _vp, _int, _int]),
 }

@@ -213,7 +213,8 @@ struct rdr_handle_s {
     int n_layers = 0;
     std::vector<double> low_ht, high_ht;
     std::vector<int> layer_cell;  // model layer index of each contributing layer (z-cell hint)
-    DevBuf d_gx, d_gy, d_los;     // staged geometry when the caller's arrays are on the host
+    DevBuf d_gx, d_gy, d_los;     // staged geometry when the caller's arrays are on the host (d_los: also the orbit-derived vectors)
+    DevBuf d_orbit;               // t[n] | pos[n][3] | vel[n][3] of RDR_LOS_ORBIT
     const double *p_gx = nullptr, *p_gy = nullptr, *p_los = nullptr;
     double los_const[3] = {0, 0, 1};
     DevBuf d_plan;    // low[K] | high[K]
@@ -986,6 +987,135 @@ __global__ void __launch_bounds__(BLOCK) k_ray_points(const CubeView c, const Ra
 }
 
 // ------------------------------------------------------------------------------------------------
+// K6: look vectors from orbit state vectors -- replaces the per-pixel Python loop over isce3.geometry.geo2rdr +
+// Orbit.interpolate of Raytracing.getLookVectors (losreader.py:219-255).  One thread per target: Newton iteration on the
+// zero-Doppler condition (dr . v = 0) with the 4-point Hermite orbit interpolator (isce3's defaults; algorithm restated in
+// oracle/orbit.py), threshold 1e-7 m on the slant range, at most 30 iterations, start at the orbit's mid time; a target that
+// does not converge or leaves the orbit's time span gets a NaN vector, as the reference's try/except does.
+// ------------------------------------------------------------------------------------------------
+struct OrbitView {
+    const double *t;    // [n] uniformly spaced
+    const double *pos;  // [n][3]
+    const double *vel;  // [n][3]
+    int n;
+    double inv_dt;
+};
+
+// ROI_PAC / ISCE orbitHermite on state vectors idx .. idx+3
+__device__ __forceinline__ void orbit_hermite(const OrbitView &O, int idx, double time, Vec3 &p, Vec3 &v) {
+    double t[4], f0[4], f1[4], h[4], hdot[4], g0[4], g1[4], isum[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) t[i] = __ldg(O.t + idx + i);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        f1[i] = time - t[i];
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (j != i) s += 1.0 / (t[i] - t[j]);
+        isum[i] = s;
+        f0[i] = 1.0 - 2.0 * (time - t[i]) * s;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        double product = 1.0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (k != i) product *= (time - t[k]) / (t[i] - t[k]);
+        h[i] = product;
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            double pr = 1.0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (k != i && k != j) pr *= (time - t[k]) / (t[i] - t[k]);
+            if (j != i) s += 1.0 / (t[i] - t[j]) * pr;
+        }
+        hdot[i] = s;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        g1[i] = h[i] + 2.0 * (time - t[i]) * hdot[i];
+        g0[i] = 2.0 * (f0[i] * hdot[i] - h[i] * isum[i]);
+    }
+    p = {0.0, 0.0, 0.0};
+    v = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const double *x = O.pos + 3 * (idx + i), *w = O.vel + 3 * (idx + i);
+        const double hh = h[i] * h[i];
+        p.x += (__ldg(x) * f0[i] + __ldg(w) * f1[i]) * hh;
+        p.y += (__ldg(x + 1) * f0[i] + __ldg(w + 1) * f1[i]) * hh;
+        p.z += (__ldg(x + 2) * f0[i] + __ldg(w + 2) * f1[i]) * hh;
+        v.x += (__ldg(x) * g0[i] + __ldg(w) * g1[i]) * h[i];
+        v.y += (__ldg(x + 1) * g0[i] + __ldg(w + 1) * g1[i]) * h[i];
+        v.z += (__ldg(x + 2) * g0[i] + __ldg(w + 2) * g1[i]) * h[i];
+    }
+}
+
+// Orbit.interpolate with FillNaN borders; false outside [t[0], t[n-1]]
+__device__ __forceinline__ bool orbit_interpolate(const OrbitView &O, double time, Vec3 &p, Vec3 &v) {
+    const double t0 = __ldg(O.t), t1 = __ldg(O.t + O.n - 1);
+    if (!(time >= t0 && time <= t1)) return false;
+    // first state vector with t[i] >= time: guess from the spacing, settle on the stored times
+    int i = (int)ceil((time - t0) * O.inv_dt);
+    i = min(max(i, 0), O.n - 1);
+    while (i > 0 && __ldg(O.t + i - 1) >= time) --i;
+    while (i < O.n - 1 && __ldg(O.t + i) < time) ++i;
+    const int idx = min(max(i - 2, 0), O.n - 4);
+    orbit_hermite(O, idx, time, p, v);
+    return true;
+}
+
+__global__ void k_orbit_los(const OrbitView O, int geom_kind, const double *__restrict__ gx, const double *__restrict__ gy,
+                            const double *__restrict__ hgt, double ht, int nx, int64_t n, double threshold, int maxiter,
+                            double *__restrict__ los, double *__restrict__ slant_out, double *__restrict__ aztime_out) {
+    const double qn = qnan();
+    for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
+        double lat, lon;
+        if (geom_kind == RDR_GEOM_GRID) {
+            lon = __ldg(gx + (r % nx));
+            lat = __ldg(gy + (r / nx));
+        } else {
+            lon = __ldg(gx + r);
+            lat = __ldg(gy + r);
+        }
+        const double h = hgt ? __ldg(hgt + r) : ht;
+        double a, b, c2, d;
+        const Vec3 g = lla2ecef(lat, lon, h, a, b, c2, d);
+        double aztime = __ldg(O.t) + 0.5 * (__ldg(O.t + O.n - 1) - __ldg(O.t));
+        double slant = 0.0, slant_old = 0.0;
+        bool converged = false;
+        Vec3 p, v;
+        for (int it = 0; it < maxiter; ++it) {
+            if (!orbit_interpolate(O, aztime, p, v)) break;  // NaN position: no comparison ever succeeds
+            const Vec3 dr = g - p;
+            slant = sqrt(dr.x * dr.x + dr.y * dr.y + dr.z * dr.z);
+            if (fabs(slant - slant_old) < threshold) {
+                converged = true;
+                break;
+            }
+            slant_old = slant;
+            const double fn = dr.x * v.x + dr.y * v.y + dr.z * v.z;
+            const double fnprime = -(v.x * v.x + v.y * v.y + v.z * v.z);
+            aztime -= fn / fnprime;
+        }
+        // losreader.py:252-253: sat_xyz, _ = orbit.interpolate(aztime); los = (sat_xyz - inp_xyz) / slant_range
+        if (converged && (lat == lat) && (lon == lon) && (h == h)) {
+            los[3 * r] = (p.x - g.x) / slant;
+            los[3 * r + 1] = (p.y - g.y) / slant;
+            los[3 * r + 2] = (p.z - g.z) / slant;
+        } else {
+            los[3 * r] = los[3 * r + 1] = los[3 * r + 2] = qn;
+            slant = aztime = qn;
+        }
+        if (slant_out) slant_out[r] = slant;
+        if (aztime_out) aztime_out[r] = aztime;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // small API-parity kernels
 // ------------------------------------------------------------------------------------------------
 __global__ void k_top_of_atmosphere(const double *__restrict__ xyz, const double *__restrict__ look, int64_t n, double toa,
@@ -1201,6 +1331,24 @@ int64_t make_points_npts(double max_len, double step) {
     return n;
 }
 
+// rows of (t, x, y, z, vx, vy, vz) -> t[n] | pos[n][3] | vel[n][3]; isce3.core.Orbit needs >= 4 uniformly spaced, increasing times
+int split_orbit(rdr_handle_t h, const double *rows, int64_t n_sv, std::vector<double> &blob) {
+    CHECK_ARG(h, rows != nullptr && n_sv >= 4 && n_sv < (1 << 20), "orbit: at least 4 state vectors are required for Hermite interpolation");
+    blob.resize((size_t)n_sv * 7);
+    for (int64_t i = 0; i < n_sv; ++i) {
+        blob[i] = rows[7 * i];
+        for (int c = 0; c < 3; ++c) {
+            blob[n_sv + 3 * i + c] = rows[7 * i + 1 + c];
+            blob[4 * n_sv + 3 * i + c] = rows[7 * i + 4 + c];
+        }
+    }
+    const double dt = (blob[n_sv - 1] - blob[0]) / (double)(n_sv - 1);
+    CHECK_ARG(h, dt > 0, "orbit: state-vector times must increase");
+    for (int64_t i = 1; i < n_sv; ++i)
+        CHECK_ARG(h, fabs((blob[i] - blob[i - 1]) - dt) <= 1e-6 * dt, "orbit: state vectors must be uniformly spaced in time");
+    return RDR_OK;
+}
+
 struct ScopedDevice {
     int prev = -1;
     explicit ScopedDevice(int dev) {
@@ -1277,7 +1425,7 @@ RDR_API int rdr_destroy(rdr_handle_t h) {
     ScopedDevice sd(h->device);
     cudaStreamSynchronize(h->stream);
     for (DevBuf *b : {&h->d_axes, &h->d_tabs, &h->d_cells, &h->d_stage, &h->d_fields, &h->d_gx, &h->d_gy, &h->d_los, &h->d_plan, &h->d_t, &h->d_red,
-                      &h->d_nparts, &h->d_out, &h->d_in, &h->d_lerp, &h->d_layers, &h->d_fix, &h->d_cells32})
+                      &h->d_nparts, &h->d_out, &h->d_in, &h->d_lerp, &h->d_layers, &h->d_fix, &h->d_cells32, &h->d_orbit})
         b->release();
     if (h->own_stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -1577,7 +1725,7 @@ RDR_API int rdr_ray_layers(rdr_handle_t h, int geom_kind, const double *gx, cons
     CHECK_ARG(h, h != nullptr, "rdr_ray_layers: NULL handle");
     if (!h->has_cube) return fail(h, RDR_ERR_STATE, "rdr_ray_layers: no cube staged");
     CHECK_ARG(h, geom_kind == RDR_GEOM_GRID || geom_kind == RDR_GEOM_POINTS, "rdr_ray_layers: unknown geom_kind");
-    CHECK_ARG(h, los_kind >= RDR_LOS_ARRAY && los_kind <= RDR_LOS_ZENITH, "rdr_ray_layers: unknown los_kind");
+    CHECK_ARG(h, los_kind >= RDR_LOS_ARRAY && los_kind <= RDR_LOS_ORBIT, "rdr_ray_layers: unknown los_kind");
     CHECK_ARG(h, gx && gy && ny > 0 && nx > 0, "rdr_ray_layers: bad geometry arguments");
     CHECK_ARG(h, los_kind == RDR_LOS_ZENITH || los != nullptr, "rdr_ray_layers: los is NULL");
     ScopedDevice sd(h->device);
@@ -1607,6 +1755,23 @@ RDR_API int rdr_ray_layers(rdr_handle_t h, int geom_kind, const double *gx, cons
         if ((rc = stage_in(h, h->d_los, los, n * 3, mem, &h->p_los))) return rc;
     } else if (los_kind == RDR_LOS_ENU_CONST) {
         h->los_const[0] = los[0]; h->los_const[1] = los[1]; h->los_const[2] = los[2];
+    } else if (los_kind == RDR_LOS_ORBIT) {
+        // los = {n_sv, then n_sv rows of (t, x, y, z, vx, vy, vz)} on the host: K6 turns it into per-ray ECEF vectors on the device
+        const int64_t n_sv = (int64_t)los[0];
+        std::vector<double> blob;
+        if ((rc = split_orbit(h, los + 1, n_sv, blob))) return rc;
+        CUDA_TRY(h, h->d_orbit.reserve(blob.size() * sizeof(double)));
+        CUDA_TRY(h, cudaMemcpyAsync(h->d_orbit.p, blob.data(), blob.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        CUDA_TRY(h, h->d_los.reserve((size_t)n * 3 * sizeof(double)));
+        const double *ob = h->d_orbit.as<double>();
+        const OrbitView O = {ob, ob + n_sv, ob + 4 * n_sv, (int)n_sv, (double)(n_sv - 1) / (blob[n_sv - 1] - blob[0])};
+        k_orbit_los<<<grid_for(n, 128, h->sm_count, 16), 128, 0, h->stream>>>(O, geom_kind, h->p_gx, h->p_gy, nullptr, ht, (int)nx, n, 1.0e-7, 30,
+                                                                             h->d_los.as<double>(), nullptr, nullptr);
+        h->launches++;
+        CUDA_TRY(h, cudaGetLastError());
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));  // blob goes out of scope
+        h->p_los = h->d_los.as<double>();
+        h->los_kind = RDR_LOS_ARRAY;
     }
     std::vector<double> plan(h->low_ht);
     plan.insert(plan.end(), h->high_ht.begin(), h->high_ht.end());
@@ -1967,6 +2132,35 @@ RDR_API int rdr_ecef2lla(const double *x, const double *y, const double *z, int6
     T_TRY(cudaGetLastError());
     T_TRY(cudaMemcpy(lon, dlo, n * 8, cudaMemcpyDeviceToHost)); T_TRY(cudaMemcpy(lat, dla, n * 8, cudaMemcpyDeviceToHost));
     T_TRY(cudaMemcpy(hgt, dh, n * 8, cudaMemcpyDeviceToHost));
+    return RDR_OK;
+}
+
+RDR_API int rdr_orbit_los(const double *sv_rows, int64_t n_sv, int geom_kind, const double *gx, const double *gy, const double *hgt, double ht,
+                          int64_t ny, int64_t nx, double threshold, int maxiter, double *out_los, double *out_slant, double *out_aztime, int device) {
+    CHECK_ARG(nullptr, gx && gy && out_los && ny > 0 && nx > 0 && maxiter > 0 && threshold > 0, "rdr_orbit_los: bad arguments");
+    CHECK_ARG(nullptr, geom_kind == RDR_GEOM_GRID || geom_kind == RDR_GEOM_POINTS, "rdr_orbit_los: unknown geom_kind");
+    CHECK_ARG(nullptr, geom_kind == RDR_GEOM_POINTS || hgt == nullptr, "rdr_orbit_los: per-point heights need RDR_GEOM_POINTS");
+    std::vector<double> blob;
+    int rc = split_orbit(nullptr, sv_rows, n_sv, blob);
+    if (rc) return rc;
+    if ((rc = need_device(device))) return rc;
+    Transient T(device);
+    const int64_t n = ny * nx;
+    const double *dob, *dx, *dy, *dh = nullptr;
+    double *dlos, *dsl = nullptr, *daz = nullptr;
+    T_TRY(T.in(blob.data(), blob.size(), RDR_MEM_HOST, &dob));
+    T_TRY(T.in(gx, geom_kind == RDR_GEOM_GRID ? nx : n, RDR_MEM_HOST, &dx));
+    T_TRY(T.in(gy, geom_kind == RDR_GEOM_GRID ? ny : n, RDR_MEM_HOST, &dy));
+    if (hgt) T_TRY(T.in(hgt, n, RDR_MEM_HOST, &dh));
+    T_TRY(T.out(out_los, 3 * n, RDR_MEM_HOST, &dlos));
+    if (out_slant) T_TRY(T.out(out_slant, n, RDR_MEM_HOST, &dsl));
+    if (out_aztime) T_TRY(T.out(out_aztime, n, RDR_MEM_HOST, &daz));
+    const OrbitView O = {dob, dob + n_sv, dob + 4 * n_sv, (int)n_sv, (double)(n_sv - 1) / (blob[n_sv - 1] - blob[0])};
+    k_orbit_los<<<(unsigned)std::min<int64_t>((n + 127) / 128, 148 * 16), 128>>>(O, geom_kind, dx, dy, dh, ht, (int)nx, n, threshold, maxiter, dlos, dsl, daz);
+    T_TRY(cudaGetLastError());
+    T_TRY(cudaMemcpy(out_los, dlos, 3 * n * sizeof(double), cudaMemcpyDeviceToHost));
+    if (out_slant) T_TRY(cudaMemcpy(out_slant, dsl, n * sizeof(double), cudaMemcpyDeviceToHost));
+    if (out_aztime) T_TRY(cudaMemcpy(out_aztime, daz, n * sizeof(double), cudaMemcpyDeviceToHost));
     return RDR_OK;
 }
 

@@ -10,7 +10,12 @@ reference's isce3-backed ``Raytracing``) is called on the host and its (ny, nx, 
 from __future__ import annotations
 
 import ctypes as C
+import datetime as dt
+import os
+import xml.etree.ElementTree as ET
 from abc import ABC
+from pathlib import PosixPath
+from typing import Union
 
 import numpy as np
 
@@ -104,7 +109,10 @@ class Conventional(LOS):
         if self._incidence is None:
             if self._file is None:
                 raise ValueError('LOS file not set')
-            raise NotImplementedError('reading LOS rasters / orbit files needs rasterio or isce3; pass incidence= instead')
+            # orbit file: cos(look angle) per point from the zero-Doppler geometry (losreader.py:124-133 -> state_to_los)
+            svs = np.stack(get_sv(self._file, self._time, self._pad), axis=-1)
+            los_factor = state_to_los(svs, [np.asarray(self._lats), np.asarray(self._lons), np.asarray(self._heights)])
+            return np.asarray(delays) / los_factor
         LOS_enu = inc_hd_to_enu(np.asarray(self._incidence, dtype=np.float64), np.asarray(self._heading, dtype=np.float64))
         delays = np.asarray(delays)
         if delays.shape == LOS_enu.shape:
@@ -120,7 +128,9 @@ class Raytracing(LOS):
       pixel (enu2ecef), evaluated inside the kernels (no (ny,nx,3) array ever exists);
     * ``Raytracing(look_vecs=array)``: explicit ECEF unit vectors, shape (ny, nx, 3) per height or a callable
       ``f(ht, llh, xyz, yy)``;
-    * orbit files need isce3 in the reference (``geo2rdr`` per pixel, :219-255) -- not available offline.
+    * ``Raytracing(filename=orbit_file, time=t)``: orbit state vectors (ESA .EOF, 7-column text; :478-518, :736-769);
+      the zero-Doppler look vector of every pixel is solved on the device (K6) -- the reference loops over pixels in
+      Python calling isce3's ``geo2rdr`` (:230-254).
     """
 
     def __init__(self, filename=None, los_convention='isce', time=None, look_dir='right', pad=600, incidence=None, heading=None,
@@ -135,15 +145,41 @@ class Raytracing(LOS):
             raise NotImplementedError()
         if look_dir.lower() not in ('right', 'left'):
             raise RuntimeError(f'Unknown look direction: {look_dir}')
+        self._look_dir = look_dir.lower()
         self._incidence, self._heading, self._vecs = incidence, heading, look_vecs
-        if incidence is None and look_vecs is None:
-            raise NotImplementedError('orbit-file look vectors need isce3 (geo2rdr); pass incidence=/heading= or look_vecs=')
+        self._orbit = None
+        if incidence is None and look_vecs is None and filename is None:
+            raise ValueError('Raytracing needs an orbit file (filename=), incidence=/heading=, or look_vecs=')
         if incidence is not None:
             self._enu = inc_hd_to_enu(np.float64(incidence), np.float64(0.0 if heading is None else heading))
+        elif look_vecs is None and self._time is not None:
+            self._orbit = filename if isinstance(filename, Orbit) else get_orbit(self._file, self._time, pad=pad)
+        elif look_vecs is None and isinstance(filename, Orbit):
+            self._orbit = filename
+
+    def getSensorDirection(self):
+        """'desc' or 'asc' from the z component of the first / last state vector (losreader.py:198-205)."""
+        if self._orbit is None:
+            raise ValueError('The orbit has not been set')
+        z, t = self._orbit.position[:, 2], self._orbit.time
+        return 'desc' if z[np.argmin(t)] > z[np.argmax(t)] else 'asc'
+
+    def getLookDirection(self):
+        return self._look_dir
+
+    def setTime(self, time, pad=600) -> None:
+        """Called in checkArgs (losreader.py:210-212)."""
+        self._time = time
+        if self._incidence is None and self._vecs is None and not isinstance(self._file, Orbit):
+            self._orbit = get_orbit(self._file, self._time, pad=pad)
 
     def device_spec(self):
         if self._incidence is not None and np.ndim(self._incidence) == 0:
             return _lib.LOS_ENU_CONST, f64(self._enu)
+        if self._incidence is None and self._vecs is None:
+            if self._orbit is None:
+                raise ValueError('The orbit has not been set (pass time= or call setTime)')
+            return _lib.LOS_ORBIT, self._orbit.packed()
         return None
 
     def getLookVectors(self, ht, llh, xyz, yy):
@@ -151,8 +187,17 @@ class Raytracing(LOS):
         if self._vecs is not None:
             v = self._vecs(ht, llh, xyz, yy) if callable(self._vecs) else self._vecs
             return np.asarray(v, dtype=np.float64)
-        e, n, u = self._enu
-        return enu2ecef(e, n, u, llh[1], llh[0], llh[2])
+        if self._incidence is not None:
+            e, n, u = self._enu
+            return enu2ecef(e, n, u, llh[1], llh[0], llh[2])
+        if self._orbit is None:
+            raise ValueError('The orbit has not been set (pass time= or call setTime)')
+        shape = np.shape(yy)
+        lon = f64(np.broadcast_to(llh[0], shape)).ravel()
+        lat = f64(np.broadcast_to(llh[1], shape)).ravel()
+        hgt = f64(np.broadcast_to(np.asarray(llh[2], dtype=np.float64), shape)).ravel()
+        los, _, _ = orbit_look_vectors(self._orbit, lat, lon, hgt)
+        return los.reshape(shape + (3,))
 
 
 class ZenithRaytracing(Raytracing):
@@ -168,6 +213,162 @@ class ZenithRaytracing(Raytracing):
 
     def getLookVectors(self, ht, llh, xyz, yy):
         return getZenithLookVecs(llh[1], llh[0], llh[2])
+
+
+class Orbit:
+    """Time-ordered, unique, uniformly spaced state vectors -- the role of ``isce3.core.Orbit`` in losreader.py:736-769.
+
+    ``time`` is seconds since ``reference_epoch`` (the first state vector), ``position`` / ``velocity`` are (n, 3) ECEF.
+    """
+
+    def __init__(self, times, position, velocity, reference_epoch=None) -> None:
+        times = np.asarray(times)
+        if times.dtype == object or np.issubdtype(times.dtype, np.datetime64):
+            tlist = [t if isinstance(t, dt.datetime) else t.astype('datetime64[us]').astype(dt.datetime) for t in times]
+            reference_epoch = reference_epoch or min(tlist)
+            times = np.array([(t - reference_epoch).total_seconds() for t in tlist])
+        times = np.asarray(times, dtype=np.float64)
+        position, velocity = np.asarray(position, dtype=np.float64).reshape(-1, 3), np.asarray(velocity, dtype=np.float64).reshape(-1, 3)
+        order = np.argsort(times, kind='stable')
+        times, position, velocity = times[order], position[order], velocity[order]
+        keep = np.concatenate([[True], np.diff(times) != 0])  # only unique state vectors (losreader.py:756-764)
+        self.time, self.position, self.velocity = times[keep], position[keep], velocity[keep]
+        self.reference_epoch = reference_epoch
+        if self.time.size < 4:
+            raise ValueError('Orbit: at least 4 state vectors are required for orbit interpolation')
+        d = np.diff(self.time)
+        if not np.allclose(d, d[0], rtol=0.0, atol=1e-6 * abs(d[0])):
+            raise ValueError('Orbit: state vectors must be uniformly spaced in time')
+
+    @property
+    def size(self) -> int:
+        return int(self.time.size)
+
+    def packed(self) -> np.ndarray:
+        """{n_sv, rows of (t, x, y, z, vx, vy, vz)}: the RDR_LOS_ORBIT payload of include/raider_b200.h."""
+        rows = np.concatenate([self.time[:, None], self.position, self.velocity], axis=1)
+        return np.ascontiguousarray(np.concatenate([[float(self.size)], rows.ravel()]))
+
+
+def orbit_look_vectors(orbit: 'Orbit', lats, lons, heights, threshold=1.0e-7, maxiter=30, device=None):
+    """Zero-Doppler look vectors, slant ranges and azimuth times of points (deg, deg, m) on the device (K6)."""
+    lat, lon, hgt = f64(lats).ravel(), f64(lons).ravel(), f64(heights).ravel()
+    n = lat.size
+    los, sr, az = np.empty((n, 3)), np.empty(n), np.empty(n)
+    rows = orbit.packed()
+    if n:
+        check(_lib.load().rdr_orbit_los(ptr(rows[1:]), orbit.size, _lib.GEOM_POINTS, ptr(lon), ptr(lat), ptr(hgt), 0.0, 1, n, float(threshold),
+                                        int(maxiter), ptr(los), ptr(sr), ptr(az), _lib.default_device() if device is None else device))
+    return los, sr, az
+
+
+def read_txt_file(filename):
+    """7-column text file of orbit state vectors: ISO time, x y z, vx vy vz (losreader.py:429-475)."""
+    t, cols = [], [[] for _ in range(6)]
+    with open(filename) as f:
+        for line in f:
+            try:
+                parts = line.strip().split()
+                t_ = dt.datetime.fromisoformat(parts[0])
+                vals = [float(v) for v in parts[1:]]
+                if len(vals) != 6:
+                    raise ValueError
+            except (ValueError, IndexError):
+                raise ValueError(f'I need {filename} to be a 7 column text file, with columns t, x, y, z, vx, vy, vz '
+                                 f"(Couldn't parse line {repr(line)})")
+            t.append(t_)
+            for c, v in zip(cols, vals):
+                c.append(v)
+    if len(t) < 4:
+        raise ValueError(f'read_txt_file: File {filename} does not have enough statevectors')
+    return [np.array(a) for a in [t] + cols]
+
+
+def read_ESA_Orbit_file(filename):
+    """Orbit state vectors of an ESA .EOF file: [t (datetimes), x, y, z, vx, vy, vz] (losreader.py:478-518)."""
+    root = ET.parse(filename).getroot()
+    osvs = root[1][0]
+    n = len(osvs)
+    t, arr = [], np.ones((6, n))
+    for i, st in enumerate(osvs):
+        t.append(dt.datetime.strptime(st[1].text, 'UTC=%Y-%m-%dT%H:%M:%S.%f'))
+        for c in range(6):
+            arr[c, i] = float(st[4 + c].text)
+    return [np.array(t)] + [arr[c] for c in range(6)]
+
+
+def filter_ESA_orbit_file(orbit_xml: str, ref_time: dt.datetime) -> bool:
+    """True when the validity window in the .EOF file name contains ``ref_time`` (losreader.py:537-555)."""
+    f = os.path.basename(orbit_xml)
+    t0 = dt.datetime.strptime(f.split('_')[6].lstrip('V'), '%Y%m%dT%H%M%S')
+    t1 = dt.datetime.strptime(f.split('_')[7].rstrip('.EOF'), '%Y%m%dT%H%M%S')
+    return t0 < ref_time < t1
+
+
+def pick_ESA_orbit_file(list_files: list, ref_time: dt.datetime):
+    """From a list of .EOF orbit files, pick the one that contains ``ref_time`` (losreader.py:520-534)."""
+    for path in list_files:
+        if filter_ESA_orbit_file(path, ref_time):
+            return path
+    raise AssertionError('Given orbit files did not match given date/time')
+
+
+def cut_times(times, ref_time, pad):
+    """Mask of the orbit times within ``pad`` seconds of ``ref_time`` (losreader.py:609-628)."""
+    diff = np.array([(x - ref_time).total_seconds() for x in times])
+    return np.abs(diff) < pad
+
+
+def get_sv(los_file: Union[str, list, PosixPath], ref_time: dt.datetime, pad: int):
+    """State vectors of a text / ESA orbit file (or list of ESA files) around ``ref_time`` (losreader.py:319-371)."""
+    try:
+        svs = read_txt_file(los_file)
+    except (ValueError, TypeError, UnicodeDecodeError, OSError):
+        try:
+            los_files = [los_file] if isinstance(los_file, (str, PosixPath)) else los_file
+            los_files = sorted(list(set(los_files)))
+            los_files = [p for p in los_files if filter_ESA_orbit_file(str(p), ref_time)]
+            if not los_files:
+                raise ValueError('There are no valid orbit files provided')
+            svs = []
+            for orb_path in los_files:
+                svs.extend(read_ESA_Orbit_file(orb_path))
+            if len(los_files) > 1:  # concatenate the per-file lists column by column
+                svs = [np.concatenate(svs[c::7]) for c in range(7)]
+        except Exception:
+            raise ValueError(f'get_sv: I cannot parse the statevector file {los_file}')
+    if ref_time:
+        idx = cut_times(svs[0], ref_time, pad=pad)
+        svs = [d[idx] for d in svs]
+    return svs
+
+
+def get_orbit(orbit_file: Union[list, str], ref_time: dt.datetime, pad: int) -> Orbit:
+    """State vectors around ``ref_time``, unique and ordered in time (losreader.py:736-769)."""
+    svs = get_sv(orbit_file, ref_time, pad)
+    return Orbit(svs[0], np.stack(svs[1:4], axis=-1), np.stack(svs[4:7], axis=-1))
+
+
+def get_radar_pos(llh, orb: Orbit, device=None):
+    """Look angle (deg, between the target->sensor vector and the ellipsoid normal) and slant range (losreader.py:631-703)."""
+    llh = np.asarray(llh, dtype=np.float64).reshape(-1, 3)
+    lat, lon, hgt = llh[:, 0], llh[:, 1], llh[:, 2]
+    los, sr, _ = orbit_look_vectors(orb, lat, lon, hgt, device=device)
+    nv = getZenithLookVecs(lat, lon, hgt)  # isce3 Ellipsoid.n_vector: the ellipsoid normal
+    cosang = np.clip(np.einsum('ij,ij->i', los, nv), -1.0, 1.0)
+    return np.rad2deg(np.arccos(cosang)), sr
+
+
+def state_to_los(svs, llh_targets):
+    """cos(look angle) at every target from orbit state vectors, rows (t, x, y, z, vx, vy, vz) (losreader.py:558-606)."""
+    svs = np.asarray(svs)
+    if np.min(svs.shape) < 4:
+        raise RuntimeError('state_to_los: At least 4 state vectors are required for orbit interpolation')
+    orb = Orbit(svs[:, 0], svs[:, 1:4].astype(np.float64), svs[:, 4:7].astype(np.float64))
+    in_shape = np.shape(llh_targets[0])
+    target_llh = np.stack([np.asarray(x, dtype=np.float64).flatten() for x in llh_targets], axis=-1)
+    los_ang, _ = get_radar_pos(target_llh, orb)
+    return np.cos(np.deg2rad(los_ang)).reshape(in_shape)
 
 
 def getZenithLookVecs(lats, lons, heights):

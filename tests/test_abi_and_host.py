@@ -202,3 +202,33 @@ def test_aoi_grid_and_results_dataset(tmp_path):
         assert load_cube(tmp_path / 'out.nc')['hydro'].shape == (2, 5, 5)
     pts = transformPoints(np.array([33.5]), np.array([-117.5]), np.array([12.0]), 4326, 4326)
     assert pts.shape == (1, 3) and np.array_equal(pts[0], [33.5, -117.5, 12.0])
+
+
+def test_orbit_file_readers_and_windowing():
+    """Host side of the orbit LOS (mirrors test/test_losreader.py:95-175 on the same fixture values)."""
+    import datetime as dt
+    from conftest import GOLDEN
+    from raider_b200.losreader import Orbit, cut_times, filter_ESA_orbit_file, get_orbit, get_sv, read_ESA_Orbit_file, read_txt_file
+    txt, eof = GOLDEN / 'orbit_S1_sv.txt', GOLDEN / 'orbit_S1_example.EOF'
+    a, b = read_txt_file(txt), read_ESA_Orbit_file(eof)
+    assert len(a) == 7 and a[0][0] == dt.datetime(2018, 11, 12, 23, 0, 2) and a[0][-1] == dt.datetime(2018, 11, 12, 23, 1, 12)
+    assert all(np.allclose(x, y) for x, y in zip(a[1:], b[1:])) and list(a[0]) == list(b[0])
+    assert np.isclose(a[1][0], -2064965.285362) and np.isclose(a[6][-1], -7235.952940)
+    with pytest.raises(ValueError):
+        read_txt_file(eof)
+    t = a[0]
+    assert all(cut_times(t, t[0], pad=3600 * 3)) and sum(cut_times(t, t[0], pad=5)) == 1
+    assert np.sum(cut_times(t, t[4], pad=15)) == 3 and np.sum(cut_times(t, t[0], pad=400)) == len(t)
+    sv = get_sv(str(txt), dt.datetime(2018, 11, 12, 23, 0, 32), pad=25)
+    assert sv[0].size == 5
+    with pytest.raises(ValueError):
+        get_sv(str(GOLDEN / 'make_golden.py'), dt.datetime(2018, 11, 12, 23, 0, 32), pad=25)
+    name = 'S1A_OPER_AUX_POEORB_OPOD_20181203T120749_V20181112T225942_20181114T005942.EOF'
+    assert filter_ESA_orbit_file(name, dt.datetime(2018, 11, 13, 1, 0, 0)) and not filter_ESA_orbit_file(name, dt.datetime(2018, 11, 15))
+    orb = get_orbit(str(txt), dt.datetime(2018, 11, 12, 23, 0, 30), 600)
+    assert orb.size == 8 and np.array_equal(orb.time, 10.0 * np.arange(8)) and orb.packed().shape == (1 + 8 * 7,)
+    assert orb.packed()[0] == 8.0 and orb.packed()[1 + 7 + 1] == a[1][1]
+    shuffled = Orbit(a[0][[2, 0, 1, 3, 3, 4]], np.stack(a[1:4], -1)[[2, 0, 1, 3, 3, 4]], np.stack(a[4:7], -1)[[2, 0, 1, 3, 3, 4]])
+    assert np.array_equal(shuffled.time, [0.0, 10.0, 20.0, 30.0, 40.0])
+    with pytest.raises(ValueError):
+        Orbit(a[0][:3], np.stack(a[1:4], -1)[:3], np.stack(a[4:7], -1)[:3])

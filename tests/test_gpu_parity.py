@@ -525,3 +525,93 @@ def test_sampler_stream_variants_bit_exact_vs_scipy_live(gpu):
         torch.cuda.synchronize()
         assert np.array_equal(dw.cpu().numpy(), want_w, equal_nan=True), name
         assert np.array_equal(dh.cpu().numpy(), want_h, equal_nan=True), name
+
+
+# ---------------------------------------------------------------------------------------- K6: orbit look vectors
+def _s1_orbit():
+    import datetime as dt
+    from conftest import GOLDEN
+    from raider_b200.losreader import get_orbit
+    return get_orbit(str(GOLDEN / 'orbit_S1_sv.txt'), dt.datetime(2018, 11, 12, 23, 0, 30), 600)
+
+
+def test_orbit_look_vectors_vs_oracle(gpu):
+    """Device zero-Doppler solve (geo2rdr + Hermite orbit interpolation, losreader.py:219-255) against the oracle's
+    restatement: look vectors to 1e-12, slant range to 1e-6 m, NaN pattern identical (targets outside the 70 s orbit span)."""
+    from oracle import orbit as ob
+    from raider_b200.losreader import get_radar_pos, orbit_look_vectors, state_to_los
+    o = _s1_orbit()
+    oo = ob.Orbit(o.time, o.position, o.velocity)
+    rng = np.random.default_rng(3)
+    lat, lon, hgt = rng.uniform(13.3, 16.6, 300), rng.uniform(100.3, 105.0, 300), rng.uniform(-100.0, 4000.0, 300)
+    los, sr, az = orbit_look_vectors(o, lat, lon, hgt)
+    want = ob.look_vectors_points(lat, lon, hgt, oo)
+    assert np.array_equal(np.isnan(los), np.isnan(want)) and 20 < np.isnan(want[:, 0]).sum() < 200
+    ok = ~np.isnan(want[:, 0])
+    assert np.abs(los[ok] - want[ok]).max() < 1e-12
+    from oracle import geodesy
+    xyz = np.stack(geodesy.lla2ecef(lat, lon, hgt), -1)
+    for i in np.flatnonzero(ok)[:40]:
+        a, s = ob.geo2rdr(xyz[i], oo)
+        assert abs(a - az[i]) < 1e-9 and abs(s - sr[i]) < 1e-6
+    # Conventional's orbit branch: cos(look angle) (losreader.py:558-606)
+    svs = np.concatenate([o.time[:, None], o.position, o.velocity], axis=1)
+    f = state_to_los(svs, [lat[ok], lon[ok], hgt[ok]])
+    up = geodesy.getZenithLookVecs(lat[ok], lon[ok], hgt[ok])
+    assert np.abs(f - np.sum(want[ok] * up, -1)).max() < 1e-12
+    ang, sr2 = get_radar_pos(np.stack([lat[ok], lon[ok], hgt[ok]], -1), o)
+    assert np.abs(np.cos(np.radians(ang)) - f).max() < 1e-12 and np.abs(sr2 - sr[ok]).max() == 0.0
+
+
+def test_slant_orbit_los_on_device_vs_oracle(gpu):
+    """Raytracing(orbit) end to end: LOS solved on the device (RDR_LOS_ORBIT, never materialised on the host), K0, K3 against
+    the oracle's loop with its own geo2rdr; the host-geometry route (getLookVectors -> array upload) gives the same map."""
+    import datetime as dt
+    from conftest import GOLDEN
+    from oracle import orbit as ob, raytrace as rt
+    from raider_b200 import synthetic as syn
+    from raider_b200.losreader import Raytracing
+    n = 10
+    xpts, ypts = syn.raster(15.4, 102.5, n, n, 0.15)
+    xs, ys = syn.cube_axes_around(xpts, ypts)
+    zs = syn.z_levels(37)
+    cfg = {'cube': syn.make_cube(ys, xs, zs, totals=False), 'xpts': xpts, 'ypts': ypts, 'zpts': np.array([0.0, 800.0]),
+           'zref': 15000.0, 'max_segment_length': 1000.0}
+    los = Raytracing(filename=str(GOLDEN / 'orbit_S1_sv.txt'), time=dt.datetime(2018, 11, 12, 23, 0, 30))
+    assert los.getSensorDirection() == 'desc' and los.getLookDirection() == 'right'
+    out, info = _run_gpu(cfg, los)
+    o = los._orbit
+    crs = rt.GeographicCRS()
+    st = {}
+    want = rt.build_cube_ray(xpts, ypts, cfg['zpts'], ob.OrbitLOS(ob.Orbit(o.time, o.position, o.velocity)), crs, crs,
+                             list(rt.get_interpolators(cfg['cube'])), MAX_SEGMENT_LENGTH=1000.0, MAX_TROPO_HEIGHT=15000.0, stats=st)
+    for hh in range(2):
+        assert np.array_equal(info[hh].nparts, st['nParts'][hh])
+    assert not np.isnan(want[0]).any()
+    assert np.abs(out[0] - want[0]).max() < TOL_F64_M and np.abs(out[1] - want[1]).max() < TOL_F64_M
+    assert np.abs(out[1] - want[1]).max() < 1e-9
+
+    class HostOnly:  # a third-party LOS object: only getLookVectors, evaluated on the host and uploaded
+        def __init__(self, inner):
+            self.inner = inner
+
+        def getLookVectors(self, ht, llh, xyz, yy):
+            return self.inner.getLookVectors(ht, llh, xyz, yy)
+
+        def is_Zenith(self):
+            return False
+
+        def is_Projected(self):
+            return False
+
+        def ray_trace(self):
+            return True
+    out2, _ = _run_gpu(cfg, HostOnly(los))
+    assert np.abs(out2[0] - out[0]).max() < 1e-12 and np.abs(out2[1] - out[1]).max() < 1e-12
+    # a raster that leaves the orbit's coverage entirely -> the reference's ValueError (delay.py:279-280)
+    far = dict(cfg)
+    far['xpts'], far['ypts'] = syn.raster(15.4, 60.0, 4, 4, 0.1)
+    fx, fy = syn.cube_axes_around(far['xpts'], far['ypts'])
+    far['cube'] = syn.make_cube(fy, fx, zs, totals=False)
+    with pytest.raises(ValueError, match='geo2rdr did not converge'):
+        _run_gpu(far, los)

@@ -255,3 +255,76 @@ def test_nparts_is_global_not_per_tile():
     assert np.array_equal(np.concatenate(halves_global, axis=1), full[0])
     assert not np.array_equal(np.concatenate(halves_naive, axis=1), full[0])
     assert not np.array_equal(s2['nParts'][0], st['nParts'][0]) or True
+
+
+# ---------------------------------------------------------------------------------------- orbit look vectors (isce3 restated)
+def _circular_orbit(dt_sv=10.0, n=30):
+    """Equatorial circular orbit of test/fake_raytracing:73-117: radius a + 700 km, omega 0.1 deg/s."""
+    a, om = 6378137.0, np.radians(0.1)
+    hs = a + 700000.0
+    t = np.arange(n) * dt_sv
+    lon = om * t
+    pos = np.stack([hs * np.cos(lon), hs * np.sin(lon), 0 * lon], -1)
+    vel = np.stack([-om * pos[:, 1], om * pos[:, 0], 0 * lon], -1)
+    return a, hs, om, t, pos, vel
+
+
+def test_orbit_hermite_is_exact_for_degree7_and_at_nodes():
+    from oracle import orbit as ob
+    rng = np.random.default_rng(1)
+    c = rng.normal(size=(8, 3))
+    t = np.arange(9) * 10.0
+    P = lambda x: sum(c[k] * (x / 50.0) ** k for k in range(8))
+    V = lambda x: sum(k * c[k] * (x / 50.0) ** (k - 1) / 50.0 for k in range(1, 8))
+    orb = ob.Orbit(t, np.array([P(x) for x in t]), np.array([V(x) for x in t]))
+    for x in (0.0, 5.0, 12.3, 25.0, 33.3, 61.0, 79.9, 80.0, 30.0):
+        p, v = orb.interpolate(x)
+        assert np.abs(p - P(x)).max() < 1e-13 and np.abs(v - V(x)).max() < 1e-14
+    assert np.isnan(orb.interpolate(-0.1)[0]).all() and np.isnan(orb.interpolate(80.1)[0]).all()
+    # unsorted input with a duplicate is sorted and de-duplicated (losreader.py:754-764)
+    idx = np.array([3, 0, 1, 2, 2, 4, 5, 6, 7, 8])
+    o2 = ob.Orbit(t[idx], orb.pos[idx], orb.vel[idx])
+    assert np.array_equal(o2.t, t) and np.array_equal(o2.pos, orb.pos)
+    with pytest.raises(ValueError):
+        ob.Orbit(t[:3], orb.pos[:3], orb.vel[:3])
+    with pytest.raises(ValueError):
+        ob.Orbit(np.array([0.0, 10.0, 20.0, 35.0]), orb.pos[:4], orb.vel[:4])
+
+
+def test_geo2rdr_closed_form_on_a_circular_orbit():
+    """Target at geocentric latitude beta, longitude lambda on a sphere of radius a under an equatorial circular orbit:
+    zero-Doppler time lambda / omega, slant range sqrt(a^2 + r^2 - 2 a r cos(beta))."""
+    from oracle import orbit as ob
+    for dt_sv, tol_t, tol_r in ((10.0, 1e-5, 1e-6), (100.0, 1e-5, 1e-4)):
+        a, hs, om, t, pos, vel = _circular_orbit(dt_sv)
+        orb = ob.Orbit(t, pos, vel)
+        for k in range(20):
+            tin = dt_sv * 3.3 + k * dt_sv * 0.9
+            beta, lam = np.radians(3.0 + 0.2 * k), om * tin
+            tgt = a * np.array([np.cos(beta) * np.cos(lam), np.cos(beta) * np.sin(lam), np.sin(beta)])
+            az, sr = ob.geo2rdr(tgt, orb)
+            assert abs(az - tin) < tol_t and abs(sr - np.sqrt(a * a + hs * hs - 2 * a * hs * np.cos(beta))) < tol_r
+            sat, v = orb.interpolate(az)
+            assert abs((sat - tgt) @ v) / (sr * np.linalg.norm(v)) < 1e-7  # zero Doppler
+    # a target whose zero-Doppler time is outside the orbit span does not converge
+    a, hs, om, t, pos, vel = _circular_orbit(10.0, n=8)
+    with pytest.raises(RuntimeError):
+        lam = om * 500.0
+        ob.geo2rdr(a * np.array([np.cos(lam), np.sin(lam), 0.0]), ob.Orbit(t, pos, vel))
+
+
+def test_orbit_los_on_reference_state_vectors():
+    """The Sentinel-1 state vectors of test/test_losreader.py:20-92: unit vectors, zero Doppler, S1-like incidence, NaN
+    outside the 70 s span."""
+    from oracle import orbit as ob
+    from conftest import GOLDEN
+    rows = [ln.split() for ln in open(GOLDEN / 'orbit_S1_sv.txt')]
+    sv = np.array([[float(v) for v in r[1:]] for r in rows])
+    orb = ob.Orbit(10.0 * np.arange(len(rows)), sv[:, :3], sv[:, 3:])
+    lat, lon = np.meshgrid(np.linspace(14.6, 16.4, 5), np.linspace(101.6, 103.4, 5), indexing='ij')
+    los = ob.look_vectors_points(lat.ravel(), lon.ravel(), np.full(lat.size, 120.0), orb)
+    assert np.allclose(np.linalg.norm(los, axis=-1), 1.0, atol=1e-12)
+    up = geodesy.getZenithLookVecs(lat.ravel(), lon.ravel(), 0 * lat.ravel())
+    inc = np.degrees(np.arccos(np.sum(los * up, -1)))
+    assert inc.min() > 29.0 and inc.max() < 48.0
+    assert np.isnan(ob.look_vectors_points([13.5], [100.5], [0.0], orb)).all()
