@@ -67,9 +67,11 @@ enum {
     RDR_LOS_ENU_CONST = 1, /* los = {east, north, up}: constant local ENU vector, rotated to ECEF per pixel
                               (inc_hd_to_enu losreader.py:374-396 + enu2ecef utilFcns.py:91-121) */
     RDR_LOS_ZENITH = 2, /* los = NULL: local zenith (getZenithLookVecs, losreader.py:302-316) */
-    RDR_LOS_ORBIT = 3   /* los = {n_sv, n_sv rows of (t [s], x, y, z, vx, vy, vz)} on the host: per-ray zero-Doppler look vectors from
+    RDR_LOS_ORBIT = 3,  /* los = {n_sv, n_sv rows of (t [s], x, y, z, vx, vy, vz)} on the host: per-ray zero-Doppler look vectors from
                            orbit state vectors, computed on the device (K6; replaces the per-pixel isce3 geo2rdr loop of
                            Raytracing.getLookVectors, losreader.py:219-255) */
+    RDR_LOS_ENU_ARRAY = 4 /* los = [n][3] local ENU unit vectors, one per ray (inc_hd_to_enu per station, losreader.py:374-396), rotated
+                           to ECEF on the device (enu2ecef); point mode only (rdr_ray_stations) */
 };
 
 /* interval semantics of the sampler */
@@ -184,6 +186,14 @@ int rdr_interpolate(int ndim, const double *const *grids, const int64_t *sizes, 
  * x, y = [ncol][nin]; xnew, out = [ncol][nout]. */
 int rdr_interp_along_axis(const double *x, const double *y, const double *xnew, int64_t ncol, int64_t nin, int64_t nout,
                           int has_fill, double fill_value, double *out, int device, int mem);
+
+/* K5 -- station (point) mode, BASELINE config C4: n rays with their own longitude / latitude / height, each traced as the reference
+ * would trace a 1 x 1 raster at that height (_build_cube_ray(xpts=[lon], ypts=[lat], zpts=[h]), delay.py:219-326): the layer
+ * plan, nParts = ceil(own length / max_segment_length) + 1 and the `.all()` clamps are per ray.  One warp per ray, layers spread
+ * over the lanes, warp-shuffle reduction.  los_kind: RDR_LOS_ARRAY (ECEF [n][3]), RDR_LOS_ENU_ARRAY ([n][3]), RDR_LOS_ENU_CONST,
+ * RDR_LOS_ZENITH, RDR_LOS_ORBIT (host payload as above).  out_nsamples (may be NULL): sum of nParts of each ray. */
+int rdr_ray_stations(rdr_handle_t h, const double *lon, const double *lat, const double *hgt, int64_t n, int los_kind, const double *los,
+                     double zref, double max_segment_length, double *out_wet, double *out_hydro, int32_t *out_nsamples, int mem);
 
 /* K6 on its own -- Raytracing.getLookVectors (losreader.py:219-255): ECEF unit vectors ground -> sensor at the zero-Doppler time
  * of every target, from n_sv uniformly spaced state-vector rows (t, x, y, z, vx, vy, vz).  Targets: a raster (RDR_GEOM_GRID:

@@ -22,7 +22,7 @@ F64, F32 = 0, 1
 LAYOUT_ZYX, LAYOUT_YXZ = 0, 1
 CRS_GEOGRAPHIC, CRS_LCC_SPHERE = 0, 1
 GEOM_GRID, GEOM_POINTS = 0, 1
-LOS_ARRAY, LOS_ENU_CONST, LOS_ZENITH, LOS_ORBIT = 0, 1, 2, 3
+LOS_ARRAY, LOS_ENU_CONST, LOS_ZENITH, LOS_ORBIT, LOS_ENU_ARRAY = 0, 1, 2, 3, 4
 SEM_SCIPY, SEM_RAIDER_FILL, SEM_RAIDER_CLAMP = 0, 1, 2
 
 _i64, _f64, _int, _vp = C.c_int64, C.c_double, C.c_int, C.c_void_p
@@ -49,6 +49,7 @@ SIGNATURES = {
     'rdr_ray_plan': (_int, [_vp, _f64, _f64, _pi64, _vp, _vp]),
     'rdr_ray_layers': (_int, [_vp, _int, _vp, _vp, _i64, _i64, _int, _vp, _f64, _f64, _vp, _vp, _int]),
     'rdr_ray_integrate': (_int, [_vp, _vp, _f64, _int, _vp, _vp, _int, _int, _vp, _vp, _int]),
+    'rdr_ray_stations': (_int, [_vp, _vp, _vp, _vp, _i64, _int, _vp, _f64, _f64, _vp, _vp, _vp, _int]),
     'rdr_ray_points': (_int, [_vp, _vp, _f64, _i64, _i64, _vp, _int, _pi64, _int]),
     'rdr_top_of_atmosphere': (_int, [_vp, _vp, _i64, _f64, _vp, _vp, _int]),
     'rdr_build_ray': (_int, [_vp, _i64, _f64, _vp, _vp, _i64, _f64, _pi64, _vp, _vp, _vp, _int]),

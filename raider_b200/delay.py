@@ -266,6 +266,50 @@ def _build_cube_ray(
         return outputArrs
 
 
+def slant_delay_points(weather_model, lats, lons, hgts, los, zref=None, MAX_SEGMENT_LENGTH=1000.0, second_epoch=None, weights=None):
+    """Ray-traced slant delays at explicit points (GNSS stations), each with its own height: BASELINE config C4.
+
+    Every point is traced exactly as the reference traces a one-pixel raster at that height --
+    ``_build_cube_ray(xpts=[lon], ypts=[lat], zpts=[h], ...)`` (delay.py:219-326): own layer plan, own ``nParts``, own
+    clamps -- but all points go through one kernel (K5, a warp per ray).  ``weather_model``: file / cube dict / interpolator
+    pair; ``second_epoch`` + ``weights=(w0, w1)`` fuse the temporal interpolation of cli/raider.py:817-819 at staging.
+    ``los``: a Raytracing object (orbit / constant incidence / per-point incidence arrays), ``Zenith``-like ray tracing, or an
+    (n, 3) array of ECEF unit vectors.  Returns ``(wet, hydro)`` in metres.
+    """
+    lats, lons, hgts = (np.asarray(a, dtype=np.float64).ravel() for a in np.broadcast_arrays(lats, lons, hgts))
+    if isinstance(weather_model, (list, tuple)) and len(weather_model) == 2:
+        cube = as_device_cube(list(weather_model))
+    else:
+        ds_in = load_cube(weather_model)
+        cube = getInterpolators(ds_in, 'pointwise')[0].cube
+    if second_epoch is not None:
+        w0, w1 = weights
+        ds1 = load_cube(second_epoch)
+        cube.blend(ds1['wet'], ds1['hydro'], w0, w1)
+    toa = float(cube.grid[2].max() - 1)
+    zref = toa if zref is None else min(float(zref), toa)
+    if isinstance(los, np.ndarray):
+        kind, payload = _lib.LOS_ARRAY, np.ascontiguousarray(los, dtype=np.float64).reshape(-1, 3)
+    else:
+        spec = los_device_spec(los, 1, lats.size)
+        inc = getattr(los, '_incidence', None)
+        if spec is not None:
+            kind, payload = spec
+        elif inc is not None:  # per-point incidence / heading arrays -> ENU on the host (trivial), ECEF on the device
+            from .losreader import inc_hd_to_enu
+            hd = getattr(los, '_heading', None)
+            enu = inc_hd_to_enu(np.broadcast_to(np.asarray(inc, dtype=np.float64), lats.shape),
+                                np.broadcast_to(np.asarray(0.0 if hd is None else hd, dtype=np.float64), lats.shape))
+            kind, payload = _lib.LOS_ENU_ARRAY, np.ascontiguousarray(enu)
+        else:
+            xyz = np.stack(lla2ecef(lats, lons, hgts), axis=-1)
+            vec = np.asarray(los.getLookVectors(hgts, [lons[None], lats[None], hgts[None]], xyz[None], lats[None]), dtype=np.float64)
+            kind, payload = _lib.LOS_ARRAY, np.ascontiguousarray(vec.reshape(-1, 3))
+    wet, hydro, ns = cube.trace_stations(lons, lats, hgts, kind, payload, zref, MAX_SEGMENT_LENGTH)
+    cube.last_station_samples = ns
+    return wet, hydro
+
+
 class _Var:
     def __init__(self, dims, data, attrs=None) -> None:
         self.dims, self.data, self.attrs = tuple(dims), np.asarray(data), dict(attrs or {})

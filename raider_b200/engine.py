@@ -150,6 +150,28 @@ class DeviceCube:
                     _lib.MEM_DEVICE if dev else _lib.MEM_HOST)
         return out, total.value
 
+    def trace_stations(self, lon, lat, hgt, los_kind, los, zref, max_segment_length):
+        """K5: every point is its own 1 x 1 raster at its own height (BASELINE C4, GNSS stations).
+
+        Returns ``(wet[n], hydro[n], nsamples[n])``; numpy in -> numpy out, torch CUDA in -> torch CUDA out.
+        """
+        dev = is_device(lon)
+        if dev:
+            import torch
+            n = lon.numel()
+            wet = torch.empty(n, dtype=torch.float64, device=lon.device)
+            hydro = torch.empty_like(wet)
+            ns = torch.empty(n, dtype=torch.int32, device=lon.device)
+        else:
+            lon, lat, hgt = f64(lon).ravel(), f64(lat).ravel(), f64(hgt).ravel()
+            n = lon.size
+            wet, hydro, ns = np.empty(n), np.empty(n), np.empty(n, dtype=np.int32)
+            if los is not None:
+                los = f64(los)
+        self.h.call('rdr_ray_stations', ptr(lon), ptr(lat), ptr(hgt), int(n), int(los_kind), ptr(los), float(zref), float(max_segment_length),
+                    ptr(wet), ptr(hydro), ptr(ns), _lib.MEM_DEVICE if dev else _lib.MEM_HOST)
+        return wet, hydro, ns
+
     def trace(self, geom_kind, gx, gy, ny, nx, los_kind, los, ht, zref, max_segment_length, out_wet, out_hydro,
               reduce_max=None, reduce_sum=None) -> TraceInfo:
         """One output height: K0 -> global reduction of the per-layer maxima / predicates -> K3.

@@ -145,3 +145,48 @@ def config_c2(n: int = 2000, nz: int = 37, table: str | None = None, max_segment
         'cube': cube, 'xpts': xpts, 'ypts': ypts, 'zpts': np.array([0.0]), 'incidence': 30.0, 'heading': -168.0,
         'zref': float(zs[-1] - 1.0), 'max_segment_length': float(max_segment_length),
     }
+
+
+def config_c4(n: int = 10000, seed: int = 7):
+    """C4: GNSS point mode -- ``n`` stations uniform in a 4 x 4 degree box, heights U(0, 3000) m, per-station incidence
+    U(5, 75) deg and heading U(0, 360) deg, two weather epochs (seeds 20200130 / 20200131) blended 0.5 / 0.5."""
+    rng = np.random.default_rng(seed)
+    lat = rng.uniform(32.0, 36.0, n)
+    lon = rng.uniform(-120.0, -116.0, n)
+    hgt = rng.uniform(0.0, 3000.0, n)
+    inc = rng.uniform(5.0, 75.0, n)
+    head = rng.uniform(0.0, 360.0, n)
+    xs, ys = cube_axes_around(np.array([-120.0, -116.0]), np.array([32.0, 36.0]), pad_deg=3.0)
+    zs = z_levels(37)
+    c0 = make_cube(ys, xs, zs, seed=20200130, totals=False)
+    c1 = make_cube(ys, xs, zs, seed=20200131, totals=False)
+    # zref well below the model top: the fixed-point layer tops of 75-degree rays overshoot by metres (losreader.py:713-716)
+    return {'cube0': c0, 'cube1': c1, 'weights': (0.5, 0.5), 'lat': lat, 'lon': lon, 'hgt': hgt, 'incidence': inc, 'heading': head,
+            'zref': 15000.0, 'max_segment_length': 1000.0}
+
+
+def circular_orbit(lat0_deg: float, lon0_deg: float, heading_deg: float = -168.0, h_sat: float = 700000.0, omega_deg_s: float = 0.06,
+                   look_angle_deg: float = 33.0, n_sv: int = 41, dt: float = 10.0):
+    """State vectors of a circular orbit whose right-looking zero-Doppler footprint passes over (lat0, lon0) at mid time.
+
+    The construction of test/fake_raytracing:73-117 (circle of radius a + h_sat, constant angular rate) generalised to an
+    inclined great circle: the sub-satellite track heads along ``heading_deg`` (clockwise from north) and is offset to the
+    left of the target so that the target is seen at roughly ``look_angle_deg`` off nadir.  Returns rows (t, x, y, z, vx, vy, vz).
+    """
+    a = 6378137.0
+    r = a + h_sat
+    lat0, lon0, hd = np.radians(lat0_deg), np.radians(lon0_deg), np.radians(heading_deg)
+    up = np.array([np.cos(lat0) * np.cos(lon0), np.cos(lat0) * np.sin(lon0), np.sin(lat0)])
+    east = np.array([-np.sin(lon0), np.cos(lon0), 0.0])
+    north = np.cross(up, east)
+    along = np.sin(hd) * east + np.cos(hd) * north           # flight direction at the target's abeam point
+    right = np.cross(along, up)                              # right of the flight direction (pointing to the target side)
+    # sub-satellite point: ground range to the left of the target
+    gr = np.radians(np.degrees(np.arcsin(r / a * np.sin(np.radians(look_angle_deg)))) - look_angle_deg)
+    nadir = np.cos(gr) * up - np.sin(gr) * right
+    om = np.radians(omega_deg_s)
+    t = dt * np.arange(n_sv)
+    ang = om * (t - t[n_sv // 2])
+    pos = r * (np.cos(ang)[:, None] * nadir[None] + np.sin(ang)[:, None] * along[None])
+    vel = r * om * (-np.sin(ang)[:, None] * nadir[None] + np.cos(ang)[:, None] * along[None])
+    return np.concatenate([t[:, None], pos, vel], axis=1)

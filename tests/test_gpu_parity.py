@@ -548,17 +548,22 @@ def test_orbit_look_vectors_vs_oracle(gpu):
     want = ob.look_vectors_points(lat, lon, hgt, oo)
     assert np.array_equal(np.isnan(los), np.isnan(want)) and 20 < np.isnan(want[:, 0]).sum() < 200
     ok = ~np.isnan(want[:, 0])
-    assert np.abs(los[ok] - want[ok]).max() < 1e-12
+    # isce3's Newton drops the acceleration term, so it converges linearly (ratio ~ slant range / orbit radius) and stops, by
+    # the 1e-7 m rule on the slant range, ~4e-6 s short of the zero-Doppler time.  Two correct implementations can therefore
+    # differ by one iteration on a rounding knife edge: <= 4e-6 s * 7.6 km/s / 800 km = 4e-8 in the unit vector.  Everywhere else
+    # they agree to rounding.
+    err = np.abs(los[ok] - want[ok]).max(axis=-1)
+    assert err.max() < 2e-7 and np.mean(err < 1e-12) > 0.9
     from oracle import geodesy
     xyz = np.stack(geodesy.lla2ecef(lat, lon, hgt), -1)
     for i in np.flatnonzero(ok)[:40]:
         a, s = ob.geo2rdr(xyz[i], oo)
-        assert abs(a - az[i]) < 1e-9 and abs(s - sr[i]) < 1e-6
+        assert abs(a - az[i]) < 1e-5 and abs(s - sr[i]) < 1e-6
     # Conventional's orbit branch: cos(look angle) (losreader.py:558-606)
     svs = np.concatenate([o.time[:, None], o.position, o.velocity], axis=1)
     f = state_to_los(svs, [lat[ok], lon[ok], hgt[ok]])
     up = geodesy.getZenithLookVecs(lat[ok], lon[ok], hgt[ok])
-    assert np.abs(f - np.sum(want[ok] * up, -1)).max() < 1e-12
+    assert np.abs(f - np.sum(want[ok] * up, -1)).max() < 2e-7
     ang, sr2 = get_radar_pos(np.stack([lat[ok], lon[ok], hgt[ok]], -1), o)
     assert np.abs(np.cos(np.radians(ang)) - f).max() < 1e-12 and np.abs(sr2 - sr[ok]).max() == 0.0
 
@@ -589,7 +594,7 @@ def test_slant_orbit_los_on_device_vs_oracle(gpu):
         assert np.array_equal(info[hh].nparts, st['nParts'][hh])
     assert not np.isnan(want[0]).any()
     assert np.abs(out[0] - want[0]).max() < TOL_F64_M and np.abs(out[1] - want[1]).max() < TOL_F64_M
-    assert np.abs(out[1] - want[1]).max() < 1e-9
+    assert np.median(np.abs(out[1] - want[1])) < 1e-10  # knife-edge pixels of the LOS solve may reach ~1e-7 m (see K6 test)
 
     class HostOnly:  # a third-party LOS object: only getLookVectors, evaluated on the host and uploaded
         def __init__(self, inner):
@@ -615,3 +620,69 @@ def test_slant_orbit_los_on_device_vs_oracle(gpu):
     far['cube'] = syn.make_cube(fy, fx, zs, totals=False)
     with pytest.raises(ValueError, match='geo2rdr did not converge'):
         _run_gpu(far, los)
+
+
+# ---------------------------------------------------------------------------------------- K5: station (point) mode, C4
+def _oracle_stations(cube, lat, lon, hgt, vecs, zref, seg):
+    """Each station as the reference would do it: a 1 x 1 raster at the station's height through _build_cube_ray."""
+    from oracle import raytrace as rt
+    crs = rt.GeographicCRS()
+    ifs = list(rt.get_interpolators(cube))
+    wet, hydro, ns = np.zeros(lat.size), np.zeros(lat.size), np.zeros(lat.size, dtype=np.int64)
+    for i in range(lat.size):
+        st = {}
+        out = rt.build_cube_ray(lon[i:i + 1], lat[i:i + 1], hgt[i:i + 1], rt.ArrayLOS(vecs[i][None, None, :]), crs, crs, ifs,
+                                MAX_SEGMENT_LENGTH=seg, MAX_TROPO_HEIGHT=zref, stats=st)
+        wet[i], hydro[i], ns[i] = out[0][0, 0, 0], out[1][0, 0, 0], int(st['nParts'][0].sum())
+    return wet, hydro, ns
+
+
+def test_station_mode_c4_vs_oracle(gpu):
+    """BASELINE C4 at oracle-feasible size: per-station height / incidence / heading, two weather epochs blended at staging
+    (cli/raider.py:817-819), one warp per ray.  Per-ray sample counts bit-exact, delays within 1e-6 m."""
+    from oracle import geodesy
+    from raider_b200 import synthetic as syn
+    from raider_b200.delay import slant_delay_points
+    from raider_b200.delayFcns import getInterpolators
+    from raider_b200.losreader import Raytracing
+    cfg = syn.config_c4(n=160)
+    lat, lon, hgt = cfg['lat'], cfg['lon'], cfg['hgt']
+    los = Raytracing(incidence=cfg['incidence'], heading=cfg['heading'])
+    wet, hydro = slant_delay_points(cfg['cube0'], lat, lon, hgt, los, zref=cfg['zref'], MAX_SEGMENT_LENGTH=cfg['max_segment_length'],
+                                    second_epoch=cfg['cube1'], weights=cfg['weights'])
+    blended = syn.blend_cubes(cfg['cube0'], cfg['cube1'], *cfg['weights'])
+    enu = geodesy.inc_hd_to_enu(cfg['incidence'], cfg['heading'])
+    vecs = geodesy.enu2ecef(enu[:, 0], enu[:, 1], enu[:, 2], lat, lon, hgt)
+    w_ref, h_ref, ns_ref = _oracle_stations(blended, lat, lon, hgt, vecs, cfg['zref'], cfg['max_segment_length'])
+    assert not np.isnan(w_ref).any()
+    assert np.abs(wet - w_ref).max() < TOL_F64_M and np.abs(hydro - h_ref).max() < TOL_F64_M
+    assert np.abs(hydro - h_ref).max() < 1e-10
+    # the same stations through explicit ECEF vectors and with the cube pair already staged; integer contract: samples per ray
+    ifs = getInterpolators(blended)
+    w2, h2 = slant_delay_points(list(ifs), lat, lon, hgt, np.ascontiguousarray(vecs), zref=cfg['zref'], MAX_SEGMENT_LENGTH=cfg['max_segment_length'])
+    assert np.abs(w2 - wet).max() < 1e-12 and np.abs(h2 - hydro).max() < 1e-12
+    assert np.array_equal(ifs[0].cube.last_station_samples, ns_ref)
+
+
+def test_station_mode_edges(gpu):
+    """Stations above zref / outside the cube / below the first model level, zenith rays equal the raster path."""
+    from raider_b200 import _lib, synthetic as syn
+    from raider_b200.delay import _build_cube_ray, slant_delay_points
+    from raider_b200.delayFcns import getInterpolators
+    from raider_b200.losreader import ZenithRaytracing
+    cfg = syn.config_c2(n=6)
+    cfg['xpts'], cfg['ypts'] = syn.raster(34.0, -118.0, 6, 6, 0.2)
+    ifs = getInterpolators(cfg['cube'])
+    xx, yy = np.meshgrid(cfg['xpts'], cfg['ypts'])
+    ras = _build_cube_ray(cfg['xpts'], cfg['ypts'], np.array([250.0]), ZenithRaytracing(), 4326, 4326, list(ifs), MAX_TROPO_HEIGHT=15000.0)
+    w, h = slant_delay_points(list(ifs), yy.ravel(), xx.ravel(), np.full(xx.size, 250.0), ZenithRaytracing(), zref=15000.0)
+    # a vertical ray has the same length for every pixel up to ~1e-9 m, so global and per-ray nParts coincide
+    assert np.abs(w - ras[0][0].ravel()).max() < 1e-9 and np.abs(h - ras[1][0].ravel()).max() < 1e-9
+    lat = np.array([34.0, 34.0, 80.0, 34.0])
+    lon = np.array([-118.0, -118.0, -118.0, -118.0])
+    hgt = np.array([20000.0, -900.0, 100.0, 14999.5])  # above zref, below the first level (clamped like delay.py:306-307), outside, < 1 m
+    w, h = slant_delay_points(list(ifs), lat, lon, hgt, ZenithRaytracing(), zref=15000.0)
+    assert w[0] == 0.0 and h[0] == 0.0 and w[3] == 0.0       # no contributing layer: zeros stay (delay.py:276-277)
+    assert np.isfinite(w[1]) and w[1] > 0 and np.isnan(w[2])
+    n0 = ifs[0].cube.last_station_samples
+    assert n0[0] == 0 and n0[3] == 0 and n0[1] > 10
