@@ -7,6 +7,7 @@ number comes out of libraider_b200.so.  Reference structure it replaces: the per
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -31,6 +32,7 @@ class TraceInfo:
     oob_above: int = 0
     n_nan_rays: int = 0
     skipped: bool = False                 # no contributing layer at the last output height (delay.py:276-277)
+    tiles: int = 1                        # row tiles the raster was walked in (HBM budget of the t-buffer)
 
 
 class DeviceCube:
@@ -173,13 +175,68 @@ class DeviceCube:
         return wet, hydro, ns
 
     def trace(self, geom_kind, gx, gy, ny, nx, los_kind, los, ht, zref, max_segment_length, out_wet, out_hydro,
-              reduce_max=None, reduce_sum=None) -> TraceInfo:
+              reduce_max=None, reduce_sum=None, max_t_bytes=None) -> TraceInfo:
         """One output height: K0 -> global reduction of the per-layer maxima / predicates -> K3.
 
         ``reduce_max`` / ``reduce_sum`` are the cross-GPU hooks (numpy array in -> reduced numpy array out); they are
         what keeps ``nParts`` (delay.py:283) and the ``.all()`` clamp (delay.py:306-307) *global* when the raster is
         sharded over ranks.  Outputs are written (not accumulated) into out_wet/out_hydro.
+
+        The along-ray distances K0 hands to K3 take 8 (K+1) bytes per ray.  When that exceeds ``max_t_bytes`` (default
+        RAIDER_B200_T_BUDGET_GB, 64 GB of the 180 GB HBM3e) the raster is walked in row tiles: a first K0 pass over all tiles
+        for the global maxima and counters, then K0 + K3 per tile with those maxima -- the same mechanism that keeps
+        multi-GPU shards identical to the unsharded raster.
         """
+        if max_t_bytes is None:
+            max_t_bytes = float(os.environ.get('RAIDER_B200_T_BUDGET_GB', '64')) * 2**30
+        nz = self.grid[2].size
+        rows_per_tile = int(max(1, max_t_bytes // (8 * nz * max(1, int(nx)))))
+        if rows_per_tile >= ny:
+            return self._trace_block(geom_kind, gx, gy, ny, nx, los_kind, los, ht, zref, max_segment_length, out_wet, out_hydro,
+                                     reduce_max, reduce_sum)
+        tiles = [(r0, min(ny, r0 + rows_per_tile)) for r0 in range(0, ny, rows_per_tile)]
+
+        def block(r0, r1):
+            if geom_kind == _lib.GEOM_GRID:
+                return gx, gy[r0:r1], (los if los_kind != _lib.LOS_ARRAY else los[r0 * nx:r1 * nx])
+            return gx[r0 * nx:r1 * nx], gy[r0 * nx:r1 * nx], (los if los_kind != _lib.LOS_ARRAY else los[r0 * nx:r1 * nx])
+
+        # pass 1: maxima and counters of every tile
+        maxlen, counts = None, None
+        for r0, r1 in tiles:
+            bx, by, bl = block(r0, r1)
+            m, c = self.ray_layers(geom_kind, bx, by, r1 - r0, nx, los_kind, bl, ht, zref)
+            maxlen = m if maxlen is None else np.maximum(maxlen, m)
+            counts = c.copy() if counts is None else np.concatenate([counts[:3] + c[:3], c[3:]])
+        if reduce_max is not None:
+            maxlen = reduce_max(maxlen)
+            counts = np.concatenate([reduce_sum(counts[:3]), counts[3:]])
+        info = TraceInfo(ht=float(ht))
+        info.n_rays, info.n_nan_rays, info.n_layers = int(counts[0]), int(counts[1]), int(counts[3])
+        clamp = bool(counts[2] == counts[0])
+        ow = out_wet.reshape(ny, nx) if hasattr(out_wet, 'reshape') else out_wet
+        oh = out_hydro.reshape(ny, nx) if hasattr(out_hydro, 'reshape') else out_hydro
+        for attempt in range(2):
+            oob_tot = np.zeros(3, dtype=np.int64)
+            for r0, r1 in tiles:
+                bx, by, bl = block(r0, r1)
+                self.ray_layers(geom_kind, bx, by, r1 - r0, nx, los_kind, bl, ht, zref)
+                nparts, oob = self.ray_integrate(maxlen, max_segment_length, clamp, ow[r0:r1], oh[r0:r1])
+                oob_tot += oob
+            first_below = oob_tot[:1] if reduce_sum is None else reduce_sum(oob_tot[:1])
+            if bool(first_below[0] == counts[0]) == clamp:
+                break
+            clamp = not clamp  # K0's hint and K3's own evaluation disagree on a knife edge: K3 rules
+            info.reruns = 1
+        info.maxlen, info.nparts = maxlen, nparts
+        info.samples_per_ray = int(nparts.sum())
+        info.clamp_low_first = clamp
+        info.oob_below, info.oob_above = int(oob_tot[1]), int(oob_tot[2])
+        info.tiles = len(tiles)
+        return info
+
+    def _trace_block(self, geom_kind, gx, gy, ny, nx, los_kind, los, ht, zref, max_segment_length, out_wet, out_hydro,
+                     reduce_max=None, reduce_sum=None) -> TraceInfo:
         info = TraceInfo(ht=float(ht))
         maxlen, counts = self.ray_layers(geom_kind, gx, gy, ny, nx, los_kind, los, ht, zref)
         if reduce_max is not None:

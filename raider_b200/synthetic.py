@@ -190,3 +190,46 @@ def circular_orbit(lat0_deg: float, lon0_deg: float, heading_deg: float = -168.0
     pos = r * (np.cos(ang)[:, None] * nadir[None] + np.sin(ang)[:, None] * along[None])
     vel = r * om * (-np.sin(ang)[:, None] * nadir[None] + np.cos(ang)[:, None] * along[None])
     return np.concatenate([t[:, None], pos, vel], axis=1)
+
+
+def raster_xy(center_lat: float, center_lon: float, ny: int, nx: int, posting_y: float, posting_x: float):
+    """Like :func:`raster` with different postings along y and x."""
+    xpts = center_lon - 0.5 * (nx - 1) * posting_x + posting_x * np.arange(nx, dtype=np.float64)
+    ypts = center_lat + 0.5 * (ny - 1) * posting_y - posting_y * np.arange(ny, dtype=np.float64)
+    return xpts, ypts
+
+
+def config_c3(ny: int = 8000, nx: int = 10000, nz: int = 50, table: str | None = None):
+    """C3: per-pixel LOS from orbit state vectors over a Sentinel-1 IW-swath-sized raster (2.5 x 1.8 degrees, 8e7 points at
+    full size), HRRR-like cube: 3 km spherical-LCC grid (models/hrrr.py:255-260) padded 15 cells, NZ = 50 (or 'hrrr57')."""
+    from .crs import LambertConformalSphere
+    lcc = LambertConformalSphere()
+    xpts, ypts = raster_xy(36.0, -98.0, ny, nx, 1.8 / ny, 2.5 / nx)
+    cx, cy = lcc.from_ll(np.array([xpts[0], xpts[-1], xpts[0], xpts[-1], -98.0, -98.0]),
+                         np.array([ypts[0], ypts[0], ypts[-1], ypts[-1], ypts[0], ypts[-1]]))
+    pad = 15 * 3000.0
+    x0, x1 = np.floor((cx.min() - pad) / 3000.0) * 3000.0, np.ceil((cx.max() + pad) / 3000.0) * 3000.0
+    y0, y1 = np.floor((cy.min() - pad) / 3000.0) * 3000.0, np.ceil((cy.max() + pad) / 3000.0) * 3000.0
+    xs = x0 + 3000.0 * np.arange(int(round((x1 - x0) / 3000.0)) + 1)
+    ys = y0 + 3000.0 * np.arange(int(round((y1 - y0) / 3000.0)) + 1)
+    X, Y = np.meshgrid(xs, ys)
+    lon_n, lat_n, _ = lcc.to_llh(X, Y, np.zeros_like(X))
+    zs = z_levels(nz) if table is None else z_levels_table(table)
+    cube = make_cube(ys, xs, zs, lat_of=lat_n, lon_of=lon_n, seed=20200130, totals=False)
+    cube['crs'] = lcc
+    return {'cube': cube, 'crs': lcc, 'xpts': xpts, 'ypts': ypts, 'zpts': np.array([0.0]), 'orbit_rows': circular_orbit(36.0, -98.0),
+            'zref': float(zs[-1] - 1.0), 'max_segment_length': 1000.0}
+
+
+def config_c5(ny: int = 12000, nx: int = 20000, nz: int = 72, table: str | None = None):
+    """C5: NISAR-scale raster (2.4e8 pixels at full size, 0.0002 deg posting), GMAO-like cube 0.25 x 0.3125 degrees
+    (models/gmao.py:47-48), NZ = 72 (or 'ml145'), fixed 30 deg incidence as C2; row-block sharded over the GPUs."""
+    xpts, ypts = raster_xy(34.0, -118.0, ny, nx, 2.4 / ny, 4.0 / nx)
+    lo_x, hi_x = np.floor((xpts[0] - 2.0) / 0.3125) * 0.3125, np.ceil((xpts[-1] + 2.0) / 0.3125) * 0.3125
+    lo_y, hi_y = np.floor((ypts[-1] - 2.0) / 0.25) * 0.25, np.ceil((ypts[0] + 2.0) / 0.25) * 0.25
+    xs = lo_x + 0.3125 * np.arange(int(round((hi_x - lo_x) / 0.3125)) + 1)
+    ys = lo_y + 0.25 * np.arange(int(round((hi_y - lo_y) / 0.25)) + 1)
+    zs = z_levels(nz) if table is None else z_levels_table(table)
+    cube = make_cube(ys, xs, zs, seed=20200130, totals=False)
+    return {'cube': cube, 'xpts': xpts, 'ypts': ypts, 'zpts': np.array([0.0]), 'incidence': 30.0, 'heading': -168.0,
+            'zref': float(zs[-1] - 1.0), 'max_segment_length': 1000.0}

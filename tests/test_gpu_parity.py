@@ -686,3 +686,51 @@ def test_station_mode_edges(gpu):
     assert np.isfinite(w[1]) and w[1] > 0 and np.isnan(w[2])
     n0 = ifs[0].cube.last_station_samples
     assert n0[0] == 0 and n0[3] == 0 and n0[1] > 10
+
+
+# ---------------------------------------------------------------------------------------- C3 / C5 at oracle-feasible sizes, tiling
+def test_c3_lcc_cube_with_orbit_los_vs_oracle(gpu):
+    """BASELINE C3 shape: HRRR-like spherical-LCC cube (3 km, NZ = 50), geographic raster, per-pixel LOS from a synthetic
+    circular orbit solved on the device; against the oracle's loop (its own LCC forward + geo2rdr)."""
+    from oracle import orbit as ob, raytrace as rt
+    from raider_b200 import synthetic as syn
+    from raider_b200.delay import _build_cube_ray
+    from raider_b200.delayFcns import getInterpolators
+    from raider_b200.losreader import Orbit, Raytracing
+    cfg = syn.config_c3(ny=9, nx=11)
+    rows = cfg['orbit_rows']
+    los = Raytracing(filename=Orbit(rows[:, 0], rows[:, 1:4], rows[:, 4:7]))
+    ifs = getInterpolators(cfg['cube'])
+    out = _build_cube_ray(cfg['xpts'], cfg['ypts'], cfg['zpts'], los, cfg['crs'], 4326, list(ifs), MAX_SEGMENT_LENGTH=cfg['max_segment_length'],
+                          MAX_TROPO_HEIGHT=cfg['zref'])
+    lcc = rt.LambertCRS()
+    assert np.allclose(lcc.params(), cfg['crs'].params(), rtol=1e-15)
+    st = {}
+    cube = {k: v for k, v in cfg['cube'].items() if k != 'crs'}
+    want = rt.build_cube_ray(cfg['xpts'], cfg['ypts'], cfg['zpts'], ob.OrbitLOS(ob.Orbit(rows[:, 0], rows[:, 1:4], rows[:, 4:7])), lcc,
+                             rt.GeographicCRS(), list(rt.get_interpolators(cube)), MAX_SEGMENT_LENGTH=cfg['max_segment_length'],
+                             MAX_TROPO_HEIGHT=cfg['zref'], stats=st)
+    assert np.array_equal(ifs[0].cube.last_info[0].nparts, st['nParts'][0])
+    assert not np.isnan(want[0]).any()
+    assert np.abs(out[0] - want[0]).max() < TOL_F64_M and np.abs(out[1] - want[1]).max() < TOL_F64_M
+
+
+def test_row_tiling_is_bit_identical(gpu, monkeypatch):
+    """HBM budget of the t-buffer: a raster walked in row tiles (global maxima first, then K0 + K3 per tile) gives the same
+    bits as the untiled raster -- the mechanism C5 relies on when 2.4e8 rays x 73 layers do not fit one GPU."""
+    from raider_b200 import synthetic as syn
+    from raider_b200.losreader import Raytracing
+    cfg = syn.config_c5(ny=61, nx=40)
+    los = Raytracing(incidence=30.0, heading=-168.0)
+    whole, info = _run_gpu(cfg, los)
+    assert info[0].tiles == 1 and info[0].n_layers == 71
+    monkeypatch.setenv('RAIDER_B200_T_BUDGET_GB', str(8 * 72 * 40 * 7 / 2**30))  # 7 rows per tile -> 9 tiles
+    tiled, info_t = _run_gpu(cfg, los)
+    assert info_t[0].tiles == 9 and np.array_equal(info_t[0].nparts, info[0].nparts)
+    assert np.array_equal(whole[0], tiled[0]) and np.array_equal(whole[1], tiled[1])
+    from oracle import raytrace as rt
+    crs = rt.GeographicCRS()
+    want = rt.build_cube_ray(cfg['xpts'], cfg['ypts'][:6], cfg['zpts'], rt.FixedIncidenceLOS(30.0, -168.0), crs, crs,
+                             list(rt.get_interpolators(cfg['cube'])), MAX_SEGMENT_LENGTH=cfg['max_segment_length'],
+                             MAX_TROPO_HEIGHT=cfg['zref'], layer_maxlen=[info[0].maxlen])
+    assert np.abs(tiled[0][0, :6] - want[0][0]).max() < TOL_F64_M and np.abs(tiled[1][0, :6] - want[1][0]).max() < TOL_F64_M
