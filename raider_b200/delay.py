@@ -190,6 +190,7 @@ def _build_cube_ray(
     outputArrs=None,
     MAX_SEGMENT_LENGTH=1000.0,
     MAX_TROPO_HEIGHT=_ZREF,
+    _out_device=None,
 ):
     """Iterate over interpolators and build a cube using raytracing (delay.py:219-326).
 
@@ -210,7 +211,11 @@ def _build_cube_ray(
         # np.zeros((nz, ny, nx)) in the reference (:248); here each slice is written straight from the device (0 + x == x),
         # so the arrays start uninitialised and only skipped slices are zero-filled
         output_created_here = True
-        outputArrs = [_lib.pinned_empty((zpts.size, ny, nx)) for mm in range(2)]   # page-locked: the kernel writes them directly
+        if _out_device is not None:   # raider_b200.dist: keep the (nz, ny, nx) maps in HBM for the all-gather
+            import torch
+            outputArrs = [torch.empty((zpts.size, ny, nx), dtype=torch.float64, device=_out_device) for mm in range(2)]
+        else:
+            outputArrs = [_lib.pinned_empty((zpts.size, ny, nx)) for mm in range(2)]   # page-locked: the kernel writes them directly
     else:
         wet = np.empty((ny, nx))
         hydro = np.empty((ny, nx))

@@ -61,6 +61,10 @@ class Comm:
         t = block if is_t else torch.as_tensor(np.ascontiguousarray(block))
         t = t.to(self.device)
         nx = t.shape[-1]
+        if int(ny) % self.world == 0:  # even blocks: one collective straight into the full map, no padding, no reassembly
+            full = torch.empty((int(ny), nx), dtype=t.dtype, device=self.device)
+            self.dist.all_gather_into_tensor(full, t.contiguous(), group=self.group)
+            return full if is_t else full.cpu().numpy()
         rows_max = -(-int(ny) // self.world)
         pad = torch.zeros((rows_max, nx), dtype=t.dtype, device=self.device)
         pad[: t.shape[0]] = t
@@ -94,13 +98,26 @@ def build_cube_ray_sharded(xpts, ypts, zpts, los, model_crs, pts_crs, interpolat
         raise ValueError(f'raster has {ypts.size} rows: too few to shard over {comm.world} ranks')
     zref = _ZREF if MAX_TROPO_HEIGHT is None else MAX_TROPO_HEIGHT
     if build_fn is None:
+        # device path: the row block stays in HBM, the all-gather runs on device tensors (NCCL over NVLink), and the full maps
+        # make one trip to page-locked host memory
+        import torch
+        from ._lib import pinned_empty
         prev = _delay._reduce_hooks
         _delay._reduce_hooks = (comm.reduce_max, comm.reduce_sum)
         try:
             local = _delay._build_cube_ray(xpts, ypts[r0:r1], zpts, los, model_crs, pts_crs, interpolators,
-                                           MAX_SEGMENT_LENGTH=MAX_SEGMENT_LENGTH, MAX_TROPO_HEIGHT=zref)
+                                           MAX_SEGMENT_LENGTH=MAX_SEGMENT_LENGTH, MAX_TROPO_HEIGHT=zref,
+                                           _out_device=torch.device('cuda', interpolators[0].cube.device))
         finally:
             _delay._reduce_hooks = prev
+        if not gather:
+            return [a.cpu().numpy() for a in local], (r0, r1)
+        out = [pinned_empty((zpts.size, ypts.size, np.size(xpts))) for _ in local]
+        for arr, dst in zip(local, out):
+            for hh in range(zpts.size):
+                torch.from_numpy(dst[hh]).copy_(comm.all_gather_rows(arr[hh], ypts.size), non_blocking=True)
+        torch.cuda.synchronize()
+        return out
     else:
         local = build_fn(xpts, ypts[r0:r1], zpts, los, model_crs, pts_crs, interpolators, MAX_SEGMENT_LENGTH=MAX_SEGMENT_LENGTH,
                          MAX_TROPO_HEIGHT=zref, reduce_max=comm.reduce_max, reduce_sum=comm.reduce_sum)
