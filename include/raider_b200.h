@@ -195,6 +195,16 @@ int rdr_interp_along_axis(const double *x, const double *y, const double *xnew, 
 int rdr_ray_stations(rdr_handle_t h, const double *lon, const double *lat, const double *hgt, int64_t n, int los_kind, const double *los,
                      double zref, double max_segment_length, double *out_wet, double *out_hydro, int32_t *out_nsamples, int mem);
 
+/* K7 -- the processing step that produces the cube (WeatherModel.load after load_weather, models/weatherModel.py:252-260):
+ * _find_e (specific humidity q, or relative humidity when hum_is_rh), _uniform_in_z (interpolate_along_axis x 3 onto `zlevels`,
+ * NaN fill, float32), _checkForNans (fillna3D), k2 e/T + k3 e/T^2 and k1 P/T, _adjust_grid (a level at zmin when zmin <
+ * zlevels[0]) and _getZTD.  Inputs: ncol columns of nl native levels, z fastest ((y, x, z) like the reference's arrays), heights
+ * ascending per column.  Outputs: [ncol][*nz_written] float32, z fastest (stage them with RDR_LAYOUT_YXZ); p/t/e outputs are
+ * optional (all three or none).  mem applies to the bulk arrays; zlevels is a host parameter vector. */
+int rdr_prepare_cube(int64_t ncol, int64_t nl, const double *zs, const double *p, const double *t, const double *hum, int hum_is_rh,
+                     const double *zlevels, int64_t nz_out, double k1, double k2, double k3, double zmin, float *wet, float *hydro,
+                     float *wet_total, float *hydro_total, float *p_out, float *t_out, float *e_out, int64_t *nz_written, int device, int mem);
+
 /* K6 on its own -- Raytracing.getLookVectors (losreader.py:219-255): ECEF unit vectors ground -> sensor at the zero-Doppler time
  * of every target, from n_sv uniformly spaced state-vector rows (t, x, y, z, vx, vy, vz).  Targets: a raster (RDR_GEOM_GRID:
  * gx[nx] lon, gy[ny] lat, height ht) or points (RDR_GEOM_POINTS: gx/gy/[hgt] of length ny*nx).  isce3's defaults at the

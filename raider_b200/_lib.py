@@ -58,6 +58,8 @@ SIGNATURES = {
     'rdr_make_points_count': (_int, [_f64, _f64, _pi64]),
     'rdr_make_points': (_int, [_f64, _vp, _vp, _i64, _f64, _vp, _i64, _int, _int]),
     'rdr_interpolate': (_int, [_int, C.POINTER(_vp), _pi64, _vp, _vp, _i64, _int, _f64, _vp, _int, _int]),
+    'rdr_prepare_cube': (_int, [_i64, _i64, _vp, _vp, _vp, _vp, _int, _vp, _i64, _f64, _f64, _f64, _f64, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                _pi64, _int, _int]),
     'rdr_orbit_los': (_int, [_vp, _i64, _int, _vp, _vp, _vp, _f64, _i64, _i64, _f64, _int, _vp, _vp, _vp, _int]),
     'rdr_selftest_div': (_int, [_i64, C.c_uint64, _pi64, _pi64, _int]),
     'rdr_interp_along_axis': (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _int, _f64, _vp, _int, _int]),

@@ -734,3 +734,43 @@ def test_row_tiling_is_bit_identical(gpu, monkeypatch):
                              list(rt.get_interpolators(cfg['cube'])), MAX_SEGMENT_LENGTH=cfg['max_segment_length'],
                              MAX_TROPO_HEIGHT=cfg['zref'], layer_maxlen=[info[0].maxlen])
     assert np.abs(tiled[0][0, :6] - want[0][0]).max() < TOL_F64_M and np.abs(tiled[1][0, :6] - want[1][0]).max() < TOL_F64_M
+
+
+# ---------------------------------------------------------------------------------------- K7: weather-model processing (f4)
+def _native_columns(ny=6, nx=7, nl=40, seed=4):
+    rng = np.random.default_rng(seed)
+    base = np.concatenate([[-60.0, 30.0], 150.0 + 42000.0 * (np.arange(1, nl - 1) / (nl - 2)) ** 2])
+    zs = base[None, None, :] * rng.normal(1.0, 0.01, (ny, nx, 1)) + rng.uniform(-40.0, 400.0, (ny, nx, 1))  # terrain-following columns
+    t = 288.15 - 6.5e-3 * np.clip(zs, None, 11000.0) + rng.normal(0, 0.5, zs.shape)
+    p = 101325.0 * np.exp(-zs / 8000.0) * (1 + rng.normal(0, 1e-3, zs.shape))
+    q = 8e-3 * np.exp(-zs / 2500.0) * (1 + 0.2 * rng.random(zs.shape))
+    return zs, p, t, q
+
+
+def test_weather_processing_vs_oracle(gpu):
+    """K7 (one kernel for WeatherModel.load after load_weather) against the oracle restatement, specific and relative humidity,
+    with and without the extra level at zmin; then the processed cube drives the zenith path."""
+    from oracle import weather as ow
+    from raider_b200.weather_prep import process_weather
+    zs, p, t, q = _native_columns()
+    zlevels = np.concatenate([[-200.0, -50.0, 0.0, 20.0], 50.0 + 41000.0 * (np.arange(1, 60) / 59.0) ** 1.7])
+    for hum, kind, zl, zmin in ((q, 'q', zlevels, -100.0), (60.0 + 30.0 * np.sin(zs / 3000.0), 'rh', zlevels[2:], -100.0)):
+        got = process_weather(zs, p, t, hum, zl, humidity_type=kind, zmin=zmin, keep_pte=True)
+        want = ow.process(zs, p, t, hum, zl, 0.776, 0.233, 3.75e3, humidity_type=kind, zmin=zmin)
+        assert np.array_equal(got['z'], want['z']) and got['wet'].shape == want['wet'].shape and got['wet'].dtype == np.float32
+        assert got['z'].size == zl.size + (1 if zmin < zl[0] else 0)
+        for k in ('p', 't', 'e', 'wet', 'hydro', 'wet_total', 'hydro_total'):
+            a, b = got[k].astype(np.float64), np.asarray(want[k], dtype=np.float64)
+            assert np.array_equal(np.isnan(a), np.isnan(b)), k
+            # float32 fields; exp() of the two libraries may differ in the last float32 bit of svp
+            assert np.allclose(a, b, rtol=3e-6, atol=1e-30), (k, np.nanmax(np.abs(a - b) / np.maximum(np.abs(b), 1e-30)))
+        assert np.isfinite(got['wet']).all() and got['t'].max() > 1e15  # levels above the column top: fillna3D's 1e16 in t
+    # the reference's small known answer (test/test_weather_model.py:178-211) through the kernel: q = 0 -> e = 0; p and t interpolate
+    zs_s = np.array([[[1., 2.], [0.9, 1.1]], [[1., 2.6], [1.1, 2.3]]])
+    p_s = np.arange(8).reshape(2, 2, 2).astype(float)
+    got = process_weather(zs_s, p_s, p_s * 2 + 300.0, np.zeros_like(p_s), np.array([1.0, 2.0]), zmin=5.0, keep_pte=True)
+    nan = np.nan
+    interp = np.array([[[0, nan], [2.5, nan]], [[4., 4.625], [nan, 6.75]]])
+    filled_p = np.where(np.isnan(interp), 0.0, interp)
+    filled_p[1, 1, 0] = 6.75  # leading NaN takes the first valid value
+    assert np.allclose(np.moveaxis(got['p'], 0, 2), filled_p, rtol=0, atol=0)

@@ -328,3 +328,70 @@ def test_orbit_los_on_reference_state_vectors():
     inc = np.degrees(np.arccos(np.sum(los * up, -1)))
     assert inc.min() > 29.0 and inc.max() < 48.0
     assert np.isnan(ob.look_vectors_points([13.5], [100.5], [0.0], orb)).all()
+
+
+# ---------------------------------------------------------------------------------------- weather-model processing (f4)
+def test_uniform_in_z_small_known_answer():
+    """test/test_weather_model.py:178-211, value for value."""
+    from oracle import weather as ow
+    nan = np.nan
+    zs = np.array([[[1., 2.], [0.9, 1.1]], [[1., 2.6], [1.1, 2.3]]])
+    p = np.arange(8).reshape(2, 2, 2).astype(float)
+    zl, po, to, eo = ow.uniform_in_z(zs, p, p * 2, p * 3)
+    want = np.array([[[0, nan], [2.5, nan]], [[4., 4.625], [nan, 6.75]]])
+    assert np.allclose(po, want, equal_nan=True, rtol=0) and np.allclose(to, want * 2, equal_nan=True, rtol=0)
+    assert np.allclose(eo, want * 3, equal_nan=True, rtol=0) and np.allclose(zl, [1, 2], rtol=0)
+    assert po.dtype == np.float32
+
+
+def test_mock_weather_model_refractivity_and_ztd():
+    """MockWeatherModel of test/test_weather_model.py:113-133 (k1 = k2 = k3 = 1), asserted there at :385-401."""
+    from oracle import weather as ow
+    nz = 32
+    zs = np.linspace(0, 1e5, nz)
+    t = np.ones((5, 7, nz))
+    e = t.copy()
+    e[:, 3:, :] = 2
+    p = np.broadcast_to(np.arange(31, -1, -1), t.shape).astype(float)
+    wet, hydro = ow.refractivity(p, t, e, 1, 1, 1)
+    true_wet = 2 * np.ones(t.shape)
+    true_wet[:, 3:] = 4
+    assert np.allclose(wet, true_wet) and np.allclose(hydro, p)
+    true_wet_ztd = 1e-6 * 2 * np.broadcast_to(np.flip(zs), t.shape).copy()
+    true_wet_ztd[:, 3:] = 2 * true_wet_ztd[:, 3:]
+    assert np.allclose(ow.get_ztd(zs, wet), true_wet_ztd)
+    true_hydro_ztd = np.zeros(t.shape)
+    for layer in range(nz):
+        true_hydro_ztd[:, :, layer] = 1e-6 * 0.5 * (zs[-1] - zs[layer]) * p[0, 0, layer]
+    assert np.allclose(ow.get_ztd(zs, hydro), true_hydro_ztd)
+    # the cumulative form used by raider_b200.synthetic is the same integral
+    assert np.allclose(np.moveaxis(syn.cumulative_total(np.moveaxis(hydro, 2, 0), zs), 0, 2), true_hydro_ztd)
+
+
+def test_fill_nans_matches_the_pandas_call_of_the_reference():
+    """fillna3D (interpolator.py:110-130) = pd.DataFrame(rows).interpolate(axis=1, limit_direction='backward') then fill."""
+    import pandas as pd
+    from oracle import weather as ow
+    rng = np.random.default_rng(2)
+    a = rng.normal(size=(4, 5, 30))
+    a[..., :3] = np.nan
+    a[1, 2, :9] = np.nan
+    a[..., -2:] = np.nan
+    a[2, 1, 10:14] = np.nan
+    a[3, 3, :] = np.nan
+    rows = a.reshape(-1, 30).copy()
+    want = pd.DataFrame(data=rows).interpolate(axis=1, limit_direction='backward').values.reshape(a.shape).copy()
+    want[np.isnan(want)] = 7.5
+    assert np.allclose(ow.fill_nans(a, fill_value=7.5), want, rtol=1e-14, atol=0)
+
+
+def test_svp_and_adjust_grid():
+    from oracle import weather as ow
+    t = np.array([200.0, 250.15, 260.0, 273.15, 300.0])
+    svp = ow.find_svp(t)
+    assert svp.dtype == np.float32 and np.all(np.diff(svp) > 0)
+    assert abs(svp[3] - 611.21) < 1e-3 and abs(svp[4] - 100 * 6.1121 * np.exp(17.502 * 26.85 / (240.97 + 26.85))) < 1e-2
+    zs, (a,) = ow.adjust_grid(np.array([0.0, 10.0]), (np.array([[[np.nan, 3.0]]]),), zmin=-100.0)
+    assert np.array_equal(zs, [-100.0, 0.0, 10.0]) and a[0, 0, 0] == 3.0 and a.shape == (1, 1, 3)
+    zs2, _ = ow.adjust_grid(np.array([-500.0, 10.0]), (np.zeros((1, 1, 2)),), zmin=-100.0)
+    assert zs2.size == 2
