@@ -753,7 +753,7 @@ def test_weather_processing_vs_oracle(gpu):
     from oracle import weather as ow
     from raider_b200.weather_prep import process_weather
     zs, p, t, q = _native_columns()
-    zlevels = np.concatenate([[-200.0, -50.0, 0.0, 20.0], 50.0 + 41000.0 * (np.arange(1, 60) / 59.0) ** 1.7])
+    zlevels = np.concatenate([[-200.0, -50.0, 0.0, 20.0], 50.0 + 44000.0 * (np.arange(1, 60) / 59.0) ** 1.7])
     for hum, kind, zl, zmin in ((q, 'q', zlevels, -100.0), (60.0 + 30.0 * np.sin(zs / 3000.0), 'rh', zlevels[2:], -100.0)):
         got = process_weather(zs, p, t, hum, zl, humidity_type=kind, zmin=zmin, keep_pte=True)
         want = ow.process(zs, p, t, hum, zl, 0.776, 0.233, 3.75e3, humidity_type=kind, zmin=zmin)
