@@ -1,0 +1,62 @@
+"""K3 variants on the C2 workload and on the 145-level table: time (CUDA events on the launching stream, L2 flushed) and
+max |difference| against the PROJ-form integrator.
+
+    python profiles/tune_k3.py
+"""
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+import torch  # noqa: E402
+
+from bench import enu_const, global_config  # noqa: E402
+from raider_b200 import _lib, synthetic as syn  # noqa: E402
+from raider_b200.engine import DeviceCube  # noqa: E402
+
+stream = torch.cuda.Stream()
+torch.cuda.set_stream(stream)
+flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device='cuda')
+enu = enu_const()
+
+
+def timed(fn, reps=5):
+    out = []
+    for _ in range(reps):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        fn()
+        b.record(stream)
+        torch.cuda.synchronize()
+        out.append(a.elapsed_time(b))
+    return float(np.median(out))
+
+
+cfg = global_config(1)
+c145 = syn.config_c2(n=2000, table='ml145')
+c145['xpts'], c145['ypts'] = cfg['xpts'], cfg['ypts']
+variants = [('general', None, None), ('fast', 5, None), ('poly', None, None)] + [('poly', m, ca) for ca in (0, 1) for m in (3, 4, 5)]
+for nm, cf in (('C2', cfg), ('ml145', c145)):
+    cube = DeviceCube.from_dict(cf['cube'], device=0)
+    cube.h.set_stream(stream.cuda_stream)
+    ny, nx = cf['ypts'].size, cf['xpts'].size
+    ow = torch.empty((ny, nx), dtype=torch.float64, device='cuda')
+    oh = torch.empty((ny, nx), dtype=torch.float64, device='cuda')
+    maxlen, counts = cube.ray_layers(_lib.GEOM_GRID, cf['xpts'], cf['ypts'], ny, nx, _lib.LOS_ENU_CONST, enu, 0.0, cf['zref'])
+    ref = None
+    for mode, minb, cache in variants:
+        os.environ['RDR_K3_MODE'] = mode
+        for k, v in (('RDR_K3_MINB', minb), ('RDR_K3_CACHE', cache)):
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = str(v)
+        t3 = timed(lambda: cube.ray_integrate(maxlen, cf['max_segment_length'], False, ow, oh))
+        w, h = ow.cpu().numpy(), oh.cpu().numpy()
+        if ref is None:
+            ref = (w, h)
+        print(f'{nm} {mode} minb={minb} cache={cache}: K3 {t3:.3f} ms  max|d wet| {np.abs(w - ref[0]).max():.2e} max|d hydro| {np.abs(h - ref[1]).max():.2e} '
+              f'fix {cube.h.last_fix_count}', flush=True)

@@ -222,6 +222,7 @@ struct rdr_handle_s {
     DevBuf d_red;     // maxlen bits [K] | counters
     DevBuf d_nparts;  // int [K] + int cell [K]
     DevBuf d_layers;  // LayerRec [K] of the fast integrator
+    DevBuf d_spans;   // int [nspan]: one-past-last layer of every span of the polynomial integrator
     DevBuf d_fix;     // int [n_rays]: rays the fast integrator handed to the PROJ-form path
     int64_t last_fix_count = -1;  // how many rays that was in the last rdr_ray_integrate (-1: fast path not used / not read back)
     DevBuf d_out;     // staging for host outputs
@@ -301,19 +302,33 @@ __global__ void k_pack_cells(const float2 *__restrict__ f, double4 *__restrict__
     }
 }
 
-// float2 [ny][nx][nz] -> LerpCell [ny-1][nx-1][nz-1] for the fast integrator (fastpath.cuh): one thread per corner column of a cell
+// float2 [ny][nx][nz] -> LerpCell [ny-1][nx-1][nz-1] for the fast integrators (fastpath.cuh): one thread per 32-byte quarter of
+// a cell record = one pair (a_2q, a_2q+1) of multilinear coefficients of both fields
 __global__ void k_pack_lerp(const float2 *__restrict__ f, double4 *__restrict__ out, int ny, int nx, int nz) {
     const int nzc = nz - 1;
     const int64_t total = (int64_t)(ny - 1) * (nx - 1) * nzc * 4;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int corner = (int)(i & 3);
+        const int quarter = (int)(i & 3);
         const int64_t cell = i >> 2;
         const int iz = (int)(cell % nzc);
         const int ix = (int)((cell / nzc) % (nx - 1));
         const int iy = (int)(cell / ((int64_t)nzc * (nx - 1)));
-        const int64_t col = (int64_t)(iy + (corner >> 1)) * nx + (ix + (corner & 1));
-        const float2 a = f[col * nz + iz], b = f[col * nz + iz + 1];
-        out[i] = make_double4((double)a.x, (double)a.y, (double)b.x - (double)a.x, (double)b.y - (double)a.y);
+        // corner columns (y, x) = 00, 01, 10, 11: value at z and its difference along z (exact: fp32 data in fp64)
+        double w[4], dw[4], hh[4], dh[4];
+#pragma unroll
+        for (int cnr = 0; cnr < 4; ++cnr) {
+            const int64_t col = (int64_t)(iy + (cnr >> 1)) * nx + (ix + (cnr & 1));
+            const float2 a = f[col * nz + iz], b = f[col * nz + iz + 1];
+            w[cnr] = (double)a.x; dw[cnr] = (double)b.x - (double)a.x;
+            hh[cnr] = (double)a.y; dh[cnr] = (double)b.y - (double)a.y;
+        }
+        double4 q;
+        if (quarter == 0) q = make_double4(w[0], hh[0], dw[0], dh[0]);
+        else if (quarter == 1) q = make_double4(w[1] - w[0], hh[1] - hh[0], dw[1] - dw[0], dh[1] - dh[0]);
+        else if (quarter == 2) q = make_double4(w[2] - w[0], hh[2] - hh[0], dw[2] - dw[0], dh[2] - dh[0]);
+        else q = make_double4((w[3] - w[2]) - (w[1] - w[0]), (hh[3] - hh[2]) - (hh[1] - hh[0]), (dw[3] - dw[2]) - (dw[1] - dw[0]),
+                              (dh[3] - dh[2]) - (dh[1] - dh[0]));
+        out[i] = q;
     }
 }
 
@@ -358,7 +373,7 @@ CubeView make_view(rdr_handle_t h) {
 // the fast integrator's view: needs a geographic cube whose horizontal axes are uniform to 1e-9 of a cell, so that the cell
 // coordinate (v - first) / d stands for the node search (t differs from the node-based one by < 1e-9: micrometres on the ground)
 bool make_fast_cube(rdr_handle_t h, FastCube &c) {
-    if (h->crs_kind != RDR_CRS_GEOGRAPHIC) return false;
+    if (h->crs_kind != RDR_CRS_GEOGRAPHIC && h->crs_kind != RDR_CRS_LCC_SPHERE) return false;
     const std::vector<double> *v[2] = {&h->ys, &h->xs};
     double inv[2], c0[2];
     for (int d = 0; d < 2; ++d) {
@@ -372,6 +387,8 @@ bool make_fast_cube(rdr_handle_t h, FastCube &c) {
     c.cells = h->d_lerp.as<LerpCell>();
     c.ny = (int)h->ny; c.nx = (int)h->nx; c.nzc = (int)h->nz - 1;
     c.y_inv = inv[0]; c.y_c0 = c0[0]; c.x_inv = inv[1]; c.x_c0 = c0[1];
+    c.crs_kind = h->crs_kind;
+    c.lcc = {h->crs[0], h->crs[1], h->crs[2], h->crs[3], h->crs[4], h->crs[5], h->crs[6]};
     return true;
 }
 
@@ -929,6 +946,208 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_ray_integrate_fast(const FastCu
             acc_w = fma(wt_half, vw, acc_w);
             acc_h = fma(wt_half, vh, acc_h);
             t_lo = t_hi;
+        }
+        if (valid) {
+            if (bad) {
+                fix_list[atomicAdd(counters + 3, 1ull)] = (int)r;
+            } else if (accumulate) {
+                out_wet[r] = (OUT)((double)out_wet[r] + acc_w);
+                out_hydro[r] = (OUT)((double)out_hydro[r] + acc_h);
+            } else {
+                __stcs(out_wet + r, (OUT)acc_w);
+                __stcs(out_hydro + r, (OUT)acc_h);
+            }
+        }
+    }
+    if ((threadIdx.x & 31) == 0 && n_first_below) atomicAdd(counters + 0, (unsigned long long)n_first_below);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3 (polynomial form): the production integrator.  The ray is cut into *spans* of whole layers (host plan: greedy, span
+// length <= RDR_K3_SPAN metres of the longest ray); per span the cube coordinates (uy, ux) and the height h are evaluated
+// exactly at four points (three new ones, the first is the previous span's last) and carried as cubics in the normalised
+// along-ray coordinate s (fastpath.cuh: < 2e-8 m in h, 5e-8 m horizontally for 8 km spans).  Every sample of delay.py:287-323
+// is then 9 DFMA of geometry + cell lookup + 14 DFMA of trilinear value instead of a Bowring inversion and two arcsines:
+// ~40 DP instructions per sample instead of ~100, and the model CRS (geographic or Lambert) only matters at the span nodes.
+// Sample positions, step counts (nParts) and trapezoid weights are the reference's; flagged rays go to k_ray_integrate in
+// list mode exactly as for k_ray_integrate_fast.
+// Dynamic shared memory: LayerRec[K] | z nodes [nz] | 1/dz [nz-1] | span ends int[nspan].
+// ------------------------------------------------------------------------------------------------
+template <typename OUT, int BLOCK, int MINB, bool LCC, bool CACHE>
+__global__ void __launch_bounds__(BLOCK, MINB) k_ray_integrate_poly(const FastCube c, const RayGeom G, int64_t n_rays, int K,
+                                                              const double *__restrict__ t_in, const LayerRec *__restrict__ layers,
+                                                              const int *__restrict__ span_end, int nspan, const double *__restrict__ znodes,
+                                                              int nz, int clamp_low_first, double zmin, OUT *__restrict__ out_wet,
+                                                              OUT *__restrict__ out_hydro, int accumulate,
+                                                              unsigned long long *__restrict__ counters, int *__restrict__ fix_list) {
+    extern __shared__ __align__(16) unsigned char fast_smem[];
+    LayerRec *s_layers = reinterpret_cast<LayerRec *>(fast_smem);
+    double *s_z = reinterpret_cast<double *>(fast_smem + (size_t)K * sizeof(LayerRec));
+    double *s_inv = s_z + nz;
+    int *s_span = reinterpret_cast<int *>(s_inv + (nz - 1));
+    for (int i = threadIdx.x; i < K; i += BLOCK) s_layers[i] = layers[i];
+    for (int i = threadIdx.x; i < nz; i += BLOCK) s_z[i] = znodes[i];
+    for (int i = threadIdx.x; i < nz - 1; i += BLOCK) s_inv[i] = 1.0 / (znodes[i + 1] - znodes[i]);
+    for (int i = threadIdx.x; i < nspan; i += BLOCK) s_span[i] = span_end[i];
+    __syncthreads();
+    const ZTable T = {s_z, s_inv, nz};
+    const double ky = RAD_TO_DEG * c.y_inv, kx = RAD_TO_DEG * c.x_inv;
+    const int64_t n_pad = (n_rays + 31) / 32 * 32;
+    unsigned n_first_below = 0;
+    for (int64_t r = blockIdx.x * (int64_t)BLOCK + threadIdx.x; r < n_pad; r += (int64_t)gridDim.x * BLOCK) {
+        const bool valid = r < n_rays;
+        const int64_t rr = valid ? r : n_rays - 1;
+        double lat, lon;
+        ray_latlon(G, rr, lat, lon);
+        RayFrame F;
+        frame_setup(lat, lon, G.ht, G.los_kind, G.los, rr, G.e, G.n, G.u, F);
+        const RayCell R = {fma(lat, c.y_inv, c.y_c0), fma(lon, c.x_inv, c.x_c0), ky, kx};
+        const double unorm = norm3(Vec3{F.uA, F.uB, F.uZ});  // |P_hi - P_lo| = |t_hi - t_lo| |u|  (losreader.py:821)
+        bool bad = LCC ? false : !F.fast_ok;
+        double acc_w = 0.0, acc_h = 0.0, vw, vh;
+        double t_a = __ldcs(t_in + rr), t_lo = t_a;
+        // the along-ray distances stream from HBM: the top of the next layer and the end of the next span are requested one
+        // layer / one span ahead of their use
+        double t_next = __ldcs(t_in + n_rays + rr);
+        double tb_next = __ldcs(t_in + (int64_t)s_span[0] * n_rays + rr);
+        RayNode n0 = node_eval<LCC>(c, F, R, t_a, bad);
+        {   // very first sample of the ray (ff = 0 of the first layer); all pixels below min(z) -> clamp (delay.py:306-307)
+            n_first_below += __popc(__ballot_sync(0xffffffffu, valid && (n0.h < zmin)));
+            sample_cell(c, s_layers[0], T, n0.uy, n0.ux, clamp_low_first ? zmin : n0.h, vw, vh, bad);
+        }
+        // CACHE: the 128-byte record of the cell the previous sample fell into stays in registers.  The samples of a layer share
+        // their z cell and a ray crosses a horizontal cell face only every few km, so most samples reuse it: the gather drops
+        // from 8 LDG.128 per sample (32 L1 wavefront cycles per warp: the limiter of the uncached kernel) to 8 per cell entered.
+        // The cell is identified by a packed key (iy | ix << 10 | iz << 20; the host checks ny, nx <= 1024, nz <= 2048), so the
+        // common case costs one compare; the address arithmetic and the loads only run when a new cell is entered.
+        unsigned held = 0xffffffffu;
+        CellData Q;
+        Cubic py, px, ph;
+        auto sample_cached = [&](const LayerRec &L, double s, double &w_out, double &h_out) {
+            const double s2 = s * s;  // Estrin: two dependent levels after s instead of Horner's three
+            const double uy = fma(s2, fma(s, py.c3, py.c2), fma(s, py.c1, py.c0));
+            const double ux = fma(s2, fma(s, px.c3, px.c2), fma(s, px.c1, px.c0));
+            const double h = fma(s2, fma(s, ph.c3, ph.c2), fma(s, ph.c1, ph.c0));
+            int iy, ix, iz = L.iz;
+            // (the span nodes keep NODE_MARGIN cells away from the cube's outer faces and the coordinates are monotone to well below
+            // that margin in between, so the per-sample indices need clamping for memory safety only)
+            const double ty = cell_coord_clamped(uy, c.ny, iy), tx = cell_coord_clamped(ux, c.nx, ix);
+            double tz = fma(h, L.inv_dz, L.neg_zlo_inv);
+            if (!(h >= L.h_lo && h < L.h_hi)) z_lookup(T, h, iz, tz, bad);
+            const unsigned key = (unsigned)iy | ((unsigned)ix << 10) | ((unsigned)iz << 20);
+            if (key != held) {
+                Q = load_cell(c.cells + ((unsigned)(iy * (c.nx - 1) + ix) * (unsigned)c.nzc + (unsigned)iz));
+                held = key;
+            }
+            eval_cell(Q, ty, tx, tz, w_out, h_out);
+        };
+        int k = 0;
+        for (int sp = 0; sp < nspan; ++sp) {
+            const int k1 = s_span[sp];
+            const double t_b = tb_next;
+            if (sp + 1 < nspan) tb_next = __ldcs(t_in + (int64_t)s_span[sp + 1] * n_rays + rr);
+            const double span = t_b - t_a;
+            bad |= !(span > 0.0);
+            const RayNode n1 = node_eval<LCC>(c, F, R, fma(span, 1.0 / 3.0, t_a), bad);
+            const RayNode n2 = node_eval<LCC>(c, F, R, fma(span, 2.0 / 3.0, t_a), bad);
+            const RayNode n3 = node_eval<LCC>(c, F, R, t_b, bad);
+            py = cubic_through(n0.uy, n1.uy, n2.uy, n3.uy);
+            px = cubic_through(n0.ux, n1.ux, n2.ux, n3.ux);
+            ph = cubic_through(n0.h, n1.h, n2.h, n3.h);
+            const double inv_span = rcp3(span);
+            for (; k < k1; ++k) {
+                const LayerRec L = s_layers[k];
+                const double t_hi = t_next;
+                if (k + 2 <= K) t_next = __ldcs(t_in + (int64_t)(k + 2) * n_rays + rr);
+                const double dt = t_hi - t_lo;
+                const double len = fabs(dt) * unorm;
+                const double wt_full = (len * 1.0e-6) * L.step;   // delay.py:315 (L.step = RN(1 / (np - 1)): 1 ulp from the division)
+                const double wt_half = 0.5 * wt_full;
+                // first sample of this layer == last sample of the previous one (evaluated once, used with both end weights)
+                acc_w = fma(wt_half, vw, acc_w);
+                acc_h = fma(wt_half, vh, acc_h);
+                // sample j sits at t_lo + (j step) dt (delay.py:287,292), i.e. at s = s_lo + j (step ds) of the span
+                const double s_lo = (t_lo - t_a) * inv_span, ds = dt * inv_span, sstep = L.step * ds;
+                double fj = 1.0;
+                int j = 1;
+                if (CACHE) {
+                    if (k + 2 < K && held != 0xffffffffu) {
+                        // the record two layers up in the column the ray is in now: requested into L1 a layer or more before its first use
+                        const LerpCell *nx2 = c.cells + ((unsigned)((int)(held & 1023u) * (c.nx - 1) + (int)((held >> 10) & 1023u)) * (unsigned)c.nzc +
+                                                         (unsigned)s_layers[k + 2].iz);
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(nx2));
+                    }
+                    for (; j + 1 < L.np - 1; j += 2) {
+                        // two interior samples as one straight-line block (two independent dependency chains: the loop is latency
+                        // bound otherwise).  Both are taken to lie in the layer's own z cell and in one horizontal cell, which is
+                        // the case for all but a few per ray; the exceptions are redone one at a time.
+                        const double sa = fma(fj, sstep, s_lo), sb = fma(fj + 1.0, sstep, s_lo);
+                        fj += 2.0;
+                        const double sa2 = sa * sa, sb2 = sb * sb;
+                        const double uya = fma(sa2, fma(sa, py.c3, py.c2), fma(sa, py.c1, py.c0)), uyb = fma(sb2, fma(sb, py.c3, py.c2), fma(sb, py.c1, py.c0));
+                        const double uxa = fma(sa2, fma(sa, px.c3, px.c2), fma(sa, px.c1, px.c0)), uxb = fma(sb2, fma(sb, px.c3, px.c2), fma(sb, px.c1, px.c0));
+                        const double h_a = fma(sa2, fma(sa, ph.c3, ph.c2), fma(sa, ph.c1, ph.c0)), h_b = fma(sb2, fma(sb, ph.c3, ph.c2), fma(sb, ph.c1, ph.c0));
+                        int iya, ixa, iyb, ixb;
+                        const double tya = cell_coord_clamped(uya, c.ny, iya), txa = cell_coord_clamped(uxa, c.nx, ixa);
+                        const double tyb = cell_coord_clamped(uyb, c.ny, iyb), txb = cell_coord_clamped(uxb, c.nx, ixb);
+                        const double tza = fma(h_a, L.inv_dz, L.neg_zlo_inv), tzb = fma(h_b, L.inv_dz, L.neg_zlo_inv);
+                        const unsigned keya = (unsigned)iya | ((unsigned)ixa << 10) | ((unsigned)L.iz << 20);
+                        const unsigned keyb = (unsigned)iyb | ((unsigned)ixb << 10) | ((unsigned)L.iz << 20);
+                        const bool regular = (keya == keyb) & (h_a >= L.h_lo) & (h_a < L.h_hi) & (h_b >= L.h_lo) & (h_b < L.h_hi);
+                        double wa, ha, wb, hb;
+                        if (regular) {
+                            if (keya != held) {
+                                Q = load_cell(c.cells + ((unsigned)(iya * (c.nx - 1) + ixa) * (unsigned)c.nzc + (unsigned)L.iz));
+                                held = keya;
+                            }
+                            eval_cell(Q, tya, txa, tza, wa, ha);
+                            eval_cell(Q, tyb, txb, tzb, wb, hb);
+                        } else {
+                            sample_cached(L, sa, wa, ha);
+                            sample_cached(L, sb, wb, hb);
+                        }
+                        acc_w = fma(wt_full, wa, acc_w);
+                        acc_h = fma(wt_full, ha, acc_h);
+                        acc_w = fma(wt_full, wb, acc_w);
+                        acc_h = fma(wt_full, hb, acc_h);
+                    }
+                    if (j < L.np - 1) {
+                        double wa, ha;
+                        sample_cached(L, fma(fj, sstep, s_lo), wa, ha);
+                        acc_w = fma(wt_full, wa, acc_w);
+                        acc_h = fma(wt_full, ha, acc_h);
+                    }
+                    sample_cached(L, s_lo + ds, vw, vh);  // the layer's last sample (ff = 1)
+                } else {
+                    for (; j + 1 < L.np - 1; j += 2) {  // two interior samples per trip: independent chains for the FP64 pipe
+                        const double sa = fma(fj, sstep, s_lo), sb = fma(fj + 1.0, sstep, s_lo);
+                        fj += 2.0;
+                        double wa, ha, wb, hb;
+                        sample_cell(c, L, T, cubic_eval(py, sa), cubic_eval(px, sa), cubic_eval(ph, sa), wa, ha, bad);
+                        sample_cell(c, L, T, cubic_eval(py, sb), cubic_eval(px, sb), cubic_eval(ph, sb), wb, hb, bad);
+                        acc_w = fma(wt_full, wa, acc_w);
+                        acc_h = fma(wt_full, ha, acc_h);
+                        acc_w = fma(wt_full, wb, acc_w);
+                        acc_h = fma(wt_full, hb, acc_h);
+                    }
+                    if (j < L.np - 1) {
+                        const double sa = fma(fj, sstep, s_lo);
+                        double wa, ha;
+                        sample_cell(c, L, T, cubic_eval(py, sa), cubic_eval(px, sa), cubic_eval(ph, sa), wa, ha, bad);
+                        acc_w = fma(wt_full, wa, acc_w);
+                        acc_h = fma(wt_full, ha, acc_h);
+                    }
+                    {   // the layer's last sample (ff = 1)
+                        const double se = s_lo + ds;
+                        sample_cell(c, L, T, cubic_eval(py, se), cubic_eval(px, se), cubic_eval(ph, se), vw, vh, bad);
+                    }
+                }
+                acc_w = fma(wt_half, vw, acc_w);
+                acc_h = fma(wt_half, vh, acc_h);
+                t_lo = t_hi;
+            }
+            t_a = t_b;
+            n0 = n3;
         }
         if (valid) {
             if (bad) {
@@ -1695,7 +1914,7 @@ RDR_API int rdr_destroy(rdr_handle_t h) {
     ScopedDevice sd(h->device);
     cudaStreamSynchronize(h->stream);
     for (DevBuf *b : {&h->d_axes, &h->d_tabs, &h->d_cells, &h->d_stage, &h->d_fields, &h->d_gx, &h->d_gy, &h->d_los, &h->d_plan, &h->d_t, &h->d_red,
-                      &h->d_nparts, &h->d_out, &h->d_in, &h->d_lerp, &h->d_layers, &h->d_fix, &h->d_cells32, &h->d_orbit})
+                      &h->d_nparts, &h->d_out, &h->d_in, &h->d_lerp, &h->d_layers, &h->d_spans, &h->d_fix, &h->d_cells32, &h->d_orbit})
         b->release();
     if (h->own_stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -2132,7 +2351,32 @@ RDR_API int rdr_ray_integrate(rdr_handle_t h, const double *maxlen, double max_s
     const int *d_np = h->d_nparts.as<int>();
     FastCube fc;
     const char *force_general = getenv("RDR_K3_GENERAL");
-    const bool fast = make_fast_cube(h, fc) && !(force_general && atoi(force_general) != 0) && n < (1ll << 31);
+    // integrator: poly (default; geographic or Lambert cube with uniform horizontal axes), fast (per-sample Bowring; geographic
+    // only), general (PROJ-form arithmetic for every sample).  RDR_K3_MODE = poly | fast | general overrides for tests / tuning.
+    const char *mode_env = getenv("RDR_K3_MODE");
+    const bool want_general = (force_general && atoi(force_general) != 0) || (mode_env && !strcmp(mode_env, "general"));
+    const bool fast_cube = make_fast_cube(h, fc) && !want_general && n < (1ll << 31);
+    // spans of the polynomial integrator: whole layers, greedy, at most `span_max` metres of the longest ray per span
+    const char *span_env = getenv("RDR_K3_SPAN");
+    const double span_max = span_env && atof(span_env) > 0 ? atof(span_env) : 8000.0;
+    std::vector<int> span_end;
+    double longest_span = 0.0;
+    {
+        double acc = 0.0;
+        for (int k = 0; k < K; ++k) {
+            if (k > 0 && acc + maxlen[k] > span_max) {
+                span_end.push_back(k);
+                longest_span = std::max(longest_span, acc);
+                acc = 0.0;
+            }
+            acc += maxlen[k];
+        }
+        span_end.push_back(K);
+        longest_span = std::max(longest_span, acc);
+    }
+    // a single layer longer than 4 spans would stretch the cubic's error bound (T^4) by > 256: leave those calls to `fast`
+    const bool poly = fast_cube && !(mode_env && !strcmp(mode_env, "fast")) && longest_span <= 4.0 * span_max;
+    const bool fast = fast_cube && (poly || fc.crs_kind == RDR_CRS_GEOGRAPHIC);
     h->last_fix_count = -1;
 #define RDR_LAUNCH_K3(T, M, LIST, COUNT)                                                                                                   \
     k_ray_integrate<T, BLOCK, M><<<grid, BLOCK, 0, h->stream>>>(c, G, n, K, h->d_t.as<double>(), d_np, d_np + K, clamp_low_first,          \
@@ -2175,7 +2419,42 @@ RDR_API int rdr_ray_integrate(rdr_handle_t h, const double *maxlen, double max_s
         case 8: RDR_LAUNCH_K3F(T, 8, P); break;       \
         default: RDR_LAUNCH_K3F(T, 5, P); break;      \
     }
-        if (out_dtype == RDR_F64) {
+        if (poly) {
+            const int nspan = (int)span_end.size();
+            CUDA_TRY(h, h->d_spans.reserve(nspan * sizeof(int)));
+            CUDA_TRY(h, cudaMemcpyAsync(h->d_spans.p, span_end.data(), nspan * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+            const size_t smem_p = smem + nspan * sizeof(int);
+#define RDR_LAUNCH_K3P(T, M, L, S)                                                                                                            \
+    k_ray_integrate_poly<T, BLOCK, M, L, S><<<grid_p, BLOCK, smem_p, h->stream>>>(fc, G, n, K, h->d_t.as<double>(), h->d_layers.as<LayerRec>(), \
+                                                                               h->d_spans.as<int>(), nspan, znodes, (int)h->nz,            \
+                                                                               clamp_low_first, h->zs.front(), static_cast<T *>(dw),       \
+                                                                               static_cast<T *>(dh), accumulate, counters, h->d_fix.as<int>())
+#define RDR_LAUNCH_K3P_M(T, L)                                                     \
+    switch (minb_p) {                                                              \
+        case 2: RDR_LAUNCH_K3P(T, 2, L, true); break;                              \
+        case 3: if (split) RDR_LAUNCH_K3P(T, 3, L, true); else RDR_LAUNCH_K3P(T, 3, L, false); break;   \
+        case 5: if (split) RDR_LAUNCH_K3P(T, 5, L, true); else RDR_LAUNCH_K3P(T, 5, L, false); break;   \
+        case 6: RDR_LAUNCH_K3P(T, 6, L, false); break;                             \
+        default: if (split) RDR_LAUNCH_K3P(T, 4, L, true); else RDR_LAUNCH_K3P(T, 4, L, false); break;  \
+    }
+            const bool lcc = fc.crs_kind == RDR_CRS_LCC_SPHERE;
+            // cell-record cache (CACHE = true): pays when a layer holds several samples (the record is reused); with ~1 sample per
+            // layer (the 145-level tables at 1000 m) the uncached form at higher occupancy is faster.  Needs the packed cell key.
+            int n_samples = 0;
+            for (int k = 0; k < K; ++k) n_samples += np_cell[k] - 1;
+            const char *cache_env = getenv("RDR_K3_CACHE");
+            const bool key_ok = h->ny <= 1024 && h->nx <= 1024 && h->nz <= 2048;
+            const bool split = key_ok && (cache_env ? atoi(cache_env) != 0 : n_samples >= 3 * K);
+            const int minb_p = tune_minb("RDR_K3_MINB", split ? 3 : 4);
+            const int grid_p = grid_for(n, BLOCK, h->sm_count, 4 * minb_p);
+            if (out_dtype == RDR_F64) {
+                if (lcc) { RDR_LAUNCH_K3P_M(double, true) } else { RDR_LAUNCH_K3P_M(double, false) }
+            } else {
+                if (lcc) { RDR_LAUNCH_K3P(float, 4, true, false); } else { RDR_LAUNCH_K3P(float, 4, false, false); }
+            }
+#undef RDR_LAUNCH_K3P_M
+#undef RDR_LAUNCH_K3P
+        } else if (out_dtype == RDR_F64) {
             if (npt == 1) { RDR_LAUNCH_K3F_M(double, 1) } else { RDR_LAUNCH_K3F_M(double, 2) }
         } else {
             RDR_LAUNCH_K3F(float, 5, 1);
