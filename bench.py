@@ -224,13 +224,25 @@ def run_ours(args):
 
     cube = DeviceCube.from_dict(cfg['cube'], device=local)
     cube.h.set_stream(stream.cuda_stream)
-    out_w = torch.empty((ny, nx), dtype=torch.float64, device='cuda')
-    out_h = torch.empty((ny, nx), dtype=torch.float64, device='cuda')
     rmax = comm.reduce_max if comm else None
     rsum = comm.reduce_sum if comm else None
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device='cuda')  # > 126 MB L2
+    # N > 1: the full maps live in peer-mapped symmetric memory and K3 stores every ray into all GPUs' copies (the all-gather of
+    # the output map fused into the integration kernel); NCCL all-gather only when symmetric memory cannot be set up
+    sym = comm.symmetric_maps(1, ny_g, nx) if comm else None
+    if sym is not None:
+        out_w, out_h = sym.maps[0][0, r0:r1], sym.maps[1][0, r0:r1]
+    else:
+        out_w = torch.empty((ny, nx), dtype=torch.float64, device='cuda')
+        out_h = torch.empty((ny, nx), dtype=torch.float64, device='cuda')
 
     def step():
+        if sym is not None:
+            sym.barrier()   # every rank is done reading the previous step's maps
+            info = cube.trace(_lib.GEOM_GRID, cfg['xpts'], ypts, ny, nx, _lib.LOS_ENU_CONST, enu, 0.0, cfg['zref'], cfg['max_segment_length'],
+                              out_w, out_h, reduce_max=rmax, reduce_sum=rsum, peers_fn=lambda a, b: sym.peer_ptrs(0, r0 + a, r0 + b))
+            sym.barrier()   # every rank's rows have landed in this GPU's maps
+            return info, sym.maps[0][0], sym.maps[1][0]
         info = cube.trace(_lib.GEOM_GRID, cfg['xpts'], ypts, ny, nx, _lib.LOS_ENU_CONST, enu, 0.0, cfg['zref'], cfg['max_segment_length'],
                           out_w, out_h, reduce_max=rmax, reduce_sum=rsum)
         if comm:
@@ -271,6 +283,12 @@ def run_ours(args):
     value = n_global / (ms_per_step * 1e-3)
     checksum = float(fw.sum().item() + fh.sum().item())
     nan_count = int(torch.isnan(fw).sum().item())
+    fused_vs_allgather = None
+    if sym is not None:
+        # the maps K3 assembled by peer stores against an NCCL all-gather of the same row blocks (outside the timed region)
+        fused_vs_allgather = max(float((comm.all_gather_rows(out_w.clone(), ny_g) - fw).abs().max().item()),
+                                 float((comm.all_gather_rows(out_h.clone(), ny_g) - fh).abs().max().item()))
+        fw, fh = fw.clone(), fh.clone()   # the e2e leg below reuses the symmetric buffers
 
     # ---- e2e through the public API with host buffers ----------------------------------------------------------
     los = Raytracing(incidence=INC, heading=HEAD)
@@ -282,8 +300,11 @@ def run_ours(args):
         ifs = getInterpolators(cube_host, device=local)                                   # cube + axes H2D
         if comm:
             from raider_b200.dist import build_cube_ray_sharded
-            return build_cube_ray_sharded(cfg['xpts'], cfg['ypts'], np.array([0.0]), los, 4326, 4326, list(ifs), comm,
-                                          MAX_SEGMENT_LENGTH=cfg['max_segment_length'], MAX_TROPO_HEIGHT=cfg['zref'])
+            # every rank's rows go to its own page-locked host block AND into every GPU's full maps, from the same kernel
+            dev_maps, host_rows = build_cube_ray_sharded(cfg['xpts'], cfg['ypts'], np.array([0.0]), los, 4326, 4326, list(ifs), comm,
+                                                         MAX_SEGMENT_LENGTH=cfg['max_segment_length'], MAX_TROPO_HEIGHT=cfg['zref'],
+                                                         gather='device', host_block=True)
+            return host_rows, dev_maps
         return _build_cube_ray(cfg['xpts'], ypts, np.array([0.0]), los, 4326, 4326, list(ifs),   # axes H2D, delay maps D2H
                                MAX_SEGMENT_LENGTH=cfg['max_segment_length'], MAX_TROPO_HEIGHT=cfg['zref'])
 
@@ -303,7 +324,10 @@ def run_ours(args):
     cube_bytes = int(cfg['cube']['wet'].nbytes + cfg['cube']['hydro'].nbytes)
     h2d = cube_bytes + 8 * (cfg['xpts'].size + ny + cfg['cube']['x'].size + cfg['cube']['y'].size + cfg['cube']['z'].size)
     d2h = 2 * 8 * n_local
-    e2e_dev_diff = float(np.abs(res[0][0][r0:r1] - fw[r0:r1].cpu().numpy()).max()) if comm else float(np.abs(res[0][0] - out_w.cpu().numpy()).max())
+    if comm:   # host rows of this rank vs the device path, and the reassembled map in this GPU's HBM vs the device path's
+        e2e_dev_diff = max(float(np.abs(res[0][0][0] - fw[r0:r1].cpu().numpy()).max()), float((res[1][0][0] - fw).abs().max().item()))
+    else:
+        e2e_dev_diff = float(np.abs(res[0][0] - out_w.cpu().numpy()).max())
 
     if rank != 0:
         if comm:
@@ -403,10 +427,15 @@ def run_ours(args):
                                f'0.001 deg posting, cube {cfg["cube"]["y"].size}x{cfg["cube"]["x"].size}x37 @0.25 deg fp32, 225 m max segment',
                    'rays_per_step': n_global, 'samples_per_ray': info.samples_per_ray, 'layers': info.n_layers,
                    'l2': 'flushed with a 256 MB write between timed steps', 'parallelism': f'row-block x{world}' if world > 1 else 'single GPU',
-                   'collectives': 'all-reduce(max K doubles) + all-reduce(sum 3 ints) + all-gather(2 delay maps)' if world > 1 else 'none'},
+                   'collectives': ('all-reduce(max K doubles) + all-reduce(sum 3 ints); output maps reassembled on every GPU by ' +
+                                   ('peer stores from K3 over NVLink (symmetric memory) + 2 signal-pad barriers' if sym is not None
+                                    else 'all_gather_into_tensor (symmetric memory unavailable)')) if world > 1 else 'none'},
         'clocks': clocks.summary(),
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'steps': e2e_steps,
-                'ms_per_step': 1e3 * t_e2e / e2e_steps, 'api': 'getInterpolators(host cube) + _build_cube_ray(host axes) -> host float64 maps',
+                'ms_per_step': 1e3 * t_e2e / e2e_steps,
+                'api': ('getInterpolators(host cube) + _build_cube_ray(host axes) -> host float64 maps' if world == 1 else
+                        'getInterpolators(host cube) + build_cube_ray_sharded(host axes, gather=device, host_block=True): every rank gets its own '
+                        'rows as host float64 arrays and the full maps in HBM; h2d/d2h bytes are per rank'),
                 'max_abs_diff_vs_device_path_m': e2e_dev_diff},
         'gpu_launches': int(launches),
         'roofline': {'kernel': 'k_sample_stream<double> (K2 trilinear_sample, unfused, TMA-bulk point stream)', 'bound': 'hbm', 'achieved': k2_gbs,
@@ -415,7 +444,7 @@ def run_ours(args):
                      'points_per_launch': npts, 'ms_per_launch': k2_ms, 'fp32_io_tier_gbs': k2_32_gbs, 'fp32_io_tier_frac': k2_32_gbs / peak},
         'fused': fused,
         'cpu_baseline': cpu,
-        'check': {'checksum': checksum, 'nan': nan_count, 'nparts_sum': int(info.samples_per_ray)},
+        'check': {'checksum': checksum, 'nan': nan_count, 'nparts_sum': int(info.samples_per_ray), 'fused_gather_vs_nccl_allgather_max_abs_diff_m': fused_vs_allgather},
     }
     print(json.dumps(line))
     if comm:

@@ -152,6 +152,15 @@ int rdr_ray_integrate(rdr_handle_t h, const double *maxlen, double max_segment_l
                       void *out_wet, void *out_hydro, int out_dtype, int accumulate,
                       int64_t *nparts_out, int64_t *oob_out, int mem);
 
+/* Multi-GPU: mirror the results of the following rdr_ray_integrate calls into up to 8 more device buffers --
+ * the same row block of the full delay maps in the HBM of the node's other GPUs, peer-mapped (torch symmetric memory /
+ * cudaIpc) by the caller.  wet[i] / hydro[i] point at the first ray of this rank's block inside peer i's maps and have the
+ * element type of the call's out_dtype.  The integration kernel stores each ray to every destination as the ray finishes
+ * (posted NVLink writes, overlapped with the integration): the all-gather that reassembles the output map, without a
+ * collective.  The caller orders the kernels of all ranks (barrier) before reading the maps.  n = 0 clears the list;
+ * accumulate != 0 calls ignore it.  The reference has no parallel delay path (delay.py:178-185 raises for nproc > 1). */
+int rdr_set_peer_outputs(rdr_handle_t h, int n, void *const *wet, void *const *hydro);
+
 /* K1b -- north_star (a): generate the 3-D sample points along each ray of the last rdr_ray_layers call, in model
  * coordinates, i.e. the per-sub-step `pts` arrays of delay.py:292-298 (replaces the role of tools/bindings makePoints3D in
  * the unfused dataflow).  Unique samples are numbered in layer-then-step order ("slots"); pts = [nslots][n_rays][3] (y, x, z)

@@ -49,6 +49,7 @@ SIGNATURES = {
     'rdr_ray_plan': (_int, [_vp, _f64, _f64, _pi64, _vp, _vp]),
     'rdr_ray_layers': (_int, [_vp, _int, _vp, _vp, _i64, _i64, _int, _vp, _f64, _f64, _vp, _vp, _int]),
     'rdr_ray_integrate': (_int, [_vp, _vp, _f64, _int, _vp, _vp, _int, _int, _vp, _vp, _int]),
+    'rdr_set_peer_outputs': (_int, [_vp, _int, _vp, _vp]),
     'rdr_ray_stations': (_int, [_vp, _vp, _vp, _vp, _i64, _int, _vp, _f64, _f64, _vp, _vp, _vp, _int]),
     'rdr_ray_points': (_int, [_vp, _vp, _f64, _i64, _i64, _vp, _int, _pi64, _int]),
     'rdr_top_of_atmosphere': (_int, [_vp, _vp, _i64, _f64, _vp, _vp, _int]),

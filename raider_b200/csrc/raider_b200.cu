@@ -178,6 +178,14 @@ struct DevBuf {
 
 constexpr int MAX_LAYERS = 1024;
 
+// extra (peer-GPU) destinations of the integrator's results: see store_result
+constexpr int RDR_MAX_PEERS = 8;
+struct PeerOut {
+    void *wet[RDR_MAX_PEERS];
+    void *hydro[RDR_MAX_PEERS];
+    int n;
+};
+
 }  // namespace
 
 struct rdr_handle_s {
@@ -225,6 +233,7 @@ struct rdr_handle_s {
     DevBuf d_spans;   // int [nspan]: one-past-last layer of every span of the polynomial integrator
     DevBuf d_fix;     // int [n_rays]: rays the fast integrator handed to the PROJ-form path
     int64_t last_fix_count = -1;  // how many rays that was in the last rdr_ray_integrate (-1: fast path not used / not read back)
+    PeerOut peers = {};  // extra (peer-GPU) destinations of the next rdr_ray_integrate: rdr_set_peer_outputs
     DevBuf d_out;     // staging for host outputs
     DevBuf d_in;      // staging for host inputs of K2
 };
@@ -625,6 +634,27 @@ struct RayGeom {
     int nx;
 };
 
+// Extra destinations of the integrator's results: the same row block of the delay maps in the HBM of the other GPUs of the node
+// (peer-mapped symmetric memory, NVLink / NVSwitch).  The integration kernel stores every ray's two results to all of them as it
+// finishes the ray -- the all-gather of SURVEY section 8(e) fused into K3 as posted peer writes: 16 B per ray and peer spread
+// over the whole integration, instead of a collective after it.
+
+template <typename OUT>
+__device__ __forceinline__ void store_result(OUT *__restrict__ out_wet, OUT *__restrict__ out_hydro, const PeerOut &peers, int64_t r, double acc_w,
+                                             double acc_h, int accumulate) {
+    if (accumulate) {
+        out_wet[r] = (OUT)((double)out_wet[r] + acc_w);
+        out_hydro[r] = (OUT)((double)out_hydro[r] + acc_h);
+        return;
+    }
+    __stcs(out_wet + r, (OUT)acc_w);
+    __stcs(out_hydro + r, (OUT)acc_h);
+    for (int p = 0; p < peers.n; ++p) {
+        static_cast<OUT *>(peers.wet[p])[r] = (OUT)acc_w;
+        static_cast<OUT *>(peers.hydro[p])[r] = (OUT)acc_h;
+    }
+}
+
 __device__ __forceinline__ void ray_setup(const RayGeom &G, int64_t r, Vec3 &g, Vec3 &u, RayRef &R) {
     double lat, lon;
     if (G.geom_kind == RDR_GEOM_GRID) {
@@ -746,7 +776,7 @@ template <typename OUT, int BLOCK, int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB) k_ray_integrate(const CubeView c, const RayGeom G, int64_t n_rays, int K,
                                                          const double *__restrict__ t_in, const int *__restrict__ nparts,
                                                          const int *__restrict__ layer_cell, int clamp_low_first, double zmin, double zmax,
-                                                         OUT *__restrict__ out_wet, OUT *__restrict__ out_hydro, int accumulate,
+                                                         OUT *__restrict__ out_wet, OUT *__restrict__ out_hydro, int accumulate, const PeerOut peers,
                                                          unsigned long long *__restrict__ counters, const int *__restrict__ list,
                                                          const unsigned long long *__restrict__ list_count) {
     // list mode (list != nullptr): only the rays the fast integrator flagged, *list_count of them (read on the device, so the
@@ -849,15 +879,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_ray_integrate(const CubeView c,
                 len = norm3(hi - lo);
             }
         }
-        if (valid) {
-            if (accumulate) {
-                out_wet[r] = (OUT)((double)out_wet[r] + acc_w);
-                out_hydro[r] = (OUT)((double)out_hydro[r] + acc_h);
-            } else {
-                __stcs(out_wet + r, (OUT)acc_w);
-                __stcs(out_hydro + r, (OUT)acc_h);
-            }
-        }
+        if (valid) store_result(out_wet, out_hydro, peers, r, acc_w, acc_h, accumulate);
     }
     // per-thread OOB counters -> warp sums -> three atomics per warp at most
     n_below = __reduce_add_sync(0xffffffffu, n_below);
@@ -881,7 +903,7 @@ template <typename OUT, int BLOCK, int MINB, int NPT>
 __global__ void __launch_bounds__(BLOCK, MINB) k_ray_integrate_fast(const FastCube c, const RayGeom G, int64_t n_rays, int K,
                                                               const double *__restrict__ t_in, const LayerRec *__restrict__ layers,
                                                               const double *__restrict__ znodes, int nz, int clamp_low_first, double zmin,
-                                                              OUT *__restrict__ out_wet, OUT *__restrict__ out_hydro, int accumulate,
+                                                              OUT *__restrict__ out_wet, OUT *__restrict__ out_hydro, int accumulate, const PeerOut peers,
                                                               unsigned long long *__restrict__ counters, int *__restrict__ fix_list) {
     extern __shared__ __align__(16) unsigned char fast_smem[];
     LayerRec *s_layers = reinterpret_cast<LayerRec *>(fast_smem);
@@ -950,12 +972,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_ray_integrate_fast(const FastCu
         if (valid) {
             if (bad) {
                 fix_list[atomicAdd(counters + 3, 1ull)] = (int)r;
-            } else if (accumulate) {
-                out_wet[r] = (OUT)((double)out_wet[r] + acc_w);
-                out_hydro[r] = (OUT)((double)out_hydro[r] + acc_h);
             } else {
-                __stcs(out_wet + r, (OUT)acc_w);
-                __stcs(out_hydro + r, (OUT)acc_h);
+                store_result(out_wet, out_hydro, peers, r, acc_w, acc_h, accumulate);
             }
         }
     }
@@ -978,7 +996,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_ray_integrate_poly(const FastCu
                                                               const double *__restrict__ t_in, const LayerRec *__restrict__ layers,
                                                               const int *__restrict__ span_end, int nspan, const double *__restrict__ znodes,
                                                               int nz, int clamp_low_first, double zmin, OUT *__restrict__ out_wet,
-                                                              OUT *__restrict__ out_hydro, int accumulate,
+                                                              OUT *__restrict__ out_hydro, int accumulate, const PeerOut peers,
                                                               unsigned long long *__restrict__ counters, int *__restrict__ fix_list) {
     extern __shared__ __align__(16) unsigned char fast_smem[];
     LayerRec *s_layers = reinterpret_cast<LayerRec *>(fast_smem);
@@ -1152,12 +1170,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_ray_integrate_poly(const FastCu
         if (valid) {
             if (bad) {
                 fix_list[atomicAdd(counters + 3, 1ull)] = (int)r;
-            } else if (accumulate) {
-                out_wet[r] = (OUT)((double)out_wet[r] + acc_w);
-                out_hydro[r] = (OUT)((double)out_hydro[r] + acc_h);
             } else {
-                __stcs(out_wet + r, (OUT)acc_w);
-                __stcs(out_hydro + r, (OUT)acc_h);
+                store_result(out_wet, out_hydro, peers, r, acc_w, acc_h, accumulate);
             }
         }
     }
@@ -2349,6 +2363,8 @@ RDR_API int rdr_ray_integrate(rdr_handle_t h, const double *maxlen, double max_s
     const CubeView c = make_view(h);
     const RayGeom G = make_geom(h);
     const int *d_np = h->d_nparts.as<int>();
+    PeerOut peers = h->peers;
+    if (accumulate) peers.n = 0;  // += has no meaning across replicas: peers only mirror freshly written maps
     FastCube fc;
     const char *force_general = getenv("RDR_K3_GENERAL");
     // integrator: poly (default; geographic or Lambert cube with uniform horizontal axes), fast (per-sample Bowring; geographic
@@ -2381,7 +2397,7 @@ RDR_API int rdr_ray_integrate(rdr_handle_t h, const double *maxlen, double max_s
 #define RDR_LAUNCH_K3(T, M, LIST, COUNT)                                                                                                   \
     k_ray_integrate<T, BLOCK, M><<<grid, BLOCK, 0, h->stream>>>(c, G, n, K, h->d_t.as<double>(), d_np, d_np + K, clamp_low_first,          \
                                                                 h->zs.front(), h->zs.back(), static_cast<T *>(dw), static_cast<T *>(dh),   \
-                                                                accumulate, counters, LIST, COUNT)
+                                                                accumulate, peers, counters, LIST, COUNT)
     if (fast) {
         // per-layer records + the z table of the fast integrator
         std::vector<LayerRec> recs(K);
@@ -2410,7 +2426,7 @@ RDR_API int rdr_ray_integrate(rdr_handle_t h, const double *maxlen, double max_s
     k_ray_integrate_fast<T, BLOCK, M, P><<<grid, BLOCK, smem, h->stream>>>(fc, G, n, K, h->d_t.as<double>(), h->d_layers.as<LayerRec>(),   \
                                                                            znodes, (int)h->nz, clamp_low_first, h->zs.front(),            \
                                                                            static_cast<T *>(dw), static_cast<T *>(dh), accumulate,         \
-                                                                           counters, h->d_fix.as<int>())
+                                                                           peers, counters, h->d_fix.as<int>())
 #define RDR_LAUNCH_K3F_M(T, P)                        \
     switch (minb) {                                   \
         case 3: RDR_LAUNCH_K3F(T, 3, P); break;       \
@@ -2428,7 +2444,7 @@ RDR_API int rdr_ray_integrate(rdr_handle_t h, const double *maxlen, double max_s
     k_ray_integrate_poly<T, BLOCK, M, L, S><<<grid_p, BLOCK, smem_p, h->stream>>>(fc, G, n, K, h->d_t.as<double>(), h->d_layers.as<LayerRec>(), \
                                                                                h->d_spans.as<int>(), nspan, znodes, (int)h->nz,            \
                                                                                clamp_low_first, h->zs.front(), static_cast<T *>(dw),       \
-                                                                               static_cast<T *>(dh), accumulate, counters, h->d_fix.as<int>())
+                                                                               static_cast<T *>(dh), accumulate, peers, counters, h->d_fix.as<int>())
 #define RDR_LAUNCH_K3P_M(T, L)                                                     \
     switch (minb_p) {                                                              \
         case 2: RDR_LAUNCH_K3P(T, 2, L, true); break;                              \
@@ -2505,6 +2521,19 @@ RDR_API int rdr_ray_integrate(rdr_handle_t h, const double *maxlen, double max_s
             oob_out[1] = (int64_t)cnt[1];  // samples below min(z) after the clamp decision
             oob_out[2] = (int64_t)cnt[2];  // samples above max(z)
         }
+    }
+    return RDR_OK;
+}
+
+RDR_API int rdr_set_peer_outputs(rdr_handle_t h, int n, void *const *wet, void *const *hydro) {
+    CHECK_ARG(h, h != nullptr, "rdr_set_peer_outputs: NULL handle");
+    CHECK_ARG(h, n >= 0 && n <= RDR_MAX_PEERS, "rdr_set_peer_outputs: at most 8 peer destinations");
+    CHECK_ARG(h, n == 0 || (wet && hydro), "rdr_set_peer_outputs: NULL pointer list");
+    h->peers.n = n;
+    for (int i = 0; i < n; ++i) {
+        CHECK_ARG(h, wet[i] && hydro[i], "rdr_set_peer_outputs: NULL destination");
+        h->peers.wet[i] = wet[i];
+        h->peers.hydro[i] = hydro[i];
     }
     return RDR_OK;
 }

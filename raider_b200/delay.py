@@ -191,6 +191,8 @@ def _build_cube_ray(
     MAX_SEGMENT_LENGTH=1000.0,
     MAX_TROPO_HEIGHT=_ZREF,
     _out_device=None,
+    _out_arrays=None,
+    _peers=None,
 ):
     """Iterate over interpolators and build a cube using raytracing (delay.py:219-326).
 
@@ -211,7 +213,9 @@ def _build_cube_ray(
         # np.zeros((nz, ny, nx)) in the reference (:248); here each slice is written straight from the device (0 + x == x),
         # so the arrays start uninitialised and only skipped slices are zero-filled
         output_created_here = True
-        if _out_device is not None:   # raider_b200.dist: keep the (nz, ny, nx) maps in HBM for the all-gather
+        if _out_arrays is not None:   # raider_b200.dist: this rank's row block inside the symmetric (peer-mapped) full maps
+            outputArrs = list(_out_arrays)
+        elif _out_device is not None:   # raider_b200.dist: keep the (nz, ny, nx) maps in HBM for the all-gather
             import torch
             outputArrs = [torch.empty((zpts.size, ny, nx), dtype=torch.float64, device=_out_device) for mm in range(2)]
         else:
@@ -251,7 +255,8 @@ def _build_cube_ray(
         # Steps 3..: layers, nParts, sub-steps, sampling, trapezoid -- all on the device
         try:
             info = cube.trace(geom[0], geom[1], geom[2], ny, nx, los_kind, los_payload, ht, MAX_TROPO_HEIGHT, MAX_SEGMENT_LENGTH,
-                              wet, hydro, reduce_max=hooks[0], reduce_sum=hooks[1])
+                              wet, hydro, reduce_max=hooks[0], reduce_sum=hooks[1],
+                              peers_fn=(lambda r0, r1, hh=hh: _peers(hh, r0, r1)) if (_peers is not None and output_created_here) else None)
         except _lib.NoLayersError:
             # if the top most height layer doesnt contribute to the integral, skip it (:276-277)
             if ht == zpts[-1]:

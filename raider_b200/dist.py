@@ -9,8 +9,14 @@ Rays are independent except for three whole-raster quantities, which is why naiv
 * the ``isnan(ray_lengths).all()`` convergence check                                 (delay.py:279)
 
 So the path shards as: contiguous row blocks of the query raster per rank (cube replicated, it is MBs), K0 on each
-rank, ONE all-reduce(MAX) of K doubles + ONE all-reduce(SUM) of 3 counters, K3 on each rank, then an all-gather of the
-two output row blocks so every rank holds the full delay map.  There is no other data-path collective.
+rank, ONE all-reduce(MAX) of K doubles + ONE all-reduce(SUM) of 3 counters, K3 on each rank, and the reassembly of the two
+output maps so every rank holds the full delay map.  There is no other data-path collective.
+
+The reassembly is fused into K3 (``SymmetricMaps``): the full maps live in symmetric memory (``torch.distributed.
+_symmetric_memory``: every rank's buffer is peer-mapped into every other rank over NVLink / NVSwitch), and the integration
+kernel stores each finished ray into the row block of *every* GPU's maps (``rdr_set_peer_outputs``): 16 B per ray and peer of
+posted NVLink writes spread over the whole integration, then one signal-pad barrier -- no all-gather after the kernel.  When
+symmetric memory cannot be set up (gloo, no P2P) the same maps are assembled with ``all_gather_into_tensor``.
 
 The same code runs under ``gloo`` on CPU tensors (tests/test_dist_gloo.py drives it with the oracle standing in for the
 kernels) and under ``nccl`` on CUDA tensors.
@@ -80,13 +86,67 @@ class Comm:
     def barrier(self):
         self.dist.barrier(group=self.group)
 
+    def symmetric_maps(self, nz: int, ny: int, nx: int):
+        """The (2, nz, ny, nx) float64 delay maps of this rank in peer-mapped symmetric memory, or None when that is unavailable.
+        One rendezvous per shape; the buffers are reused by later calls of the same shape."""
+        cache = self.__dict__.setdefault('_symm', {})
+        key = (int(nz), int(ny), int(nx))
+        if key not in cache:
+            try:
+                cache[key] = SymmetricMaps(self, *key)
+            except Exception as e:  # no P2P / unsupported backend: NCCL all-gather instead
+                import logging
+                logging.getLogger(__name__).warning('symmetric memory unavailable (%r): falling back to all_gather_into_tensor', e)
+                cache[key] = None
+        return cache[key]
+
+
+class SymmetricMaps:
+    """Full (wet, hydro) delay maps replicated in the HBM of every rank, written by peer stores from the integration kernels."""
+
+    def __init__(self, comm: Comm, nz: int, ny: int, nx: int) -> None:
+        import torch
+        import torch.distributed._symmetric_memory as symm
+        if comm.device.type != 'cuda':
+            raise RuntimeError('symmetric memory needs the nccl backend on CUDA devices')
+        if comm.world > 8:
+            raise RuntimeError('rdr_set_peer_outputs takes at most 8 destinations')
+        self.comm, self.nz, self.ny, self.nx = comm, nz, ny, nx
+        self.maps = symm.empty((2, nz, ny, nx), dtype=torch.float64, device=comm.device)
+        group = comm.group if comm.group is not None else comm.dist.group.WORLD
+        self.hdl = symm.rendezvous(self.maps, group)
+        self.base = [int(a) for a in self.hdl.buffer_ptrs]
+        if len(self.base) != comm.world or self.base[comm.rank] != self.maps.data_ptr():
+            raise RuntimeError('symmetric-memory rendezvous returned unexpected buffer pointers')
+
+    def block(self, r0: int, r1: int):
+        """This rank's own rows of both maps: two (nz, r1 - r0, nx) views whose [hh] slices are contiguous."""
+        return [self.maps[0][:, r0:r1], self.maps[1][:, r0:r1]]
+
+    def peer_ptrs(self, hh: int, r0: int, r1: int, include_self: bool = False):
+        """Addresses of rows [r0, r1) of height slice hh inside every other rank's maps (8-byte elements)."""
+        wet, hydro = [], []
+        for q, b in enumerate(self.base):
+            if q == self.comm.rank and not include_self:
+                continue
+            wet.append(b + 8 * ((0 * self.nz + hh) * self.ny + r0) * self.nx)
+            hydro.append(b + 8 * ((1 * self.nz + hh) * self.ny + r0) * self.nx)
+        return wet, hydro
+
+    def barrier(self) -> None:
+        """Signal-pad barrier on the current CUDA stream: every rank's kernels before it have completed (their peer stores
+        included) before any rank's work after it starts."""
+        self.hdl.barrier()
+
 
 def build_cube_ray_sharded(xpts, ypts, zpts, los, model_crs, pts_crs, interpolators, comm: Comm, MAX_SEGMENT_LENGTH=1000.0,
-                           MAX_TROPO_HEIGHT=None, gather=True, build_fn=None):
+                           MAX_TROPO_HEIGHT=None, gather=True, build_fn=None, host_block=False):
     """``_build_cube_ray`` with the raster row-sharded over ``comm``'s ranks.
 
     Every rank passes the FULL ``xpts``/``ypts``; rank r integrates rows ``shard_rows(ny, r, world)`` with the global
-    reductions hooked in, and (``gather=True``) all ranks return the full ``[wet, hydro]`` (nz, ny, nx) maps.
+    reductions hooked in, and (``gather=True``) all ranks return the full ``[wet, hydro]`` (nz, ny, nx) maps as host arrays.
+    ``gather='device'`` (nccl) leaves the reassembled maps in HBM and returns them as CUDA tensors -- with ``host_block=True``
+    as ``(device_maps, host_rows)``, the rank's own rows having been written to page-locked host memory by the same kernel.
     ``build_fn(xpts, ypts_block, ..., reduce_max=, reduce_sum=)`` defaults to the device path.
     """
     from . import delay as _delay
@@ -102,16 +162,46 @@ def build_cube_ray_sharded(xpts, ypts, zpts, los, model_crs, pts_crs, interpolat
         # make one trip to page-locked host memory
         import torch
         from ._lib import pinned_empty
+        sym = comm.symmetric_maps(zpts.size, ypts.size, np.size(xpts)) if gather else None
+        cube = interpolators[0].cube
         prev = _delay._reduce_hooks
         _delay._reduce_hooks = (comm.reduce_max, comm.reduce_sum)
         try:
-            local = _delay._build_cube_ray(xpts, ypts[r0:r1], zpts, los, model_crs, pts_crs, interpolators,
-                                           MAX_SEGMENT_LENGTH=MAX_SEGMENT_LENGTH, MAX_TROPO_HEIGHT=zref,
-                                           _out_device=torch.device('cuda', interpolators[0].cube.device))
+            if sym is not None:
+                # fused reassembly: the kernels of this rank write its rows into every rank's maps; barriers on the stream the
+                # kernels run on fence the maps against the previous call's readers and publish them afterwards
+                cube.h.set_stream(torch.cuda.current_stream().cuda_stream)
+                sym.barrier()
+                if host_block:   # this rank's rows also land in page-locked host memory, written by the same kernel
+                    local = _delay._build_cube_ray(xpts, ypts[r0:r1], zpts, los, model_crs, pts_crs, interpolators,
+                                                   MAX_SEGMENT_LENGTH=MAX_SEGMENT_LENGTH, MAX_TROPO_HEIGHT=zref,
+                                                   _peers=lambda hh, a, b: sym.peer_ptrs(hh, r0 + a, r0 + b, include_self=True))
+                else:
+                    local = _delay._build_cube_ray(xpts, ypts[r0:r1], zpts, los, model_crs, pts_crs, interpolators,
+                                                   MAX_SEGMENT_LENGTH=MAX_SEGMENT_LENGTH, MAX_TROPO_HEIGHT=zref, _out_arrays=sym.block(r0, r1),
+                                                   _peers=lambda hh, a, b: sym.peer_ptrs(hh, r0 + a, r0 + b))
+                sym.barrier()
+            else:
+                local = _delay._build_cube_ray(xpts, ypts[r0:r1], zpts, los, model_crs, pts_crs, interpolators,
+                                               MAX_SEGMENT_LENGTH=MAX_SEGMENT_LENGTH, MAX_TROPO_HEIGHT=zref,
+                                               _out_device=torch.device('cuda', cube.device))
         finally:
             _delay._reduce_hooks = prev
         if not gather:
             return [a.cpu().numpy() for a in local], (r0, r1)
+        if sym is not None and gather == 'device':
+            # full maps stay in HBM (valid until the next sharded call of the same shape); with host_block the rank's own rows
+            # are returned as host arrays as well
+            return ([sym.maps[0], sym.maps[1]], local) if host_block else [sym.maps[0], sym.maps[1]]
+        if sym is not None:
+            out = [pinned_empty((zpts.size, ypts.size, np.size(xpts))) for _ in range(2)]
+            for f in range(2):
+                torch.from_numpy(out[f]).copy_(sym.maps[f], non_blocking=True)
+            torch.cuda.synchronize()
+            return out
+        if gather == 'device':   # no symmetric memory: NCCL all-gather, maps stay in HBM
+            full = [torch.stack([comm.all_gather_rows(arr[hh], ypts.size) for hh in range(zpts.size)]) for arr in local]
+            return (full, [a.cpu().numpy() for a in local]) if host_block else full
         out = [pinned_empty((zpts.size, ypts.size, np.size(xpts))) for _ in local]
         for arr, dst in zip(local, out):
             for hh in range(zpts.size):

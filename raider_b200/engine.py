@@ -117,8 +117,21 @@ class DeviceCube:
                     ptr(maxlen), ptr(counts), _lib.MEM_DEVICE if dev else _lib.MEM_HOST)
         return maxlen[: counts[3]].copy(), counts
 
-    def ray_integrate(self, maxlen, max_segment_length, clamp_low_first, out_wet, out_hydro, accumulate=False):
-        """K3 on the rays of the last ray_layers call.  Returns (nparts[K], oob[3])."""
+    def ray_integrate(self, maxlen, max_segment_length, clamp_low_first, out_wet, out_hydro, accumulate=False, peers=None):
+        """K3 on the rays of the last ray_layers call.  Returns (nparts[K], oob[3]).
+
+        ``peers = (wet_ptrs, hydro_ptrs)``: device addresses (ints) of the same row block inside the delay maps of the node's
+        other GPUs (peer-mapped symmetric memory); the kernel mirrors every ray's results there as it finishes the ray
+        (rdr_set_peer_outputs) -- the all-gather of the output map fused into the integration.
+        """
+        if peers is not None and len(peers[0]):
+            n = len(peers[0])
+            pw, ph = (C.c_void_p * n)(*[int(a) for a in peers[0]]), (C.c_void_p * n)(*[int(a) for a in peers[1]])
+            self.h.call('rdr_set_peer_outputs', n, pw, ph)
+            try:
+                return self.ray_integrate(maxlen, max_segment_length, clamp_low_first, out_wet, out_hydro, accumulate)
+            finally:
+                self.h.call('rdr_set_peer_outputs', 0, None, None)
         maxlen = f64(maxlen)
         nparts = np.zeros(maxlen.size, dtype=np.int64)
         oob = np.zeros(3, dtype=np.int64)
@@ -175,7 +188,7 @@ class DeviceCube:
         return wet, hydro, ns
 
     def trace(self, geom_kind, gx, gy, ny, nx, los_kind, los, ht, zref, max_segment_length, out_wet, out_hydro,
-              reduce_max=None, reduce_sum=None, max_t_bytes=None) -> TraceInfo:
+              reduce_max=None, reduce_sum=None, max_t_bytes=None, peers_fn=None) -> TraceInfo:
         """One output height: K0 -> global reduction of the per-layer maxima / predicates -> K3.
 
         ``reduce_max`` / ``reduce_sum`` are the cross-GPU hooks (numpy array in -> reduced numpy array out); they are
@@ -186,6 +199,8 @@ class DeviceCube:
         RAIDER_B200_T_BUDGET_GB, 64 GB of the 180 GB HBM3e) the raster is walked in row tiles: a first K0 pass over all tiles
         for the global maxima and counters, then K0 + K3 per tile with those maxima -- the same mechanism that keeps
         multi-GPU shards identical to the unsharded raster.
+
+        ``peers_fn(r0, r1)`` -> ``(wet_ptrs, hydro_ptrs)`` for rows [r0, r1) of this call's block: see ``ray_integrate``.
         """
         if max_t_bytes is None:
             max_t_bytes = float(os.environ.get('RAIDER_B200_T_BUDGET_GB', '64')) * 2**30
@@ -193,7 +208,7 @@ class DeviceCube:
         rows_per_tile = int(max(1, max_t_bytes // (8 * nz * max(1, int(nx)))))
         if rows_per_tile >= ny:
             return self._trace_block(geom_kind, gx, gy, ny, nx, los_kind, los, ht, zref, max_segment_length, out_wet, out_hydro,
-                                     reduce_max, reduce_sum)
+                                     reduce_max, reduce_sum, peers_fn(0, ny) if peers_fn else None)
         tiles = [(r0, min(ny, r0 + rows_per_tile)) for r0 in range(0, ny, rows_per_tile)]
 
         def block(r0, r1):
@@ -221,7 +236,8 @@ class DeviceCube:
             for r0, r1 in tiles:
                 bx, by, bl = block(r0, r1)
                 self.ray_layers(geom_kind, bx, by, r1 - r0, nx, los_kind, bl, ht, zref)
-                nparts, oob = self.ray_integrate(maxlen, max_segment_length, clamp, ow[r0:r1], oh[r0:r1])
+                nparts, oob = self.ray_integrate(maxlen, max_segment_length, clamp, ow[r0:r1], oh[r0:r1],
+                                                 peers=peers_fn(r0, r1) if peers_fn else None)
                 oob_tot += oob
             first_below = oob_tot[:1] if reduce_sum is None else reduce_sum(oob_tot[:1])
             if bool(first_below[0] == counts[0]) == clamp:
@@ -236,7 +252,7 @@ class DeviceCube:
         return info
 
     def _trace_block(self, geom_kind, gx, gy, ny, nx, los_kind, los, ht, zref, max_segment_length, out_wet, out_hydro,
-                     reduce_max=None, reduce_sum=None) -> TraceInfo:
+                     reduce_max=None, reduce_sum=None, peers=None) -> TraceInfo:
         info = TraceInfo(ht=float(ht))
         maxlen, counts = self.ray_layers(geom_kind, gx, gy, ny, nx, los_kind, los, ht, zref)
         if reduce_max is not None:
@@ -244,11 +260,11 @@ class DeviceCube:
             counts = np.concatenate([reduce_sum(counts[:3]), counts[3:]])
         info.n_rays, info.n_nan_rays, info.n_layers = int(counts[0]), int(counts[1]), int(counts[3])
         clamp = bool(counts[2] == counts[0])
-        nparts, oob = self.ray_integrate(maxlen, max_segment_length, clamp, out_wet, out_hydro)
+        nparts, oob = self.ray_integrate(maxlen, max_segment_length, clamp, out_wet, out_hydro, peers=peers)
         first_below = oob[:1] if reduce_sum is None else reduce_sum(oob[:1])
         if bool(first_below[0] == counts[0]) != clamp:  # K0's hint and K3's own evaluation disagree on a knife edge: K3 rules
             clamp = not clamp
-            nparts, oob = self.ray_integrate(maxlen, max_segment_length, clamp, out_wet, out_hydro)
+            nparts, oob = self.ray_integrate(maxlen, max_segment_length, clamp, out_wet, out_hydro, peers=peers)
             info.reruns = 1
         info.maxlen, info.nparts = maxlen, nparts
         info.samples_per_ray = int(nparts.sum())

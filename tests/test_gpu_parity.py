@@ -216,7 +216,7 @@ def _run_gpu(cfg, los, **kw):
     from raider_b200.delay import _build_cube_ray
     from raider_b200.delayFcns import getInterpolators
     ifs = getInterpolators(cfg['cube'])
-    out = _build_cube_ray(cfg['xpts'], cfg['ypts'], cfg['zpts'], los, 4326, 4326, list(ifs), MAX_SEGMENT_LENGTH=cfg['max_segment_length'],
+    out = _build_cube_ray(cfg['xpts'], cfg['ypts'], cfg['zpts'], los, cfg.get('crs', 4326), 4326, list(ifs), MAX_SEGMENT_LENGTH=cfg['max_segment_length'],
                           MAX_TROPO_HEIGHT=cfg['zref'], **kw)
     return out, ifs[0].cube.last_info
 
@@ -734,6 +734,68 @@ def test_row_tiling_is_bit_identical(gpu, monkeypatch):
                              list(rt.get_interpolators(cfg['cube'])), MAX_SEGMENT_LENGTH=cfg['max_segment_length'],
                              MAX_TROPO_HEIGHT=cfg['zref'], layer_maxlen=[info[0].maxlen])
     assert np.abs(tiled[0][0, :6] - want[0][0]).max() < TOL_F64_M and np.abs(tiled[1][0, :6] - want[1][0]).max() < TOL_F64_M
+
+
+def test_k3_integrator_forms_agree(gpu, monkeypatch):
+    """The three forms of K3 -- polynomial (default: per-span cubics of the cube coordinates through exact nodes), fast (Bowring
+    per sample) and general (PROJ-form arithmetic per sample) -- against the oracle and against each other, on the geometries
+    that stress the polynomial: steep incidence (long spans), high latitude, thick top layers, short spans, cached / uncached
+    cell records, a Lambert cube, rays that leave the cube (handed to the PROJ-form path with their NaN pattern)."""
+    from oracle import raytrace as rt
+    from raider_b200 import synthetic as syn
+    from raider_b200.losreader import Raytracing
+    crs = rt.GeographicCRS()
+
+    def forms(cfg, los, settings):
+        res = {}
+        for name, env in settings.items():
+            for k in ('RDR_K3_MODE', 'RDR_K3_SPAN', 'RDR_K3_CACHE', 'RDR_K3_MINB'):
+                monkeypatch.delenv(k, raising=False)
+            for k, v in env.items():
+                monkeypatch.setenv(k, v)
+            res[name] = _run_gpu(cfg, los)
+        for k in ('RDR_K3_MODE', 'RDR_K3_SPAN', 'RDR_K3_CACHE', 'RDR_K3_MINB'):
+            monkeypatch.delenv(k, raising=False)
+        return res
+
+    settings = {'poly': {}, 'poly_nocache': {'RDR_K3_CACHE': '0'}, 'poly_cache_m4': {'RDR_K3_CACHE': '1', 'RDR_K3_MINB': '4'},
+                'poly_span2k': {'RDR_K3_SPAN': '2000'}, 'poly_span20k': {'RDR_K3_SPAN': '20000'}, 'fast': {'RDR_K3_MODE': 'fast'},
+                'general': {'RDR_K3_MODE': 'general'}}
+    cases = [(_c2_small(24, 0.05), 30.0, -168.0, 225.0), (_c2_small(24, 0.05), 62.0, 77.0, 500.0), (_c2_small(16, 0.05, table='ml145'), 45.0, 10.0, 1000.0)]
+    hi = syn.config_c2(n=16)   # 72 N: meridians converge, the cube cells are 9 km wide in x
+    hi['xpts'], hi['ypts'] = syn.raster(72.0, 25.0, 16, 16, 0.05)
+    xs, ys = syn.cube_axes_around(hi['xpts'], hi['ypts'])
+    hi['cube'] = syn.make_cube(ys, xs, syn.z_levels(37), totals=False)
+    cases.append((hi, 40.0, -100.0, 225.0))
+    for cfg, inc, head, seg in cases:
+        cfg = dict(cfg, max_segment_length=seg)
+        st = {}
+        want = rt.build_cube_ray(cfg['xpts'], cfg['ypts'], cfg['zpts'], rt.FixedIncidenceLOS(inc, head), crs, crs, list(rt.get_interpolators(cfg['cube'])),
+                                 MAX_SEGMENT_LENGTH=seg, MAX_TROPO_HEIGHT=cfg['zref'], stats=st)
+        assert not np.isnan(want[0]).any()
+        res = forms(cfg, Raytracing(incidence=inc, heading=head), settings)
+        for name, (out, info) in res.items():
+            assert np.array_equal(info[0].nparts, st['nParts'][0]), name
+            for f in (0, 1):
+                assert np.abs(out[f] - want[f]).max() < TOL_F64_M, (name, inc)
+                # the forms differ from each other by rounding only: 1e-9 m is 1000x inside the contract
+                assert np.abs(out[f] - res['general'][0][f]).max() < 1e-9, (name, inc, float(np.abs(out[f] - res['general'][0][f]).max()))
+    # rays leaving the cube: the polynomial integrator hands them over; NaN pattern and values as the PROJ-form path alone
+    m = 40
+    xp, yp = syn.raster(34.0, -118.0, m, m, 0.004)
+    xs, ys = syn.cube_axes_around(xp, yp, pad_deg=0.0)
+    edge = {'cube': syn.make_cube(ys, xs, syn.z_levels(37), totals=False), 'xpts': xp, 'ypts': yp, 'zpts': np.array([0.0]),
+            'zref': float(syn.z_levels(37)[-1] - 1), 'max_segment_length': 225.0}
+    res = forms(edge, Raytracing(incidence=30.0, heading=-168.0), {'poly': {}, 'general': {'RDR_K3_MODE': 'general'}})
+    a, b = res['poly'][0], res['general'][0]
+    assert np.isnan(b[0]).any() and not np.isnan(b[0]).all()
+    assert np.array_equal(np.isnan(a[0]), np.isnan(b[0])) and np.nanmax(np.abs(a[0] - b[0])) < 1e-9 and np.nanmax(np.abs(a[1] - b[1])) < 1e-9
+    # Lambert cube (C3 shape): polynomial nodes through the PROJ-form inverse + Lambert forward vs every sample through them
+    c3 = syn.config_c3(ny=12, nx=14)
+    res = forms(c3, Raytracing(incidence=37.0, heading=-168.0), {'poly': {}, 'poly_nocache': {'RDR_K3_CACHE': '0'}, 'general': {'RDR_K3_MODE': 'general'}})
+    for name in ('poly', 'poly_nocache'):
+        for f in (0, 1):
+            assert np.abs(res[name][0][f] - res['general'][0][f]).max() < 1e-9, name
 
 
 # ---------------------------------------------------------------------------------------- K7: weather-model processing (f4)
