@@ -60,6 +60,20 @@ class Comm:
         """all-reduce(SUM) of the predicate counters: keeps the .all() tests global (delay.py:279,306-311)."""
         return self._allreduce(np.asarray(arr, dtype=np.int64), self.dist.ReduceOp.SUM)
 
+    def reduce_pair(self, maxlen, counts):
+        """Both reductions of the step in one collective: every rank contributes K maxima + 3 counters (as doubles: counts stay
+        far below 2^53), one all-gather of world x (K + 3) doubles, MAX / SUM taken locally."""
+        torch = self.torch
+        maxlen, counts = np.asarray(maxlen, dtype=np.float64), np.asarray(counts, dtype=np.int64)
+        mine = torch.as_tensor(np.concatenate([maxlen, counts.astype(np.float64)])).to(self.device)
+        allv = torch.empty((self.world, mine.numel()), dtype=torch.float64, device=self.device)
+        self.dist.all_gather_into_tensor(allv, mine, group=self.group)
+        allv = allv.cpu().numpy()
+        k = maxlen.size
+        # NaN maxima (a rank whose rays all failed) must not win or vanish silently: np.max propagates NaN like the all-reduce(MAX) of NCCL does not;
+        # the reference's own nanmax-free `.max()` (delay.py:283) propagates, so propagate
+        return allv[:, :k].max(axis=0), np.rint(allv[:, k:].sum(axis=0)).astype(np.int64)
+
     def all_gather_rows(self, block, ny: int):
         """Reassemble an (ny, nx) map from per-rank row blocks (uneven blocks are padded to the largest)."""
         torch = self.torch

@@ -223,9 +223,7 @@ class DeviceCube:
             m, c = self.ray_layers(geom_kind, bx, by, r1 - r0, nx, los_kind, bl, ht, zref)
             maxlen = m if maxlen is None else np.maximum(maxlen, m)
             counts = c.copy() if counts is None else np.concatenate([counts[:3] + c[:3], c[3:]])
-        if reduce_max is not None:
-            maxlen = reduce_max(maxlen)
-            counts = np.concatenate([reduce_sum(counts[:3]), counts[3:]])
+        maxlen, counts = _global_plan(maxlen, counts, reduce_max, reduce_sum)
         info = TraceInfo(ht=float(ht))
         info.n_rays, info.n_nan_rays, info.n_layers = int(counts[0]), int(counts[1]), int(counts[3])
         clamp = bool(counts[2] == counts[0])
@@ -255,9 +253,7 @@ class DeviceCube:
                      reduce_max=None, reduce_sum=None, peers=None) -> TraceInfo:
         info = TraceInfo(ht=float(ht))
         maxlen, counts = self.ray_layers(geom_kind, gx, gy, ny, nx, los_kind, los, ht, zref)
-        if reduce_max is not None:
-            maxlen = reduce_max(maxlen)
-            counts = np.concatenate([reduce_sum(counts[:3]), counts[3:]])
+        maxlen, counts = _global_plan(maxlen, counts, reduce_max, reduce_sum)
         info.n_rays, info.n_nan_rays, info.n_layers = int(counts[0]), int(counts[1]), int(counts[3])
         clamp = bool(counts[2] == counts[0])
         nparts, oob = self.ray_integrate(maxlen, max_segment_length, clamp, out_wet, out_hydro, peers=peers)
@@ -271,6 +267,19 @@ class DeviceCube:
         info.clamp_low_first = clamp
         info.oob_below, info.oob_above = int(oob[1]), int(oob[2])
         return info
+
+
+def _global_plan(maxlen, counts, reduce_max, reduce_sum):
+    """Per-layer maxima (MAX) and the three predicate counters (SUM) over all ranks.  When the hooks belong to an object that
+    offers ``reduce_pair`` (raider_b200.dist.Comm) both travel in ONE collective instead of two."""
+    if reduce_max is None:
+        return maxlen, counts
+    pair = getattr(getattr(reduce_max, '__self__', None), 'reduce_pair', None)
+    if pair is not None:
+        m, c3 = pair(maxlen, counts[:3])
+    else:
+        m, c3 = reduce_max(maxlen), reduce_sum(counts[:3])
+    return m, np.concatenate([c3, counts[3:]])
 
 
 def los_device_spec(los, ny: int, nx: int):
