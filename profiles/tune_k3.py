@@ -60,3 +60,28 @@ for nm, cf in (('C2', cfg), ('ml145', c145)):
             ref = (w, h)
         print(f'{nm} {mode} minb={minb} cache={cache}: K3 {t3:.3f} ms  max|d wet| {np.abs(w - ref[0]).max():.2e} max|d hydro| {np.abs(h - ref[1]).max():.2e} '
               f'fix {cube.h.last_fix_count}', flush=True)
+
+# K0: Newton iterates on the span cubics of h(t) (default) vs on Bowring heights
+for nm, cf, inc in (('C2', cfg, 30.0), ('ml145', c145, 30.0), ('C2 60deg', cfg, 60.0)):
+    from raider_b200.losreader import inc_hd_to_enu
+    e = np.ascontiguousarray(inc_hd_to_enu(np.float64(inc), np.float64(-168.0)))
+    cube = DeviceCube.from_dict(cf['cube'], device=0)
+    cube.h.set_stream(stream.cuda_stream)
+    ny, nx = cf['ypts'].size, cf['xpts'].size
+    ow = torch.empty((ny, nx), dtype=torch.float64, device='cuda')
+    oh = torch.empty((ny, nx), dtype=torch.float64, device='cuda')
+    ref = None
+    for mode in ('exact', 'cubic'):
+        os.environ['RDR_K0_MODE'] = mode
+        for minb in (6, 8):
+            os.environ['RDR_K0_MINB'] = str(minb)
+            lay = lambda: cube.ray_layers(_lib.GEOM_GRID, cf['xpts'], cf['ypts'], ny, nx, _lib.LOS_ENU_CONST, e, 0.0, cf['zref'])
+            maxlen, counts = lay()
+            t0 = timed(lay)
+            nparts, _ = cube.ray_integrate(maxlen, cf['max_segment_length'], False, ow, oh)
+            w, h = ow.cpu().numpy(), oh.cpu().numpy()
+            if ref is None:
+                ref = (maxlen, w, h, nparts)
+            print(f'{nm} K0 {mode} minb={minb}: {t0:.3f} ms  max|d maxlen| {np.abs(maxlen - ref[0]).max():.2e} m  nParts equal {np.array_equal(nparts, ref[3])}  '
+                  f'max|d wet| {np.nanmax(np.abs(w - ref[1])):.2e} max|d hydro| {np.nanmax(np.abs(h - ref[2])):.2e}  nan {int(np.isnan(w).sum())}', flush=True)
+    os.environ.pop('RDR_K0_MODE'); os.environ.pop('RDR_K0_MINB')

@@ -733,9 +733,93 @@ __device__ __forceinline__ void ray_layers_one(const RayFrame &F, int K, const d
     }
 }
 
+// K0 with the height along the ray as a piecewise cubic.  h(t) is smooth along a straight ray (fastpath.cuh): on uniform spans
+// of K0_SPAN metres the cubic through four exact heights misses the PROJ-form height by < 1e-8 m (T^4 scaling of the 2e-8 m measured
+// at 8 km), below the ~3e-9 m rounding noise of that height by little.  Every Newton iterate of getTopOfAtmosphere
+// (losreader.py:720-733) then costs one cubic evaluation (a span lookup in thread-local memory + 3 DFMA) instead of a Bowring
+// inversion (~50 DP instructions), and the exact heights needed are 3 per span instead of 3 per *layer* (20 for the first):
+// 30 instead of 119 on C2, 48 instead of 452 on the 145-level tables.  The iteration itself -- start at t = toa, three (ten)
+// updates divided by the cos factor -- is the reference's.  Spans are built lazily as the iterates climb; the iterate t = toa
+// of an oblique ray lies far below the solution, which is why all spans of the ray are kept.
+constexpr double K0_SPAN = 6000.0;
+constexpr int K0_MAX_SPANS = 64;  // 384 km of ray: incidence up to ~78 deg through an 80 km model; longer rays take the exact form
+
+struct HeightSpans {
+    Cubic c[K0_MAX_SPANS];
+    int built;
+    double h_node;  // exact height at the end of the last built span
+};
+
+__device__ __forceinline__ double span_height(const RayFrame &F, HeightSpans &S, double t) {
+    const double u = t * (1.0 / K0_SPAN);
+    const int j = min(max((int)u, 0), K0_MAX_SPANS - 1);
+    while (S.built <= j) {  // (a NaN t gives j = 0: built once, NaN propagates through the evaluation)
+        const double t0 = (double)S.built * K0_SPAN;
+        const double t1 = t0 + K0_SPAN / 3.0, t2 = t0 + 2.0 * K0_SPAN / 3.0, t3 = t0 + K0_SPAN;
+        const double h1 = frame_height(fma(t1, F.uA, F.A0), t1 * F.uB, fma(t1, F.uZ, F.Z0));
+        const double h2 = frame_height(fma(t2, F.uA, F.A0), t2 * F.uB, fma(t2, F.uZ, F.Z0));
+        const double h3 = frame_height(fma(t3, F.uA, F.A0), t3 * F.uB, fma(t3, F.uZ, F.Z0));
+        S.c[S.built] = cubic_through(S.h_node, h1, h2, h3);
+        S.h_node = h3;
+        ++S.built;
+    }
+    return cubic_eval(S.c[j], u - (double)j);
+}
+
+template <int ITERS>
+__device__ __forceinline__ double span_top_of_atmosphere(const RayFrame &F, HeightSpans &S, double toa, double rfactor) {
+    double t = toa;
+#pragma unroll 1
+    for (int it = 0; it < ITERS; ++it) t += (toa - span_height(F, S, t)) * rfactor;
+    return t;
+}
+
+// returns false (nothing stored that matters) when the ray is too long for the span table: the caller redoes the warp exactly
+__device__ __forceinline__ bool ray_layers_cubic(const RayFrame &F, int K, const double *__restrict__ plan, double *__restrict__ t_out,
+                                                 int64_t n_rays, int64_t r, bool valid, int lane, double zmin, double zref_top,
+                                                 unsigned long long *smax, bool &any_nan) {
+    HeightSpans S;
+    S.built = 0;
+    S.h_node = frame_height(F.A0, 0.0, F.Z0);
+    const double unorm = norm3(Vec3{F.uA, F.uB, F.uZ});
+    double t_lo = 0.0, t_hi = 0.0, rcosf = 1.0;
+    for (int k = 0; k < K; ++k) {
+        const double a = __ldg(plan + k), b = __ldg(plan + K + k);
+        if (k == 0) {
+            t_lo = span_top_of_atmosphere<10>(F, S, a, 1.0);
+            t_hi = span_top_of_atmosphere<10>(F, S, b, 1.0);
+        } else {
+            t_lo = t_hi;
+            t_hi = span_top_of_atmosphere<3>(F, S, b, rcosf);
+        }
+        const double len = fabs(t_hi - t_lo) * unorm;  // |P_hi - P_lo| (losreader.py:821): the points are g + t u
+        if (k == 0) {
+            rcosf = len / (b - a);  // 1 / cos_factor of losreader.py:824-825
+            // the last layer top sits near (zref - ht) / cos_factor: does the span table reach it?  Decided per warp, before
+            // anything is stored or counted, so that the exact form can redo the warp from scratch.  (NaN: runs on, stays NaN)
+            const bool too_long = (zref_top - a) * rcosf * 1.05 + 2.0 * K0_SPAN > (double)K0_MAX_SPANS * K0_SPAN;
+            if (__any_sync(0xffffffffu, too_long)) return false;
+            if (valid) __stcs(t_out + r, t_lo);
+            // hint for the whole-raster clamp of delay.py:306-307: height of the very first sample, evaluated exactly on the
+            // point K3 will reconstruct (K3 re-evaluates the predicate itself and has the last word)
+            const double h0 = frame_height(fma(t_lo, F.uA, F.A0), t_lo * F.uB, fma(t_lo, F.uZ, F.Z0));
+            const unsigned below = __ballot_sync(0xffffffffu, valid && (h0 < zmin));
+            if (lane == 0 && below) atomicAdd(&smax[K + 1], (unsigned long long)__popc(below));
+        }
+        if (valid) __stcs(t_out + (int64_t)(k + 1) * n_rays + r, t_hi);
+        const bool isn = !(len == len);
+        any_nan |= isn;
+        const unsigned long long bits = (valid && !isn) ? (unsigned long long)__double_as_longlong(len) : 0ull;
+        const unsigned long long m = warp_max_bits(bits);
+        if (lane == 0 && m > smax[k]) atomicMax(&smax[k], m);
+    }
+    return true;
+}
+
 template <int BLOCK, int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB) k_ray_layers(const RayGeom G, int64_t n_rays, int K, const double *__restrict__ plan,
-                                                      double *__restrict__ t_out, unsigned long long *__restrict__ red, double zmin) {
+                                                      double *__restrict__ t_out, unsigned long long *__restrict__ red, double zmin,
+                                                      int use_cubic) {
     extern __shared__ unsigned long long smax[];  // [K + 2]
     for (int i = threadIdx.x; i < K + 2; i += BLOCK) smax[i] = 0ull;
     __syncthreads();
@@ -750,10 +834,13 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_ray_layers(const RayGeom G, int
         frame_setup(lat, lon, G.ht, G.los_kind, G.los, rr, G.e, G.n, G.u, F);
         bool any_nan = false;
         // the branch is taken per warp (all lanes vote): the ballots / REDUX inside need the full warp
-        if (__all_sync(0xffffffffu, F.fast_ok))
-            ray_layers_one<false>(F, K, plan, t_out, n_rays, r, valid, lane, zmin, smax, any_nan);
-        else
+        if (__all_sync(0xffffffffu, F.fast_ok)) {
+            // (a warp whose rays are too long for the span table bails out of the cubic form before storing or counting anything)
+            if (!use_cubic || !ray_layers_cubic(F, K, plan, t_out, n_rays, r, valid, lane, zmin, __ldg(plan + 2 * K - 1), smax, any_nan))
+                ray_layers_one<false>(F, K, plan, t_out, n_rays, r, valid, lane, zmin, smax, any_nan);
+        } else {
             ray_layers_one<true>(F, K, plan, t_out, n_rays, r, valid, lane, zmin, smax, any_nan);
+        }
         const unsigned nn = __ballot_sync(0xffffffffu, valid && any_nan);
         if (lane == 0 && nn) atomicAdd(&smax[K], (unsigned long long)__popc(nn));
     }
@@ -2287,9 +2374,11 @@ RDR_API int rdr_ray_layers(rdr_handle_t h, int geom_kind, const double *gx, cons
     const int minb = tune_minb("RDR_K0_MINB", 8);
     const int grid = grid_for(n, BLOCK, h->sm_count, 4 * minb);
     const size_t smem = (K + 2) * sizeof(unsigned long long);
+    const char *k0_env = getenv("RDR_K0_MODE");  // cubic (default) | exact: Newton iterates on the span cubics of h(t) or on Bowring heights
+    const int use_cubic = !(k0_env && !strcmp(k0_env, "exact"));
 #define RDR_LAUNCH_K0(M)                                                                                                              \
     k_ray_layers<BLOCK, M><<<grid, BLOCK, smem, h->stream>>>(make_geom(h), n, K, h->d_plan.as<double>(), h->d_t.as<double>(),          \
-                                                            h->d_red.as<unsigned long long>(), h->zs.front())
+                                                            h->d_red.as<unsigned long long>(), h->zs.front(), use_cubic)
     switch (minb) {
         case 4: RDR_LAUNCH_K0(4); break;
         case 5: RDR_LAUNCH_K0(5); break;
