@@ -749,16 +749,17 @@ def test_k3_integrator_forms_agree(gpu, monkeypatch):
     def forms(cfg, los, settings):
         res = {}
         for name, env in settings.items():
-            for k in ('RDR_K3_MODE', 'RDR_K3_SPAN', 'RDR_K3_CACHE', 'RDR_K3_MINB'):
+            for k in ('RDR_K3_MODE', 'RDR_K3_SPAN', 'RDR_K3_CACHE', 'RDR_K3_MINB', 'RDR_K0_MODE'):
                 monkeypatch.delenv(k, raising=False)
             for k, v in env.items():
                 monkeypatch.setenv(k, v)
             res[name] = _run_gpu(cfg, los)
-        for k in ('RDR_K3_MODE', 'RDR_K3_SPAN', 'RDR_K3_CACHE', 'RDR_K3_MINB'):
+        for k in ('RDR_K3_MODE', 'RDR_K3_SPAN', 'RDR_K3_CACHE', 'RDR_K3_MINB', 'RDR_K0_MODE'):
             monkeypatch.delenv(k, raising=False)
         return res
 
-    settings = {'poly': {}, 'poly_nocache': {'RDR_K3_CACHE': '0'}, 'poly_cache_m4': {'RDR_K3_CACHE': '1', 'RDR_K3_MINB': '4'},
+    # (+ K0 with Bowring heights at every Newton iterate instead of the span cubics of h(t): 'k0_exact')
+    settings = {'poly': {}, 'k0_exact': {'RDR_K0_MODE': 'exact'}, 'poly_nocache': {'RDR_K3_CACHE': '0'}, 'poly_cache_m4': {'RDR_K3_CACHE': '1', 'RDR_K3_MINB': '4'},
                 'poly_span2k': {'RDR_K3_SPAN': '2000'}, 'poly_span20k': {'RDR_K3_SPAN': '20000'}, 'fast': {'RDR_K3_MODE': 'fast'},
                 'general': {'RDR_K3_MODE': 'general'}}
     cases = [(_c2_small(24, 0.05), 30.0, -168.0, 225.0), (_c2_small(24, 0.05), 62.0, 77.0, 500.0), (_c2_small(16, 0.05, table='ml145'), 45.0, 10.0, 1000.0)]
@@ -774,6 +775,7 @@ def test_k3_integrator_forms_agree(gpu, monkeypatch):
                                  MAX_SEGMENT_LENGTH=seg, MAX_TROPO_HEIGHT=cfg['zref'], stats=st)
         assert not np.isnan(want[0]).any()
         res = forms(cfg, Raytracing(incidence=inc, heading=head), settings)
+        assert np.abs(res['poly'][1][0].maxlen - res['k0_exact'][1][0].maxlen).max() < 1e-7   # layer lengths: cubic vs Bowring iterates
         for name, (out, info) in res.items():
             assert np.array_equal(info[0].nparts, st['nParts'][0]), name
             for f in (0, 1):
@@ -796,6 +798,25 @@ def test_k3_integrator_forms_agree(gpu, monkeypatch):
     for name in ('poly', 'poly_nocache'):
         for f in (0, 1):
             assert np.abs(res[name][0][f] - res['general'][0][f]).max() < 1e-9, name
+
+
+def test_k0_very_oblique_rays_take_the_exact_form(gpu, monkeypatch):
+    """80 deg incidence through the 145-level table: the ray is longer than K0's span table (384 km), the warp redoes its layers
+    with Bowring heights; layer maxima / nParts must not depend on which form ran, and match the oracle.  The rays leave the
+    cube on the way up (NaN delays, as in the reference: delay.py:187-188)."""
+    from oracle import raytrace as rt
+    from raider_b200.losreader import Raytracing
+    cfg = _c2_small(8, 0.05, table='ml145')
+    crs = rt.GeographicCRS()
+    st = {}
+    want = rt.build_cube_ray(cfg['xpts'], cfg['ypts'], cfg['zpts'], rt.FixedIncidenceLOS(80.0, -168.0), crs, crs, list(rt.get_interpolators(cfg['cube'])),
+                             MAX_SEGMENT_LENGTH=cfg['max_segment_length'], MAX_TROPO_HEIGHT=cfg['zref'], stats=st)
+    out, info = _run_gpu(cfg, Raytracing(incidence=80.0, heading=-168.0))
+    monkeypatch.setenv('RDR_K0_MODE', 'exact')
+    out_e, info_e = _run_gpu(cfg, Raytracing(incidence=80.0, heading=-168.0))
+    assert np.array_equal(info[0].maxlen, info_e[0].maxlen)          # the very same code ran
+    assert np.array_equal(info[0].nparts, st['nParts'][0])
+    assert np.array_equal(np.isnan(out[0]), np.isnan(want[0])) and np.isnan(want[0]).all()
 
 
 # ---------------------------------------------------------------------------------------- K7: weather-model processing (f4)
