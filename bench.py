@@ -441,7 +441,8 @@ def run_ours(args):
         'roofline': {'kernel': 'k_sample_stream<double> (K2 trilinear_sample, unfused, TMA-bulk point stream)', 'bound': 'hbm', 'achieved': k2_gbs,
                      'peak': peak, 'unit': 'GB/s', 'frac': k2_gbs / peak, 'traffic': k2_traffic, 'traffic_source': k2_traffic_src,
                      'algorithmic_bytes_per_launch': k2_bytes, 'peak_source': peak_src, 'bytes_per_point': 40,
-                     'points_per_launch': npts, 'ms_per_launch': k2_ms, 'fp32_io_tier_gbs': k2_32_gbs, 'fp32_io_tier_frac': k2_32_gbs / peak},
+                     'points_per_launch': npts, 'ms_per_launch': k2_ms, 'fp32_io_tier_gbs': k2_32_gbs, 'fp32_io_tier_frac': k2_32_gbs / peak,
+                     'fp32_tier_kernel': 'k_sample_stream_f32 (fp32 coordinates, arithmetic and values, 20 B/point; L1-bandwidth bound: 100 B/point through L1)'},
         'fused': fused,
         'cpu_baseline': cpu,
         'check': {'checksum': checksum, 'nan': nan_count, 'nparts_sum': int(info.samples_per_ray), 'fused_gather_vs_nccl_allgather_max_abs_diff_m': fused_vs_allgather},

@@ -24,11 +24,13 @@ pts = torch.empty((nslots, n * n, 3), dtype=torch.float64, device='cuda')
 cube.ray_points(maxlen, cfg['max_segment_length'], slot0=100, nslots=nslots, out=pts)
 npts = nslots * n * n
 p32 = pts.to(torch.float32)
-for dt, P, bpp in ((torch.float64, pts, 40), (torch.float32, p32, 20)):
+for dt, P, bpp, arith in ((torch.float64, pts, 40, 'f64'), (torch.float32, p32, 20, 'f64'), (torch.float32, p32, 20, 'f32')):
     sw = torch.empty(npts, dtype=dt, device='cuda')
     sh = torch.empty_like(sw)
-    for ppt in (1, 2, 3, 4):
+    os.environ['RDR_K2_F32_ARITH'] = '1' if arith == 'f32' else '0'
+    for ppt in ((1, 2, 4) if arith == 'f32' else (2,)):
         os.environ['RDR_K2_PPT'] = str(ppt)
+        os.environ['RDR_K2_PPT32'] = str(ppt)
         for _ in range(3):
             cube.sample(P.view(-1, 3), out=(sw, sh))
         torch.cuda.synchronize()
@@ -41,4 +43,4 @@ for dt, P, bpp in ((torch.float64, pts, 40), (torch.float32, p32, 20)):
             torch.cuda.synchronize()
             ts.append(a.elapsed_time(b))
         t = float(np.median(ts))
-        print(f'{str(dt):14s} ppt={ppt}: {t:.3f} ms  {npts * bpp / t / 1e6:.1f} GB/s  frac {npts * bpp / t / 1e6 / 6534.8:.3f}  checksum {float(sw.double().sum()):.6f}')
+        print(f'{str(dt):14s} arith={arith} ppt={ppt}: {t:.3f} ms  {npts * bpp / t / 1e6:.1f} GB/s  frac {npts * bpp / t / 1e6 / 6534.8:.3f}  checksum {float(sw.double().sum()):.6f}')

@@ -205,7 +205,7 @@ struct rdr_handle_s {
     double crs[7] = {0, 0, 0, 0, 0, 0, 0};
     DevBuf d_axes;   // ys | xs | zs (nodes)
     DevBuf d_tabs;   // per axis: interval records (double4) then first-guess bins (uint16)
-    size_t tab_cell_off[3] = {0, 0, 0}, tab_bin_off[3] = {0, 0, 0};
+    size_t tab_cell_off[3] = {0, 0, 0}, tab_bin_off[3] = {0, 0, 0}, tab_rec32_off[3] = {0, 0, 0};
     int tab_nbin[3] = {0, 0, 0};
     DevBuf d_cells;  // double4 [ny][nx][nz-1]  {wet[z], hydro[z], wet[z+1], hydro[z+1]}
     DevBuf d_cells32;  // float4 [ny][nx][nz-1]: the same records in fp32 for the streaming sampler K2
@@ -374,6 +374,27 @@ CubeView make_view(rdr_handle_t h) {
         for (size_t i = 0; i + 1 < v[d]->size() && a.exact_uniform; ++i)
             if ((*v[d])[i] + a.d != (*v[d])[i + 1] || (*v[d])[i + 1] - (*v[d])[i] != a.d) a.exact_uniform = 0;
     }
+    Axis32 *a32[3] = {&c.fy, &c.fx, &c.fz};
+    for (int d = 0; d < 3; ++d) {
+        const Axis &a = *ax[d];
+        Axis32 &f = *a32[d];
+        f.rec = reinterpret_cast<const float4 *>(tabs + h->tab_rec32_off[d]);
+        f.bin = a.bin;
+        f.n = a.n;
+        f.nbin = a.nbin;
+        f.uniform = a.uniform;
+        f.g_first = (float)a.g_first;
+        f.inv_d = (float)a.inv_d;
+        f.inv_bw = (float)a.inv_bw;
+        f.first_cmp = (float)a.g_first;
+        if ((double)f.first_cmp < a.g_first) f.first_cmp = nextafterf(f.first_cmp, INFINITY);   // RU32(g[0])
+        f.last_cmp = (float)a.g_last;
+        if ((double)f.last_cmp > a.g_last) f.last_cmp = nextafterf(f.last_cmp, -INFINITY);      // RD32(g[n-1])
+        f.d = (float)a.d;
+        f.exact32 = a.exact_uniform && (double)f.d == a.d;
+        for (size_t i = 0; i < v[d]->size() && f.exact32; ++i)
+            if ((double)fmaf((float)i, f.d, f.g_first) != (*v[d])[i]) f.exact32 = 0;
+    }
     c.crs_kind = h->crs_kind;
     c.lcc = {h->crs[0], h->crs[1], h->crs[2], h->crs[3], h->crs[4], h->crs[5], h->crs[6]};
     return c;
@@ -430,6 +451,20 @@ int build_axis_tables(rdr_handle_t h) {
             bins[b] = (unsigned short)i;  // interval holding the start of bin b; the device verifies against the nodes either way
         }
         blob.insert(blob.end(), reinterpret_cast<char *>(bins.data()), reinterpret_cast<char *>(bins.data() + bins.size()));
+        while (blob.size() % 32) blob.push_back(0);
+        // fp32 interval records of the fp32 sampler tier (sampler.cuh: Axis32)
+        h->tab_rec32_off[d] = blob.size();
+        std::vector<float> rec32(4 * (size_t)(n - 1));
+        for (int k = 0; k + 1 < n; ++k) {
+            const float lo_hi = (float)g[k];
+            rec32[4 * k] = lo_hi;
+            rec32[4 * k + 1] = (float)(g[k] - (double)lo_hi);
+            float hi = (float)g[k + 1];
+            if ((double)hi < g[k + 1]) hi = nextafterf(hi, INFINITY);  // RU32: v >= hi <=> v >= g[k+1] for every fp32 v
+            rec32[4 * k + 2] = hi;
+            rec32[4 * k + 3] = (float)(1.0 / (g[k + 1] - g[k]));
+        }
+        blob.insert(blob.end(), reinterpret_cast<char *>(rec32.data()), reinterpret_cast<char *>(rec32.data() + rec32.size()));
         while (blob.size() % 32) blob.push_back(0);
     }
     CUDA_TRY(h, h->d_tabs.reserve(blob.size()));
@@ -573,6 +608,175 @@ __global__ void __launch_bounds__(K2_THREADS) k_sample_stream(const CubeView c, 
             sample_scipy<MXY, GUESS_BINS>(c, (double)pts[3 * i], (double)pts[3 * i + 1], (double)pts[3 * i + 2], iy, ix, iz, w, hh);
             out_wet[i] = (T)w;
             out_hydro[i] = (T)hh;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2, fp32 tier: the same point stream (TMA-bulk ring) with fp32 coordinates in, fp32 values out and fp32 ARITHMETIC -- the
+// 1e-3 m tier of north_star.  20 B per point: at the HBM roofline a warp of 32 points has ~110 issue slots, which the fp64
+// arithmetic of k_sample_stream (188 instructions per point, half-rate pipe) cannot meet; this form needs ~85 fp32 / integer
+// instructions.  Semantics are scipy's: NaN outside the closed box (decided exactly on the fp32 inputs, see Axis32), NaN in ->
+// NaN out, last node inclusive, NaN corners poison; values agree with scipy evaluated at the same fp32 points to ~1e-6 of
+// the field's range (fp32 rounding of t and of the lerps), far inside the tier's tolerance.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int guess32(const Axis32 &a, float v) {
+    if (a.uniform) {  // floor((v - g0) / d) by directed rounding against 2^23 + 2^22: no F2I
+        const float s = __fadd_rd((v - a.g_first) * a.inv_d, 12582912.0f);
+        return min(max(__float_as_int(s) - 0x4b400000, 0), a.n - 2);
+    }
+    const int b = (int)((v - a.g_first) * a.inv_bw);
+    return (int)__ldg(a.bin + min(max(b, 0), a.nbin - 1));
+}
+
+__device__ __forceinline__ float locate32(const Axis32 &a, float v, int &i, float4 r) {
+    // num = v - g[i] rounded once; its sign is exact (v - lo_hi is exact and a multiple of the ulp, |lo_lo| < ulp / 2), and
+    // v >= hi <=> v >= g[i+1] exactly (hi = RU32(g[i+1])): the interval is scipy's, not a neighbour within rounding of a node
+    float num = (v - r.x) - r.y;
+    if (num < 0.0f || v >= r.z) {  // guess one off (rounding of the guess, node hit, the inclusive last node); clamped for OOB / NaN
+        const int last = a.n - 2;
+        while (num < 0.0f && i > 0) {
+            r = __ldg(a.rec + --i);
+            num = (v - r.x) - r.y;
+        }
+        while (v >= r.z && i < last) {
+            r = __ldg(a.rec + ++i);
+            num = (v - r.x) - r.y;
+        }
+    }
+    return num * r.w;
+}
+
+// exact32 axis: interval and fraction without a table -- floor by directed rounding, node = fmaf(i, d, g0) exactly
+__device__ __forceinline__ float locate32_exact(const Axis32 &a, float v, int &i) {
+    const float s = __fadd_rd((v - a.g_first) * a.inv_d, 12582912.0f);
+    const int raw = __float_as_int(s) - 0x4b400000;
+    i = min(max(raw, 0), a.n - 2);
+    float lo = fmaf((float)i, a.d, a.g_first);
+    if (v < lo || v >= lo + a.d) {  // the product rounded across a node, the inclusive last node, out of bounds
+        const int last = a.n - 2;
+        while (v < lo && i > 0) lo = fmaf((float)(--i), a.d, a.g_first);
+        while (v >= lo + a.d && i < last) lo = fmaf((float)(++i), a.d, a.g_first);
+    }
+    return (v - lo) * a.inv_d;
+}
+
+template <int PPT, bool XY_EXACT>
+__global__ void __launch_bounds__(K2_THREADS) k_sample_stream_f32(const CubeView c, const float *__restrict__ pts, int64_t n,
+                                                                float *__restrict__ out_wet, float *__restrict__ out_hydro) {
+    constexpr int TILE = K2_THREADS * PPT;
+    constexpr uint32_t TILE_BYTES = TILE * 3 * sizeof(float);
+    extern __shared__ __align__(128) unsigned char k2_smem[];
+    uint64_t *full = reinterpret_cast<uint64_t *>(k2_smem + K2_STAGES * TILE_BYTES);
+    const int64_t ntiles = n / TILE;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < K2_STAGES; ++s) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < K2_STAGES; ++s) {
+            const int64_t tile = blockIdx.x + (int64_t)s * gridDim.x;
+            if (tile < ntiles) {
+                mbar_expect_tx(&full[s], TILE_BYTES);
+                tma_load_1d(k2_smem + s * TILE_BYTES, pts + tile * TILE * 3, TILE_BYTES, &full[s]);
+            }
+        }
+    }
+    const int nzc = c.fz.n - 1;
+    const unsigned row = (unsigned)c.fx.n * (unsigned)nzc;
+    const float qnanf = __int_as_float(0x7fc00000);
+    auto sample = [&](const float (&y)[PPT], const float (&x)[PPT], const float (&z)[PPT], float (&vw)[PPT], float (&vh)[PPT]) {
+        int iy[PPT], ix[PPT], iz[PPT];
+        float4 ry[PPT], rx[PPT], rz[PPT];
+#pragma unroll
+        for (int p = 0; p < PPT; ++p) {  // guesses, then all interval records in flight
+            if (!XY_EXACT) {
+                iy[p] = guess32(c.fy, y[p]);
+                ix[p] = guess32(c.fx, x[p]);
+            }
+            iz[p] = guess32(c.fz, z[p]);
+        }
+#pragma unroll
+        for (int p = 0; p < PPT; ++p) {
+            if (!XY_EXACT) {
+                ry[p] = __ldg(c.fy.rec + iy[p]);
+                rx[p] = __ldg(c.fx.rec + ix[p]);
+            }
+            rz[p] = __ldg(c.fz.rec + iz[p]);
+        }
+        float ty[PPT], tx[PPT], tz[PPT];
+#pragma unroll
+        for (int p = 0; p < PPT; ++p) {
+            ty[p] = XY_EXACT ? locate32_exact(c.fy, y[p], iy[p]) : locate32(c.fy, y[p], iy[p], ry[p]);
+            tx[p] = XY_EXACT ? locate32_exact(c.fx, x[p], ix[p]) : locate32(c.fx, x[p], ix[p], rx[p]);
+            tz[p] = locate32(c.fz, z[p], iz[p], rz[p]);
+        }
+        float4 c00[PPT], c01[PPT], c10[PPT], c11[PPT];
+#pragma unroll
+        for (int p = 0; p < PPT; ++p) {  // 4 x LDG.128: the z-pair of both fields at the four corner columns
+            const float4 *q = c.cells32 + ((unsigned)iy[p] * row + (unsigned)ix[p] * (unsigned)nzc + (unsigned)iz[p]);
+            c00[p] = __ldg(q);
+            c01[p] = __ldg(q + nzc);
+            c10[p] = __ldg(q + row);
+            c11[p] = __ldg(q + row + nzc);
+        }
+#pragma unroll
+        for (int p = 0; p < PPT; ++p) {
+            const float w00 = fmaf(tz[p], c00[p].z - c00[p].x, c00[p].x), h00 = fmaf(tz[p], c00[p].w - c00[p].y, c00[p].y);
+            const float w01 = fmaf(tz[p], c01[p].z - c01[p].x, c01[p].x), h01 = fmaf(tz[p], c01[p].w - c01[p].y, c01[p].y);
+            const float w10 = fmaf(tz[p], c10[p].z - c10[p].x, c10[p].x), h10 = fmaf(tz[p], c10[p].w - c10[p].y, c10[p].y);
+            const float w11 = fmaf(tz[p], c11[p].z - c11[p].x, c11[p].x), h11 = fmaf(tz[p], c11[p].w - c11[p].y, c11[p].y);
+            const float w0 = fmaf(tx[p], w01 - w00, w00), h0 = fmaf(tx[p], h01 - h00, h00);
+            const float w1 = fmaf(tx[p], w11 - w10, w10), h1 = fmaf(tx[p], h11 - h10, h10);
+            const bool inb = (y[p] >= c.fy.first_cmp) & (y[p] <= c.fy.last_cmp) & (x[p] >= c.fx.first_cmp) & (x[p] <= c.fx.last_cmp) &
+                             (z[p] >= c.fz.first_cmp) & (z[p] <= c.fz.last_cmp);  // false for NaN coordinates too
+            vw[p] = inb ? fmaf(ty[p], w1 - w0, w0) : qnanf;
+            vh[p] = inb ? fmaf(ty[p], h1 - h0, h0) : qnanf;
+        }
+    };
+    int it = 0;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const int s = it % K2_STAGES;
+        mbar_wait(&full[s], (uint32_t)(it / K2_STAGES) & 1u);
+        const float *tp = reinterpret_cast<const float *>(k2_smem + s * TILE_BYTES);
+        float y[PPT], x[PPT], z[PPT], w[PPT], hh[PPT];
+#pragma unroll
+        for (int p = 0; p < PPT; ++p) {
+            const int q = threadIdx.x + p * K2_THREADS;
+            y[p] = tp[3 * q];
+            x[p] = tp[3 * q + 1];
+            z[p] = tp[3 * q + 2];
+        }
+        sample(y, x, z, w, hh);
+        const int64_t base = tile * TILE;
+#pragma unroll
+        for (int p = 0; p < PPT; ++p) {
+            __stcs(out_wet + base + threadIdx.x + p * K2_THREADS, w[p]);
+            __stcs(out_hydro + base + threadIdx.x + p * K2_THREADS, hh[p]);
+        }
+        __syncthreads();  // every thread has read stage s: it can be refilled
+        if (threadIdx.x == 0) {
+            const int64_t next = tile + (int64_t)K2_STAGES * gridDim.x;
+            if (next < ntiles) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_expect_tx(&full[s], TILE_BYTES);
+                tma_load_1d(k2_smem + s * TILE_BYTES, pts + next * TILE * 3, TILE_BYTES, &full[s]);
+            }
+        }
+    }
+    if (blockIdx.x == 0) {  // ragged tail (< TILE points): the same arithmetic on plain loads, one point at a time
+        for (int64_t i = ntiles * TILE + threadIdx.x; i < n; i += K2_THREADS) {
+            float y[PPT], x[PPT], z[PPT], w[PPT], hh[PPT];
+#pragma unroll
+            for (int p = 0; p < PPT; ++p) {
+                y[p] = pts[3 * i];
+                x[p] = pts[3 * i + 1];
+                z[p] = pts[3 * i + 2];
+            }
+            sample(y, x, z, w, hh);
+            out_wet[i] = w[0];
+            out_hydro[i] = hh[0];
         }
     }
 }
@@ -2227,7 +2431,30 @@ RDR_API int rdr_sample(rdr_handle_t h, const void *pts, int64_t n, void *out_wet
         if (dtype == RDR_F64) {
             if (exact_uni) RDR_LAUNCH_K2_P(double, GUESS_EXACT_UNIFORM); else if (uni) RDR_LAUNCH_K2_P(double, GUESS_UNIFORM); else RDR_LAUNCH_K2_P(double, GUESS_BINS);
         } else {
-            if (exact_uni) RDR_LAUNCH_K2_P(float, GUESS_EXACT_UNIFORM); else if (uni) RDR_LAUNCH_K2_P(float, GUESS_UNIFORM); else RDR_LAUNCH_K2_P(float, GUESS_BINS);
+            // fp32 tier: fp32 arithmetic (k_sample_stream_f32) unless RDR_K2_F32_ARITH=0 asks for the fp64 arithmetic on fp32 I/O
+            const char *f32_env = getenv("RDR_K2_F32_ARITH");
+            if (!(f32_env && atoi(f32_env) == 0)) {
+#define RDR_LAUNCH_K2F(P, E)                                                                                                        \
+    do {                                                                                                                         \
+        const size_t smem = K2_STAGES * (K2_THREADS * P) * 3 * es + K2_STAGES * sizeof(uint64_t);                                \
+        const int64_t ntiles = std::max<int64_t>(1, n / (K2_THREADS * P));                                                       \
+        CUDA_TRY(h, cudaFuncSetAttribute(k_sample_stream_f32<P, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+        int occ = 1;                                                                                                             \
+        CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sample_stream_f32<P, E>, K2_THREADS, smem));           \
+        const int g = (int)std::min<int64_t>(ntiles, (int64_t)h->sm_count * std::max(1, occ));                                   \
+        k_sample_stream_f32<P, E><<<g, K2_THREADS, smem, h->stream>>>(c, static_cast<const float *>(dpts), n,                    \
+                                                                      static_cast<float *>(dw), static_cast<float *>(dh));       \
+    } while (0)
+                const char *ppt32_env = getenv("RDR_K2_PPT32");
+                const int ppt32 = ppt32_env ? atoi(ppt32_env) : 4;
+                const bool xy32 = c.fy.exact32 && c.fx.exact32 && !(noexact && atoi(noexact) != 0);
+                if (xy32) {
+                    if (ppt32 == 1) RDR_LAUNCH_K2F(1, true); else if (ppt32 == 2) RDR_LAUNCH_K2F(2, true); else RDR_LAUNCH_K2F(4, true);
+                } else {
+                    if (ppt32 == 1) RDR_LAUNCH_K2F(1, false); else if (ppt32 == 2) RDR_LAUNCH_K2F(2, false); else RDR_LAUNCH_K2F(4, false);
+                }
+#undef RDR_LAUNCH_K2F
+            } else if (exact_uni) RDR_LAUNCH_K2_P(float, GUESS_EXACT_UNIFORM); else if (uni) RDR_LAUNCH_K2_P(float, GUESS_UNIFORM); else RDR_LAUNCH_K2_P(float, GUESS_BINS);
         }
 #undef RDR_LAUNCH_K2_P
 #undef RDR_LAUNCH_K2

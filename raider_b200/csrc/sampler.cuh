@@ -36,7 +36,24 @@ struct Axis {
     double d, inv_dx;
 };
 
+// fp32 view of an axis for the fp32 tier of the streaming sampler (k_sample_stream_f32): per interval one 16-byte record
+// {lo_hi, lo_lo, hi, inv} with g[i] = lo_hi + lo_lo to fp32 x fp32 precision (so (v - lo_hi) - lo_lo is the exact difference
+// rounded once, with the exact sign), hi = RU32(g[i+1]) for the walk, inv = RN32(1 / (g[i+1] - g[i])).  first_cmp / last_cmp are RU32(g[0]) /
+// RD32(g[n-1]): for an fp32 coordinate v, v >= first_cmp <=> v >= g[0] and v <= last_cmp <=> v <= g[n-1] *exactly*, so the
+// out-of-bounds rule of scipy (NaN outside the closed box) is reproduced bit for bit on fp32 inputs.
+struct Axis32 {
+    const float4 *rec;
+    const unsigned short *bin;
+    int n, nbin, uniform;
+    float g_first, inv_d, inv_bw, first_cmp, last_cmp;
+    // exact32: every node is exactly g_first + i d in fp32 (0.25 / 0.3125 / 0.5 degree grids ...): the interval record is rebuilt
+    // in registers (one FFMA) instead of loaded
+    int exact32;
+    float d;
+};
+
 struct CubeView {
+    Axis32 fy, fx, fz;
     // cells32[(iy*nx + ix)*(nz-1) + iz] = the same z-pair record in fp32 (16 bytes): what the streaming sampler K2 loads -- its
     // limiter is L1 wavefronts (bytes delivered per lane), and 8 F2F conversions on the XU pipe are cheaper than 64 more bytes
     const float4 *cells32;

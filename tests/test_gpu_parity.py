@@ -525,6 +525,18 @@ def test_sampler_stream_variants_bit_exact_vs_scipy_live(gpu):
         torch.cuda.synchronize()
         assert np.array_equal(dw.cpu().numpy(), want_w, equal_nan=True), name
         assert np.array_equal(dh.cpu().numpy(), want_h, equal_nan=True), name
+        # fp32 tier (k_sample_stream_f32: fp32 coordinates, fp32 arithmetic, fp32 values) against scipy evaluated at the very same
+        # fp32 points: the NaN pattern (closed-box rule, NaN coordinates) is exact, values agree to fp32 rounding of t and the lerps
+        pts32 = pts.astype(np.float32)
+        p64 = pts32.astype(np.float64)
+        ref_w = RGI((ys, xs, zs), wet.transpose(1, 2, 0), method='linear', bounds_error=False, fill_value=np.nan)(p64)
+        ref_h = RGI((ys, xs, zs), hydro.transpose(1, 2, 0), method='linear', bounds_error=False, fill_value=np.nan)(p64)
+        for got_w32, got_h32 in (cube.sample(pts32), tuple(t.cpu().numpy() for t in cube.sample(torch.from_numpy(pts32).cuda()))):
+            assert got_w32.dtype == np.float32
+            assert np.array_equal(np.isnan(got_w32), np.isnan(ref_w)), name
+            ok = ~np.isnan(ref_w)
+            assert np.abs(got_w32[ok] - ref_w[ok]).max() < 2e-5 * 150.0, (name, float(np.abs(got_w32[ok] - ref_w[ok]).max()))
+            assert np.abs(got_h32[ok] - ref_h[ok]).max() < 2e-5 * 400.0, (name, float(np.abs(got_h32[ok] - ref_h[ok]).max()))
 
 
 # ---------------------------------------------------------------------------------------- K6: orbit look vectors
