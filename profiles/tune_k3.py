@@ -38,7 +38,7 @@ def timed(fn, reps=5):
 cfg = global_config(1)
 c145 = syn.config_c2(n=2000, table='ml145')
 c145['xpts'], c145['ypts'] = cfg['xpts'], cfg['ypts']
-variants = [('general', None, None), ('fast', 5, None), ('poly', None, None)] + [('poly', m, ca) for ca in (0, 1) for m in (3, 4, 5)]
+variants = [('general', None, None, None), ('fast', 5, None, None), ('poly', None, None, None)] + [('poly', m, 1, q) for q in (0, 1) for m in (3, 4)] + [('poly', 4, 0, 0)]
 for nm, cf in (('C2', cfg), ('ml145', c145)):
     cube = DeviceCube.from_dict(cf['cube'], device=0)
     cube.h.set_stream(stream.cuda_stream)
@@ -47,9 +47,9 @@ for nm, cf in (('C2', cfg), ('ml145', c145)):
     oh = torch.empty((ny, nx), dtype=torch.float64, device='cuda')
     maxlen, counts = cube.ray_layers(_lib.GEOM_GRID, cf['xpts'], cf['ypts'], ny, nx, _lib.LOS_ENU_CONST, enu, 0.0, cf['zref'])
     ref = None
-    for mode, minb, cache in variants:
+    for mode, minb, cache, quad in variants:
         os.environ['RDR_K3_MODE'] = mode
-        for k, v in (('RDR_K3_MINB', minb), ('RDR_K3_CACHE', cache)):
+        for k, v in (('RDR_K3_MINB', minb), ('RDR_K3_CACHE', cache), ('RDR_K3_QUAD', quad)):
             if v is None:
                 os.environ.pop(k, None)
             else:
@@ -58,7 +58,7 @@ for nm, cf in (('C2', cfg), ('ml145', c145)):
         w, h = ow.cpu().numpy(), oh.cpu().numpy()
         if ref is None:
             ref = (w, h)
-        print(f'{nm} {mode} minb={minb} cache={cache}: K3 {t3:.3f} ms  max|d wet| {np.abs(w - ref[0]).max():.2e} max|d hydro| {np.abs(h - ref[1]).max():.2e} '
+        print(f'{nm} {mode} minb={minb} cache={cache} quad={quad}: K3 {t3:.3f} ms  max|d wet| {np.abs(w - ref[0]).max():.2e} max|d hydro| {np.abs(h - ref[1]).max():.2e} '
               f'fix {cube.h.last_fix_count}', flush=True)
 
 # K0: Newton iterates on the span cubics of h(t) (default) vs on Bowring heights

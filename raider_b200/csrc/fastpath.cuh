@@ -207,6 +207,10 @@ struct LayerRec {
 // neighbour scipy would pick: the two piecewise-linear branches differ there by |slope change| * 1e-4 m < 1e-5 N-units, i.e.
 // < 1e-14 m of delay per sample.  The first / last node of the model keep their exact rule (below / above -> NaN).
 constexpr double LAYER_TOL = 1.0e-4;
+// Layer quadrature (k_ray_integrate_poly): how far the two end points of a layer may lie outside the layer's own cell.  They
+// are handled exactly (end corrections), the bound only has to keep the *second* sample inside: layers under quadrature are
+// >= 450 m of ray with >= 3 intervals, i.e. >= 100 m between samples.
+constexpr double LAYER_QUAD_TOL = 2.0;
 
 // z nodes + reciprocal cell thicknesses in shared memory: lookup for samples whose height is not inside their layer's own cell
 // (the reference's fixed-point iteration leaves the layer tops of oblique rays metres away from the nominal height)

@@ -1288,7 +1288,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_ray_integrate_poly(const FastCu
                                                               const int *__restrict__ span_end, int nspan, const double *__restrict__ znodes,
                                                               int nz, int clamp_low_first, double zmin, OUT *__restrict__ out_wet,
                                                               OUT *__restrict__ out_hydro, int accumulate, const PeerOut peers,
-                                                              unsigned long long *__restrict__ counters, int *__restrict__ fix_list) {
+                                                              unsigned long long *__restrict__ counters, int *__restrict__ fix_list, int quad) {
     extern __shared__ __align__(16) unsigned char fast_smem[];
     LayerRec *s_layers = reinterpret_cast<LayerRec *>(fast_smem);
     double *s_z = reinterpret_cast<double *>(fast_smem + (size_t)K * sizeof(LayerRec));
@@ -1332,6 +1332,15 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_ray_integrate_poly(const FastCu
         unsigned held = 0xffffffffu;
         CellData Q;
         Cubic py, px, ph;
+        // horizontal cell (iy | ix << 10) and height of the last sample evaluated: the start of the next layer
+        unsigned last_hkey;
+        double last_h = clamp_low_first ? zmin : n0.h, last_ty, last_tx;
+        {
+            int iy0, ix0;
+            last_ty = cell_coord_clamped(n0.uy, c.ny, iy0);
+            last_tx = cell_coord_clamped(n0.ux, c.nx, ix0);
+            last_hkey = (unsigned)iy0 | ((unsigned)ix0 << 10);
+        }
         auto sample_cached = [&](const LayerRec &L, double s, double &w_out, double &h_out) {
             const double s2 = s * s;  // Estrin: two dependent levels after s instead of Horner's three
             const double uy = fma(s2, fma(s, py.c3, py.c2), fma(s, py.c1, py.c0));
@@ -1349,6 +1358,10 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_ray_integrate_poly(const FastCu
                 held = key;
             }
             eval_cell(Q, ty, tx, tz, w_out, h_out);
+            last_hkey = key & 0xfffffu;
+            last_h = h;
+            last_ty = ty;
+            last_tx = tx;
         };
         int k = 0;
         for (int sp = 0; sp < nspan; ++sp) {
@@ -1372,13 +1385,86 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_ray_integrate_poly(const FastCu
                 const double len = fabs(dt) * unorm;
                 const double wt_full = (len * 1.0e-6) * L.step;   // delay.py:315 (L.step = RN(1 / (np - 1)): 1 ulp from the division)
                 const double wt_half = 0.5 * wt_full;
-                // first sample of this layer == last sample of the previous one (evaluated once, used with both end weights)
-                acc_w = fma(wt_half, vw, acc_w);
-                acc_h = fma(wt_half, vh, acc_h);
                 // sample j sits at t_lo + (j step) dt (delay.py:287,292), i.e. at s = s_lo + j (step ds) of the span
                 const double s_lo = (t_lo - t_a) * inv_span, ds = dt * inv_span, sstep = L.step * ds;
                 double fj = 1.0;
                 int j = 1;
+                bool layer_done = false;
+                double end_w = 0.0, end_h = 0.0;
+                if (CACHE && quad && L.np >= 4) {
+                    // Layer quadrature.  Inside ONE cube cell the interpolant is a cubic p along the (straight) segment, up to the
+                    // ~1e-5 curvature of the coordinates; for a cubic the composite trapezoid sum over n intervals is *exactly*
+                    //     T_n[p] = (p(0) + 4 p(1/2) + p(1)) / 6 + (p(0) - 2 p(1/2) + p(1)) / (3 n^2)
+                    // (Euler-Maclaurin stops after the h^2 term, p'(1) - p'(0) = 4 x the second central difference, Simpson is
+                    // exact), so the n - 1 interior samples of delay.py:287-323 are replaced by the one in the middle of the layer:
+                    // the sum the reference forms, to ~1e-15 m per layer (the quartic remainder).
+                    // The layer's two END samples need not lie in the cell: Newton leaves the layer tops mm .. m off their nodes
+                    // (losreader.py:720-733).  p(0), p(1) are then the cell's own polynomial continued to the end points, and
+                    // the sum gets the two end corrections (f - p) / (2 n) with f the interpolant's value in the cell the end
+                    // point really lies in -- exact as long as only the end samples are outside (LAYER_QUAD_TOL << sample spacing).
+                    // A layer that crosses a horizontal cell face is summed sample by sample below.
+                    const double sm = fma(0.5, ds, s_lo), se = s_lo + ds;
+                    const double sm2 = sm * sm, se2 = se * se;
+                    const double uym = fma(sm2, fma(sm, py.c3, py.c2), fma(sm, py.c1, py.c0)), uye = fma(se2, fma(se, py.c3, py.c2), fma(se, py.c1, py.c0));
+                    const double uxm = fma(sm2, fma(sm, px.c3, px.c2), fma(sm, px.c1, px.c0)), uxe = fma(se2, fma(se, px.c3, px.c2), fma(se, px.c1, px.c0));
+                    const double h_m = fma(sm2, fma(sm, ph.c3, ph.c2), fma(sm, ph.c1, ph.c0)), h_e = fma(se2, fma(se, ph.c3, ph.c2), fma(se, ph.c1, ph.c0));
+                    int iym, ixm, iye, ixe;
+                    const double tym = cell_coord_clamped(uym, c.ny, iym), txm = cell_coord_clamped(uxm, c.nx, ixm);
+                    const double tye = cell_coord_clamped(uye, c.ny, iye), txe = cell_coord_clamped(uxe, c.nx, ixe);
+                    const unsigned hkm = (unsigned)iym | ((unsigned)ixm << 10), hke = (unsigned)iye | ((unsigned)ixe << 10);
+                    const double z_hi = T.z[L.iz + 1];
+                    const bool top_cell = L.iz + 2 >= T.nz;  // nothing above: the end point must be inside (it is: zref < max(z))
+                    const bool one_cell = (hkm == hke) & (hkm == last_hkey) & (last_h >= L.z_lo - LAYER_QUAD_TOL) & (h_m >= L.z_lo) & (h_m < z_hi) &
+                                          (h_e >= L.z_lo) & (top_cell ? (h_e <= z_hi) : (h_e < z_hi + LAYER_QUAD_TOL));
+                    if (one_cell) {
+                        const unsigned key = hkm | ((unsigned)L.iz << 20);
+                        if (key != held) {
+                            Q = load_cell(c.cells + ((unsigned)(iym * (c.nx - 1) + ixm) * (unsigned)c.nzc + (unsigned)L.iz));
+                            held = key;
+                        }
+                        double p0w = vw, p0h = vh, mw, mh, p1w, p1h;
+                        const double tz0 = fma(last_h, L.inv_dz, L.neg_zlo_inv), tzm = fma(h_m, L.inv_dz, L.neg_zlo_inv), tze = fma(h_e, L.inv_dz, L.neg_zlo_inv);
+                        if (last_h < L.z_lo) eval_cell(Q, last_ty, last_tx, tz0, p0w, p0h);  // start point below the cell
+                        eval_cell(Q, tym, txm, tzm, mw, mh);
+                        eval_cell(Q, tye, txe, tze, p1w, p1h);
+                        end_w = p1w;
+                        end_h = p1h;
+                        // The one term beyond a cubic that matters: the fractions are quadratics b u + q u^2 (q ~ 1e-4: curvature of
+                        // latitude / longitude / height along the chord), so the triple product a7 ty tx tz carries
+                        // a7 (qy bx bz + by qx bz + by bx qz) u^4, and T_n[u^4] differs from the three-point formula by
+                        // kappa_n = -1/120 + 1/(24 n^2) - 1/(30 n^4).  (1e-11 m per thick layer on a cube with O(1) mixed differences;
+                        // everything of higher order is < 1e-13 m.)
+                        const double qy = 2.0 * ((last_ty + tye) - 2.0 * tym), by = (tye - last_ty) - qy;
+                        const double qx = 2.0 * ((last_tx + txe) - 2.0 * txm), bx = (txe - last_tx) - qx;
+                        const double qz = 2.0 * ((tz0 + tze) - 2.0 * tzm), bz = (tze - tz0) - qz;
+                        const double st2 = L.step * L.step;
+                        const double g4 = fma(qy, bx * bz, by * fma(qx, bz, bx * qz)) * fma(st2, fma(st2, -1.0 / 30.0, 1.0 / 24.0), -1.0 / 120.0);
+                        const double e4w = Q.q3.z * g4, e4h = Q.q3.w * g4;
+                        if (!top_cell && h_e >= z_hi) {  // end point above the cell: its value in the cell it lies in (the next layer's)
+                            Q = load_cell(c.cells + ((unsigned)(iym * (c.nx - 1) + ixm) * (unsigned)c.nzc + (unsigned)(L.iz + 1)));
+                            held = hkm | ((unsigned)(L.iz + 1) << 20);
+                            eval_cell(Q, tye, txe, (h_e - z_hi) * T.inv[L.iz + 1], end_w, end_h);
+                        }
+                        const double W = len * 1.0e-6, cn = st2 * (1.0 / 3.0), hn = 0.5 * L.step;
+                        double tw = fma(fma(-2.0, mw, p0w + p1w), cn, fma(fma(4.0, mw, p0w + p1w), 1.0 / 6.0, e4w));
+                        double th = fma(fma(-2.0, mh, p0h + p1h), cn, fma(fma(4.0, mh, p0h + p1h), 1.0 / 6.0, e4h));
+                        tw = fma((vw - p0w) + (end_w - p1w), hn, tw);
+                        th = fma((vh - p0h) + (end_h - p1h), hn, th);
+                        acc_w = fma(W, tw, acc_w);
+                        acc_h = fma(W, th, acc_h);
+                        last_hkey = hke;
+                        last_h = h_e;
+                        last_ty = tye;
+                        last_tx = txe;
+                        vw = end_w;
+                        vh = end_h;
+                        layer_done = true;
+                    }
+                }
+                if (!layer_done) {
+                // first sample of this layer == last sample of the previous one (evaluated once, used with both end weights)
+                acc_w = fma(wt_half, vw, acc_w);
+                acc_h = fma(wt_half, vh, acc_h);
                 if (CACHE) {
                     if (k + 2 < K && held != 0xffffffffu) {
                         // the record two layers up in the column the ray is in now: requested into L1 a layer or more before its first use
@@ -1453,6 +1539,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_ray_integrate_poly(const FastCu
                 }
                 acc_w = fma(wt_half, vw, acc_w);
                 acc_h = fma(wt_half, vh, acc_h);
+                }  // !layer_done
                 t_lo = t_hi;
             }
             t_a = t_b;
@@ -2760,7 +2847,7 @@ RDR_API int rdr_ray_integrate(rdr_handle_t h, const double *maxlen, double max_s
     k_ray_integrate_poly<T, BLOCK, M, L, S><<<grid_p, BLOCK, smem_p, h->stream>>>(fc, G, n, K, h->d_t.as<double>(), h->d_layers.as<LayerRec>(), \
                                                                                h->d_spans.as<int>(), nspan, znodes, (int)h->nz,            \
                                                                                clamp_low_first, h->zs.front(), static_cast<T *>(dw),       \
-                                                                               static_cast<T *>(dh), accumulate, peers, counters, h->d_fix.as<int>())
+                                                                               static_cast<T *>(dh), accumulate, peers, counters, h->d_fix.as<int>(), quad)
 #define RDR_LAUNCH_K3P_M(T, L)                                                     \
     switch (minb_p) {                                                              \
         case 2: RDR_LAUNCH_K3P(T, 2, L, true); break;                              \
@@ -2777,6 +2864,8 @@ RDR_API int rdr_ray_integrate(rdr_handle_t h, const double *maxlen, double max_s
             const char *cache_env = getenv("RDR_K3_CACHE");
             const bool key_ok = h->ny <= 1024 && h->nx <= 1024 && h->nz <= 2048;
             const bool split = key_ok && (cache_env ? atoi(cache_env) != 0 : n_samples >= 3 * K);
+            const char *quad_env = getenv("RDR_K3_QUAD");  // layer quadrature (closed-form trapezoid sum per one-cell layer): on unless 0
+            const int quad = !(quad_env && atoi(quad_env) == 0);
             const int minb_p = tune_minb("RDR_K3_MINB", split ? 3 : 4);
             const int grid_p = grid_for(n, BLOCK, h->sm_count, 4 * minb_p);
             if (out_dtype == RDR_F64) {
