@@ -2777,7 +2777,7 @@ RDR_API int rdr_ray_integrate(rdr_handle_t h, const double *maxlen, double max_s
     const bool fast_cube = make_fast_cube(h, fc) && !want_general && n < (1ll << 31);
     // spans of the polynomial integrator: whole layers, greedy, at most `span_max` metres of the longest ray per span
     const char *span_env = getenv("RDR_K3_SPAN");
-    const double span_max = span_env && atof(span_env) > 0 ? atof(span_env) : 8000.0;
+    const double span_max = span_env && atof(span_env) > 0 ? atof(span_env) : 12000.0;
     std::vector<int> span_end;
     double longest_span = 0.0;
     {
@@ -2866,7 +2866,7 @@ RDR_API int rdr_ray_integrate(rdr_handle_t h, const double *maxlen, double max_s
             const bool split = key_ok && (cache_env ? atoi(cache_env) != 0 : n_samples >= 3 * K);
             const char *quad_env = getenv("RDR_K3_QUAD");  // layer quadrature (closed-form trapezoid sum per one-cell layer): on unless 0
             const int quad = !(quad_env && atoi(quad_env) == 0);
-            const int minb_p = tune_minb("RDR_K3_MINB", split ? 3 : 4);
+            const int minb_p = tune_minb("RDR_K3_MINB", 4);
             const int grid_p = grid_for(n, BLOCK, h->sm_count, 4 * minb_p);
             if (out_dtype == RDR_F64) {
                 if (lcc) { RDR_LAUNCH_K3P_M(double, true) } else { RDR_LAUNCH_K3P_M(double, false) }
