@@ -395,3 +395,45 @@ def test_svp_and_adjust_grid():
     assert np.array_equal(zs, [-100.0, 0.0, 10.0]) and a[0, 0, 0] == 3.0 and a.shape == (1, 1, 3)
     zs2, _ = ow.adjust_grid(np.array([-500.0, 10.0]), (np.zeros((1, 1, 2)),), zmin=-100.0)
     assert zs2.size == 2
+
+
+def test_layer_quadrature_identity():
+    """The closed form K3 uses for a layer whose samples share one cube cell: for a cubic p the
+    composite trapezoid sum over n intervals -- what delay.py:287-323 forms with nParts = n + 1 samples -- is exactly
+    (p(0) + 4 p(1/2) + p(1)) / 6 + (p(0) - 2 p(1/2) + p(1)) / (3 n^2); a u^4 term adds kappa_n = -1/120 + 1/(24 n^2) - 1/(30 n^4)
+    times its coefficient; an end sample that differs from the polynomial (it lies in the neighbouring cell) adds (f - p) / (2 n)."""
+    rng = np.random.default_rng(11)
+
+    def trapezoid_sum(f, n):
+        u = np.arange(n + 1) / n
+        w = np.ones(n + 1)
+        w[0] = w[-1] = 0.5
+        return float((w * f(u)).sum() / n)
+
+    def three_point(f, n):
+        f0, fm, f1 = f(0.0), f(0.5), f(1.0)
+        return (f0 + 4 * fm + f1) / 6 + (f0 - 2 * fm + f1) / (3 * n * n)
+
+    for n in (1, 2, 3, 5, 8, 14, 33):
+        kappa = -1 / 120 + 1 / (24 * n * n) - 1 / (30 * n ** 4)
+        for _ in range(50):
+            c = rng.normal(0, 1, 5)
+            cubic = lambda u: c[0] + u * (c[1] + u * (c[2] + u * c[3]))
+            assert abs(trapezoid_sum(cubic, n) - three_point(cubic, n)) < 1e-14
+            quartic = lambda u: cubic(u) + c[4] * u ** 4
+            assert abs(trapezoid_sum(quartic, n) - (three_point(quartic, n) + c[4] * kappa)) < 1e-14
+            d0, d1 = rng.normal(0, 1e-3, 2)   # end samples off the polynomial (neighbouring cell)
+            kinked = lambda u: cubic(u) + np.where(np.asarray(u) == 0.0, d0, 0.0) + np.where(np.asarray(u) == 1.0, d1, 0.0)
+            assert abs(trapezoid_sum(kinked, n) - (three_point(cubic, n) + (d0 + d1) / (2 * n))) < 1e-14
+    # the trilinear interpolant of one cell along a chord with slightly curved coordinates: the u^4 coefficient is
+    # a7 (qy bx bz + by qx bz + by bx qz) to first order in the curvatures q
+    for _ in range(200):
+        a = rng.normal(0, 1, 8) * np.array([300, 30, 3, 1, 3, 1, 0.5, 2.0])
+        al, be, q = rng.uniform(0, 0.4, 3), rng.uniform(0, 0.5, 3) * np.array([0.1, 0.1, 1.9]), rng.normal(0, 1e-4, 3)
+        co = lambda u, i: al[i] + be[i] * u + q[i] * u * u
+        M = lambda ty, tx, tz: (a[0] + a[1] * tz) + tx * (a[2] + a[3] * tz) + ty * ((a[4] + a[5] * tz) + tx * (a[6] + a[7] * tz))
+        f = lambda u: M(co(u, 0), co(u, 1), co(u, 2))
+        n = int(rng.integers(3, 15))
+        kappa = -1 / 120 + 1 / (24 * n * n) - 1 / (30 * n ** 4)
+        g4 = q[0] * be[1] * be[2] + be[0] * q[1] * be[2] + be[0] * be[1] * q[2]
+        assert abs(trapezoid_sum(f, n) - (three_point(f, n) + a[7] * g4 * kappa)) < 2e-9   # N-units; x 1e-6 x 3 km = 6e-15 m
