@@ -831,6 +831,48 @@ def test_k0_very_oblique_rays_take_the_exact_form(gpu, monkeypatch):
     assert np.array_equal(np.isnan(out[0]), np.isnan(want[0])) and np.isnan(want[0]).all()
 
 
+def test_peer_outputs_mirror_the_maps(gpu):
+    """rdr_set_peer_outputs (the all-gather fused into K3, raider_b200.dist.SymmetricMaps): every destination receives the same
+    bits as the primary output -- here the "peers" are two more buffers on the same GPU, at a row offset inside larger maps, for
+    the polynomial integrator, the PROJ-form list pass (rays leaving the cube) and the general integrator; += calls ignore them."""
+    import torch
+    from raider_b200 import _lib, synthetic as syn
+    from raider_b200.engine import DeviceCube
+    from raider_b200.losreader import inc_hd_to_enu
+    m = 40
+    xp, yp = syn.raster(34.0, -118.0, m, m, 0.004)
+    xs, ys = syn.cube_axes_around(xp, yp, pad_deg=0.0)          # no padding: slanted rays leave the cube -> list pass runs
+    zs = syn.z_levels(37)
+    cube = DeviceCube.from_dict(syn.make_cube(ys, xs, zs, totals=False), device=0)
+    enu = np.ascontiguousarray(inc_hd_to_enu(np.float64(30.0), np.float64(-168.0)))
+    maxlen, counts = cube.ray_layers(_lib.GEOM_GRID, xp, yp, m, m, _lib.LOS_ENU_CONST, enu, 0.0, float(zs[-1] - 1))
+    for mode in ('poly', 'general'):
+        import os
+        os.environ['RDR_K3_MODE'] = mode
+        try:
+            ow = torch.full((m, m), -1.0, dtype=torch.float64, device='cuda')
+            oh = torch.full((m, m), -1.0, dtype=torch.float64, device='cuda')
+            big = [torch.full((2, 3 * m, m), -7.0, dtype=torch.float64, device='cuda') for _ in range(2)]   # two "peer" map pairs
+            row0 = m  # this rank's block starts at row m of the 3m-row maps
+            peers = ([b[0, row0:].data_ptr() for b in big], [b[1, row0:].data_ptr() for b in big])
+            cube.ray_integrate(maxlen, 225.0, False, ow, oh, peers=peers)
+            torch.cuda.synchronize()
+            assert cube.h.last_fix_count != 0 if mode == 'poly' else True
+            for b in big:
+                assert torch.equal(torch.nan_to_num(b[0, row0:row0 + m], nan=123.0), torch.nan_to_num(ow, nan=123.0))
+                assert torch.equal(torch.nan_to_num(b[1, row0:row0 + m], nan=123.0), torch.nan_to_num(oh, nan=123.0))
+                assert bool((b[:, :row0] == -7.0).all()) and bool((b[:, row0 + m:] == -7.0).all())     # nothing outside the block
+            assert bool(torch.isnan(ow).any()) and bool(torch.isfinite(ow).any())
+            # the list is consumed by the call: a later plain call writes no peer
+            for b in big:
+                b.fill_(-7.0)
+            cube.ray_integrate(maxlen, 225.0, False, ow, oh)
+            torch.cuda.synchronize()
+            assert all(bool((b == -7.0).all()) for b in big)
+        finally:
+            os.environ.pop('RDR_K3_MODE', None)
+
+
 # ---------------------------------------------------------------------------------------- K7: weather-model processing (f4)
 def _native_columns(ny=6, nx=7, nl=40, seed=4):
     rng = np.random.default_rng(seed)
