@@ -531,7 +531,9 @@ def test_sampler_stream_variants_bit_exact_vs_scipy_live(gpu):
         p64 = pts32.astype(np.float64)
         ref_w = RGI((ys, xs, zs), wet.transpose(1, 2, 0), method='linear', bounds_error=False, fill_value=np.nan)(p64)
         ref_h = RGI((ys, xs, zs), hydro.transpose(1, 2, 0), method='linear', bounds_error=False, fill_value=np.nan)(p64)
-        for got_w32, got_h32 in (cube.sample(pts32), tuple(t.cpu().numpy() for t in cube.sample(torch.from_numpy(pts32).cuda()))):
+        dev32 = cube.sample(torch.from_numpy(pts32).cuda())   # device stream: asynchronous on the handle's stream
+        torch.cuda.synchronize()
+        for got_w32, got_h32 in (cube.sample(pts32), tuple(t.cpu().numpy() for t in dev32)):
             assert got_w32.dtype == np.float32
             assert np.array_equal(np.isnan(got_w32), np.isnan(ref_w)), name
             ok = ~np.isnan(ref_w)
