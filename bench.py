@@ -53,7 +53,8 @@ def measured_peak_gbs():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons sampled every 200 ms during the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks + throttle reasons sampled every 50 ms during the timed regions (B200_PROFILING.md): the device-resident
+    steps, the end-to-end steps and the K2 / K3 kernel timings all run inside it."""
     Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
          'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
 
@@ -62,7 +63,7 @@ class ClockSampler:
 
     def __enter__(self):
         try:
-            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '200', '-i', str(self.idx)],
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '50', '-i', str(self.idx)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -107,6 +108,13 @@ def global_config(n_gpus: int):
     zs = syn.z_levels(37)
     cube = syn.make_cube(ys, xs, zs, totals=False)
     return {'cube': cube, 'xpts': xpts, 'ypts': ypts, 'zref': float(zs[-1] - 1.0), 'max_segment_length': 225.0}
+
+
+def workload_config(world: int, cube: dict) -> dict:
+    """The `config` both arms print: BASELINE.json configs[1] (C2), 2000 x 2000 rays per GPU."""
+    return {'workload': f'C2 slant delay: {N_SIDE}x{N_SIDE} rays per GPU ({N_SIDE * world}x{N_SIDE} global), fixed {INC} deg incidence, heading {HEAD}, '
+                        f'0.001 deg posting, cube {cube["y"].size}x{cube["x"].size}x37 @0.25 deg fp32, 225 m max segment',
+            'rays_per_step': N_SIDE * world * N_SIDE}
 
 
 def enu_const():
@@ -179,8 +187,9 @@ def run_reference(args):
     print(json.dumps({
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': 1e3 * dt / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
-        'data': 'synthetic', 'config': {'workload': 'C2 slant delay 2000x2000 rays, 30deg, NZ=37, 225 m segments (bounded sample per step)',
-                                        'rays_per_step': n_step},
+        'data': 'synthetic', 'config': dict(workload_config(1, cfg['cube']), reference_sample_rays_per_step=n_step,
+                                            note='each step integrates a bounded sample of the workload (rows of the same raster, same cube, '
+                                                 'same samples per ray); rays/s is per ray actually integrated'),
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
@@ -264,14 +273,15 @@ def run_ours(args):
     # ---- timed region: device-resident value -------------------------------------------------------------------
     l0 = cube.h.launches
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    with ClockSampler(local) as clocks:
-        sync_all()
-        for a, b in ev:
-            flush.zero_()            # L2 flush between timed iterations (the t-buffer alone is > L2, this makes it explicit)
-            a.record(stream)
-            info, fw, fh = step()
-            b.record(stream)
-        sync_all()
+    clocks = ClockSampler(local)
+    clocks.__enter__()               # closed after the last timed loop (K2 / K3 kernel timings on rank 0, e2e on the others)
+    sync_all()
+    for a, b in ev:
+        flush.zero_()            # L2 flush between timed iterations (the t-buffer alone is > L2, this makes it explicit)
+        a.record(stream)
+        info, fw, fh = step()
+        b.record(stream)
+    sync_all()
     ms = np.array([a.elapsed_time(b) for a, b in ev])
     launches = cube.h.launches - l0
     t_local = float(ms.sum())
@@ -330,6 +340,7 @@ def run_ours(args):
         e2e_dev_diff = float(np.abs(res[0][0] - out_w.cpu().numpy()).max())
 
     if rank != 0:
+        clocks.__exit__()
         if comm:
             dist.destroy_process_group()
         return
@@ -396,6 +407,7 @@ def run_ours(args):
         torch.cuda.synchronize()
         k3.append(a.elapsed_time(b))
     k3_ms = float(np.mean(k3))
+    clocks.__exit__()
     uniq = int(info.samples_per_ray - info.n_layers + 1)
     fused = {
         'kernel': 'k_ray_integrate<double>', 'ms': k3_ms, 'bound': 'fp64 issue (not HBM): see DESIGN.md',
@@ -423,9 +435,7 @@ def run_ours(args):
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
         'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': f'C2 slant delay: {N_SIDE}x{N_SIDE} rays per GPU ({ny_g}x{nx} global), fixed {INC} deg incidence, heading {HEAD}, '
-                               f'0.001 deg posting, cube {cfg["cube"]["y"].size}x{cfg["cube"]["x"].size}x37 @0.25 deg fp32, 225 m max segment',
-                   'rays_per_step': n_global, 'samples_per_ray': info.samples_per_ray, 'layers': info.n_layers,
+        'config': {**workload_config(world, cfg['cube']), 'samples_per_ray': info.samples_per_ray, 'layers': info.n_layers,
                    'l2': 'flushed with a 256 MB write between timed steps', 'parallelism': f'row-block x{world}' if world > 1 else 'single GPU',
                    'collectives': ('all-reduce(max K doubles) + all-reduce(sum 3 ints); output maps reassembled on every GPU by ' +
                                    ('peer stores from K3 over NVLink (symmetric memory) + 2 signal-pad barriers' if sym is not None
