@@ -66,9 +66,9 @@ class Comm:
         torch = self.torch
         maxlen, counts = np.asarray(maxlen, dtype=np.float64), np.asarray(counts, dtype=np.int64)
         mine = torch.as_tensor(np.concatenate([maxlen, counts.astype(np.float64)])).to(self.device)
-        allv = torch.empty((self.world, mine.numel()), dtype=torch.float64, device=self.device)
-        self.dist.all_gather_into_tensor(allv, mine, group=self.group)
-        allv = allv.cpu().numpy()
+        flat = torch.empty(self.world * mine.numel(), dtype=torch.float64, device=self.device)  # (gloo wants the flat layout)
+        self.dist.all_gather_into_tensor(flat, mine, group=self.group)
+        allv = flat.cpu().numpy().reshape(self.world, mine.numel())
         k = maxlen.size
         # NaN maxima (a rank whose rays all failed) must not win or vanish silently: np.max propagates NaN like the all-reduce(MAX) of NCCL does not;
         # the reference's own nanmax-free `.max()` (delay.py:283) propagates, so propagate

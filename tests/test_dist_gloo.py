@@ -67,9 +67,14 @@ def _worker(rank, world, port, q):
         naive = rt.build_cube_ray(cfg['xpts'], cfg['ypts'][r0:r1], zpts, rt.ArrayLOS(vecs[r0:r1]), crs, crs, ifs,
                                   MAX_SEGMENT_LENGTH=cfg['max_segment_length'], MAX_TROPO_HEIGHT=cfg['zref'])
         gathered = comm.all_gather_rows(np.full((r1 - r0, 4), float(rank)), 13)
+        # both reductions of a step in one collective (what engine._global_plan uses when the hooks come from a Comm)
+        from raider_b200.engine import _global_plan
+        pm, pc = comm.reduce_pair(np.array([float(rank), 5.0 - rank, 2.5]), np.array([rank + 1, 10, 0]))
+        gm, gc = _global_plan(np.array([float(rank), 5.0 - rank, 2.5]), np.array([rank + 1, 10, 0, 33], dtype=np.int64), comm.reduce_max, comm.reduce_sum)
+        pair_ok = pm.tolist() == [1.0, 5.0, 2.5] and pc.tolist() == [3, 20, 0] and gm.tolist() == pm.tolist() and gc.tolist() == [3, 20, 0, 33]
         q.put((rank, bool(np.array_equal(out[0], full[0]) and np.array_equal(out[1], full[1])), out[0].shape,
                bool(np.array_equal(naive[0], full[0][:, r0:r1])), gathered[:, 0].tolist(),
-               comm.reduce_max(np.array([float(rank), 5.0 - rank])).tolist(), comm.reduce_sum(np.array([rank + 1, 10])).tolist()))
+               comm.reduce_max(np.array([float(rank), 5.0 - rank])).tolist(), comm.reduce_sum(np.array([rank + 1, 10])).tolist(), pair_ok))
     finally:
         dist.destroy_process_group()
 
@@ -98,7 +103,8 @@ def test_world_size_2_gloo_sharded_equals_unsharded():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    for rank, same, shape, naive_same, gathered, rmax, rsum in res:
+    for rank, same, shape, naive_same, gathered, rmax, rsum, pair_ok in res:
+        assert pair_ok, 'reduce_pair / _global_plan disagree with the separate MAX and SUM reductions'
         assert same, 'sharded result differs from the unsharded oracle although the maxima were reduced globally'
         assert shape == (2, 13, 9)
         assert gathered == [0.0] * 7 + [1.0] * 6          # uneven row blocks reassembled in order
