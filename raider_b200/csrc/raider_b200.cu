@@ -1288,7 +1288,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_ray_integrate_poly(const FastCu
                                                               const int *__restrict__ span_end, int nspan, const double *__restrict__ znodes,
                                                               int nz, int clamp_low_first, double zmin, OUT *__restrict__ out_wet,
                                                               OUT *__restrict__ out_hydro, int accumulate, const PeerOut peers,
-                                                              unsigned long long *__restrict__ counters, int *__restrict__ fix_list, int quad) {
+                                                              unsigned long long *__restrict__ counters, int *__restrict__ fix_list, int quad,
+                                                              int tile_map) {
     extern __shared__ __align__(16) unsigned char fast_smem[];
     LayerRec *s_layers = reinterpret_cast<LayerRec *>(fast_smem);
     double *s_z = reinterpret_cast<double *>(fast_smem + (size_t)K * sizeof(LayerRec));
@@ -1303,7 +1304,16 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_ray_integrate_poly(const FastCu
     const double ky = RAD_TO_DEG * c.y_inv, kx = RAD_TO_DEG * c.x_inv;
     const int64_t n_pad = (n_rays + 31) / 32 * 32;
     unsigned n_first_below = 0;
-    for (int64_t r = blockIdx.x * (int64_t)BLOCK + threadIdx.x; r < n_pad; r += (int64_t)gridDim.x * BLOCK) {
+    for (int64_t q = blockIdx.x * (int64_t)BLOCK + threadIdx.x; q < n_pad; q += (int64_t)gridDim.x * BLOCK) {
+        // tile_map: a warp takes a compact tile of the raster (8 x 4 pixels) instead of 32 pixels of one row.  The layers in which the rays of a
+        // warp cross a horizontal cell face are summed sample by sample (per thread, the others wait): a compact tile crosses
+        // a face within fewer layers than a 32-pixel row does.  (The along-ray distances are indexed by ray, not by thread.)
+        int64_t r = q;
+        if (tile_map) {  // tile_map = log2(tile width): 2^tile_map x 2^(5 - tile_map) pixels
+            const int64_t tile = q >> 5, per_band = G.nx >> tile_map, band = tile / per_band;
+            const int lane = (int)(q & 31);
+            r = ((band << (5 - tile_map)) + (lane >> tile_map)) * G.nx + ((tile - band * per_band) << tile_map) + (lane & ((1 << tile_map) - 1));
+        }
         const bool valid = r < n_rays;
         const int64_t rr = valid ? r : n_rays - 1;
         double lat, lon;
@@ -2847,7 +2857,7 @@ RDR_API int rdr_ray_integrate(rdr_handle_t h, const double *maxlen, double max_s
     k_ray_integrate_poly<T, BLOCK, M, L, S><<<grid_p, BLOCK, smem_p, h->stream>>>(fc, G, n, K, h->d_t.as<double>(), h->d_layers.as<LayerRec>(), \
                                                                                h->d_spans.as<int>(), nspan, znodes, (int)h->nz,            \
                                                                                clamp_low_first, h->zs.front(), static_cast<T *>(dw),       \
-                                                                               static_cast<T *>(dh), accumulate, peers, counters, h->d_fix.as<int>(), quad)
+                                                                               static_cast<T *>(dh), accumulate, peers, counters, h->d_fix.as<int>(), quad, tile_map)
 #define RDR_LAUNCH_K3P_M(T, L)                                                     \
     switch (minb_p) {                                                              \
         case 2: RDR_LAUNCH_K3P(T, 2, L, true); break;                              \
@@ -2866,6 +2876,9 @@ RDR_API int rdr_ray_integrate(rdr_handle_t h, const double *maxlen, double max_s
             const bool split = key_ok && (cache_env ? atoi(cache_env) != 0 : n_samples >= 3 * K);
             const char *quad_env = getenv("RDR_K3_QUAD");  // layer quadrature (closed-form trapezoid sum per one-cell layer): on unless 0
             const int quad = !(quad_env && atoi(quad_env) == 0);
+            const char *tile_env = getenv("RDR_K3_TILE");  // compact ray tiles per warp (regular rasters whose sides divide)
+            int tile_map = tile_env ? atoi(tile_env) : 3;   // log2 of the tile width: 3 -> 8 x 4 pixels; 0 = rows of 32
+            if (tile_map < 0 || tile_map > 4 || h->geom_kind != RDR_GEOM_GRID || h->ray_nx % (1 << tile_map) || h->ray_ny % (32 >> tile_map)) tile_map = 0;
             const int minb_p = tune_minb("RDR_K3_MINB", 4);
             const int grid_p = grid_for(n, BLOCK, h->sm_count, 4 * minb_p);
             if (out_dtype == RDR_F64) {
