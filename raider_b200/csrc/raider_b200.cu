@@ -970,11 +970,34 @@ __device__ __forceinline__ double span_height(const RayFrame &F, HeightSpans &S,
     return cubic_eval(S.c[j], u - (double)j);
 }
 
+// one span of the table held in registers: the later Newton iterates of consecutive layers climb monotonically, so the span
+// they fall into changes every few layers only -- the table (thread-local memory) is read on a span change, not per iterate
+struct SpanCursor {
+    Cubic c;
+    double jf;  // index of the held span as a double; -2: nothing held (t / span + 2 >= 1 for every t the iteration can reach)
+};
+
+__device__ __forceinline__ double cursor_height(const RayFrame &F, HeightSpans &S, SpanCursor &cur, double t) {
+    double s = fma(t, 1.0 / K0_SPAN, -cur.jf);
+    if (!(s >= 0.0 && s < 1.0)) {  // left the held span (NaN: span 0 is taken and the evaluation propagates the NaN)
+        const double u = t * (1.0 / K0_SPAN);
+        const int j = min(max((int)u, 0), K0_MAX_SPANS - 1);
+        (void)span_height(F, S, t);  // builds the table up to span j if need be
+        cur.c = S.c[j];
+        cur.jf = (double)j;
+        s = u - cur.jf;
+    }
+    return cubic_eval(cur.c, s);
+}
+
+// the first iterate of a layer sits at t = toa, far below the solution for an oblique ray: it has its own cursor (`low`, climbing
+// with the layer heights); the others stay near the solution (`high`)
 template <int ITERS>
-__device__ __forceinline__ double span_top_of_atmosphere(const RayFrame &F, HeightSpans &S, double toa, double rfactor) {
-    double t = toa;
+__device__ __forceinline__ double span_top_of_atmosphere(const RayFrame &F, HeightSpans &S, SpanCursor &low, SpanCursor &high, double toa,
+                                                         double rfactor) {
+    double t = toa + (toa - cursor_height(F, S, low, toa)) * rfactor;
 #pragma unroll 1
-    for (int it = 0; it < ITERS; ++it) t += (toa - span_height(F, S, t)) * rfactor;
+    for (int it = 1; it < ITERS; ++it) t += (toa - cursor_height(F, S, high, t)) * rfactor;
     return t;
 }
 
@@ -985,16 +1008,18 @@ __device__ __forceinline__ bool ray_layers_cubic(const RayFrame &F, int K, const
     HeightSpans S;
     S.built = 0;
     S.h_node = frame_height(F.A0, 0.0, F.Z0);
+    SpanCursor low, high;
+    low.jf = high.jf = -2.0;
     const double unorm = norm3(Vec3{F.uA, F.uB, F.uZ});
     double t_lo = 0.0, t_hi = 0.0, rcosf = 1.0;
     for (int k = 0; k < K; ++k) {
         const double a = __ldg(plan + k), b = __ldg(plan + K + k);
         if (k == 0) {
-            t_lo = span_top_of_atmosphere<10>(F, S, a, 1.0);
-            t_hi = span_top_of_atmosphere<10>(F, S, b, 1.0);
+            t_lo = span_top_of_atmosphere<10>(F, S, low, high, a, 1.0);
+            t_hi = span_top_of_atmosphere<10>(F, S, low, high, b, 1.0);
         } else {
             t_lo = t_hi;
-            t_hi = span_top_of_atmosphere<3>(F, S, b, rcosf);
+            t_hi = span_top_of_atmosphere<3>(F, S, low, high, b, rcosf);
         }
         const double len = fabs(t_hi - t_lo) * unorm;  // |P_hi - P_lo| (losreader.py:821): the points are g + t u
         if (k == 0) {
