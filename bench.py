@@ -394,6 +394,37 @@ def run_ours(args):
     b.record(stream)
     torch.cuda.synchronize()
     k2_32_gbs = (npts * 20 + cube_bytes) / (a.elapsed_time(b) / 10 * 1e-3) / 1e9
+    # CPU samplers beside K2: the installed scipy RGI the reference's delay path calls (delayFcns.py:55-56), 1
+    # thread, and the reference's own native RAiDER.interpolate.interpolate compiled from /root/reference (oracle/_ref), with
+    # its max_threads = 8 cap (module.cpp:81,293) -- both fields, on a bounded sample of the same points
+    cpu_sampler = None
+    if world == 1:
+        try:
+            from scipy.interpolate import RegularGridInterpolator as RGI
+            from oracle import build_ref
+            n_cpu = 2_000_000
+            hp = pts.view(-1, 3)[:: max(1, npts // n_cpu)][:n_cpu].cpu().numpy()
+            ys_, xs_, zs_ = (np.asarray(cfg['cube'][k], dtype=np.float64) for k in ('y', 'x', 'z'))
+            vals = [np.ascontiguousarray(cfg['cube'][k].transpose(1, 2, 0), dtype=np.float64) for k in ('wet', 'hydro')]
+            t0 = time.perf_counter()
+            ref_vals = [RGI((ys_, xs_, zs_), v, method='linear', bounds_error=False, fill_value=np.nan)(hp) for v in vals]
+            t_scipy = time.perf_counter() - t0
+            cpu_sampler = {'sample_points': int(hp.shape[0]), 'scipy_rgi_points_per_s': hp.shape[0] / t_scipy, 'scipy_threads': 1}
+            gw = torch.empty(hp.shape[0], dtype=torch.float64, device='cuda')
+            gh = torch.empty_like(gw)
+            cube.sample(torch.from_numpy(hp).cuda(), out=(gw, gh))
+            torch.cuda.synchronize()
+            cpu_sampler['k2_bit_identical_to_scipy_on_sample'] = bool(np.array_equal(gw.cpu().numpy(), ref_vals[0], equal_nan=True) and
+                                                                     np.array_equal(gh.cpu().numpy(), ref_vals[1], equal_nan=True))
+            if build_ref.available():
+                interp = build_ref.load('interpolate')
+                t0 = time.perf_counter()
+                nat = [interp.interpolate((ys_, xs_, zs_), v, hp, fill_value=np.nan, max_threads=8) for v in vals]
+                t_nat = time.perf_counter() - t0
+                cpu_sampler.update({'raider_interpolate_points_per_s': hp.shape[0] / t_nat, 'raider_interpolate_threads': 8,
+                                    'raider_interpolate_max_abs_diff_vs_scipy': float(np.nanmax(np.abs(nat[0] - ref_vals[0])))})
+        except Exception as e:  # the checker is optional equipment of the bench, never of the product
+            cpu_sampler = {'unavailable': repr(e)}
     del pts, pts32, sw, sh, sw32, sh32
 
     # ---- K3 alone (events around the integrate launch) for the fused accounts -----------------------------------
@@ -452,7 +483,8 @@ def run_ours(args):
                      'peak': peak, 'unit': 'GB/s', 'frac': k2_gbs / peak, 'traffic': k2_traffic, 'traffic_source': k2_traffic_src,
                      'algorithmic_bytes_per_launch': k2_bytes, 'peak_source': peak_src, 'bytes_per_point': 40,
                      'points_per_launch': npts, 'ms_per_launch': k2_ms, 'fp32_io_tier_gbs': k2_32_gbs, 'fp32_io_tier_frac': k2_32_gbs / peak,
-                     'fp32_tier_kernel': 'k_sample_stream_f32 (fp32 coordinates, arithmetic and values, 20 B/point; L1-bandwidth bound: 100 B/point through L1)'},
+                     'fp32_tier_kernel': 'k_sample_stream_f32 (fp32 coordinates, arithmetic and values, 20 B/point; L1-bandwidth bound: 100 B/point through L1)',
+                     'points_per_s': npts / (k2_ms * 1e-3), 'cpu_samplers': cpu_sampler},
         'fused': fused,
         'cpu_baseline': cpu,
         'check': {'checksum': checksum, 'nan': nan_count, 'nparts_sum': int(info.samples_per_ray), 'fused_gather_vs_nccl_allgather_max_abs_diff_m': fused_vs_allgather},
