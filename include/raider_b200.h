@@ -14,6 +14,9 @@
  *     Small parameter vectors (axes, layer tables, maxlen) are always host pointers.
  *   - caller allocates every output; the library never frees caller memory; scratch lives in the handle.
  *   - one handle = one device + one stream; calls on a handle are serialised by the caller.
+ *   - RDR_MEM_HOST calls are synchronous (outputs are complete on return).  RDR_MEM_DEVICE calls that return nothing to the
+ *     host (rdr_sample, rdr_ray_points, ...) are enqueued on the handle's stream and return at once: order later work by
+ *     rdr_set_stream (run on the consumer's stream) or rdr_synchronize.
  *   - no exception crosses the boundary; rdr_last_error() gives the message for the last failing call.
  *   - there is no CPU fallback: without a CUDA device rdr_create() fails with RDR_ERR_CUDA.
  */
