@@ -126,6 +126,9 @@ int rdr_sample(rdr_handle_t h, const void *pts, int64_t n, void *out_wet, void *
  * Query axes are in the cube's own CRS (model_crs == pts_crs branch, delay.py:210-211). */
 int rdr_sample_grid(rdr_handle_t h, const double *xpts, int64_t nx, const double *ypts, int64_t ny, double ht,
                     double *out_wet, double *out_hydro, int mem);
+/* The whole loop of _build_cube (delay.py:205-214) in one launch: every output height zpts[k]; out = [nh][ny][nx] f64. */
+int rdr_sample_grid_levels(rdr_handle_t h, const double *xpts, int64_t nx, const double *ypts, int64_t ny, const double *zpts, int64_t nh,
+                           double *out_wet, double *out_hydro, int mem);
 
 /* ---------------------------------------------------------------- K0 + K3: ray tracing ------------------ */
 /* Scalar layer decisions of build_ray (losreader.py:785-809) for the staged cube: writes up to nz-1 (low, high)

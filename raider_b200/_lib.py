@@ -46,6 +46,7 @@ SIGNATURES = {
     'rdr_blend_cube': (_int, [_vp, _vp, _vp, _int, _f64, _f64, _int]),
     'rdr_sample': (_int, [_vp, _vp, _i64, _vp, _vp, _int, _int, _int]),
     'rdr_sample_grid': (_int, [_vp, _vp, _i64, _vp, _i64, _f64, _vp, _vp, _int]),
+    'rdr_sample_grid_levels': (_int, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _int]),
     'rdr_ray_plan': (_int, [_vp, _f64, _f64, _pi64, _vp, _vp]),
     'rdr_ray_layers': (_int, [_vp, _int, _vp, _vp, _i64, _i64, _int, _vp, _f64, _f64, _vp, _vp, _int]),
     'rdr_ray_integrate': (_int, [_vp, _vp, _f64, _int, _vp, _vp, _int, _int, _vp, _vp, _int]),

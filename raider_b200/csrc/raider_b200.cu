@@ -813,14 +813,16 @@ __global__ void __launch_bounds__(BLOCK) k_sample_points(const CubeView c, const
 }
 
 // _build_cube for one height: points generated on device from the query axes (delay.py:211)
-__global__ void k_sample_grid(const CubeView c, const double *__restrict__ xpts, int nx, const double *__restrict__ ypts, int ny, double ht,
-                              double *__restrict__ out_wet, double *__restrict__ out_hydro) {
-    const int64_t n = (int64_t)ny * nx;
+// (zpts[nh]: all output heights of _build_cube in one launch, out[nh][ny][nx])
+__global__ void k_sample_grid(const CubeView c, const double *__restrict__ xpts, int nx, const double *__restrict__ ypts, int ny,
+                              const double *__restrict__ zpts, int nh, double *__restrict__ out_wet, double *__restrict__ out_hydro) {
+    const int64_t plane = (int64_t)ny * nx, n = plane * nh;
     for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
-        const int j = (int)(r / nx), i = (int)(r % nx);
+        const int64_t q = r % plane;
+        const int j = (int)(q / nx), i = (int)(q % nx);
         double vw, vh;
         int iy = -1, ix = -1, iz = -1;
-        sample_scipy<GUESS_BINS, GUESS_BINS>(c, __ldg(ypts + j), __ldg(xpts + i), ht, iy, ix, iz, vw, vh);
+        sample_scipy<GUESS_BINS, GUESS_BINS>(c, __ldg(ypts + j), __ldg(xpts + i), __ldg(zpts + r / plane), iy, ix, iz, vw, vh);
         out_wet[r] = vw;
         out_hydro[r] = vh;
     }
@@ -2600,25 +2602,26 @@ RDR_API int rdr_sample(rdr_handle_t h, const void *pts, int64_t n, void *out_wet
     return RDR_OK;
 }
 
-RDR_API int rdr_sample_grid(rdr_handle_t h, const double *xpts, int64_t nx, const double *ypts, int64_t ny, double ht, double *out_wet,
-                            double *out_hydro, int mem) {
-    CHECK_ARG(h, h != nullptr, "rdr_sample_grid: NULL handle");
-    if (!h->has_cube) return fail(h, RDR_ERR_STATE, "rdr_sample_grid: no cube staged");
-    CHECK_ARG(h, xpts && ypts && out_wet && out_hydro && nx > 0 && ny > 0, "rdr_sample_grid: bad arguments");
+RDR_API int rdr_sample_grid_levels(rdr_handle_t h, const double *xpts, int64_t nx, const double *ypts, int64_t ny, const double *zpts, int64_t nh,
+                                   double *out_wet, double *out_hydro, int mem) {
+    CHECK_ARG(h, h != nullptr, "rdr_sample_grid_levels: NULL handle");
+    if (!h->has_cube) return fail(h, RDR_ERR_STATE, "rdr_sample_grid_levels: no cube staged");
+    CHECK_ARG(h, xpts && ypts && zpts && out_wet && out_hydro && nx > 0 && ny > 0 && nh > 0, "rdr_sample_grid_levels: bad arguments");
     ScopedDevice sd(h->device);
-    const int64_t n = nx * ny;
-    const double *dx, *dy;
+    const int64_t n = nx * ny * nh;
+    const double *dx, *dy, *dz;
     int rc;
     // query axes are small parameter vectors: always host
     if ((rc = stage_in(h, h->d_gx, xpts, nx, RDR_MEM_HOST, &dx))) return rc;
     if ((rc = stage_in(h, h->d_gy, ypts, ny, RDR_MEM_HOST, &dy))) return rc;
+    if ((rc = stage_in(h, h->d_plan, zpts, nh, RDR_MEM_HOST, &dz))) return rc;
     double *dw = out_wet, *dh = out_hydro;
     if (mem == RDR_MEM_HOST) {
         CUDA_TRY(h, h->d_out.reserve(n * 2 * sizeof(double)));
         dw = h->d_out.as<double>();
         dh = dw + n;
     }
-    k_sample_grid<<<grid_for(n, 256, h->sm_count, 8), 256, 0, h->stream>>>(make_view(h), dx, (int)nx, dy, (int)ny, ht, dw, dh);
+    k_sample_grid<<<grid_for(n, 256, h->sm_count, 8), 256, 0, h->stream>>>(make_view(h), dx, (int)nx, dy, (int)ny, dz, (int)nh, dw, dh);
     h->launches++;
     CUDA_TRY(h, cudaGetLastError());
     if (mem == RDR_MEM_HOST) {
@@ -2626,8 +2629,13 @@ RDR_API int rdr_sample_grid(rdr_handle_t h, const double *xpts, int64_t nx, cons
         CUDA_TRY(h, cudaMemcpyAsync(out_hydro, dh, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     }
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-    h->has_rays = false;  // d_gx/d_gy were reused
+    h->has_rays = false;  // d_gx / d_gy / d_plan were reused
     return RDR_OK;
+}
+
+RDR_API int rdr_sample_grid(rdr_handle_t h, const double *xpts, int64_t nx, const double *ypts, int64_t ny, double ht, double *out_wet,
+                            double *out_hydro, int mem) {
+    return rdr_sample_grid_levels(h, xpts, nx, ypts, ny, &ht, 1, out_wet, out_hydro, mem);
 }
 
 // ------------------------------------------------------------------------------------------------

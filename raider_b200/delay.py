@@ -156,8 +156,10 @@ def _build_cube(xpts, ypts, zpts, model_crs, pts_crs, interpolators):
     """Iterate over interpolators and build a cube using Zenith (delay.py:196-216)."""
     xpts, ypts, zpts = (np.asarray(a, dtype=np.float64) for a in (xpts, ypts, zpts))
     model_crs, pts_crs = parse_crs(model_crs), parse_crs(pts_crs)
-    outputArrs = [np.zeros((zpts.size, ypts.size, xpts.size)) for mm in range(len(interpolators))]
     cube = as_device_cube(interpolators, crs=model_crs) if len(interpolators) == 2 else None
+    if cube is not None and model_crs == pts_crs:
+        return list(cube.sample_grid_levels(xpts, ypts, zpts))   # the whole height loop in one launch
+    outputArrs = [np.zeros((zpts.size, ypts.size, xpts.size)) for mm in range(len(interpolators))]
 
     for ii, ht in enumerate(zpts):
         if model_crs != pts_crs:

@@ -97,6 +97,14 @@ class DeviceCube:
         self.h.call('rdr_sample_grid', ptr(xpts), xpts.size, ptr(ypts), ypts.size, float(ht), ptr(w), ptr(hy), _lib.MEM_HOST)
         return w, hy
 
+    def sample_grid_levels(self, xpts, ypts, zpts):
+        """Every height of ``_build_cube`` (delay.py:205-214) in one launch: two (nh, ny, nx) arrays."""
+        xpts, ypts, zpts = f64(xpts), f64(ypts), f64(np.atleast_1d(zpts))
+        w = np.empty((zpts.size, ypts.size, xpts.size))
+        hy = np.empty((zpts.size, ypts.size, xpts.size))
+        self.h.call('rdr_sample_grid_levels', ptr(xpts), xpts.size, ptr(ypts), ypts.size, ptr(zpts), zpts.size, ptr(w), ptr(hy), _lib.MEM_HOST)
+        return w, hy
+
     # ------------------------------------------------------------------------------------ K0 + K3
     def ray_plan(self, ht: float, zref: float):
         n = C.c_int64(0)
