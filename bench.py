@@ -5,14 +5,16 @@
 
 A *step* is one pass of the hot path over one batch of synthetic input: the C2 raster (2000 x 2000 rays per GPU, fixed
 30 deg incidence, NZ = 37 cube, 225 m segments => ~296 samples/ray, one output height):  K0 ray_layers -> global
-max/predicate reduction -> K3 ray_integrate (-> all-gather of the two delay maps when N > 1).
+max/predicate reduction -> K3 ray_integrate; when N > 1, K3 also stores every ray into the full maps of all GPUs (peer-mapped
+symmetric memory over NVLink: the all-gather of the output maps, fused into the kernel; NCCL all-gather as the fallback).
 
 One JSON line on stdout (rank 0):
   value     rays/s, whole job, geometry + cube resident in HBM, outputs left in HBM, CUDA events, max over ranks
   e2e       rays/s through the reference-facing API (getInterpolators + _build_cube_ray) with HOST buffers: cube H2D,
             axes H2D, both delay maps D2H inside the timed region
   roofline  the unfused trilinear-sample kernel K2 on materialised sample points of the same rays (40 B/point fp64),
-            achieved HBM GB/s vs MEASURED_PEAKS.json -- the kernel north_star puts the HBM-roofline claim on
+            achieved HBM GB/s vs MEASURED_PEAKS.json -- the kernel north_star puts the HBM-roofline claim on; with the fp32
+            tier (20 B/point) and the CPU samplers (scipy RGI, the reference's native interpolate) on a bounded sample beside it
   fused     the K3 kernel's own byte accounts (it is fp64-issue bound, not HBM bound)
   cpu_baseline  the oracle port (NumPy + scipy restatement of the reference loops) on a bounded sub-raster, 1 core
 
@@ -441,7 +443,8 @@ def run_ours(args):
     clocks.__exit__()
     uniq = int(info.samples_per_ray - info.n_layers + 1)
     fused = {
-        'kernel': 'k_ray_integrate<double>', 'ms': k3_ms, 'bound': 'fp64 issue (not HBM): see DESIGN.md',
+        'kernel': 'k_ray_integrate_poly<double> (span cubics + layer quadrature; flagged rays: k_ray_integrate list pass)', 'ms': k3_ms,
+        'bound': 'fp64 issue, three-register DFMAs at 3 cycles (not HBM): see DESIGN.md section 4',
         'algorithmic_bytes_per_ray': 16 + 8 * (info.n_layers + 1),
         'hbm_gbs': n_local * (16 + 8 * (info.n_layers + 1)) / (k3_ms * 1e-3) / 1e9,
         'equivalent_unfused_gbs': n_local * info.samples_per_ray * 40 / (k3_ms * 1e-3) / 1e9,
