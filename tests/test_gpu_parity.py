@@ -833,6 +833,35 @@ def test_k0_very_oblique_rays_take_the_exact_form(gpu, monkeypatch):
     assert np.array_equal(np.isnan(out[0]), np.isnan(want[0])) and np.isnan(want[0]).all()
 
 
+def test_nan_nodes_poison_like_the_reference(gpu):
+    """A NaN node of the cube poisons every sample whose cell touches it, zero weight or not (0 * NaN = NaN in
+    scipy and in interpolate.cpp:165-174; cubes are only *warned* about, delayFcns.py:43-44): rays through such a cell come out
+    NaN, all others are untouched -- through the closed-form layer sums, the per-sample loops and the PROJ-form integrator alike."""
+    from oracle import raytrace as rt
+    from raider_b200.losreader import Raytracing
+    cfg = _c2_small(20, 0.09)
+    cube = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in cfg['cube'].items()}
+    ny, nx = cube['y'].size, cube['x'].size
+    cube['wet'][20, ny // 2, nx // 2] = np.nan        # mid troposphere (thick layer: quadrature), one column
+    cube['hydro'][3, ny // 2 - 1, nx // 2] = np.nan   # near the ground (thin layers: per-sample path), the column south of it
+    cfg = dict(cfg, cube=cube)
+    crs = rt.GeographicCRS()
+    want = rt.build_cube_ray(cfg['xpts'], cfg['ypts'], cfg['zpts'], rt.FixedIncidenceLOS(30.0, -168.0), crs, crs, list(rt.get_interpolators(cube)),
+                             MAX_SEGMENT_LENGTH=cfg['max_segment_length'], MAX_TROPO_HEIGHT=cfg['zref'])
+    assert 0 < np.isnan(want[0]).sum() < want[0].size and 0 < np.isnan(want[1]).sum() < want[1].size
+    for mode in ('poly', 'general'):
+        import os
+        os.environ['RDR_K3_MODE'] = mode
+        try:
+            out, _ = _run_gpu(cfg, Raytracing(incidence=30.0, heading=-168.0))
+        finally:
+            os.environ.pop('RDR_K3_MODE', None)
+        for f in (0, 1):
+            assert np.array_equal(np.isnan(out[f]), np.isnan(want[f])), (mode, f)
+            ok = ~np.isnan(want[f])
+            assert np.abs(out[f][ok] - want[f][ok]).max() < TOL_F64_M, (mode, f)
+
+
 def test_peer_outputs_mirror_the_maps(gpu):
     """rdr_set_peer_outputs (the all-gather fused into K3, raider_b200.dist.SymmetricMaps): every destination receives the same
     bits as the primary output -- here the "peers" are two more buffers on the same GPU, at a row offset inside larger maps, for
