@@ -471,7 +471,7 @@ def run_ours(args):
         'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
         'config': {**workload_config(world, cfg['cube']), 'samples_per_ray': info.samples_per_ray, 'layers': info.n_layers,
                    'l2': 'flushed with a 256 MB write between timed steps', 'parallelism': f'row-block x{world}' if world > 1 else 'single GPU',
-                   'collectives': ('all-reduce(max K doubles) + all-reduce(sum 3 ints); output maps reassembled on every GPU by ' +
+                   'collectives': ('one all-gather of K per-layer maxima + 3 counters per rank (max / sum taken locally); output maps reassembled on every GPU by ' +
                                    ('peer stores from K3 over NVLink (symmetric memory) + 2 signal-pad barriers' if sym is not None
                                     else 'all_gather_into_tensor (symmetric memory unavailable)')) if world > 1 else 'none'},
         'clocks': clocks.summary(),

@@ -9,8 +9,11 @@ Rays are independent except for three whole-raster quantities, which is why naiv
 * the ``isnan(ray_lengths).all()`` convergence check                                 (delay.py:279)
 
 So the path shards as: contiguous row blocks of the query raster per rank (cube replicated, it is MBs), K0 on each
-rank, ONE all-reduce(MAX) of K doubles + ONE all-reduce(SUM) of 3 counters, K3 on each rank, and the reassembly of the two
-output maps so every rank holds the full delay map.  There is no other data-path collective.
+rank, ONE collective carrying the K per-layer maxima (MAX) and the 3 predicate counters (SUM) of every rank, K3 on each rank,
+and the reassembly of the two output maps so every rank holds the full delay map.  There is no other data-path collective.
+(The clamp predicate of delay.py:306-307 is decided from K0's globally reduced count of first samples below min(z); K3's own
+re-evaluation of it -- bitwise the same heights except for polar rays and projected cubes -- is only cross-checked in
+single-process runs, where that costs nothing.)
 
 The reassembly is fused into K3 (``SymmetricMaps``): the full maps live in symmetric memory (``torch.distributed.
 _symmetric_memory``: every rank's buffer is peer-mapped into every other rank over NVLink / NVSwitch), and the integration

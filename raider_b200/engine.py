@@ -245,8 +245,9 @@ class DeviceCube:
                 nparts, oob = self.ray_integrate(maxlen, max_segment_length, clamp, ow[r0:r1], oh[r0:r1],
                                                  peers=peers_fn(r0, r1) if peers_fn else None)
                 oob_tot += oob
-            first_below = oob_tot[:1] if reduce_sum is None else reduce_sum(oob_tot[:1])
-            if bool(first_below[0] == counts[0]) == clamp:
+            # K3 re-evaluates the first-sample predicate on its own heights (bitwise K0's for all but polar / projected-cube rays).
+            # A single process checks it for free; across ranks K0's globally reduced count stands -- one collective less per step
+            if reduce_sum is not None or bool(oob_tot[0] == counts[0]) == clamp:
                 break
             clamp = not clamp  # K0's hint and K3's own evaluation disagree on a knife edge: K3 rules
             info.reruns = 1
@@ -265,8 +266,8 @@ class DeviceCube:
         info.n_rays, info.n_nan_rays, info.n_layers = int(counts[0]), int(counts[1]), int(counts[3])
         clamp = bool(counts[2] == counts[0])
         nparts, oob = self.ray_integrate(maxlen, max_segment_length, clamp, out_wet, out_hydro, peers=peers)
-        first_below = oob[:1] if reduce_sum is None else reduce_sum(oob[:1])
-        if bool(first_below[0] == counts[0]) != clamp:  # K0's hint and K3's own evaluation disagree on a knife edge: K3 rules
+        # (across ranks K0's globally reduced count stands: see trace())
+        if reduce_sum is None and bool(oob[0] == counts[0]) != clamp:  # K0's hint and K3's own evaluation disagree on a knife edge: K3 rules
             clamp = not clamp
             nparts, oob = self.ray_integrate(maxlen, max_segment_length, clamp, out_wet, out_hydro, peers=peers)
             info.reruns = 1
