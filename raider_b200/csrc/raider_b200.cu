@@ -2873,14 +2873,6 @@ RDR_API int rdr_ray_integrate(rdr_handle_t h, const double *maxlen, double max_s
                                                                            znodes, (int)h->nz, clamp_low_first, h->zs.front(),            \
                                                                            static_cast<T *>(dw), static_cast<T *>(dh), accumulate,         \
                                                                            peers, counters, h->d_fix.as<int>())
-#define RDR_LAUNCH_K3F_M(T, P)                        \
-    switch (minb) {                                   \
-        case 3: RDR_LAUNCH_K3F(T, 3, P); break;       \
-        case 4: RDR_LAUNCH_K3F(T, 4, P); break;       \
-        case 6: RDR_LAUNCH_K3F(T, 6, P); break;       \
-        case 8: RDR_LAUNCH_K3F(T, 8, P); break;       \
-        default: RDR_LAUNCH_K3F(T, 5, P); break;      \
-    }
         if (poly) {
             const int nspan = (int)span_end.size();
             CUDA_TRY(h, h->d_spans.reserve(nspan * sizeof(int)));
@@ -2924,11 +2916,11 @@ RDR_API int rdr_ray_integrate(rdr_handle_t h, const double *maxlen, double max_s
 #undef RDR_LAUNCH_K3P_M
 #undef RDR_LAUNCH_K3P
         } else if (out_dtype == RDR_F64) {
-            if (npt == 1) { RDR_LAUNCH_K3F_M(double, 1) } else { RDR_LAUNCH_K3F_M(double, 2) }
+            // (the per-sample Bowring form is kept for tests / comparisons: one occupancy variant, one or two samples per trip)
+            if (npt == 1) RDR_LAUNCH_K3F(double, 5, 1); else RDR_LAUNCH_K3F(double, 5, 2);
         } else {
             RDR_LAUNCH_K3F(float, 5, 1);
         }
-#undef RDR_LAUNCH_K3F_M
 #undef RDR_LAUNCH_K3F
         h->launches++;
         CUDA_TRY(h, cudaGetLastError());
