@@ -187,8 +187,13 @@ def build_cube_ray_sharded(xpts, ypts, zpts, los, model_crs, pts_crs, interpolat
             if sym is not None:
                 # fused reassembly: the kernels of this rank write its rows into every rank's maps; barriers on the stream the
                 # kernels run on fence the maps against the previous call's readers and publish them afterwards
-                cube.h.set_stream(torch.cuda.current_stream().cuda_stream)
+                cur = torch.cuda.current_stream()
+                cube.h.set_stream(cur.cuda_stream)
                 sym.barrier()
+                if cur.cuda_stream == 0:
+                    # the legacy default stream cannot be handed to the library (NULL = the handle's own stream): order the
+                    # fence before the kernels on the host instead (they end with a stream synchronise of their own)
+                    cur.synchronize()
                 if host_block:   # this rank's rows also land in page-locked host memory, written by the same kernel
                     local = _delay._build_cube_ray(xpts, ypts[r0:r1], zpts, los, model_crs, pts_crs, interpolators,
                                                    MAX_SEGMENT_LENGTH=MAX_SEGMENT_LENGTH, MAX_TROPO_HEIGHT=zref,
