@@ -232,3 +232,20 @@ def test_orbit_file_readers_and_windowing():
     assert np.array_equal(shuffled.time, [0.0, 10.0, 20.0, 30.0, 40.0])
     with pytest.raises(ValueError):
         Orbit(a[0][:3], np.stack(a[1:4], -1)[:3], np.stack(a[4:7], -1)[:3])
+
+
+def test_symmetric_maps_peer_addresses():
+    """Address arithmetic of the fused gather (raider_b200.dist.SymmetricMaps.peer_ptrs): row block [r0, r1) of height slice hh
+    inside every other rank's (2, nz, ny, nx) float64 maps -- no GPU needed for the arithmetic."""
+    from types import SimpleNamespace
+    from raider_b200.dist import SymmetricMaps
+    sm = object.__new__(SymmetricMaps)
+    sm.comm = SimpleNamespace(rank=1, world=3)
+    sm.nz, sm.ny, sm.nx = 2, 10, 7
+    sm.base = [1000, 5000, 9000]
+    wet, hydro = sm.peer_ptrs(1, 4, 6)
+    plane = 10 * 7 * 8
+    assert wet == [1000 + (1 * plane + 4 * 7 * 8), 9000 + (1 * plane + 4 * 7 * 8)]                 # ranks 0 and 2, height slice 1, row 4
+    assert hydro == [b + 2 * plane for b in wet]                                                    # the hydro maps follow the nz wet slices
+    wet_all, hydro_all = sm.peer_ptrs(0, 0, 10, include_self=True)
+    assert wet_all == [1000, 5000, 9000] and hydro_all == [1000 + 2 * plane, 5000 + 2 * plane, 9000 + 2 * plane]
