@@ -1,10 +1,16 @@
 // libraider_b200.so -- hand-written sm_100a kernels + C ABI for the RAiDER slant/zenith delay hot path.
 // See include/raider_b200.h for the boundary and DESIGN.md for the kernel inventory:
-//   K0 k_ray_layers     build_ray/getTopOfAtmosphere over a raster + global per-layer max length
-//   K3 k_ray_integrate  fused sub-step point generation + ECEF->model + trilinear wet/hydro + trapezoid
-//   K2 k_sample_*       unfused trilinear sampler (points streamed from HBM) -- the HBM-roofline kernel
-//   K1 k_make_points    makePoints{0..3}D
-//   K4 k_interp_axis    interpolate_along_axis;  k_interp_nd  RAiDER.interpolate.interpolate
+//   K0 k_ray_layers          build_ray/getTopOfAtmosphere over a raster (Newton iterates on span cubics of h(t)) + global
+//                            per-layer max length
+//   K3 k_ray_integrate_poly  the production integrator: span cubics of the cube coordinates, closed-form layer sums, register-held
+//                            cell record; also stores the results into the other GPUs' maps (rdr_set_peer_outputs)
+//      k_ray_integrate_fast  per-sample Bowring form (tests / comparisons);  k_ray_integrate  PROJ-form per sample (flagged rays, any CRS)
+//   K2 k_sample_stream*      unfused trilinear sampler (points streamed from HBM through a TMA-bulk ring) -- the HBM-roofline kernel;
+//                            k_sample_stream_f32 its fp32 tier
+//   K1 k_make_points         makePoints{0..3}D;  K1b k_ray_points  the sample points of the rays
+//   K4 k_interp_axis         interpolate_along_axis;  k_interp_nd  RAiDER.interpolate.interpolate
+//   K5 k_ray_stations        station / point mode (one warp per ray);  K6 k_orbit_los  look vectors from orbit state vectors
+//   K7 k_prepare_columns     weather-model processing (find_e, uniform_in_z, fillna, refractivity, ZTD)
 // No CPU fallback lives here: every entry point needs a CUDA device.
 #include "../../include/raider_b200.h"
 
