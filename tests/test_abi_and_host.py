@@ -249,3 +249,25 @@ def test_symmetric_maps_peer_addresses():
     assert hydro == [b + 2 * plane for b in wet]                                                    # the hydro maps follow the nz wet slices
     wet_all, hydro_all = sm.peer_ptrs(0, 0, 10, include_self=True)
     assert wet_all == [1000, 5000, 9000] and hydro_all == [1000 + 2 * plane, 5000 + 2 * plane, 9000 + 2 * plane]
+
+
+@pytest.mark.timeout(600)
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU port of the reference loops on all host cores): one JSON line with the contract's keys,
+    the same metric / unit / workload as the GPU arm, no GPU launches."""
+    import json
+    import subprocess
+    import sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parents[1]
+    res = subprocess.run([sys.executable, str(root / 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '0'], capture_output=True,
+                         text=True, timeout=550, cwd=root)
+    assert res.returncode == 0, res.stderr[-2000:]
+    line = json.loads(res.stdout.strip().splitlines()[-1])
+    assert line['impl'] == 'reference' and line['unit'] == 'rays/s' and line['higher_is_better'] is True and line['vs_baseline'] is None
+    assert line['value'] > 0 and line['gpu_launches'] == 0 and line['dtype'] == 'f64' and line['data'] == 'synthetic'
+    assert line['cpu_baseline']['kind'] == 'port' and line['cpu_baseline']['cores'] >= 1 and line['cpu_baseline']['value'] == line['value']
+    assert line['e2e'] == {'value': line['value'], 'unit': 'rays/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
+    sys.path.insert(0, str(root))
+    import bench
+    assert line['metric'] == bench.METRIC and line['config']['workload'].startswith('C2 slant delay: 2000x2000 rays per GPU')
