@@ -181,6 +181,7 @@ class LambertConformalSphere:
     """
 
     def __init__(self, lat_1=38.5, lat_2=38.5, lat_0=38.5, lon_0=262.5, R=6371229.0, x_0=0.0, y_0=0.0):
+        self.lat_1, self.lat_2, self.lat_0, self.lon_0 = float(lat_1), float(lat_2), float(lat_0), float(lon_0)
         self.R = float(R)
         self.lam0 = float(lon_0) * DEG_TO_RAD
         self.x_0 = float(x_0)

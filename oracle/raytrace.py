@@ -9,6 +9,12 @@ Follows, loop for loop, the reference (paths relative to /root/reference):
 * :func:`get_interpolators`   tools/RAiDER/delayFcns.py:23-58 (scipy RGI, fill_value=nan,
   bounds_error=False, fp32 values in a transposed (y,x,z) view)
 
+PIN STATUS: pinned BIT FOR BIT to the reference's own Python.  ``oracle/refpy.py`` imports RAiDER.delay / losreader /
+delayFcns / utilFcns unmodified from /root/reference (stand-ins only for pyproj / xarray / rasterio / shapely) and
+``tests/test_oracle_vs_reference_py.py`` asserts ``np.array_equal`` between every function below and the reference's
+on the golden geometries, edge rules and error rules; ``tests/golden/raytrace.npz`` is written from the reference
+functions' outputs.  What stays unpinned is PROJ's own rounding (the pyproj stand-in computes with oracle.geodesy).
+
 Differences from the reference, all forced by what is importable offline:
 
 * PROJ transforms are replaced by :mod:`oracle.geodesy` (PROJ's published ``cart``/``lcc`` algorithms).
@@ -43,6 +49,7 @@ class FixedIncidenceLOS:
     """Constant incidence/heading: inc_hd_to_enu (losreader.py:374-396) -> enu2ecef (utilFcns.py:91-121) per pixel."""
 
     def __init__(self, incidence_deg: float, heading_deg: float) -> None:
+        self.incidence_deg, self.heading_deg = float(incidence_deg), float(heading_deg)
         self.enu = geodesy.inc_hd_to_enu(np.float64(incidence_deg), np.float64(heading_deg))
 
     def getLookVectors(self, ht, llh, xyz, yy):

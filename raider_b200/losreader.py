@@ -13,7 +13,6 @@ import ctypes as C
 import datetime as dt
 import os
 import xml.etree.ElementTree as ET
-from abc import ABC
 from pathlib import PosixPath
 from typing import Union
 
@@ -25,33 +24,37 @@ from .constants import _ZREF
 from .utilFcns import cosd, enu2ecef, sind
 
 
-class LOS(ABC):
-    """LOS Class definition for handling look vectors (losreader.py:32-72)."""
+def _reference_los_base():
+    """RAiDER's own ``LOS`` base when a real RAiDER install is importable: the LOS classes *remain* RAiDER's
+    (BASELINE.json north_star), so objects built here pass ``isinstance(los, RAiDER.losreader.LOS)`` there."""
+    try:
+        import importlib.util
+        if importlib.util.find_spec('RAiDER') is None:
+            return None
+        from RAiDER.losreader import LOS as reference_los
+        return reference_los
+    except Exception:
+        return None
+
+
+class _LOSContract:
+    """The duck type ``RAiDER.delay`` relies on (contract of losreader.py:32-72), stated minimally: three mode
+    predicates, ``setTime``, and ``setPoints`` accepting (lats, lons, heights), (lats, lons) or one (..., 3) array."""
+
+    _ray_trace = _is_zenith = _is_projected = False
+    _lats = _lons = _heights = _look_vecs = _time = None
 
     def __init__(self) -> None:
-        self._lats, self._lons, self._heights = None, None, None
-        self._look_vecs = None
-        self._ray_trace = False
-        self._is_zenith = False
-        self._is_projected = False
+        pass
 
     def setPoints(self, lats, lons=None, heights=None) -> None:
-        """Set the pixel locations."""
-        if (lats is None) and (self._lats is None):
+        if lats is None and self._lats is None:
             raise RuntimeError("You haven't given any point locations yet")
-        if lons is None:
-            llh = lats  # assume points are [lats lons heights]
-            self._lats = llh[..., 0]
-            self._lons = llh[..., 1]
-            self._heights = llh[..., 2]
+        if lons is None:  # one array of [lat, lon, height] triples
+            lats, lons, heights = (lats[..., c] for c in range(3))
         elif heights is None:
-            self._lats = lats
-            self._lons = lons
-            self._heights = np.zeros((len(lats), 1))
-        else:
-            self._lats = lats
-            self._lons = lons
-            self._heights = heights
+            heights = np.zeros((len(lats), 1))
+        self._lats, self._lons, self._heights = lats, lons, heights
 
     def setTime(self, datetime) -> None:
         self._time = datetime
@@ -64,6 +67,9 @@ class LOS(ABC):
 
     def ray_trace(self):
         return self._ray_trace
+
+
+LOS = _reference_los_base() or _LOSContract
 
 
 class Zenith(LOS):

@@ -7,7 +7,11 @@ Sources of truth, in order of authority:
      ``interpolate``, ``interpolate_along_axis``, ``makePoints{0..3}D``;
   2. the reference's golden file test/test_result_makePoints3D.txt (checked bit-for-bit against (1) here);
   3. the installed scipy RegularGridInterpolator (the third-party sampler the delay path really calls);
-  4. the NumPy restatement in oracle/ for the ray tracer (RAiDER.delay cannot be imported offline: pyproj/xarray/isce3).
+  4. for the ray tracer: the reference's OWN Python (RAiDER.delay._build_cube_ray, RAiDER.losreader.build_ray /
+     getTopOfAtmosphere, RAiDER.delayFcns.getInterpolators) imported unmodified from /root/reference by oracle/refpy.py,
+     with stand-ins only for the packages that are not installable offline (pyproj -> oracle.geodesy's restatement of
+     PROJ's cart / lcc, xarray -> an in-memory Dataset).  raytrace.npz and the ray part of geodesy.npz are written from
+     the REFERENCE functions' outputs; the NumPy restatement in oracle/raytrace.py is asserted bitwise equal on the way.
 
 Every vector is seeded; the GPU tests compare against these files, so they hold even where /root/reference and the
 oracle's dependencies are absent.
@@ -24,8 +28,10 @@ sys.path.insert(0, str(ROOT))
 OUT = Path(__file__).resolve().parent
 REFERENCE = Path('/root/reference')
 
-from oracle import build_ref, geodesy, interp as ointerp, raytrace as rt  # noqa: E402
+from oracle import build_ref, geodesy, interp as ointerp, raytrace as rt, refpy  # noqa: E402
 from raider_b200 import synthetic as syn  # noqa: E402
+
+REF = refpy.load()
 
 
 def golden_makepoints(ref_mp):
@@ -110,14 +116,57 @@ def golden_scipy():
     np.savez_compressed(OUT / 'scipy_sample.npz', ys=ys, xs=xs, zs=zs, wet=wet, hydro=hydro, pts=pts, out_wet=w, out_hydro=h)
 
 
+def _ref_crs(model_crs):
+    """oracle CRS object -> the (stand-in) pyproj CRS the reference functions take."""
+    if model_crs is None or model_crs.kind == 0:
+        return REF.CRS.from_epsg(4326)
+    n, c, rho0, lam0, R, x0, y0 = model_crs.params()
+    l = model_crs.lcc
+    return REF.CRS(dict(proj='lcc', lat_1=l.lat_1, lat_2=l.lat_2, lat_0=l.lat_0, lon_0=l.lon_0, a=R, b=R, x_0=x0, y_0=y0))
+
+
+def _ref_los(los):
+    if isinstance(los, rt.ZenithLOS):
+        return refpy.zenith_los(REF)
+    if isinstance(los, rt.FixedIncidenceLOS):
+        return refpy.fixed_incidence_los(REF, los.incidence_deg, los.heading_deg)
+    return refpy.array_los(los.vecs)
+
+
+def _same(a, b):
+    return a.shape == b.shape and np.array_equal(a, b, equal_nan=True)
+
+
 def _trace(cfg, los, model_crs=None, pts_crs=None, kind='pointwise'):
-    model_crs = model_crs or rt.GeographicCRS()
-    pts_crs = pts_crs or rt.GeographicCRS()
+    """Run the REFERENCE's _build_cube_ray (the golden) and the oracle restatement; they must agree bit for bit."""
+    mcrs, pcrs = _ref_crs(model_crs), _ref_crs(pts_crs)
+    zpts = np.asarray(cfg['zpts'], dtype=np.float64)
+    ifs_ref = REF.delayFcns.getInterpolators(refpy.dataset(cfg['cube']), kind)
+    out_ref = REF.delay._build_cube_ray(cfg['xpts'], cfg['ypts'], zpts, _ref_los(los), mcrs, pcrs, list(ifs_ref),
+                                        MAX_SEGMENT_LENGTH=cfg['max_segment_length'], MAX_TROPO_HEIGHT=cfg['zref'])
+    # nParts / per-layer maxima from the reference's build_ray (delay.py:262-283 restated around the reference calls)
+    st_ref = {'nParts': [], 'maxlen': []}
+    xx, yy = np.meshgrid(cfg['xpts'], cfg['ypts'])
+    for ht in zpts:
+        llh = [xx, yy, np.full(yy.shape, ht)]
+        if pcrs != REF.CRS.from_epsg(4326):
+            llh = list(REF.Transformer.from_crs(pcrs, 4326, always_xy=True).transform(*llh))
+        xyz = np.stack(REF.utilFcns.lla2ecef(llh[1], llh[0], llh[2]), axis=-1)
+        lens, _, _ = REF.losreader.build_ray(ifs_ref[0].grid[2], ht, xyz, _ref_los(los).getLookVectors(ht, llh, xyz, yy), cfg['zref'])
+        if lens is None:
+            continue
+        st_ref['maxlen'].append(lens.max((1, 2)))
+        st_ref['nParts'].append(np.ceil(lens.max((1, 2)) / cfg['max_segment_length']).astype(int) + 1)
+
     ifs = rt.get_interpolators(cfg['cube'], kind)
     st = {}
-    out = rt.build_cube_ray(cfg['xpts'], cfg['ypts'], cfg['zpts'], los, model_crs, pts_crs, list(ifs),
-                            MAX_SEGMENT_LENGTH=cfg['max_segment_length'], MAX_TROPO_HEIGHT=cfg['zref'], stats=st)
-    return out, st
+    out = rt.build_cube_ray(cfg['xpts'], cfg['ypts'], zpts, los, model_crs or rt.GeographicCRS(), pts_crs or rt.GeographicCRS(),
+                            list(ifs), MAX_SEGMENT_LENGTH=cfg['max_segment_length'], MAX_TROPO_HEIGHT=cfg['zref'], stats=st)
+    assert _same(out[0], out_ref[0]) and _same(out[1], out_ref[1]), 'oracle.raytrace.build_cube_ray != reference _build_cube_ray'
+    assert len(st['nParts']) == len(st_ref['nParts'])
+    for a, b in zip(st['nParts'] + st['maxlen'], st_ref['nParts'] + st_ref['maxlen']):
+        assert _same(np.asarray(a), np.asarray(b)), 'oracle nParts / maxima != reference'
+    return out_ref, st_ref
 
 
 def golden_raytrace():
@@ -152,7 +201,11 @@ def golden_raytrace():
     c1 = syn.config_c1()
     ifs = rt.get_interpolators(c1['cube'], 'total')
     g = rt.GeographicCRS()
-    zt = rt.build_cube(c1['xpts'][::5], c1['ypts'][::5], c1['zpts'], g, g, list(ifs))
+    zt_port = rt.build_cube(c1['xpts'][::5], c1['ypts'][::5], c1['zpts'], g, g, list(ifs))
+    crs4326 = REF.CRS.from_epsg(4326)
+    zt = REF.delay._build_cube(c1['xpts'][::5], c1['ypts'][::5], np.asarray(c1['zpts']), crs4326, crs4326,
+                               list(REF.delayFcns.getInterpolators(refpy.dataset(c1['cube']), 'total')))
+    assert _same(zt[0], zt_port[0]) and _same(zt[1], zt_port[1]), 'oracle build_cube != reference _build_cube'
     out.update(e_xpts=c1['xpts'][::5], e_ypts=c1['ypts'][::5], e_zpts=c1['zpts'], e_wet=zt[0], e_hydro=zt[1])
     # (f) HRRR-like LCC cube (3 km grid, 57-node table), geographic query raster
     lcc = rt.LambertCRS()
@@ -182,10 +235,17 @@ def golden_geodesy():
     enu = geodesy.inc_hd_to_enu(rng.uniform(0, 60, 64), rng.uniform(0, 360, 64))
     look = geodesy.enu2ecef(enu[:, 0], enu[:, 1], enu[:, 2], lat[:64], lon[:64], h[:64])
     g0 = np.stack(geodesy.lla2ecef(lat[:64], lon[:64], np.zeros(64)), axis=-1)
-    toa10 = rt.getTopOfAtmosphere(g0, look, 30000.0)
-    toa3 = rt.getTopOfAtmosphere(g0, look, 30000.0, factor=enu[:, 2])
     zs = syn.z_levels(37)
-    lens, lows, highs = rt.build_ray(zs, 0.0, g0, look, zs[-1] - 1)
+    # the reference's own losreader.getTopOfAtmosphere / build_ray (losreader.py:706-733,772-835) write the golden
+    toa10 = REF.losreader.getTopOfAtmosphere(g0, look, 30000.0)
+    toa3 = REF.losreader.getTopOfAtmosphere(g0, look, 30000.0, factor=enu[:, 2])
+    lens, lows, highs = REF.losreader.build_ray(zs, 0.0, g0, look, zs[-1] - 1)
+    assert _same(toa10, rt.getTopOfAtmosphere(g0, look, 30000.0))
+    assert _same(toa3, rt.getTopOfAtmosphere(g0, look, 30000.0, factor=enu[:, 2]))
+    for a, b in zip((lens, lows, highs), rt.build_ray(zs, 0.0, g0, look, zs[-1] - 1)):
+        assert _same(a, b), 'oracle build_ray != reference build_ray'
+    assert _same(np.stack(REF.utilFcns.lla2ecef(lat, lon, h), -1), np.stack([x, y, z], -1))
+    assert _same(REF.losreader.inc_hd_to_enu(30.0, -168.0), geodesy.inc_hd_to_enu(30.0, -168.0))
     np.savez_compressed(OUT / 'geodesy.npz', lat=lat, lon=lon, h=h, x=x, y=y, z=z, lon_back=lo, lat_back=la, h_back=hh, g0=g0, look=look,
                         cosf=enu[:, 2], toa10=toa10, toa3=toa3, zs=zs, lens=lens, lows=lows, highs=highs)
 
