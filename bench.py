@@ -247,12 +247,14 @@ def run_ours(args):
         out_w = torch.empty((ny, nx), dtype=torch.float64, device='cuda')
         out_h = torch.empty((ny, nx), dtype=torch.float64, device='cuda')
 
+    if sym is not None:
+        cube.set_exchange(rank, world, sym.xchg_ptrs)   # K0's maxima / counters meet on the device (k_publish -> barrier -> k_plan)
+
     def step():
         if sym is not None:
-            sym.barrier()   # every rank is done reading the previous step's maps
+            # one fused step: K0 -> publish -> barrier -> device plan -> K3 (+ peer stores of its rows) -> barrier; no host in between
             info = cube.trace(_lib.GEOM_GRID, cfg['xpts'], ypts, ny, nx, _lib.LOS_ENU_CONST, enu, 0.0, cfg['zref'], cfg['max_segment_length'],
-                              out_w, out_h, reduce_max=rmax, reduce_sum=rsum, peers_fn=lambda a, b: sym.peer_ptrs(0, r0 + a, r0 + b))
-            sym.barrier()   # every rank's rows have landed in this GPU's maps
+                              out_w, out_h, peers_fn=lambda a, b: sym.peer_ptrs(0, r0 + a, r0 + b), exchange=sym)
             return info, sym.maps[0][0], sym.maps[1][0]
         info = cube.trace(_lib.GEOM_GRID, cfg['xpts'], ypts, ny, nx, _lib.LOS_ENU_CONST, enu, 0.0, cfg['zref'], cfg['max_segment_length'],
                           out_w, out_h, reduce_max=rmax, reduce_sum=rsum)

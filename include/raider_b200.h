@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define RDR_ABI_VERSION 1
+#define RDR_ABI_VERSION 2
 
 typedef struct rdr_handle_s *rdr_handle_t;
 
@@ -157,6 +157,51 @@ int rdr_ray_layers(rdr_handle_t h, int geom_kind, const double *gx, const double
 int rdr_ray_integrate(rdr_handle_t h, const double *maxlen, double max_segment_length, int clamp_low_first,
                       void *out_wet, void *out_hydro, int out_dtype, int accumulate,
                       int64_t *nparts_out, int64_t *oob_out, int mem);
+
+/* ---------------------------------------------------------------- the fused step: K0 -> plan -> K3 without the host ---- */
+/* status bits of the device-side step plan (rdr_trace_result info[0] / info[1]) */
+enum {
+    RDR_PLAN_ABSURD = 1,        /* a per-layer maximum is NaN / absurd: ceil(max / MAX_SEGMENT_LENGTH) is not a step count (delay.py:283) */
+    RDR_PLAN_ALL_NAN = 2,       /* np.isnan(ray_lengths).all() over the WHOLE raster, all ranks (delay.py:279-280 raises ValueError) */
+    RDR_PLAN_KNIFE_EDGE = 4,    /* some max / MAX_SEGMENT_LENGTH lies within 1e-6 of an integer: nParts (delay.py:283) is decided by the
+                                   last bits of the maximum; when K0 ran in its default form the step is NOT integrated and the caller
+                                   redoes it with RDR_TRACE_EXACT_K0 */
+    RDR_PLAN_SPAN_TOO_LONG = 8  /* one layer is longer than the span cubics of the polynomial integrators allow: redo with mode 1 */
+};
+/* flags of rdr_trace_begin */
+enum {
+    RDR_TRACE_EXACT_K0 = 1,      /* Newton iterates of getTopOfAtmosphere (losreader.py:720-733) on PROJ-form (Bowring) heights instead of
+                                    on span cubics of h(t): layer maxima to ~1e-9 m of the reference's instead of ~1e-8 m */
+    RDR_TRACE_NO_KNIFE_GUARD = 2 /* integrate even on an nParts knife edge (tuning runs) */
+};
+/* The same three stages as rdr_ray_layers / rdr_ray_integrate, but nothing returns to the host in between: K0's per-layer maxima
+ * and predicate counters stay in HBM, a one-CTA kernel turns them into the step plan (nParts of delay.py:283, layer records, spans,
+ * the `.all()` clamp of delay.py:306-307, the all-NaN check of delay.py:279), and the integration kernels read the plan from
+ * device memory.  rdr_trace_begin and rdr_trace_finish only enqueue work on the handle's stream (device-resident or page-locked
+ * outputs are complete once the stream reaches that point; other host outputs once rdr_trace_result returns).
+ *
+ * Across GPUs (rdr_set_exchange): rdr_trace_begin also stores this rank's K + 3 words into its slot of every peer's exchange
+ * buffer; the caller puts ONE barrier on the stream (all ranks' rdr_trace_begin work done) before rdr_trace_finish, whose plan
+ * kernel takes MAX / SUM over the slots -- the all-reduce of SURVEY 8(e) without NCCL or the host -- and a second barrier after it
+ * (which also publishes the delay maps written through rdr_set_peer_outputs).
+ *   force_clamp   -1: the plan decides the clamp of delay.py:306-307 from K0's global count; 0 / 1: forced (redo after a cross-check miss)
+ *   mode          0: polynomial integrators (quadrature + thin-layer kernels); 1: per-sample Bowring form; 2: PROJ-form for every sample
+ * rdr_trace_result synchronises the stream and reports the step:
+ *   maxlen_out[n_layers], nparts_out[n_layers]  global maxima and the integer step counts used (may be NULL)
+ *   info_out[20] = {status, blocked, n_layers, n_rays, n_nan_rays, K0's #first samples below min(z), K3's own count of the same,
+ *                   clamp used, #samples below min(z), #samples above max(z), #rays redone in PROJ form, knife-edge layer or -1,
+ *                   k_split (layers handled by the thin-layer kernel), n_spans, K0 ran on span cubics, K3 ran the polynomial form,
+ *                   #CTA passes of the thin-layer kernel with TMA-staged record columns, #passes without, 0, 0};
+ *                   counts 3..6 are global (all ranks), 8..10 and 16..17 this rank's.  blocked != 0: nothing was integrated. */
+int rdr_trace_begin(rdr_handle_t h, int geom_kind, const double *gx, const double *gy, int64_t ny, int64_t nx, int los_kind,
+                    const double *los, double ht, double zref, int flags, int mem);
+int rdr_trace_finish(rdr_handle_t h, double max_segment_length, int force_clamp, int mode, void *out_wet, void *out_hydro,
+                     int out_dtype, int accumulate, int mem);
+int rdr_trace_result(rdr_handle_t h, double *maxlen_out, int64_t *nparts_out, int64_t *info_out);
+/* bufs[q] = device address of rank q's exchange buffer (rdr_exchange_bytes(world) bytes each, zero-initialised, peer-mapped: torch
+ * symmetric memory / cudaIpc), bufs[rank] being this rank's own.  world = 0 detaches. */
+int rdr_set_exchange(rdr_handle_t h, int rank, int world, void *const *bufs);
+int64_t rdr_exchange_bytes(int world);
 
 /* Multi-GPU: mirror the results of the following rdr_ray_integrate calls into up to 8 more device buffers --
  * the same row block of the full delay maps in the HBM of the node's other GPUs, peer-mapped (torch symmetric memory /

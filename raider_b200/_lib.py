@@ -24,6 +24,10 @@ CRS_GEOGRAPHIC, CRS_LCC_SPHERE = 0, 1
 GEOM_GRID, GEOM_POINTS = 0, 1
 LOS_ARRAY, LOS_ENU_CONST, LOS_ZENITH, LOS_ORBIT, LOS_ENU_ARRAY = 0, 1, 2, 3, 4
 SEM_SCIPY, SEM_RAIDER_FILL, SEM_RAIDER_CLAMP = 0, 1, 2
+PLAN_ABSURD, PLAN_ALL_NAN, PLAN_KNIFE_EDGE, PLAN_SPAN_TOO_LONG = 1, 2, 4, 8
+TRACE_EXACT_K0, TRACE_NO_KNIFE_GUARD = 1, 2
+K3_AUTO, K3_FAST, K3_GENERAL = 0, 1, 2
+ABI_VERSION = 2
 
 _i64, _f64, _int, _vp = C.c_int64, C.c_double, C.c_int, C.c_void_p
 _pd = C.POINTER(C.c_double)
@@ -51,6 +55,11 @@ SIGNATURES = {
     'rdr_ray_layers': (_int, [_vp, _int, _vp, _vp, _i64, _i64, _int, _vp, _f64, _f64, _vp, _vp, _int]),
     'rdr_ray_integrate': (_int, [_vp, _vp, _f64, _int, _vp, _vp, _int, _int, _vp, _vp, _int]),
     'rdr_set_peer_outputs': (_int, [_vp, _int, _vp, _vp]),
+    'rdr_trace_begin': (_int, [_vp, _int, _vp, _vp, _i64, _i64, _int, _vp, _f64, _f64, _int, _int]),
+    'rdr_trace_finish': (_int, [_vp, _f64, _int, _int, _vp, _vp, _int, _int, _int]),
+    'rdr_trace_result': (_int, [_vp, _vp, _vp, _vp]),
+    'rdr_set_exchange': (_int, [_vp, _int, _int, _vp]),
+    'rdr_exchange_bytes': (_i64, [_int]),
     'rdr_ray_stations': (_int, [_vp, _vp, _vp, _vp, _i64, _int, _vp, _f64, _f64, _vp, _vp, _vp, _int]),
     'rdr_ray_points': (_int, [_vp, _vp, _f64, _i64, _i64, _vp, _int, _pi64, _int]),
     'rdr_top_of_atmosphere': (_int, [_vp, _vp, _i64, _f64, _vp, _vp, _int]),
@@ -86,8 +95,8 @@ def load():
         fn = getattr(lib, name)  # AttributeError here = header/library mismatch
         fn.restype = res
         fn.argtypes = args
-    if lib.rdr_abi_version() != 1:
-        raise ImportError(f'{path}: ABI version {lib.rdr_abi_version()} != 1')
+    if lib.rdr_abi_version() != ABI_VERSION:
+        raise ImportError(f'{path}: ABI version {lib.rdr_abi_version()} != {ABI_VERSION}')
     _lib = lib
     return lib
 

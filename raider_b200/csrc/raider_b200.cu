@@ -242,6 +242,16 @@ struct rdr_handle_s {
     PeerOut peers = {};  // extra (peer-GPU) destinations of the next rdr_ray_integrate: rdr_set_peer_outputs
     DevBuf d_out;     // staging for host outputs
     DevBuf d_in;      // staging for host inputs of K2
+    DevBuf d_devplan; // DevPlan: the step plan k_plan builds on the device
+    DevBuf d_part;    // double [2][n_rays]: partial sums the quadrature kernel hands to the thin-layer kernel
+    bool thin_ok = true;        // the record array carries the prefetch padding (always, kept for clarity)
+    bool k0_was_cubic = true;   // last K0 ran on span cubics (default) rather than on Bowring heights
+    bool last_k3_poly = false;
+    int trace_flags = 0;
+    double last_max_seg = 0;
+    // cross-GPU exchange of the K0 words (rdr_set_exchange): peer-mapped buffers of 2 x world x XCHG_STRIDE words per rank
+    int xchg_world = 0, xchg_rank = 0, xchg_parity = 0;
+    void *xchg_bufs[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
 namespace {
@@ -945,110 +955,106 @@ __device__ __forceinline__ void ray_layers_one(const RayFrame &F, int K, const d
     }
 }
 
-// K0 with the height along the ray as a piecewise cubic.  h(t) is smooth along a straight ray (fastpath.cuh): on uniform spans
-// of K0_SPAN metres the cubic through four exact heights misses the PROJ-form height by < 1e-8 m (T^4 scaling of the 2e-8 m measured
-// at 8 km), below the ~3e-9 m rounding noise of that height by little.  Every Newton iterate of getTopOfAtmosphere
-// (losreader.py:720-733) then costs one cubic evaluation (a span lookup in thread-local memory + 3 DFMA) instead of a Bowring
-// inversion (~50 DP instructions), and the exact heights needed are 3 per span instead of 3 per *layer* (20 for the first):
-// 30 instead of 119 on C2, 48 instead of 452 on the 145-level tables.  The iteration itself -- start at t = toa, three (ten)
-// updates divided by the cos factor -- is the reference's.  Spans are built lazily as the iterates climb; the iterate t = toa
-// of an oblique ray lies far below the solution, which is why all spans of the ray are kept.
-constexpr double K0_SPAN = 6000.0;
-constexpr int K0_MAX_SPANS = 64;  // 384 km of ray: incidence up to ~78 deg through an 80 km model; longer rays take the exact form
+// K0 with the height along the ray as ONE polynomial.  h(t) along a straight ray is so smooth (k-th derivative ~ r^(1-k)) that the
+// degree-7 interpolant through eight exact (PROJ-form) heights at t = i L / 7, L = the length of the whole ray, misses the exact
+// height by < 1e-8 m for every incidence up to 80 deg (L = 500 km) -- which is the rounding noise of the PROJ-form height itself
+// (p / cos(phi) - N at |h| ~ 1e5 m; measured 5 .. 8e-9 m against the oracle for 0 .. 80 deg incidence, 0 .. 80 deg latitude,
+// three headings, two output heights: profiles/k0_septic_accuracy.py).  Every Newton iterate of getTopOfAtmosphere
+// (losreader.py:720-733) is then 8 DFMA instead of a Bowring inversion (~50 DP instructions), and a ray needs 8 exact heights
+// in all: instead of 3 per layer (119 on C2, 452 on the 145-node tables), and instead of the 3 per 6-km span of the first form of
+// this idea (30 / 48), whose span tables lived in thread-local memory (1.6 GB of DRAM write-backs per 4e6 rays on the 145-node
+// table).  The iteration itself -- start at t = toa, three (ten) updates divided by the cos factor -- is the reference's.
+//   coefficient k of x^k, x = 2 t / L - 1, from the node values:  c = V^-1 f,  V^-1 exact rationals rounded once
+__constant__ double c_septic_inv[8][8] = {
+    {-5.0 / 2048.0, 49.0 / 2048.0, -245.0 / 2048.0, 1225.0 / 2048.0, 1225.0 / 2048.0, -245.0 / 2048.0, 49.0 / 2048.0, -5.0 / 2048.0},
+    {5.0 / 2048.0, -343.0 / 10240.0, 1715.0 / 6144.0, -8575.0 / 2048.0, 8575.0 / 2048.0, -1715.0 / 6144.0, 343.0 / 10240.0, -5.0 / 2048.0},
+    {12691.0 / 92160.0, -24451.0 / 18432.0, 63651.0 / 10240.0, -92659.0 / 18432.0, -92659.0 / 18432.0, 63651.0 / 10240.0, -24451.0 / 18432.0, 12691.0 / 92160.0},
+    {-12691.0 / 92160.0, 171157.0 / 92160.0, -148519.0 / 10240.0, 648613.0 / 18432.0, -648613.0 / 18432.0, 148519.0 / 10240.0, -171157.0 / 92160.0, 12691.0 / 92160.0},
+    {-16807.0 / 18432.0, 141659.0 / 18432.0, -36015.0 / 2048.0, 199283.0 / 18432.0, 199283.0 / 18432.0, -36015.0 / 2048.0, 141659.0 / 18432.0, -16807.0 / 18432.0},
+    {16807.0 / 18432.0, -991613.0 / 92160.0, 84035.0 / 2048.0, -1394981.0 / 18432.0, 1394981.0 / 18432.0, -84035.0 / 2048.0, 991613.0 / 92160.0, -16807.0 / 18432.0},
+    {117649.0 / 92160.0, -117649.0 / 18432.0, 117649.0 / 10240.0, -117649.0 / 18432.0, -117649.0 / 18432.0, 117649.0 / 10240.0, -117649.0 / 18432.0, 117649.0 / 92160.0},
+    {-117649.0 / 92160.0, 823543.0 / 92160.0, -823543.0 / 30720.0, 823543.0 / 18432.0, -823543.0 / 18432.0, 823543.0 / 30720.0, -823543.0 / 92160.0, 117649.0 / 92160.0},
+};
+constexpr double K0_MAX_RAY = 6.0e5;  // rays longer than this (incidence beyond ~82 deg through an 80 km model) take the exact form
 
-struct HeightSpans {
-    Cubic c[K0_MAX_SPANS];
-    int built;
-    double h_node;  // exact height at the end of the last built span
+struct Septic {
+    double c[8];
+    double two_over_L;
 };
 
-__device__ __forceinline__ double span_height(const RayFrame &F, HeightSpans &S, double t) {
-    const double u = t * (1.0 / K0_SPAN);
-    const int j = min(max((int)u, 0), K0_MAX_SPANS - 1);
-    while (S.built <= j) {  // (a NaN t gives j = 0: built once, NaN propagates through the evaluation)
-        const double t0 = (double)S.built * K0_SPAN;
-        const double t1 = t0 + K0_SPAN / 3.0, t2 = t0 + 2.0 * K0_SPAN / 3.0, t3 = t0 + K0_SPAN;
-        const double h1 = frame_height(fma(t1, F.uA, F.A0), t1 * F.uB, fma(t1, F.uZ, F.Z0));
-        const double h2 = frame_height(fma(t2, F.uA, F.A0), t2 * F.uB, fma(t2, F.uZ, F.Z0));
-        const double h3 = frame_height(fma(t3, F.uA, F.A0), t3 * F.uB, fma(t3, F.uZ, F.Z0));
-        S.c[S.built] = cubic_through(S.h_node, h1, h2, h3);
-        S.h_node = h3;
-        ++S.built;
-    }
-    return cubic_eval(S.c[j], u - (double)j);
+__device__ __forceinline__ double septic_height(const Septic &S, double t) {
+    const double x = fma(t, S.two_over_L, -1.0);
+    double r = fma(x, S.c[7], S.c[6]);
+#pragma unroll
+    for (int k = 5; k >= 0; --k) r = fma(x, r, S.c[k]);
+    return r;
 }
 
-// one span of the table held in registers: the later Newton iterates of consecutive layers climb monotonically, so the span
-// they fall into changes every few layers only -- the table (thread-local memory) is read on a span change, not per iterate
-struct SpanCursor {
-    Cubic c;
-    double jf;  // index of the held span as a double; -2: nothing held (t / span + 2 >= 1 for every t the iteration can reach)
-};
-
-__device__ __forceinline__ double cursor_height(const RayFrame &F, HeightSpans &S, SpanCursor &cur, double t) {
-    double s = fma(t, 1.0 / K0_SPAN, -cur.jf);
-    if (!(s >= 0.0 && s < 1.0)) {  // left the held span (NaN: span 0 is taken and the evaluation propagates the NaN)
-        const double u = t * (1.0 / K0_SPAN);
-        const int j = min(max((int)u, 0), K0_MAX_SPANS - 1);
-        (void)span_height(F, S, t);  // builds the table up to span j if need be
-        cur.c = S.c[j];
-        cur.jf = (double)j;
-        s = u - cur.jf;
-    }
-    return cubic_eval(cur.c, s);
-}
-
-// the first iterate of a layer sits at t = toa, far below the solution for an oblique ray: it has its own cursor (`low`, climbing
-// with the layer heights); the others stay near the solution (`high`)
 template <int ITERS>
-__device__ __forceinline__ double span_top_of_atmosphere(const RayFrame &F, HeightSpans &S, SpanCursor &low, SpanCursor &high, double toa,
-                                                         double rfactor) {
-    double t = toa + (toa - cursor_height(F, S, low, toa)) * rfactor;
-#pragma unroll 1
-    for (int it = 1; it < ITERS; ++it) t += (toa - cursor_height(F, S, high, t)) * rfactor;
+__device__ __forceinline__ double septic_top_of_atmosphere(const Septic &S, double toa, double rfactor) {
+    double t = toa;
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) t = fma(toa - septic_height(S, t), rfactor, t);
     return t;
 }
 
-// returns false (nothing stored that matters) when the ray is too long for the span table: the caller redoes the warp exactly
-__device__ __forceinline__ bool ray_layers_cubic(const RayFrame &F, int K, const double *__restrict__ plan, double *__restrict__ t_out,
-                                                 int64_t n_rays, int64_t r, bool valid, int lane, double zmin, double zref_top,
-                                                 unsigned long long *smax, bool &any_nan) {
-    HeightSpans S;
-    S.built = 0;
-    S.h_node = frame_height(F.A0, 0.0, F.Z0);
-    SpanCursor low, high;
-    low.jf = high.jf = -2.0;
+// returns false (nothing stored or counted) when a ray of the warp is too long for the polynomial: the caller redoes the warp exactly.
+// s_plan: low[K] | high[K] in shared memory.
+__device__ __forceinline__ bool ray_layers_septic(const RayFrame &F, double ht, int K, const double *__restrict__ s_plan,
+                                                  double *__restrict__ t_out, int64_t n_rays, int64_t r, bool valid, int lane, double zmin,
+                                                  unsigned long long *smax, bool &any_nan) {
     const double unorm = norm3(Vec3{F.uA, F.uB, F.uZ});
-    double t_lo = 0.0, t_hi = 0.0, rcosf = 1.0;
-    for (int k = 0; k < K; ++k) {
-        const double a = __ldg(plan + k), b = __ldg(plan + K + k);
-        if (k == 0) {
-            t_lo = span_top_of_atmosphere<10>(F, S, low, high, a, 1.0);
-            t_hi = span_top_of_atmosphere<10>(F, S, low, high, b, 1.0);
-        } else {
-            t_lo = t_hi;
-            t_hi = span_top_of_atmosphere<3>(F, S, low, high, b, rcosf);
+    // length of the whole ray from the incidence at the ground point: cos = look . ellipsoid normal (curvature only shortens it)
+    const double cos0 = fma(F.uA, F.clat, F.uZ * F.slat) / unorm;
+    const double L = fma(1.05, (s_plan[2 * K - 1] - fmin(ht, s_plan[0])) / cos0, 100.0);
+    const bool too_long = !(L > 0.0 && L < K0_MAX_RAY);  // (NaN look vectors land here too: the exact form propagates the NaN)
+    if (__any_sync(0xffffffffu, too_long)) return false;
+    Septic S;
+    {
+        double f[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const double ti = L * ((double)i / 7.0);
+            f[i] = frame_height(fma(ti, F.uA, F.A0), ti * F.uB, fma(ti, F.uZ, F.Z0));
         }
-        const double len = fabs(t_hi - t_lo) * unorm;  // |P_hi - P_lo| (losreader.py:821): the points are g + t u
-        if (k == 0) {
-            rcosf = len / (b - a);  // 1 / cos_factor of losreader.py:824-825
-            // the last layer top sits near (zref - ht) / cos_factor: does the span table reach it?  Decided per warp, before
-            // anything is stored or counted, so that the exact form can redo the warp from scratch.  (NaN: runs on, stays NaN)
-            const bool too_long = (zref_top - a) * rcosf * 1.05 + 2.0 * K0_SPAN > (double)K0_MAX_SPANS * K0_SPAN;
-            if (__any_sync(0xffffffffu, too_long)) return false;
-            if (valid) __stcs(t_out + r, t_lo);
-            // hint for the whole-raster clamp of delay.py:306-307: height of the very first sample, evaluated exactly on the
-            // point K3 will reconstruct (K3 re-evaluates the predicate itself and has the last word)
-            const double h0 = frame_height(fma(t_lo, F.uA, F.A0), t_lo * F.uB, fma(t_lo, F.uZ, F.Z0));
-            const unsigned below = __ballot_sync(0xffffffffu, valid && (h0 < zmin));
-            if (lane == 0 && below) atomicAdd(&smax[K + 1], (unsigned long long)__popc(below));
+#pragma unroll
+        for (int i = 1; i < 8; ++i) f[i] -= f[0];  // differences from the ground height: the products below stay at the size of the variation
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            double a = c_septic_inv[k][1] * f[1];
+#pragma unroll
+            for (int i = 2; i < 8; ++i) a = fma(c_septic_inv[k][i], f[i], a);
+            S.c[k] = a;
         }
-        if (valid) __stcs(t_out + (int64_t)(k + 1) * n_rays + r, t_hi);
+        S.c[0] += f[0];
+        S.two_over_L = 2.0 / L;
+    }
+    const double a0 = s_plan[0], b0 = s_plan[K];
+    double t_lo = septic_top_of_atmosphere<10>(S, a0, 1.0);
+    double t_hi = septic_top_of_atmosphere<10>(S, b0, 1.0);
+    double len = fabs(t_hi - t_lo) * unorm;  // |P_hi - P_lo| (losreader.py:821): the points are g + t u
+    const double rcosf = len / (b0 - a0);    // 1 / cos_factor of losreader.py:824-825
+    {
+        // hint for the whole-raster clamp of delay.py:306-307: height of the very first sample, evaluated exactly on the point K3
+        // will reconstruct (K3 re-evaluates the predicate itself and has the last word)
+        const double h0 = frame_height(fma(t_lo, F.uA, F.A0), t_lo * F.uB, fma(t_lo, F.uZ, F.Z0));
+        const unsigned below = __ballot_sync(0xffffffffu, valid && (h0 < zmin));
+        if (lane == 0 && below) atomicAdd(&smax[K + 1], (unsigned long long)__popc(below));
+    }
+    double *tp = t_out + r;
+    if (valid) __stcs(tp, t_lo);
+    for (int k = 0;;) {
+        tp += n_rays;
+        if (valid) __stcs(tp, t_hi);
         const bool isn = !(len == len);
         any_nan |= isn;
         const unsigned long long bits = (valid && !isn) ? (unsigned long long)__double_as_longlong(len) : 0ull;
         const unsigned long long m = warp_max_bits(bits);
         if (lane == 0 && m > smax[k]) atomicMax(&smax[k], m);
+        if (++k == K) break;
+        t_lo = t_hi;
+        t_hi = septic_top_of_atmosphere<3>(S, s_plan[K + k], rcosf);
+        len = fabs(t_hi - t_lo) * unorm;
     }
     return true;
 }
@@ -1056,9 +1062,11 @@ __device__ __forceinline__ bool ray_layers_cubic(const RayFrame &F, int K, const
 template <int BLOCK, int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB) k_ray_layers(const RayGeom G, int64_t n_rays, int K, const double *__restrict__ plan,
                                                       double *__restrict__ t_out, unsigned long long *__restrict__ red, double zmin,
-                                                      int use_cubic) {
-    extern __shared__ unsigned long long smax[];  // [K + 2]
+                                                      int use_poly) {
+    extern __shared__ unsigned long long smax[];  // [K + 2] maxima / counters | low[K] | high[K]
+    double *s_plan = reinterpret_cast<double *>(smax + K + 2);
     for (int i = threadIdx.x; i < K + 2; i += BLOCK) smax[i] = 0ull;
+    for (int i = threadIdx.x; i < 2 * K; i += BLOCK) s_plan[i] = plan[i];
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const int64_t n_pad = (n_rays + 31) / 32 * 32;
@@ -1072,8 +1080,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_ray_layers(const RayGeom G, int
         bool any_nan = false;
         // the branch is taken per warp (all lanes vote): the ballots / REDUX inside need the full warp
         if (__all_sync(0xffffffffu, F.fast_ok)) {
-            // (a warp whose rays are too long for the span table bails out of the cubic form before storing or counting anything)
-            if (!use_cubic || !ray_layers_cubic(F, K, plan, t_out, n_rays, r, valid, lane, zmin, __ldg(plan + 2 * K - 1), smax, any_nan))
+            // (a warp with a ray too long for the polynomial bails out of that form before storing or counting anything)
+            if (!use_poly || !ray_layers_septic(F, G.ht, K, s_plan, t_out, n_rays, r, valid, lane, zmin, smax, any_nan))
                 ray_layers_one<false>(F, K, plan, t_out, n_rays, r, valid, lane, zmin, smax, any_nan);
         } else {
             ray_layers_one<true>(F, K, plan, t_out, n_rays, r, valid, lane, zmin, smax, any_nan);
@@ -1088,6 +1096,160 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_ray_layers(const RayGeom G, int
             if (i < K) atomicMax(red + i, v); else atomicAdd(red + i, v);
         }
     }
+    if (blockIdx.x == 0 && threadIdx.x == 0) red[K + 2] = (unsigned long long)n_rays;  // the slot carries the call's ray count (k_plan)
+}
+
+// ------------------------------------------------------------------------------------------------
+// The step plan, built ON THE DEVICE between K0 and K3 (k_plan, one CTA): everything the host used to derive from K0's maxima
+// -- nParts = ceil(max / MAX_SEGMENT_LENGTH) + 1 (delay.py:283), the per-layer records, the spans of the polynomial
+// integrator, the whole-raster clamp predicate (delay.py:306-307), the all-NaN check (delay.py:279) -- so that K0 -> K3 needs
+// no host round trip (no cudaStreamSynchronize, no D2H, no collective through the host).  Across GPUs every rank stores its
+// K maxima + 3 counters into a slot of every peer's exchange buffer (k_publish: peer-mapped symmetric memory over NVLink),
+// the caller orders the ranks with one signal-pad barrier on the stream, and k_plan takes MAX / SUM over the slots: the
+// all-reduce of SURVEY 8(e), without NCCL and without the host.  The host reads the plan back after the step
+// (rdr_trace_result), when it synchronises for the results anyway.
+// ------------------------------------------------------------------------------------------------
+constexpr int LERP_PAD = 8;  // records of padding behind the cell-record array (prefetch distance bound of k_ray_integrate_thin)
+constexpr int XCHG_STRIDE = MAX_LAYERS + 8;  // words per rank slot: maxima bits [K] | #NaN rays | #first sample below | #rays | K3's #first sample below
+// |maxlen / S - nearest integer| below which nParts is declared a knife edge: the default K0 reproduces the reference's maxima
+// to ~1e-8 m (span cubics of h(t)), the exact form to ~1e-9 m; 1e-6 of a segment is 1 mm at the default 1000 m
+constexpr double KNIFE_EPS = 1.0e-6;
+
+// written into `part` by the quadrature kernel for a ray it put on the fix list (a NaN no arithmetic produces)
+constexpr long long PART_FLAGGED = 0x7ff8dead00000001LL;
+
+struct DevPlan {
+    int status;           // RDR_PLAN_* bits seen
+    int blocked;          // status & block_mask: non-zero -> the integration kernels do nothing (the host redoes / raises)
+    int K, nspan;
+    int k_split;          // layers [0, k_split): thin-layer kernel, [k_split, K): quadrature kernel
+    int span_split;       // spans  [0, span_split) belong to the thin part
+    int clamp_low_first;  // delay.py:306-307 decided from K0's global count
+    int knife_layer;      // a layer whose maxlen / S is within KNIFE_EPS of an integer (-1: none)
+    long long n_rays, n_nan, n_below;  // global counters
+    double longest_span;
+    double maxlen[MAX_LAYERS];
+    int nparts[MAX_LAYERS];
+    int layer_cell[MAX_LAYERS];
+    int span_end[MAX_LAYERS];
+    LayerRec layers[MAX_LAYERS];
+};
+
+__global__ void __launch_bounds__(256) k_plan(const unsigned long long *__restrict__ slots, int world, int stride, int K,
+                                              const int *__restrict__ layer_cell, const double *__restrict__ zs, int nz, double max_seg,
+                                              double span_max, int thin_min, int force_clamp, int block_mask, DevPlan *__restrict__ P,
+                                              unsigned long long *__restrict__ k3_counters) {
+    __shared__ int s_status, s_knife;
+    __shared__ int s_np[MAX_LAYERS];
+    __shared__ double s_len[MAX_LAYERS];
+    if (threadIdx.x == 0) {
+        s_status = 0;
+        s_knife = -1;
+    }
+    if (threadIdx.x < 6) k3_counters[threadIdx.x] = 0ull;  // 4 integration counters + staged / unstaged CTA passes of the thin kernel
+    __syncthreads();
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+        unsigned long long m = 0ull;
+        for (int q = 0; q < world; ++q) m = max(m, slots[(size_t)q * stride + k]);  // MAX over ranks on the IEEE bits (lengths >= 0)
+        const double len = __longlong_as_double((long long)m);
+        const double x = len / max_seg;
+        const double qn = ceil(x);
+        int st = 0, np = 2;
+        if (qn == qn && qn < 1.0e7) {
+            np = (int)qn + 1;  // nParts = ceil(max / MAX_SEGMENT_LENGTH).astype(int) + 1   (delay.py:283)
+            if (np < 2) np = 2;  // a zero-length layer would divide by zero in the reference (np.linspace(0, 1, 1)); keep 2
+        } else {
+            st |= RDR_PLAN_ABSURD;
+        }
+        const double fr = x - floor(x);
+        if (len > 0.0 && (fr < KNIFE_EPS || fr > 1.0 - KNIFE_EPS)) {
+            st |= RDR_PLAN_KNIFE_EDGE;
+            atomicMax(&s_knife, k);
+        }
+        const int iz = layer_cell[k];
+        const double z_lo = zs[iz], z_hi = zs[iz + 1];
+        LayerRec r;
+        r.z_lo = z_lo;
+        r.inv_dz = 1.0 / (z_hi - z_lo);
+        r.neg_zlo_inv = -z_lo * r.inv_dz;
+        r.h_lo = iz == 0 ? z_lo : z_lo - LAYER_TOL;                                             // below the first node: NaN rule
+        r.h_hi = iz == nz - 2 ? __longlong_as_double(__double_as_longlong(z_hi) + (z_hi >= 0 ? 1 : -1)) : z_hi + LAYER_TOL;  // the last node is inclusive
+        r.step = 1.0 / (double)(np - 1);
+        r.np = np;
+        r.iz = iz;
+        P->layers[k] = r;
+        P->maxlen[k] = len;
+        P->nparts[k] = np;
+        P->layer_cell[k] = iz;
+        s_np[k] = np;
+        s_len[k] = len;
+        if (st) atomicOr(&s_status, st);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        long long n_nan = 0, n_below = 0, n_rays = 0;
+        for (int q = 0; q < world; ++q) {
+            n_nan += (long long)slots[(size_t)q * stride + K];
+            n_below += (long long)slots[(size_t)q * stride + K + 1];
+            n_rays += (long long)slots[(size_t)q * stride + K + 2];
+        }
+        int st = s_status;
+        if (n_nan == n_rays) st |= RDR_PLAN_ALL_NAN;  // np.isnan(ray_lengths).all() over the WHOLE raster (delay.py:279)
+        // thin-layer part: the leading run of layers with <= 3 samples (the 145-node tables at 1000 m: ~115 of 139 layers)
+        int n_thin = 0, last_thin = -1;
+        for (int k = 0; k < K; ++k)
+            if (s_np[k] <= 3) {
+                ++n_thin;
+                last_thin = k;
+            }
+        int k_split = 0;
+        if (thin_min > 0 && n_thin >= thin_min) {
+            // cut where the thin layers stop dominating: the longest prefix in which >= 3/4 of the layers are thin
+            int seen = 0;
+            for (int k = 0; k <= last_thin; ++k) {
+                seen += s_np[k] <= 3;
+                if (s_np[k] <= 3 && 4 * seen >= 3 * (k + 1)) k_split = k + 1;
+            }
+            if (k_split < thin_min) k_split = 0;
+        }
+        // spans of the polynomial integrators: whole layers, greedy, <= span_max metres of the longest ray, cut at k_split
+        int nspan = 0, span_split = 0;
+        double acc = 0.0, longest = 0.0;
+        for (int k = 0; k < K; ++k) {
+            if (k > 0 && (acc + s_len[k] > span_max || k == k_split)) {
+                P->span_end[nspan++] = k;
+                longest = fmax(longest, acc);
+                acc = 0.0;
+                if (k == k_split) span_split = nspan;
+            }
+            acc += s_len[k];
+        }
+        P->span_end[nspan++] = K;
+        longest = fmax(longest, acc);
+        if (k_split == K) span_split = nspan;
+        // a single layer longer than 4 spans would stretch the cubic's error bound (T^4) by > 256
+        if (longest > 4.0 * span_max) st |= RDR_PLAN_SPAN_TOO_LONG;
+        P->status = st;
+        P->blocked = st & block_mask;
+        P->K = K;
+        P->nspan = nspan;
+        P->k_split = k_split;
+        P->span_split = span_split;
+        P->clamp_low_first = force_clamp >= 0 ? force_clamp : (n_below == n_rays);
+        P->knife_layer = s_knife;
+        P->n_rays = n_rays;
+        P->n_nan = n_nan;
+        P->n_below = n_below;
+        P->longest_span = longest;
+    }
+}
+
+// every rank's K0 words -> slot `rank` of every peer's exchange buffer (and of its own)
+__global__ void k_publish(const unsigned long long *__restrict__ src, int nwords, int dst_off, const PeerOut dst) {
+    for (int i = threadIdx.x; i < nwords; i += blockDim.x) {
+        const unsigned long long v = src[i];
+        for (int p = 0; p < dst.n; ++p) static_cast<unsigned long long *>(dst.wet[p])[dst_off + i] = v;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1098,8 +1260,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_ray_layers(const RayGeom G, int
 // ------------------------------------------------------------------------------------------------
 template <typename OUT, int BLOCK, int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB) k_ray_integrate(const CubeView c, const RayGeom G, int64_t n_rays, int K,
-                                                         const double *__restrict__ t_in, const int *__restrict__ nparts,
-                                                         const int *__restrict__ layer_cell, int clamp_low_first, double zmin, double zmax,
+                                                         const double *__restrict__ t_in, const DevPlan *__restrict__ P, double zmin, double zmax,
                                                          OUT *__restrict__ out_wet, OUT *__restrict__ out_hydro, int accumulate, const PeerOut peers,
                                                          unsigned long long *__restrict__ counters, const int *__restrict__ list,
                                                          const unsigned long long *__restrict__ list_count) {
@@ -1107,7 +1268,10 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_ray_integrate(const CubeView c,
     // launch needs no host round trip and is a no-op when nothing was flagged); their first samples were already counted
     const int lane = threadIdx.x & 31;
     const int64_t n_items = list ? (int64_t)*list_count : n_rays;
-    if (n_items == 0) return;
+    if (n_items == 0 || P->blocked) return;
+    const int *__restrict__ nparts = P->nparts;
+    const int *__restrict__ layer_cell = P->layer_cell;
+    const int clamp_low_first = P->clamp_low_first;
     const int64_t n_pad = (n_items + 31) / 32 * 32;
     unsigned n_below = 0, n_above = 0, n_first_below = 0;
     for (int64_t idx = blockIdx.x * (int64_t)BLOCK + threadIdx.x; idx < n_pad; idx += (int64_t)gridDim.x * BLOCK) {
@@ -1225,10 +1389,13 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_ray_integrate(const CubeView c,
 // ------------------------------------------------------------------------------------------------
 template <typename OUT, int BLOCK, int MINB, int NPT>
 __global__ void __launch_bounds__(BLOCK, MINB) k_ray_integrate_fast(const FastCube c, const RayGeom G, int64_t n_rays, int K,
-                                                              const double *__restrict__ t_in, const LayerRec *__restrict__ layers,
-                                                              const double *__restrict__ znodes, int nz, int clamp_low_first, double zmin,
+                                                              const double *__restrict__ t_in, const DevPlan *__restrict__ P,
+                                                              const double *__restrict__ znodes, int nz, double zmin,
                                                               OUT *__restrict__ out_wet, OUT *__restrict__ out_hydro, int accumulate, const PeerOut peers,
                                                               unsigned long long *__restrict__ counters, int *__restrict__ fix_list) {
+    if (P->blocked) return;
+    const LayerRec *__restrict__ layers = P->layers;
+    const int clamp_low_first = P->clamp_low_first;
     extern __shared__ __align__(16) unsigned char fast_smem[];
     LayerRec *s_layers = reinterpret_cast<LayerRec *>(fast_smem);
     double *s_z = reinterpret_cast<double *>(fast_smem + (size_t)K * sizeof(LayerRec));
@@ -1315,23 +1482,32 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_ray_integrate_fast(const FastCu
 // list mode exactly as for k_ray_integrate_fast.
 // Dynamic shared memory: LayerRec[K] | z nodes [nz] | 1/dz [nz-1] | span ends int[nspan].
 // ------------------------------------------------------------------------------------------------
-template <typename OUT, int BLOCK, int MINB, bool LCC, bool CACHE>
-__global__ void __launch_bounds__(BLOCK, MINB) k_ray_integrate_poly(const FastCube c, const RayGeom G, int64_t n_rays, int K,
-                                                              const double *__restrict__ t_in, const LayerRec *__restrict__ layers,
-                                                              const int *__restrict__ span_end, int nspan, const double *__restrict__ znodes,
-                                                              int nz, int clamp_low_first, double zmin, OUT *__restrict__ out_wet,
+template <typename OUT, int BLOCK, int MINB, bool LCC, bool CACHE, bool FROM0>
+__global__ void __launch_bounds__(BLOCK, MINB) k_ray_integrate_poly(const FastCube c, const RayGeom G, int64_t n_rays,
+                                                              const double *__restrict__ t_in, const DevPlan *__restrict__ P,
+                                                              const double *__restrict__ znodes, int nz, double zmin, OUT *__restrict__ out_wet,
                                                               OUT *__restrict__ out_hydro, int accumulate, const PeerOut peers,
                                                               unsigned long long *__restrict__ counters, int *__restrict__ fix_list, int quad,
-                                                              int tile_map) {
+                                                              int tile_map, double *__restrict__ part) {
+    // layers [k0, K) / spans [sp0, nspan) of the device plan are this kernel's; a non-empty thin part [0, k0) is integrated by
+    // k_ray_integrate_thin, which runs after this kernel and adds the partial sums left in `part`
+    // Two instantiations are launched back to back and the plan picks one: FROM0 (no thin part: the whole ray, k0 = sp0 = 0 known at
+    // compile time -- the C2-type case, where the registers the two variables would take are spills) or the upper part only.
+    if (P->blocked) return;
+    const int K = P->K, nspan = P->nspan;
+    if (FROM0 != (P->k_split == 0)) return;
+    const int k0 = FROM0 ? 0 : P->k_split, sp0 = FROM0 ? 0 : P->span_split;
+    if (k0 >= K) return;
+    const int clamp_low_first = P->clamp_low_first;
     extern __shared__ __align__(16) unsigned char fast_smem[];
     LayerRec *s_layers = reinterpret_cast<LayerRec *>(fast_smem);
     double *s_z = reinterpret_cast<double *>(fast_smem + (size_t)K * sizeof(LayerRec));
     double *s_inv = s_z + nz;
     int *s_span = reinterpret_cast<int *>(s_inv + (nz - 1));
-    for (int i = threadIdx.x; i < K; i += BLOCK) s_layers[i] = layers[i];
+    for (int i = threadIdx.x; i < K; i += BLOCK) s_layers[i] = P->layers[i];
     for (int i = threadIdx.x; i < nz; i += BLOCK) s_z[i] = znodes[i];
     for (int i = threadIdx.x; i < nz - 1; i += BLOCK) s_inv[i] = 1.0 / (znodes[i + 1] - znodes[i]);
-    for (int i = threadIdx.x; i < nspan; i += BLOCK) s_span[i] = span_end[i];
+    for (int i = threadIdx.x; i < nspan; i += BLOCK) s_span[i] = P->span_end[i];
     __syncthreads();
     const ZTable T = {s_z, s_inv, nz};
     const double ky = RAD_TO_DEG * c.y_inv, kx = RAD_TO_DEG * c.x_inv;
@@ -1357,16 +1533,18 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_ray_integrate_poly(const FastCu
         const double unorm = norm3(Vec3{F.uA, F.uB, F.uZ});  // |P_hi - P_lo| = |t_hi - t_lo| |u|  (losreader.py:821)
         bool bad = LCC ? false : !F.fast_ok;
         double acc_w = 0.0, acc_h = 0.0, vw, vh;
-        double t_a = __ldcs(t_in + rr), t_lo = t_a;
+        double t_a = __ldcs(t_in + (int64_t)k0 * n_rays + rr), t_lo = t_a;
         // the along-ray distances stream from HBM: the top of the next layer and the end of the next span are requested one
         // layer / one span ahead of their use
-        double t_next = __ldcs(t_in + n_rays + rr);
-        double tb_next = __ldcs(t_in + (int64_t)s_span[0] * n_rays + rr);
+        double t_next = __ldcs(t_in + (int64_t)(k0 + 1) * n_rays + rr);
+        double tb_next = __ldcs(t_in + (int64_t)s_span[sp0] * n_rays + rr);
         RayNode n0 = node_eval<LCC>(c, F, R, t_a, bad);
-        {   // very first sample of the ray (ff = 0 of the first layer); all pixels below min(z) -> clamp (delay.py:306-307)
+        const bool clamp_first = (k0 == 0) && clamp_low_first;
+        if (k0 == 0) {
+            // very first sample of the ray (ff = 0 of the first layer); all pixels below min(z) -> clamp (delay.py:306-307)
             n_first_below += __popc(__ballot_sync(0xffffffffu, valid && (n0.h < zmin)));
-            sample_cell(c, s_layers[0], T, n0.uy, n0.ux, clamp_low_first ? zmin : n0.h, vw, vh, bad);
         }
+        sample_cell(c, s_layers[k0], T, n0.uy, n0.ux, clamp_first ? zmin : n0.h, vw, vh, bad);
         // CACHE: the 128-byte record of the cell the previous sample fell into stays in registers.  The samples of a layer share
         // their z cell and a ray crosses a horizontal cell face only every few km, so most samples reuse it: the gather drops
         // from 8 LDG.128 per sample (32 L1 wavefront cycles per warp: the limiter of the uncached kernel) to 8 per cell entered.
@@ -1377,7 +1555,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_ray_integrate_poly(const FastCu
         Cubic py, px, ph;
         // horizontal cell (iy | ix << 10) and height of the last sample evaluated: the start of the next layer
         unsigned last_hkey;
-        double last_h = clamp_low_first ? zmin : n0.h, last_ty, last_tx;
+        double last_h = clamp_first ? zmin : n0.h, last_ty, last_tx;
         {
             int iy0, ix0;
             last_ty = cell_coord_clamped(n0.uy, c.ny, iy0);
@@ -1406,8 +1584,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_ray_integrate_poly(const FastCu
             last_ty = ty;
             last_tx = tx;
         };
-        int k = 0;
-        for (int sp = 0; sp < nspan; ++sp) {
+        int k = k0;
+        for (int sp = sp0; sp < nspan; ++sp) {
             const int k1 = s_span[sp];
             const double t_b = tb_next;
             if (sp + 1 < nspan) tb_next = __ldcs(t_in + (int64_t)s_span[sp + 1] * n_rays + rr);
@@ -1591,12 +1769,263 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_ray_integrate_poly(const FastCu
         if (valid) {
             if (bad) {
                 fix_list[atomicAdd(counters + 3, 1ull)] = (int)r;
+                if (k0 > 0) __stcs(part + r, __longlong_as_double(PART_FLAGGED));  // the ray is on the fix list: the thin kernel leaves it alone
+            } else if (k0 > 0) {  // the thin-layer kernel finishes the ray
+                __stcs(part + r, acc_w);
+                __stcs(part + n_rays + r, acc_h);
             } else {
                 store_result(out_wet, out_hydro, peers, r, acc_w, acc_h, accumulate);
             }
         }
     }
     if ((threadIdx.x & 31) == 0 && n_first_below) atomicAdd(counters + 0, (unsigned long long)n_first_below);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3 (thin-layer form): layers [0, k_split) of the device plan -- the run of layers with <= 3 samples each that the real
+// processed cubes consist of below ~20 km (145-node tables at the reference's 1000 m segments: ~115 of 139 layers hold 2
+// samples, models/model_levels.py:12, delay.py:283).  There the quadrature kernel has nothing to sum in closed form and its
+// per-layer bookkeeping is the cost; this kernel is the lean loop: one sample per layer (the layer top; the interface sample is
+// shared by both layers as everywhere), geometry from the span cubics, and a cell lookup that costs two subtractions and two
+// integer compares while the ray stays in its horizontal cell (the floor values are held; a cell is ~25 km wide, a thin layer
+// moves the ray ~100 m).  Every sample needs a new 128-byte record (the z cell changes with every layer), so the records of the
+// layers ahead are requested into L1 `pf_cells` layers early (they are consecutive lines: z is the fastest axis of the record
+// array) and the along-ray distances into L2 `pf_t` layers early -- the uncached polynomial kernel spent 53 % of its stall
+// samples on the long scoreboard here (profiles/r01f ml145).  Sample positions, step counts and weights are the reference's.
+// Runs after k_ray_integrate_poly (which leaves the partial sums of layers [k_split, K) in `part`) and stores the results.
+// ------------------------------------------------------------------------------------------------
+// both fields of a cell record through a generic pointer (the record may sit in shared memory: staged columns)
+__device__ __forceinline__ void trilinear_cell_g(const LerpCell *q, double ty, double tx, double tz, double &vw, double &vh) {
+    const double4 q0 = q->q0, q1 = q->q1, q2 = q->q2, q3 = q->q3;
+    const double w0 = fma(tz, q0.z, q0.x), h0 = fma(tz, q0.w, q0.y);
+    const double w1 = fma(tz, q1.z, q1.x), h1 = fma(tz, q1.w, q1.y);
+    const double w2 = fma(tz, q2.z, q2.x), h2 = fma(tz, q2.w, q2.y);
+    const double w3 = fma(tz, q3.z, q3.x), h3 = fma(tz, q3.w, q3.y);
+    vw = fma(ty, fma(tx, w3, w2), fma(tx, w1, w0));
+    vh = fma(ty, fma(tx, h3, h2), fma(tx, h1, h0));
+}
+
+// STAGE: the north_star form -- the CTA's footprint of the cube is staged in shared memory by the TMA engine.  The 128 rays
+// of a CTA pass sit in 1-4 horizontal cells over the whole thin part (a 32 x 4 pixel tile is ~3 km wide, the rays drift
+// ~10 km below 20 km, a cell is ~25 km); the record columns of those cells -- contiguous in memory, z fastest -- are
+// copied with one cp.async.bulk each (UBLKCP) onto an mbarrier, `n_slots` columns at most (what fits beside MINB CTAs per
+// SM).  A sample then reads its record with 8 LDS.128 at ~30 cycles instead of 8 LDG.128 from L2 at ~600 under load
+// (profiles/r02a: 59 % of the stall samples of the unstaged kernel sit on the first use of those loads).  Rays whose cell is
+// not staged (footprint larger than the slots: km-scale grids) read the record from global memory as before.
+template <typename OUT, int BLOCK, int MINB, bool LCC, bool STAGE>
+__global__ void __launch_bounds__(BLOCK, MINB) k_ray_integrate_thin(const FastCube c, const RayGeom G, int64_t n_rays,
+                                                              const double *__restrict__ t_in, const DevPlan *__restrict__ P,
+                                                              const double *__restrict__ znodes, int nz, double zmin, OUT *__restrict__ out_wet,
+                                                              OUT *__restrict__ out_hydro, int accumulate, const PeerOut peers,
+                                                              unsigned long long *__restrict__ counters, int *__restrict__ fix_list, int tile_map,
+                                                              const double *__restrict__ part, int pf_cells, int pf_t, int n_slots,
+                                                              unsigned long long *__restrict__ stage_stats) {
+    if (P->blocked) return;
+    const int K = P->K, k_end = P->k_split, nspan = P->span_split;
+    if (k_end == 0) return;
+    const int clamp_low_first = P->clamp_low_first;
+    extern __shared__ __align__(128) unsigned char fast_smem[];
+    LayerRec *s_layers = reinterpret_cast<LayerRec *>(fast_smem);
+    double *s_z = reinterpret_cast<double *>(fast_smem + (size_t)K * sizeof(LayerRec));
+    double *s_inv = s_z + nz;
+    int *s_span = reinterpret_cast<int *>(s_inv + (nz - 1));
+    // staging area: mbarrier | per-warp bounding boxes | record columns (128-byte aligned)
+    const size_t stage_off = (((size_t)K * sizeof(LayerRec) + (2 * (size_t)nz - 1) * sizeof(double) + (size_t)K * sizeof(int)) + 127) / 128 * 128;
+    uint64_t *s_bar = reinterpret_cast<uint64_t *>(fast_smem + stage_off);
+    int *s_wbox = reinterpret_cast<int *>(fast_smem + stage_off + 16);            // [BLOCK / 32][4]
+    const LerpCell *s_cols = reinterpret_cast<const LerpCell *>(fast_smem + stage_off + 128);
+    for (int i = threadIdx.x; i < k_end; i += BLOCK) s_layers[i] = P->layers[i];
+    for (int i = threadIdx.x; i < nz; i += BLOCK) s_z[i] = znodes[i];
+    for (int i = threadIdx.x; i < nz - 1; i += BLOCK) s_inv[i] = 1.0 / (znodes[i + 1] - znodes[i]);
+    for (int i = threadIdx.x; i < nspan; i += BLOCK) s_span[i] = P->span_end[i];
+    // z cells the thin part can touch: its own layers' cells and one neighbour each way (layer tops sit mm .. m off their nodes)
+    const int iz_lo = max(P->layer_cell[0] - 1, 0), iz_hi = min(P->layer_cell[k_end - 1] + 1, c.nzc - 1), ncl = iz_hi - iz_lo + 1;
+    if (STAGE && threadIdx.x == 0) mbar_init(s_bar, 1);
+    __syncthreads();
+    const ZTable T = {s_z, s_inv, nz};
+    const double ky = RAD_TO_DEG * c.y_inv, kx = RAD_TO_DEG * c.x_inv;
+    const int64_t n_pad = (n_rays + BLOCK - 1) / BLOCK * BLOCK;  // whole CTAs walk the loop together (barriers inside)
+    const int64_t pf_t_off = (int64_t)pf_t * n_rays;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned n_first_below = 0, phase = 0;
+    unsigned long long n_staged = 0, n_unstaged = 0;
+    for (int64_t q0 = blockIdx.x * (int64_t)BLOCK; q0 < n_pad; q0 += (int64_t)gridDim.x * BLOCK) {
+        const int64_t q = q0 + threadIdx.x;
+        int64_t r = q;
+        if (tile_map) {  // as in k_ray_integrate_poly
+            const int64_t tile = q >> 5, per_band = G.nx >> tile_map, band = tile / per_band;
+            r = ((band << (5 - tile_map)) + (lane >> tile_map)) * G.nx + ((tile - band * per_band) << tile_map) + (lane & ((1 << tile_map) - 1));
+        }
+        const bool valid = r < n_rays;
+        const int64_t rr = valid ? r : n_rays - 1;
+        double lat, lon;
+        ray_latlon(G, rr, lat, lon);
+        RayFrame F;
+        frame_setup(lat, lon, G.ht, G.los_kind, G.los, rr, G.e, G.n, G.u, F);
+        const RayCell R = {fma(lat, c.y_inv, c.y_c0), fma(lon, c.x_inv, c.x_c0), ky, kx};
+        const double u6 = norm3(Vec3{F.uA, F.uB, F.uZ}) * 1.0e-6;  // |P_hi - P_lo| 1e-6 = |t_hi - t_lo| |u| 1e-6  (losreader.py:821, delay.py:315)
+        bool bad = LCC ? false : !F.fast_ok;
+        double acc_w = 0.0, acc_h = 0.0, vw, vh;
+        const double *tp = t_in + rr;  // row k of the distances: bottom of layer k
+        double t_a = __ldcs(tp), t_lo = t_a;
+        tp += n_rays;
+        double t_next = __ldcs(tp);
+        double tb_next = __ldcs(t_in + (int64_t)s_span[0] * n_rays + rr);
+        RayNode n0 = node_eval<LCC>(c, F, R, t_a, bad);
+        // ---- footprint of this CTA pass: bounding box of the horizontal cells at the two ends of the thin part -> staged columns
+        int bx0 = 0, by0 = 0, nbx = 0, nby = 0;   // box origin and extent (cells); nbx = 0: nothing staged
+        if (STAGE) {
+            const RayNode ne = node_eval<LCC>(c, F, R, __ldcs(t_in + (int64_t)k_end * n_rays + rr), bad);
+            int ia, ib, ja, jb;
+            (void)cell_coord_clamped(n0.uy, c.ny, ia);
+            (void)cell_coord_clamped(ne.uy, c.ny, ib);
+            (void)cell_coord_clamped(n0.ux, c.nx, ja);
+            (void)cell_coord_clamped(ne.ux, c.nx, jb);
+            const int w_ylo = __reduce_min_sync(0xffffffffu, min(ia, ib)), w_yhi = __reduce_max_sync(0xffffffffu, max(ia, ib));
+            const int w_xlo = __reduce_min_sync(0xffffffffu, min(ja, jb)), w_xhi = __reduce_max_sync(0xffffffffu, max(ja, jb));
+            __syncthreads();  // the previous pass is done with the boxes and the columns
+            if (lane == 0) {
+                s_wbox[4 * warp] = w_ylo; s_wbox[4 * warp + 1] = w_yhi; s_wbox[4 * warp + 2] = w_xlo; s_wbox[4 * warp + 3] = w_xhi;
+            }
+            __syncthreads();
+            int ylo = s_wbox[0], yhi = s_wbox[1], xlo = s_wbox[2], xhi = s_wbox[3];
+#pragma unroll
+            for (int w = 1; w < BLOCK / 32; ++w) {
+                ylo = min(ylo, s_wbox[4 * w]); yhi = max(yhi, s_wbox[4 * w + 1]);
+                xlo = min(xlo, s_wbox[4 * w + 2]); xhi = max(xhi, s_wbox[4 * w + 3]);
+            }
+            const int ncols = (yhi - ylo + 1) * (xhi - xlo + 1);
+            if (ncols <= n_slots) {  // (CTA-uniform)
+                by0 = ylo; bx0 = xlo; nby = yhi - ylo + 1; nbx = xhi - xlo + 1;
+                const uint32_t col_bytes = (uint32_t)ncl * (uint32_t)sizeof(LerpCell);
+                if (threadIdx.x == 0) {
+                    mbar_expect_tx(s_bar, (uint32_t)ncols * col_bytes);
+                    for (int j = 0; j < ncols; ++j) {
+                        const int cy = by0 + j / nbx, cx = bx0 + j % nbx;
+                        tma_load_1d(const_cast<LerpCell *>(s_cols) + (size_t)j * ncl, c.cells + ((size_t)(cy * (c.nx - 1) + cx) * c.nzc + iz_lo), col_bytes, s_bar);
+                    }
+                }
+                mbar_wait(s_bar, phase);
+                phase ^= 1u;
+                n_staged += threadIdx.x == 0;
+            } else {
+                n_unstaged += threadIdx.x == 0;
+            }
+        }
+        // very first sample of the ray (ff = 0 of the first layer); all pixels below min(z) -> clamp (delay.py:306-307)
+        n_first_below += __popc(__ballot_sync(0xffffffffu, valid && (n0.h < zmin)));
+        sample_cell(c, s_layers[0], T, n0.uy, n0.ux, clamp_low_first ? zmin : n0.h, vw, vh, bad);
+        // the horizontal cell the ray is in: index, floor values of the cell coordinates, record column (biased by -iz_lo when staged)
+        int iy, ix;
+        double fy, fx;
+        const LerpCell *col;
+        auto enter_cell = [&](double uy, double ux) {
+            const double sy = __dadd_rd(uy, c_fast.floor_magic), sx = __dadd_rd(ux, c_fast.floor_magic);
+            iy = min(max(__double2loint(sy), 0), c.ny - 2);
+            ix = min(max(__double2loint(sx), 0), c.nx - 2);
+            fy = sy - c_fast.floor_magic;
+            fx = sx - c_fast.floor_magic;
+            const int cy = iy - by0, cx = ix - bx0;
+            if (STAGE && (unsigned)cy < (unsigned)nby && (unsigned)cx < (unsigned)nbx)
+                col = s_cols + ((cy * nbx + cx) * ncl - iz_lo);
+            else
+                col = c.cells + (unsigned)(iy * (c.nx - 1) + ix) * (unsigned)c.nzc;
+        };
+        enter_cell(n0.uy, n0.ux);
+        Cubic py, px, ph;
+        auto sample = [&](const LayerRec &L, double s, double &w_out, double &h_out) {
+            const double s2 = s * s;  // Estrin, as in k_ray_integrate_poly (same rounding)
+            const double uy = fma(s2, fma(s, py.c3, py.c2), fma(s, py.c1, py.c0));
+            const double ux = fma(s2, fma(s, px.c3, px.c2), fma(s, px.c1, px.c0));
+            const double h = fma(s2, fma(s, ph.c3, ph.c2), fma(s, ph.c1, ph.c0));
+            double ty = uy - fy, tx = ux - fx;
+            // 0 <= t < 1  <=>  the high word of t, as an unsigned, is below that of 1.0 (negative and NaN have larger high words)
+            if (((unsigned)__double2hiint(ty) >= 0x3ff00000u) | ((unsigned)__double2hiint(tx) >= 0x3ff00000u)) {
+                enter_cell(uy, ux);
+                ty = uy - fy;
+                tx = ux - fx;
+            }
+            int iz = L.iz;
+            double tz = fma(h, L.inv_dz, L.neg_zlo_inv);
+            const LerpCell *rec = col + iz;
+            if (!(h >= L.h_lo && h < L.h_hi)) {  // (rare) not in the layer's own cell: whatever cell it is, straight from global memory
+                z_lookup(T, h, iz, tz, bad);
+                rec = c.cells + ((unsigned)(iy * (c.nx - 1) + ix) * (unsigned)c.nzc + (unsigned)iz);
+            }
+            if (!STAGE && pf_cells) asm volatile("prefetch.global.L1 [%0];" ::"l"(rec + pf_cells));  // (the record array is padded at its end)
+            trilinear_cell_g(rec, ty, tx, tz, w_out, h_out);
+        };
+        int k = 0;
+        for (int sp = 0; sp < nspan; ++sp) {
+            const int k1 = s_span[sp];
+            const double t_b = tb_next;
+            if (sp + 1 < nspan) tb_next = __ldcs(t_in + (int64_t)s_span[sp + 1] * n_rays + rr);
+            const double span = t_b - t_a;
+            bad |= !(span > 0.0);
+            const RayNode n1 = node_eval<LCC>(c, F, R, fma(span, 1.0 / 3.0, t_a), bad);
+            const RayNode n2 = node_eval<LCC>(c, F, R, fma(span, 2.0 / 3.0, t_a), bad);
+            const RayNode n3 = node_eval<LCC>(c, F, R, t_b, bad);
+            py = cubic_through(n0.uy, n1.uy, n2.uy, n3.uy);
+            px = cubic_through(n0.ux, n1.ux, n2.ux, n3.ux);
+            ph = cubic_through(n0.h, n1.h, n2.h, n3.h);
+            const double inv_span = rcp3(span);
+            for (; k < k1; ++k) {
+                const LayerRec L = s_layers[k];
+                const double t_hi = t_next;
+                tp += n_rays;  // row k + 2
+                if (k + 2 <= K) t_next = __ldcs(tp);
+                if (pf_t && k + 2 + pf_t <= K) asm volatile("prefetch.global.L2 [%0];" ::"l"(tp + pf_t_off));
+                const double dt = t_hi - t_lo;
+                const double wt_full = (fabs(dt) * u6) * L.step;  // delay.py:315
+                const double wt_half = 0.5 * wt_full;
+                double ew, eh;
+                if (L.np == 2) {
+                    // one interval: 0.5 w (f(lo) + f(hi)); the sample at the layer top sits at t_hi
+                    sample(L, (t_hi - t_a) * inv_span, ew, eh);
+                    acc_w = fma(wt_half, vw + ew, acc_w);
+                    acc_h = fma(wt_half, vh + eh, acc_h);
+                } else {
+                    const double s_lo = (t_lo - t_a) * inv_span, ds = dt * inv_span, sstep = L.step * ds;
+                    acc_w = fma(wt_half, vw, acc_w);
+                    acc_h = fma(wt_half, vh, acc_h);
+                    double fj = 1.0;
+                    for (int j = 1; j < L.np - 1; ++j, fj += 1.0) {
+                        double wa, ha;
+                        sample(L, fma(fj, sstep, s_lo), wa, ha);
+                        acc_w = fma(wt_full, wa, acc_w);
+                        acc_h = fma(wt_full, ha, acc_h);
+                    }
+                    sample(L, s_lo + ds, ew, eh);  // the layer's last sample (ff = 1)
+                    acc_w = fma(wt_half, ew, acc_w);
+                    acc_h = fma(wt_half, eh, acc_h);
+                }
+                vw = ew;
+                vh = eh;
+                t_lo = t_hi;
+            }
+            t_a = t_b;
+            n0 = n3;
+        }
+        if (valid) {
+            const double pw = k_end < K ? __ldcs(part + r) : 0.0;  // the layers above were summed by k_ray_integrate_poly
+            if (k_end < K && __double_as_longlong(pw) == PART_FLAGGED) {
+                // already on the fix list
+            } else if (bad) {
+                fix_list[atomicAdd(counters + 3, 1ull)] = (int)r;
+            } else {
+                if (k_end < K) {
+                    acc_w += pw;
+                    acc_h += __ldcs(part + n_rays + r);
+                }
+                store_result(out_wet, out_hydro, peers, r, acc_w, acc_h, accumulate);
+            }
+        }
+    }
+    if (lane == 0 && n_first_below) atomicAdd(counters + 0, (unsigned long long)n_first_below);
+    if (STAGE && stage_stats && threadIdx.x == 0) {
+        if (n_staged) atomicAdd(stage_stats, n_staged);
+        if (n_unstaged) atomicAdd(stage_stats + 1, n_unstaged);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -2349,7 +2778,8 @@ RDR_API int rdr_destroy(rdr_handle_t h) {
     ScopedDevice sd(h->device);
     cudaStreamSynchronize(h->stream);
     for (DevBuf *b : {&h->d_axes, &h->d_tabs, &h->d_cells, &h->d_stage, &h->d_fields, &h->d_gx, &h->d_gy, &h->d_los, &h->d_plan, &h->d_t, &h->d_red,
-                      &h->d_nparts, &h->d_out, &h->d_in, &h->d_lerp, &h->d_layers, &h->d_spans, &h->d_fix, &h->d_cells32, &h->d_orbit})
+                      &h->d_nparts, &h->d_out, &h->d_in, &h->d_lerp, &h->d_layers, &h->d_spans, &h->d_fix, &h->d_cells32, &h->d_orbit, &h->d_devplan,
+                      &h->d_part})
         b->release();
     if (h->own_stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -2448,7 +2878,8 @@ static int pack_cells(rdr_handle_t h) {
                                                                                             h->d_cells32.as<float4>(), ncol, (int)h->nz);
     h->launches++;
     const int64_t nlerp = (h->ny - 1) * (h->nx - 1) * (h->nz - 1) * 4;
-    CUDA_TRY(h, h->d_lerp.reserve(nlerp * sizeof(double4)));
+    // (+ LERP_PAD records: the thin-layer kernel prefetches up to that many records past the one it reads)
+    CUDA_TRY(h, h->d_lerp.reserve((nlerp + 4 * LERP_PAD) * sizeof(double4)));
     k_pack_lerp<<<grid_for(nlerp, 256, h->sm_count, 16), 256, 0, h->stream>>>(h->d_fields.as<float2>(), h->d_lerp.as<double4>(), (int)h->ny,
                                                                               (int)h->nx, (int)h->nz);
     h->launches++;
@@ -2673,15 +3104,15 @@ static RayGeom make_geom(rdr_handle_t h) {
     return G;
 }
 
-RDR_API int rdr_ray_layers(rdr_handle_t h, int geom_kind, const double *gx, const double *gy, int64_t ny, int64_t nx, int los_kind,
-                           const double *los, double ht, double zref, double *maxlen_out, int64_t *counts_out, int mem) {
-    CHECK_ARG(h, h != nullptr, "rdr_ray_layers: NULL handle");
-    if (!h->has_cube) return fail(h, RDR_ERR_STATE, "rdr_ray_layers: no cube staged");
-    CHECK_ARG(h, geom_kind == RDR_GEOM_GRID || geom_kind == RDR_GEOM_POINTS, "rdr_ray_layers: unknown geom_kind");
-    CHECK_ARG(h, los_kind >= RDR_LOS_ARRAY && los_kind <= RDR_LOS_ORBIT, "rdr_ray_layers: unknown los_kind");
-    CHECK_ARG(h, gx && gy && ny > 0 && nx > 0, "rdr_ray_layers: bad geometry arguments");
-    CHECK_ARG(h, los_kind == RDR_LOS_ZENITH || los != nullptr, "rdr_ray_layers: los is NULL");
-    ScopedDevice sd(h->device);
+// ---- K0: everything up to (and including) the launch; nothing is read back ---------------------------------------------------
+static int k0_enqueue(rdr_handle_t h, int geom_kind, const double *gx, const double *gy, int64_t ny, int64_t nx, int los_kind,
+                      const double *los, double ht, double zref, int exact_k0, int mem, const char *who) {
+    CHECK_ARG(h, h != nullptr, std::string(who) + ": NULL handle");
+    if (!h->has_cube) return fail(h, RDR_ERR_STATE, std::string(who) + ": no cube staged");
+    CHECK_ARG(h, geom_kind == RDR_GEOM_GRID || geom_kind == RDR_GEOM_POINTS, std::string(who) + ": unknown geom_kind");
+    CHECK_ARG(h, los_kind >= RDR_LOS_ARRAY && los_kind <= RDR_LOS_ORBIT, std::string(who) + ": unknown los_kind");
+    CHECK_ARG(h, gx && gy && ny > 0 && nx > 0, std::string(who) + ": bad geometry arguments");
+    CHECK_ARG(h, los_kind == RDR_LOS_ZENITH || los != nullptr, std::string(who) + ": los is NULL");
     h->has_rays = false;
     const int64_t n = ny * nx;
     h->n_rays = n; h->ray_ny = ny; h->ray_nx = nx;
@@ -2690,10 +3121,8 @@ RDR_API int rdr_ray_layers(rdr_handle_t h, int geom_kind, const double *gx, cons
     layer_plan(h->zs, ht, zref, h->low_ht, h->high_ht, h->layer_cell);
     const int K = (int)h->low_ht.size();
     h->n_layers = K;
-    if (counts_out) {
-        counts_out[0] = n; counts_out[1] = 0; counts_out[2] = 0; counts_out[3] = K;
-    }
-    if (K == 0) return fail(h, RDR_ERR_NO_LAYERS, "rdr_ray_layers: no model layer contributes between ht and zref");
+    if (K == 0) return fail(h, RDR_ERR_NO_LAYERS, std::string(who) + ": no model layer contributes between ht and zref");
+    CHECK_ARG(h, K <= MAX_LAYERS, std::string(who) + ": more than 1024 contributing layers");
     int rc;
     // geometry: grid axes are parameter vectors (host); point lists and LOS arrays are bulk (per `mem`)
     if (geom_kind == RDR_GEOM_GRID) {
@@ -2726,19 +3155,23 @@ RDR_API int rdr_ray_layers(rdr_handle_t h, int geom_kind, const double *gx, cons
         h->p_los = h->d_los.as<double>();
         h->los_kind = RDR_LOS_ARRAY;
     }
+    // low[K] | high[K] | layer cell int[K] (read by k_plan)
     std::vector<double> plan(h->low_ht);
     plan.insert(plan.end(), h->high_ht.begin(), h->high_ht.end());
+    plan.resize(2 * (size_t)K + ((size_t)K + 1) / 2);
+    memcpy(plan.data() + 2 * (size_t)K, h->layer_cell.data(), (size_t)K * sizeof(int));
     CUDA_TRY(h, h->d_plan.reserve(plan.size() * sizeof(double)));
     CUDA_TRY(h, cudaMemcpyAsync(h->d_plan.p, plan.data(), plan.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(h, h->d_t.reserve((size_t)(K + 1) * n * sizeof(double)));
-    CUDA_TRY(h, h->d_red.reserve((K + 8) * sizeof(unsigned long long)));
+    CUDA_TRY(h, h->d_red.reserve((XCHG_STRIDE + 8) * sizeof(unsigned long long)));
     CUDA_TRY(h, cudaMemsetAsync(h->d_red.p, 0, (K + 8) * sizeof(unsigned long long), h->stream));
     constexpr int BLOCK = 128;
-    const int minb = tune_minb("RDR_K0_MINB", 8);
+    const int minb = tune_minb("RDR_K0_MINB", 6);
     const int grid = grid_for(n, BLOCK, h->sm_count, 4 * minb);
-    const size_t smem = (K + 2) * sizeof(unsigned long long);
+    const size_t smem = (K + 2) * sizeof(unsigned long long) + 2 * (size_t)K * sizeof(double);
     const char *k0_env = getenv("RDR_K0_MODE");  // cubic (default) | exact: Newton iterates on the span cubics of h(t) or on Bowring heights
-    const int use_cubic = !(k0_env && !strcmp(k0_env, "exact"));
+    const int use_cubic = !exact_k0 && !(k0_env && !strcmp(k0_env, "exact"));
+    h->k0_was_cubic = use_cubic != 0;
 #define RDR_LAUNCH_K0(M)                                                                                                              \
     k_ray_layers<BLOCK, M><<<grid, BLOCK, smem, h->stream>>>(make_geom(h), n, K, h->d_plan.as<double>(), h->d_t.as<double>(),          \
                                                             h->d_red.as<unsigned long long>(), h->zs.front(), use_cubic)
@@ -2751,48 +3184,43 @@ RDR_API int rdr_ray_layers(rdr_handle_t h, int geom_kind, const double *gx, cons
 #undef RDR_LAUNCH_K0
     h->launches++;
     CUDA_TRY(h, cudaGetLastError());
-    std::vector<unsigned long long> red(K + 2);
-    CUDA_TRY(h, cudaMemcpyAsync(red.data(), h->d_red.p, (K + 2) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
-    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-    if (maxlen_out)
-        for (int k = 0; k < K; ++k) memcpy(&maxlen_out[k], &red[k], sizeof(double));
-    if (counts_out) {
-        counts_out[1] = (int64_t)red[K];
-        counts_out[2] = (int64_t)red[K + 1];
-    }
     h->has_rays = true;
-    if ((int64_t)red[K] == n) return fail(h, RDR_ERR_ALL_NAN, "geo2rdr did not converge. Check orbit coverage");
     return RDR_OK;
 }
 
-RDR_API int rdr_ray_integrate(rdr_handle_t h, const double *maxlen, double max_segment_length, int clamp_low_first, void *out_wet,
-                              void *out_hydro, int out_dtype, int accumulate, int64_t *nparts_out, int64_t *oob_out, int mem) {
-    CHECK_ARG(h, h != nullptr, "rdr_ray_integrate: NULL handle");
-    if (!h->has_cube || !h->has_rays) return fail(h, RDR_ERR_STATE, "rdr_ray_integrate: call rdr_ray_layers first");
-    CHECK_ARG(h, maxlen && out_wet && out_hydro, "rdr_ray_integrate: NULL pointer");
-    CHECK_ARG(h, max_segment_length > 0, "rdr_ray_integrate: max_segment_length must be positive");
-    CHECK_ARG(h, out_dtype == RDR_F64 || out_dtype == RDR_F32, "rdr_ray_integrate: out_dtype must be RDR_F64 or RDR_F32");
-    ScopedDevice sd(h->device);
+// ---- k_plan: MAX / SUM over the slots, nParts, layer records, spans, predicates -> the device plan ------------------------------
+static int plan_enqueue(rdr_handle_t h, const unsigned long long *slots, int world, double max_segment_length, int force_clamp, int block_mask) {
+    const int K = h->n_layers;
+    CUDA_TRY(h, h->d_devplan.reserve(sizeof(DevPlan)));
+    const char *span_env = getenv("RDR_K3_SPAN");
+    const double span_max = span_env && atof(span_env) > 0 ? atof(span_env) : 12000.0;
+    const char *thin_env = getenv("RDR_K3_THIN_MIN");  // fewest thin layers (<= 3 samples) that are worth the thin-layer kernel; 0: never
+    const int thin_min = thin_env ? atoi(thin_env) : 16;
+    unsigned long long *counters = h->d_red.as<unsigned long long>() + XCHG_STRIDE;
+    const int *d_cell = reinterpret_cast<const int *>(h->d_plan.as<double>() + 2 * (size_t)K);
+    const double *znodes = h->d_axes.as<double>() + h->ny + h->nx;
+    k_plan<<<1, 256, 0, h->stream>>>(slots, world, XCHG_STRIDE, K, d_cell, znodes, (int)h->nz, max_segment_length, span_max,
+                                     h->thin_ok ? thin_min : 0, force_clamp, block_mask, h->d_devplan.as<DevPlan>(), counters);
+    h->launches++;
+    CUDA_TRY(h, cudaGetLastError());
+    h->last_max_seg = max_segment_length;
+    return RDR_OK;
+}
+
+template <typename KERNEL>
+static cudaError_t allow_smem(KERNEL k, size_t smem) {
+    // > 48 KB of dynamic shared memory (models with more than ~600 levels) needs the opt-in
+    return smem > 48 * 1024 ? cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) : cudaSuccess;
+}
+
+// ---- K3: the integration kernels on the device plan; `mode`: 0 auto (poly + thin), 1 fast, 2 general -----------------------------
+static int k3_enqueue(rdr_handle_t h, void *out_wet, void *out_hydro, int out_dtype, int accumulate, int mem, int mode, bool *staged) {
     const int K = h->n_layers;
     const int64_t n = h->n_rays;
-    // nParts = ceil(max / MAX_SEGMENT_LENGTH).astype(int) + 1   (delay.py:283) -- the bit-exact integer contract
-    std::vector<int> np_cell(2 * K);
-    for (int k = 0; k < K; ++k) {
-        const double q = ceil(maxlen[k] / max_segment_length);
-        CHECK_ARG(h, q == q && q < 1e7, "rdr_ray_integrate: per-layer max length is NaN or absurd");
-        int np = (int)q + 1;
-        if (np < 2) np = 2;  // a zero-length layer would divide by zero in the reference (np.linspace(0,1,1)); keep 2
-        np_cell[k] = np;
-        np_cell[K + k] = h->layer_cell[k];
-        if (nparts_out) nparts_out[k] = np;
-    }
-    CUDA_TRY(h, h->d_nparts.reserve(2 * K * sizeof(int)));
-    CUDA_TRY(h, cudaMemcpyAsync(h->d_nparts.p, np_cell.data(), 2 * K * sizeof(int), cudaMemcpyHostToDevice, h->stream));
-    unsigned long long *counters = h->d_red.as<unsigned long long>() + K + 2;
-    CUDA_TRY(h, cudaMemsetAsync(counters, 0, 4 * sizeof(unsigned long long), h->stream));
     const size_t es = out_dtype == RDR_F64 ? 8 : 4;
+    unsigned long long *counters = h->d_red.as<unsigned long long>() + XCHG_STRIDE;
     void *dw = out_wet, *dh = out_hydro;
-    bool staged_out = false;
+    *staged = false;
     if (mem == RDR_MEM_HOST) {
         // page-locked result arrays (rdr_host_alloc) are written by the kernel itself: 16 B per ray of posted PCIe writes spread
         // over the whole integration instead of a 2 x n x 8 B copy after it
@@ -2801,7 +3229,7 @@ RDR_API int rdr_ray_integrate(rdr_handle_t h, const double *maxlen, double max_s
             dw = aw;
             dh = ah;
         } else {
-            staged_out = true;
+            *staged = true;
             CUDA_TRY(h, h->d_out.reserve(2 * n * es));
             dw = h->d_out.p;
             dh = static_cast<char *>(h->d_out.p) + n * es;
@@ -2814,7 +3242,8 @@ RDR_API int rdr_ray_integrate(rdr_handle_t h, const double *maxlen, double max_s
     constexpr int BLOCK = 128;
     const CubeView c = make_view(h);
     const RayGeom G = make_geom(h);
-    const int *d_np = h->d_nparts.as<int>();
+    const DevPlan *P = h->d_devplan.as<DevPlan>();
+    const double *t_in = h->d_t.as<double>();
     PeerOut peers = h->peers;
     if (accumulate) peers.n = 0;  // += has no meaning across replicas: peers only mirror freshly written maps
     FastCube fc;
@@ -2822,114 +3251,137 @@ RDR_API int rdr_ray_integrate(rdr_handle_t h, const double *maxlen, double max_s
     // integrator: poly (default; geographic or Lambert cube with uniform horizontal axes), fast (per-sample Bowring; geographic
     // only), general (PROJ-form arithmetic for every sample).  RDR_K3_MODE = poly | fast | general overrides for tests / tuning.
     const char *mode_env = getenv("RDR_K3_MODE");
-    const bool want_general = (force_general && atoi(force_general) != 0) || (mode_env && !strcmp(mode_env, "general"));
+    const bool want_general = mode == 2 || (force_general && atoi(force_general) != 0) || (mode_env && !strcmp(mode_env, "general"));
     const bool fast_cube = make_fast_cube(h, fc) && !want_general && n < (1ll << 31);
-    // spans of the polynomial integrator: whole layers, greedy, at most `span_max` metres of the longest ray per span
-    const char *span_env = getenv("RDR_K3_SPAN");
-    const double span_max = span_env && atof(span_env) > 0 ? atof(span_env) : 12000.0;
-    std::vector<int> span_end;
-    double longest_span = 0.0;
-    {
-        double acc = 0.0;
-        for (int k = 0; k < K; ++k) {
-            if (k > 0 && acc + maxlen[k] > span_max) {
-                span_end.push_back(k);
-                longest_span = std::max(longest_span, acc);
-                acc = 0.0;
-            }
-            acc += maxlen[k];
-        }
-        span_end.push_back(K);
-        longest_span = std::max(longest_span, acc);
-    }
-    // a single layer longer than 4 spans would stretch the cubic's error bound (T^4) by > 256: leave those calls to `fast`
-    const bool poly = fast_cube && !(mode_env && !strcmp(mode_env, "fast")) && longest_span <= 4.0 * span_max;
+    const bool poly = fast_cube && mode != 1 && !(mode_env && !strcmp(mode_env, "fast"));
     const bool fast = fast_cube && (poly || fc.crs_kind == RDR_CRS_GEOGRAPHIC);
+    h->last_k3_poly = poly;
     h->last_fix_count = -1;
 #define RDR_LAUNCH_K3(T, M, LIST, COUNT)                                                                                                   \
-    k_ray_integrate<T, BLOCK, M><<<grid, BLOCK, 0, h->stream>>>(c, G, n, K, h->d_t.as<double>(), d_np, d_np + K, clamp_low_first,          \
-                                                                h->zs.front(), h->zs.back(), static_cast<T *>(dw), static_cast<T *>(dh),   \
-                                                                accumulate, peers, counters, LIST, COUNT)
+    k_ray_integrate<T, BLOCK, M><<<grid, BLOCK, 0, h->stream>>>(c, G, n, K, t_in, P, h->zs.front(), h->zs.back(), static_cast<T *>(dw),   \
+                                                                static_cast<T *>(dh), accumulate, peers, counters, LIST, COUNT)
     if (fast) {
-        // per-layer records + the z table of the fast integrator
-        std::vector<LayerRec> recs(K);
-        for (int k = 0; k < K; ++k) {
-            const int iz = h->layer_cell[k];
-            const double z_lo = h->zs[iz], z_hi = h->zs[iz + 1];
-            recs[k].z_lo = z_lo;
-            recs[k].inv_dz = 1.0 / (z_hi - z_lo);
-            recs[k].neg_zlo_inv = -z_lo * recs[k].inv_dz;
-            recs[k].h_lo = iz == 0 ? z_lo : z_lo - LAYER_TOL;                                      // below the first node: NaN rule
-            recs[k].h_hi = iz == (int)h->nz - 2 ? nextafter(z_hi, INFINITY) : z_hi + LAYER_TOL;    // the last node is inclusive
-            recs[k].step = 1.0 / (double)(np_cell[k] - 1);
-            recs[k].np = np_cell[k];
-            recs[k].iz = iz;
-        }
-        CUDA_TRY(h, h->d_layers.reserve(K * sizeof(LayerRec)));
-        CUDA_TRY(h, cudaMemcpyAsync(h->d_layers.p, recs.data(), K * sizeof(LayerRec), cudaMemcpyHostToDevice, h->stream));
-        CUDA_TRY(h, h->d_fix.reserve(std::max<size_t>(n * sizeof(int), 16)));
-        const int minb = tune_minb("RDR_K3_MINB", 5);
-        const int grid = grid_for(n, BLOCK, h->sm_count, 4 * minb);
+        CUDA_TRY(h, h->d_fix.reserve(std::max<size_t>(2 * n * sizeof(int), 16)));
         const size_t smem = K * sizeof(LayerRec) + (2 * (size_t)h->nz - 1) * sizeof(double);
         const double *znodes = h->d_axes.as<double>() + h->ny + h->nx;
-        const char *npt_env = getenv("RDR_K3_NPT");
-        const int npt = npt_env ? atoi(npt_env) : 1;
-#define RDR_LAUNCH_K3F(T, M, P)                                                                                                            \
-    k_ray_integrate_fast<T, BLOCK, M, P><<<grid, BLOCK, smem, h->stream>>>(fc, G, n, K, h->d_t.as<double>(), h->d_layers.as<LayerRec>(),   \
-                                                                           znodes, (int)h->nz, clamp_low_first, h->zs.front(),            \
-                                                                           static_cast<T *>(dw), static_cast<T *>(dh), accumulate,         \
-                                                                           peers, counters, h->d_fix.as<int>())
         if (poly) {
-            const int nspan = (int)span_end.size();
-            CUDA_TRY(h, h->d_spans.reserve(nspan * sizeof(int)));
-            CUDA_TRY(h, cudaMemcpyAsync(h->d_spans.p, span_end.data(), nspan * sizeof(int), cudaMemcpyHostToDevice, h->stream));
-            const size_t smem_p = smem + nspan * sizeof(int);
-#define RDR_LAUNCH_K3P(T, M, L, S)                                                                                                            \
-    k_ray_integrate_poly<T, BLOCK, M, L, S><<<grid_p, BLOCK, smem_p, h->stream>>>(fc, G, n, K, h->d_t.as<double>(), h->d_layers.as<LayerRec>(), \
-                                                                               h->d_spans.as<int>(), nspan, znodes, (int)h->nz,            \
-                                                                               clamp_low_first, h->zs.front(), static_cast<T *>(dw),       \
-                                                                               static_cast<T *>(dh), accumulate, peers, counters, h->d_fix.as<int>(), quad, tile_map)
-#define RDR_LAUNCH_K3P_M(T, L)                                                     \
-    switch (minb_p) {                                                              \
-        case 2: RDR_LAUNCH_K3P(T, 2, L, true); break;                              \
-        case 3: if (split) RDR_LAUNCH_K3P(T, 3, L, true); else RDR_LAUNCH_K3P(T, 3, L, false); break;   \
-        case 5: if (split) RDR_LAUNCH_K3P(T, 5, L, true); else RDR_LAUNCH_K3P(T, 5, L, false); break;   \
-        case 6: RDR_LAUNCH_K3P(T, 6, L, false); break;                             \
-        default: if (split) RDR_LAUNCH_K3P(T, 4, L, true); else RDR_LAUNCH_K3P(T, 4, L, false); break;  \
-    }
+            const size_t smem_p = smem + (size_t)K * sizeof(int);
             const bool lcc = fc.crs_kind == RDR_CRS_LCC_SPHERE;
-            // cell-record cache (CACHE = true): pays when a layer holds several samples (the record is reused); with ~1 sample per
-            // layer (the 145-level tables at 1000 m) the uncached form at higher occupancy is faster.  Needs the packed cell key.
-            int n_samples = 0;
-            for (int k = 0; k < K; ++k) n_samples += np_cell[k] - 1;
+            // cell-record cache (CACHE = true) + layer quadrature: the thick layers.  Needs the packed cell key.
             const char *cache_env = getenv("RDR_K3_CACHE");
             const bool key_ok = h->ny <= 1024 && h->nx <= 1024 && h->nz <= 2048;
-            const bool split = key_ok && (cache_env ? atoi(cache_env) != 0 : n_samples >= 3 * K);
+            const bool split = key_ok && (cache_env ? atoi(cache_env) != 0 : true);
             const char *quad_env = getenv("RDR_K3_QUAD");  // layer quadrature (closed-form trapezoid sum per one-cell layer): on unless 0
             const int quad = !(quad_env && atoi(quad_env) == 0);
-            const char *tile_env = getenv("RDR_K3_TILE");  // compact ray tiles per warp (regular rasters whose sides divide)
-            // log2 of the tile width: 3 -> 8 x 4 pixels; 0 = rows of 32.  Tiles pay where divergence is the cost (the cached /
-            // quadrature path); with ~1 sample per layer (145-level tables) rows of 32 keep the loads contiguous and are 10 % faster
-            int tile_map = tile_env ? atoi(tile_env) : (split ? 3 : 0);
-            if (tile_map < 0 || tile_map > 4 || h->geom_kind != RDR_GEOM_GRID || h->ray_nx % (1 << tile_map) || h->ray_ny % (32 >> tile_map)) tile_map = 0;
+            const bool tiles_ok = h->geom_kind == RDR_GEOM_GRID;
+            auto tile_for = [&](const char *env, int dflt) {
+                // log2 of the pixel-tile width a warp takes: 3 -> 8 x 4 pixels; 0 = 32 pixels of a row
+                const char *v = getenv(env);
+                int t = v ? atoi(v) : dflt;
+                if (t < 0 || t > 4 || !tiles_ok || h->ray_nx % (1 << t) || h->ray_ny % (32 >> t)) t = 0;
+                return t;
+            };
+            // tiles pay where divergence is the cost (the cached / quadrature path)
+            const int tile_map = tile_for("RDR_K3_TILE", split ? 3 : 0);
+            const int tile_thin = tile_for("RDR_K3_THIN_TILE", 3);
             const int minb_p = tune_minb("RDR_K3_MINB", 4);
             const int grid_p = grid_for(n, BLOCK, h->sm_count, 4 * minb_p);
+            CUDA_TRY(h, h->d_part.reserve(std::max<size_t>(2 * n * sizeof(double), 16)));
+            double *part = h->d_part.as<double>();
+#define RDR_LAUNCH_K3P1(T, M, L, S, F0)                                                                                                          \
+    do {                                                                                                                                         \
+        CUDA_TRY(h, allow_smem(k_ray_integrate_poly<T, BLOCK, M, L, S, F0>, smem_p));                                                            \
+        k_ray_integrate_poly<T, BLOCK, M, L, S, F0><<<grid_p, BLOCK, smem_p, h->stream>>>(fc, G, n, t_in, P, znodes, (int)h->nz, h->zs.front(),  \
+                                                                                       static_cast<T *>(dw), static_cast<T *>(dh), accumulate,  \
+                                                                                       peers, counters, h->d_fix.as<int>(), quad, tile_map,     \
+                                                                                       part);                                                   \
+        h->launches++;                                                                                                                           \
+    } while (0)
+#define RDR_LAUNCH_K3P(T, M, L, S)                       \
+    do {                                                 \
+        RDR_LAUNCH_K3P1(T, M, L, S, true);               \
+        if (h->thin_ok) RDR_LAUNCH_K3P1(T, M, L, S, false); \
+    } while (0)
+#define RDR_LAUNCH_K3P_M(T, L)                                                     \
+    switch (minb_p) {                                                              \
+        case 3: if (split) RDR_LAUNCH_K3P(T, 3, L, true); else RDR_LAUNCH_K3P(T, 3, L, false); break;   \
+        default: if (split) RDR_LAUNCH_K3P(T, 4, L, true); else RDR_LAUNCH_K3P(T, 4, L, false); break;  \
+    }
             if (out_dtype == RDR_F64) {
                 if (lcc) { RDR_LAUNCH_K3P_M(double, true) } else { RDR_LAUNCH_K3P_M(double, false) }
             } else {
-                if (lcc) { RDR_LAUNCH_K3P(float, 4, true, false); } else { RDR_LAUNCH_K3P(float, 4, false, false); }
+                if (lcc) RDR_LAUNCH_K3P(float, 4, true, false); else RDR_LAUNCH_K3P(float, 4, false, false);
             }
 #undef RDR_LAUNCH_K3P_M
 #undef RDR_LAUNCH_K3P
-        } else if (out_dtype == RDR_F64) {
-            // (the per-sample Bowring form is kept for tests / comparisons: one occupancy variant, one or two samples per trip)
-            if (npt == 1) RDR_LAUNCH_K3F(double, 5, 1); else RDR_LAUNCH_K3F(double, 5, 2);
+#undef RDR_LAUNCH_K3P1
+            CUDA_TRY(h, cudaGetLastError());
+            if (h->thin_ok) {
+                // the thin-layer part of the plan (no-op when the plan has none); runs second and stores the results
+                const char *pfc_env = getenv("RDR_K3_THIN_PF"), *pft_env = getenv("RDR_K3_THIN_PFT"), *st_env = getenv("RDR_K3_THIN_STAGE");
+                const int pf_cells = pfc_env ? std::min(std::max(atoi(pfc_env), 0), LERP_PAD) : 0;
+                const int pf_t = pft_env ? std::max(atoi(pft_env), 0) : 6;
+                const int minb_t = tune_minb("RDR_K3_THIN_MINB", 3);
+                const int grid_t = grid_for(n, BLOCK, h->sm_count, 4 * minb_t);
+                // staged record columns (north_star: cube staged into shared memory via TMA): as many column slots of K + 2 records as
+                // fit beside minb_t CTAs per SM (227 KB per SM, 1 KB reserved per CTA)
+                const size_t base_t = (smem_p + 127) / 128 * 128 + 128;
+                const size_t col_bytes = ((size_t)K + 2) * sizeof(LerpCell);
+                const size_t budget = (size_t)227 * 1024 / minb_t - 1024;
+                int n_slots = budget > base_t ? (int)std::min<size_t>((budget - base_t) / col_bytes, 16) : 0;
+                if (st_env) n_slots = std::min(n_slots, std::max(atoi(st_env), 0));
+                const bool stage = n_slots > 0;
+                const size_t smem_t = stage ? base_t + (size_t)n_slots * col_bytes : smem_p;
+                unsigned long long *stage_stats = h->d_red.as<unsigned long long>() + XCHG_STRIDE + 4;
+#define RDR_LAUNCH_K3T(T, M, L, ST)                                                                                                        \
+    do {                                                                                                                                    \
+        CUDA_TRY(h, allow_smem(k_ray_integrate_thin<T, BLOCK, M, L, ST>, smem_t));                                                          \
+        if (ST) CUDA_TRY(h, cudaFuncSetAttribute(k_ray_integrate_thin<T, BLOCK, M, L, ST>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)); \
+        k_ray_integrate_thin<T, BLOCK, M, L, ST><<<grid_t, BLOCK, smem_t, h->stream>>>(fc, G, n, t_in, P, znodes, (int)h->nz, h->zs.front(), \
+                                                                                    static_cast<T *>(dw), static_cast<T *>(dh), accumulate, \
+                                                                                    peers, counters, h->d_fix.as<int>(), tile_thin, part,  \
+                                                                                    pf_cells, pf_t, n_slots, stage_stats);                 \
+    } while (0)
+#define RDR_LAUNCH_K3T_S(T, M, L) \
+    do { if (stage) RDR_LAUNCH_K3T(T, M, L, true); else RDR_LAUNCH_K3T(T, M, L, false); } while (0)
+#define RDR_LAUNCH_K3T_M(T, L)                          \
+    switch (minb_t) {                                   \
+        case 4: RDR_LAUNCH_K3T_S(T, 4, L); break;       \
+        case 5: RDR_LAUNCH_K3T_S(T, 5, L); break;       \
+        default: RDR_LAUNCH_K3T_S(T, 3, L); break;      \
+    }
+                if (out_dtype == RDR_F64) {
+                    if (lcc) { RDR_LAUNCH_K3T_M(double, true) } else { RDR_LAUNCH_K3T_M(double, false) }
+                } else {
+                    if (lcc) RDR_LAUNCH_K3T_S(float, 3, true); else RDR_LAUNCH_K3T_S(float, 3, false);
+                }
+#undef RDR_LAUNCH_K3T_M
+#undef RDR_LAUNCH_K3T_S
+#undef RDR_LAUNCH_K3T
+                h->launches++;
+                CUDA_TRY(h, cudaGetLastError());
+            }
         } else {
-            RDR_LAUNCH_K3F(float, 5, 1);
-        }
+            // (the per-sample Bowring form is kept for tests / comparisons: one occupancy variant, one or two samples per trip)
+            const int grid = grid_for(n, BLOCK, h->sm_count, 4 * 5);
+            const char *npt_env = getenv("RDR_K3_NPT");
+            const int npt = npt_env ? atoi(npt_env) : 1;
+#define RDR_LAUNCH_K3F(T, M, NP)                                                                                                           \
+    do {                                                                                                                                    \
+        CUDA_TRY(h, allow_smem(k_ray_integrate_fast<T, BLOCK, M, NP>, smem));                                                               \
+        k_ray_integrate_fast<T, BLOCK, M, NP><<<grid, BLOCK, smem, h->stream>>>(fc, G, n, K, t_in, P, znodes, (int)h->nz, h->zs.front(),   \
+                                                                               static_cast<T *>(dw), static_cast<T *>(dh), accumulate,     \
+                                                                               peers, counters, h->d_fix.as<int>());                       \
+    } while (0)
+            if (out_dtype == RDR_F64) {
+                if (npt == 1) RDR_LAUNCH_K3F(double, 5, 1); else RDR_LAUNCH_K3F(double, 5, 2);
+            } else {
+                RDR_LAUNCH_K3F(float, 5, 1);
+            }
 #undef RDR_LAUNCH_K3F
-        h->launches++;
-        CUDA_TRY(h, cudaGetLastError());
+            h->launches++;
+            CUDA_TRY(h, cudaGetLastError());
+        }
         // flagged rays -> PROJ-form integrator in list mode; the count stays on the device (no-op launch when it is zero)
         {
             const int grid = grid_for(n, BLOCK, h->sm_count, 4 * 4);
@@ -2958,20 +3410,210 @@ RDR_API int rdr_ray_integrate(rdr_handle_t h, const double *maxlen, double max_s
         CUDA_TRY(h, cudaGetLastError());
     }
 #undef RDR_LAUNCH_K3
-    unsigned long long cnt[4] = {0, 0, 0, 0};
-    if (staged_out) {
+    if (*staged) {
         CUDA_TRY(h, cudaMemcpyAsync(out_wet, dw, n * es, cudaMemcpyDeviceToHost, h->stream));
         CUDA_TRY(h, cudaMemcpyAsync(out_hydro, dh, n * es, cudaMemcpyDeviceToHost, h->stream));
     }
+    return RDR_OK;
+}
+
+RDR_API int rdr_ray_layers(rdr_handle_t h, int geom_kind, const double *gx, const double *gy, int64_t ny, int64_t nx, int los_kind,
+                           const double *los, double ht, double zref, double *maxlen_out, int64_t *counts_out, int mem) {
+    CHECK_ARG(h, h != nullptr, "rdr_ray_layers: NULL handle");
+    ScopedDevice sd(h->device);
+    if (counts_out) {
+        counts_out[0] = ny * nx; counts_out[1] = 0; counts_out[2] = 0; counts_out[3] = 0;
+    }
+    int rc = k0_enqueue(h, geom_kind, gx, gy, ny, nx, los_kind, los, ht, zref, 0, mem, "rdr_ray_layers");
+    if (rc) return rc;
+    const int K = h->n_layers;
+    std::vector<unsigned long long> red(K + 2);
+    CUDA_TRY(h, cudaMemcpyAsync(red.data(), h->d_red.p, (K + 2) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (maxlen_out)
+        for (int k = 0; k < K; ++k) memcpy(&maxlen_out[k], &red[k], sizeof(double));
+    if (counts_out) {
+        counts_out[1] = (int64_t)red[K];
+        counts_out[2] = (int64_t)red[K + 1];
+        counts_out[3] = K;
+    }
+    // (every ray of THIS call being NaN is not an error here: the reference's np.isnan(ray_lengths).all() (delay.py:279) is over the
+    // whole raster, a call may be one row tile or one rank's block -- the caller decides on the summed counts)
+    return RDR_OK;
+}
+
+RDR_API int rdr_ray_integrate(rdr_handle_t h, const double *maxlen, double max_segment_length, int clamp_low_first, void *out_wet,
+                              void *out_hydro, int out_dtype, int accumulate, int64_t *nparts_out, int64_t *oob_out, int mem) {
+    CHECK_ARG(h, h != nullptr, "rdr_ray_integrate: NULL handle");
+    if (!h->has_cube || !h->has_rays) return fail(h, RDR_ERR_STATE, "rdr_ray_integrate: call rdr_ray_layers first");
+    CHECK_ARG(h, maxlen && out_wet && out_hydro, "rdr_ray_integrate: NULL pointer");
+    CHECK_ARG(h, max_segment_length > 0, "rdr_ray_integrate: max_segment_length must be positive");
+    CHECK_ARG(h, out_dtype == RDR_F64 || out_dtype == RDR_F32, "rdr_ray_integrate: out_dtype must be RDR_F64 or RDR_F32");
+    ScopedDevice sd(h->device);
+    const int K = h->n_layers;
+    // nParts = ceil(max / MAX_SEGMENT_LENGTH).astype(int) + 1   (delay.py:283) -- the bit-exact integer contract.  The host
+    // restates it for its caller; the kernels take it from the device plan (k_plan), which gets the caller's maxima as its slot
+    std::vector<unsigned long long> slot(K + 3, 0ull);
+    double acc = 0.0, longest = 0.0;
+    const char *span_env = getenv("RDR_K3_SPAN");
+    const double span_max = span_env && atof(span_env) > 0 ? atof(span_env) : 12000.0;
+    for (int k = 0; k < K; ++k) {
+        const double q = ceil(maxlen[k] / max_segment_length);
+        CHECK_ARG(h, q == q && q < 1e7 && maxlen[k] >= 0, "rdr_ray_integrate: per-layer max length is NaN or absurd");
+        int np = (int)q + 1;
+        if (np < 2) np = 2;
+        if (nparts_out) nparts_out[k] = np;
+        memcpy(&slot[k], &maxlen[k], sizeof(double));
+        if (k > 0 && acc + maxlen[k] > span_max) {
+            longest = std::max(longest, acc);
+            acc = 0.0;
+        }
+        acc += maxlen[k];
+    }
+    longest = std::max(longest, acc);
+    slot[K + 2] = (unsigned long long)h->n_rays;
+    unsigned long long *d_slot = h->d_red.as<unsigned long long>();
+    CUDA_TRY(h, cudaMemcpyAsync(d_slot, slot.data(), slot.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, h->stream));
+    int rc;
+    if ((rc = plan_enqueue(h, d_slot, 1, max_segment_length, clamp_low_first ? 1 : 0, RDR_PLAN_ABSURD))) return rc;
+    bool staged = false;
+    // a single layer longer than 4 spans would stretch the cubic's error bound (T^4) by > 256: leave those calls to `fast`
+    if ((rc = k3_enqueue(h, out_wet, out_hydro, out_dtype, accumulate, mem, longest <= 4.0 * span_max ? 0 : 1, &staged))) return rc;
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));  // `slot` goes out of scope; host outputs are complete on return
     if (oob_out || mem == RDR_MEM_HOST) {
-        CUDA_TRY(h, cudaMemcpyAsync(cnt, counters, sizeof(cnt), cudaMemcpyDeviceToHost, h->stream));
-        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-        if (fast) h->last_fix_count = (int64_t)cnt[3];
+        unsigned long long cnt[4] = {0, 0, 0, 0};
+        CUDA_TRY(h, cudaMemcpy(cnt, h->d_red.as<unsigned long long>() + XCHG_STRIDE, sizeof(cnt), cudaMemcpyDeviceToHost));
+        h->last_fix_count = (int64_t)cnt[3];
         if (oob_out) {
             oob_out[0] = (int64_t)cnt[0];  // first sample below min(z) (pre-clamp)
             oob_out[1] = (int64_t)cnt[1];  // samples below min(z) after the clamp decision
             oob_out[2] = (int64_t)cnt[2];  // samples above max(z)
         }
+    }
+    return RDR_OK;
+}
+
+// ---- the fused step: K0 -> [exchange] -> k_plan -> K3 with no host synchronisation in between ---------------------------------
+RDR_API int rdr_set_exchange(rdr_handle_t h, int rank, int world, void *const *bufs) {
+    CHECK_ARG(h, h != nullptr, "rdr_set_exchange: NULL handle");
+    CHECK_ARG(h, world >= 0 && world <= RDR_MAX_PEERS, "rdr_set_exchange: at most 8 ranks");
+    CHECK_ARG(h, world == 0 || (bufs && rank >= 0 && rank < world), "rdr_set_exchange: bad rank / buffer list");
+    h->xchg_world = world;
+    h->xchg_rank = rank;
+    h->xchg_parity = 0;
+    for (int i = 0; i < world; ++i) {
+        CHECK_ARG(h, bufs[i] != nullptr, "rdr_set_exchange: NULL buffer");
+        h->xchg_bufs[i] = bufs[i];
+    }
+    return RDR_OK;
+}
+
+RDR_API int64_t rdr_exchange_bytes(int world) { return (int64_t)2 * world * XCHG_STRIDE * (int64_t)sizeof(unsigned long long); }
+
+static int publish(rdr_handle_t h, const unsigned long long *src, int nwords, int word_off) {
+    PeerOut dst = {};
+    dst.n = h->xchg_world;
+    for (int i = 0; i < h->xchg_world; ++i) dst.wet[i] = h->xchg_bufs[i];
+    const int off = (h->xchg_parity * h->xchg_world + h->xchg_rank) * XCHG_STRIDE + word_off;
+    k_publish<<<1, 256, 0, h->stream>>>(src, nwords, off, dst);
+    h->launches++;
+    CUDA_TRY(h, cudaGetLastError());
+    return RDR_OK;
+}
+
+RDR_API int rdr_trace_begin(rdr_handle_t h, int geom_kind, const double *gx, const double *gy, int64_t ny, int64_t nx, int los_kind,
+                            const double *los, double ht, double zref, int flags, int mem) {
+    CHECK_ARG(h, h != nullptr, "rdr_trace_begin: NULL handle");
+    ScopedDevice sd(h->device);
+    int rc = k0_enqueue(h, geom_kind, gx, gy, ny, nx, los_kind, los, ht, zref, (flags & RDR_TRACE_EXACT_K0) != 0, mem, "rdr_trace_begin");
+    if (rc) return rc;
+    h->trace_flags = flags;
+    if (h->xchg_world > 0) {
+        h->xchg_parity ^= 1;
+        return publish(h, h->d_red.as<unsigned long long>(), h->n_layers + 3, 0);
+    }
+    return RDR_OK;
+}
+
+RDR_API int rdr_trace_finish(rdr_handle_t h, double max_segment_length, int force_clamp, int mode, void *out_wet, void *out_hydro,
+                             int out_dtype, int accumulate, int mem) {
+    CHECK_ARG(h, h != nullptr, "rdr_trace_finish: NULL handle");
+    if (!h->has_cube || !h->has_rays) return fail(h, RDR_ERR_STATE, "rdr_trace_finish: call rdr_trace_begin first");
+    CHECK_ARG(h, out_wet && out_hydro, "rdr_trace_finish: NULL pointer");
+    CHECK_ARG(h, max_segment_length > 0, "rdr_trace_finish: max_segment_length must be positive");
+    CHECK_ARG(h, out_dtype == RDR_F64 || out_dtype == RDR_F32, "rdr_trace_finish: out_dtype must be RDR_F64 or RDR_F32");
+    CHECK_ARG(h, mode >= 0 && mode <= 2, "rdr_trace_finish: mode must be 0 (auto), 1 (fast) or 2 (general)");
+    ScopedDevice sd(h->device);
+    const unsigned long long *slots = h->d_red.as<unsigned long long>();
+    int world = 1;
+    if (h->xchg_world > 0) {
+        slots = static_cast<const unsigned long long *>(h->xchg_bufs[h->xchg_rank]) + (size_t)h->xchg_parity * h->xchg_world * XCHG_STRIDE;
+        world = h->xchg_world;
+    }
+    // what stops the integration kernels (the host reads the status back and redoes the step / raises):
+    //   absurd maxima, every ray NaN, a single layer too long for the span cubics (mode 0 only), and -- when K0 ran in its
+    //   default (span-cubic) form -- an nParts knife edge, which is redone with the exact K0 (detect, don't hide)
+    int block = RDR_PLAN_ABSURD | RDR_PLAN_ALL_NAN;
+    if (mode == 0) block |= RDR_PLAN_SPAN_TOO_LONG;
+    if (h->k0_was_cubic && !(h->trace_flags & RDR_TRACE_NO_KNIFE_GUARD)) block |= RDR_PLAN_KNIFE_EDGE;
+    int rc;
+    if ((rc = plan_enqueue(h, slots, world, max_segment_length, force_clamp, block))) return rc;
+    bool staged = false;
+    if ((rc = k3_enqueue(h, out_wet, out_hydro, out_dtype, accumulate, mem, mode, &staged))) return rc;
+    if (h->xchg_world > 0)  // K3's own count of first samples below min(z): the cross-check of the clamp predicate, summed in rdr_trace_result
+        return publish(h, h->d_red.as<unsigned long long>() + XCHG_STRIDE, 1, h->n_layers + 3);
+    return RDR_OK;
+}
+
+RDR_API int rdr_trace_result(rdr_handle_t h, double *maxlen_out, int64_t *nparts_out, int64_t *info_out) {
+    CHECK_ARG(h, h != nullptr, "rdr_trace_result: NULL handle");
+    if (!h->has_rays || !h->d_devplan.p) return fail(h, RDR_ERR_STATE, "rdr_trace_result: no step to report");
+    ScopedDevice sd(h->device);
+    const int K = h->n_layers;
+    std::vector<unsigned char> buf(offsetof(DevPlan, nparts) + (size_t)K * sizeof(int));
+    unsigned long long cnt[6];
+    CUDA_TRY(h, cudaMemcpyAsync(buf.data(), h->d_devplan.p, buf.size(), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(cnt, h->d_red.as<unsigned long long>() + XCHG_STRIDE, sizeof(cnt), cudaMemcpyDeviceToHost, h->stream));
+    std::vector<unsigned long long> k3_below(std::max(h->xchg_world, 1), 0ull);
+    if (h->xchg_world > 0) {
+        const unsigned long long *base = static_cast<const unsigned long long *>(h->xchg_bufs[h->xchg_rank]) + (size_t)h->xchg_parity * h->xchg_world * XCHG_STRIDE;
+        for (int q = 0; q < h->xchg_world; ++q)
+            CUDA_TRY(h, cudaMemcpyAsync(&k3_below[q], base + (size_t)q * XCHG_STRIDE + K + 3, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+    }
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    const DevPlan *P = reinterpret_cast<const DevPlan *>(buf.data());
+    if (maxlen_out) memcpy(maxlen_out, buf.data() + offsetof(DevPlan, maxlen), (size_t)K * sizeof(double));
+    if (nparts_out) {
+        const int *np = reinterpret_cast<const int *>(buf.data() + offsetof(DevPlan, nparts));
+        for (int k = 0; k < K; ++k) nparts_out[k] = np[k];
+    }
+    h->last_fix_count = (int64_t)cnt[3];
+    if (info_out) {
+        unsigned long long below3 = cnt[0];
+        if (h->xchg_world > 0) {
+            below3 = 0;
+            for (int q = 0; q < h->xchg_world; ++q) below3 += k3_below[q];
+        }
+        info_out[0] = P->status;
+        info_out[1] = P->blocked;
+        info_out[2] = K;
+        info_out[3] = P->n_rays;
+        info_out[4] = P->n_nan;
+        info_out[5] = P->n_below;           // K0's global count of first samples below min(z)
+        info_out[6] = (int64_t)below3;      // K3's own (global) count of the same: the cross-check
+        info_out[7] = P->clamp_low_first;
+        info_out[8] = (int64_t)cnt[1];      // samples below min(z) after the clamp decision (this rank)
+        info_out[9] = (int64_t)cnt[2];      // samples above max(z) (this rank)
+        info_out[10] = (int64_t)cnt[3];     // rays handed to the PROJ-form integrator (this rank)
+        info_out[11] = P->knife_layer;
+        info_out[12] = P->k_split;
+        info_out[13] = P->nspan;
+        info_out[14] = h->k0_was_cubic ? 1 : 0;
+        info_out[15] = h->last_k3_poly ? 1 : 0;
+        info_out[16] = (int64_t)cnt[4];     // CTA passes of the thin-layer kernel whose record columns were staged in shared memory
+        info_out[17] = (int64_t)cnt[5];     // ... and those that read the records from global memory (footprint larger than the slots)
+        info_out[18] = 0;
+        info_out[19] = 0;
     }
     return RDR_OK;
 }

@@ -195,6 +195,8 @@ def _build_cube_ray(
     _out_device=None,
     _out_arrays=None,
     _peers=None,
+    _exchange=None,
+    _on_skip=None,
 ):
     """Iterate over interpolators and build a cube using raytracing (delay.py:219-326).
 
@@ -223,8 +225,10 @@ def _build_cube_ray(
         else:
             outputArrs = [_lib.pinned_empty((zpts.size, ny, nx)) for mm in range(2)]   # page-locked: the kernel writes them directly
     else:
-        wet = np.empty((ny, nx))
-        hydro = np.empty((ny, nx))
+        # scratch for one height in page-locked memory: the kernel writes it directly (no staged device-to-host copy), the
+        # accumulation into the caller's arrays (:323) stays on the host
+        wet = _lib.pinned_empty((ny, nx))
+        hydro = _lib.pinned_empty((ny, nx))
 
     spec = los_device_spec(los, ny, nx)
     geographic_pts = isinstance(pts_crs, Geographic)
@@ -258,7 +262,8 @@ def _build_cube_ray(
         try:
             info = cube.trace(geom[0], geom[1], geom[2], ny, nx, los_kind, los_payload, ht, MAX_TROPO_HEIGHT, MAX_SEGMENT_LENGTH,
                               wet, hydro, reduce_max=hooks[0], reduce_sum=hooks[1],
-                              peers_fn=(lambda r0, r1, hh=hh: _peers(hh, r0, r1)) if (_peers is not None and output_created_here) else None)
+                              peers_fn=(lambda r0, r1, hh=hh: _peers(hh, r0, r1)) if (_peers is not None and output_created_here) else None,
+                              exchange=_exchange)
         except _lib.NoLayersError:
             # if the top most height layer doesnt contribute to the integral, skip it (:276-277)
             if ht == zpts[-1]:
@@ -266,6 +271,8 @@ def _build_cube_ray(
                 if output_created_here:
                     wet[...] = 0.0
                     hydro[...] = 0.0
+                if _on_skip is not None:   # raider_b200.dist: the rows of the other ranks in this rank's full maps are zero as well
+                    _on_skip(hh)
                 continue
             # the reference evaluates np.isnan(None) here and dies with a TypeError (:279); say why instead
             raise TypeError(f'no weather-model layer contributes between height {ht} and MAX_TROPO_HEIGHT={MAX_TROPO_HEIGHT}')

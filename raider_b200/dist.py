@@ -9,11 +9,13 @@ Rays are independent except for three whole-raster quantities, which is why naiv
 * the ``isnan(ray_lengths).all()`` convergence check                                 (delay.py:279)
 
 So the path shards as: contiguous row blocks of the query raster per rank (cube replicated, it is MBs), K0 on each
-rank, ONE collective carrying the K per-layer maxima (MAX) and the 3 predicate counters (SUM) of every rank, K3 on each rank,
-and the reassembly of the two output maps so every rank holds the full delay map.  There is no other data-path collective.
-(The clamp predicate of delay.py:306-307 is decided from K0's globally reduced count of first samples below min(z); K3's own
-re-evaluation of it -- bitwise the same heights except for polar rays and projected cubes -- is only cross-checked in
-single-process runs, where that costs nothing.)
+rank, ONE exchange carrying the K per-layer maxima (MAX) and the 3 predicate counters (SUM) of every rank, K3 on each rank,
+and the reassembly of the two output maps so every rank holds the full delay map.  There is no other data-path exchange.
+Under NCCL with peer access the exchange never touches the host: every rank's K0 stores its K + 3 words into a slot of every
+peer's exchange buffer (symmetric memory, ``rdr_set_exchange``), one signal-pad barrier orders the ranks on the stream, and a
+one-CTA kernel on every rank takes MAX / SUM over the slots and builds the step plan on the device (``k_plan``).  K3's own
+re-evaluation of the clamp predicate of delay.py:306-307 rides the same slots (one more word per rank) and is cross-checked
+after the closing barrier, exactly as in a single-process run.
 
 The reassembly is fused into K3 (``SymmetricMaps``): the full maps live in symmetric memory (``torch.distributed.
 _symmetric_memory``: every rank's buffer is peer-mapped into every other rank over NVLink / NVSwitch), and the integration
@@ -135,6 +137,16 @@ class SymmetricMaps:
         self.base = [int(a) for a in self.hdl.buffer_ptrs]
         if len(self.base) != comm.world or self.base[comm.rank] != self.maps.data_ptr():
             raise RuntimeError('symmetric-memory rendezvous returned unexpected buffer pointers')
+        # exchange slots of the device-side plan (rdr_set_exchange): 2 parities x world slots of K + 3 words per rank
+        from . import _lib
+        words = int(_lib.load().rdr_exchange_bytes(comm.world)) // 8
+        self.xchg = symm.empty((words,), dtype=torch.int64, device=comm.device)
+        self.xchg.zero_()
+        self.xchg_hdl = symm.rendezvous(self.xchg, group)
+        self.xchg_ptrs = [int(a) for a in self.xchg_hdl.buffer_ptrs]
+        self.stream = torch.cuda.Stream(device=comm.device)
+        torch.cuda.synchronize(comm.device)
+        comm.barrier()   # every rank's slots are zeroed before anyone publishes into them
 
     def block(self, r0: int, r1: int):
         """This rank's own rows of both maps: two (nz, r1 - r0, nx) views whose [hh] slices are contiguous."""
@@ -154,6 +166,11 @@ class SymmetricMaps:
         """Signal-pad barrier on the current CUDA stream: every rank's kernels before it have completed (their peer stores
         included) before any rank's work after it starts."""
         self.hdl.barrier()
+
+    def zero_slice(self, hh: int) -> None:
+        """A height slice no rank integrates (no contributing layer at the last output height, delay.py:276-277) is zero in the
+        reference (np.zeros, delay.py:248): nobody's kernel writes it, so every rank clears all rows of it in its own maps."""
+        self.maps[:, hh].zero_()
 
 
 def build_cube_ray_sharded(xpts, ypts, zpts, los, model_crs, pts_crs, interpolators, comm: Comm, MAX_SEGMENT_LENGTH=1000.0,
@@ -185,24 +202,29 @@ def build_cube_ray_sharded(xpts, ypts, zpts, los, model_crs, pts_crs, interpolat
         _delay._reduce_hooks = (comm.reduce_max, comm.reduce_sum)
         try:
             if sym is not None:
-                # fused reassembly: the kernels of this rank write its rows into every rank's maps; barriers on the stream the
-                # kernels run on fence the maps against the previous call's readers and publish them afterwards
-                cur = torch.cuda.current_stream()
-                cube.h.set_stream(cur.cuda_stream)
-                sym.barrier()
-                if cur.cuda_stream == 0:
-                    # the legacy default stream cannot be handed to the library (NULL = the handle's own stream): order the
-                    # fence before the kernels on the host instead (they end with a stream synchronise of their own)
-                    cur.synchronize()
-                if host_block:   # this rank's rows also land in page-locked host memory, written by the same kernel
-                    local = _delay._build_cube_ray(xpts, ypts[r0:r1], zpts, los, model_crs, pts_crs, interpolators,
-                                                   MAX_SEGMENT_LENGTH=MAX_SEGMENT_LENGTH, MAX_TROPO_HEIGHT=zref,
-                                                   _peers=lambda hh, a, b: sym.peer_ptrs(hh, r0 + a, r0 + b, include_self=True))
-                else:
-                    local = _delay._build_cube_ray(xpts, ypts[r0:r1], zpts, los, model_crs, pts_crs, interpolators,
-                                                   MAX_SEGMENT_LENGTH=MAX_SEGMENT_LENGTH, MAX_TROPO_HEIGHT=zref, _out_arrays=sym.block(r0, r1),
-                                                   _peers=lambda hh, a, b: sym.peer_ptrs(hh, r0 + a, r0 + b))
-                sym.barrier()
+                # fused step per height (engine._trace_block): K0 -> k_publish (K + 3 words into every rank's exchange slots) ->
+                # barrier -> k_plan (MAX / SUM over the slots on the device) -> K3 (stores its rows into every rank's maps) -> barrier.
+                # No NCCL collective, no host round trip; everything runs on one side stream the barriers are enqueued on as well
+                # (the legacy default stream cannot be handed to the library)
+                side = sym.stream
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    cube.h.set_stream(side.cuda_stream)
+                    cube.set_exchange(comm.rank, comm.world, sym.xchg_ptrs)
+                    try:
+                        if host_block:   # this rank's rows also land in page-locked host memory, written by the same kernel
+                            local = _delay._build_cube_ray(xpts, ypts[r0:r1], zpts, los, model_crs, pts_crs, interpolators,
+                                                           MAX_SEGMENT_LENGTH=MAX_SEGMENT_LENGTH, MAX_TROPO_HEIGHT=zref,
+                                                           _peers=lambda hh, a, b: sym.peer_ptrs(hh, r0 + a, r0 + b, include_self=True),
+                                                           _exchange=sym, _on_skip=sym.zero_slice)
+                        else:
+                            local = _delay._build_cube_ray(xpts, ypts[r0:r1], zpts, los, model_crs, pts_crs, interpolators,
+                                                           MAX_SEGMENT_LENGTH=MAX_SEGMENT_LENGTH, MAX_TROPO_HEIGHT=zref, _out_arrays=sym.block(r0, r1),
+                                                           _peers=lambda hh, a, b: sym.peer_ptrs(hh, r0 + a, r0 + b),
+                                                           _exchange=sym, _on_skip=sym.zero_slice)
+                    finally:
+                        cube.set_exchange(0, 0, None)
+                torch.cuda.current_stream().wait_stream(side)
             else:
                 local = _delay._build_cube_ray(xpts, ypts[r0:r1], zpts, los, model_crs, pts_crs, interpolators,
                                                MAX_SEGMENT_LENGTH=MAX_SEGMENT_LENGTH, MAX_TROPO_HEIGHT=zref,

@@ -33,6 +33,12 @@ class TraceInfo:
     n_nan_rays: int = 0
     skipped: bool = False                 # no contributing layer at the last output height (delay.py:276-277)
     tiles: int = 1                        # row tiles the raster was walked in (HBM budget of the t-buffer)
+    k_split: int = 0                      # layers integrated by the thin-layer kernel
+    n_spans: int = 0
+    staged_passes: int = 0                # CTA passes of the thin-layer kernel with TMA-staged record columns / without
+    unstaged_passes: int = 0
+    knife_edge_redo: bool = False         # nParts hung on the last bits of a maximum: the step was redone with the exact K0
+    knife_edge_layer: int = -1            # ... and still does with the exact K0 (reported, delay.py:283)
 
 
 class DeviceCube:
@@ -196,7 +202,7 @@ class DeviceCube:
         return wet, hydro, ns
 
     def trace(self, geom_kind, gx, gy, ny, nx, los_kind, los, ht, zref, max_segment_length, out_wet, out_hydro,
-              reduce_max=None, reduce_sum=None, max_t_bytes=None, peers_fn=None) -> TraceInfo:
+              reduce_max=None, reduce_sum=None, max_t_bytes=None, peers_fn=None, exchange=None) -> TraceInfo:
         """One output height: K0 -> global reduction of the per-layer maxima / predicates -> K3.
 
         ``reduce_max`` / ``reduce_sum`` are the cross-GPU hooks (numpy array in -> reduced numpy array out); they are
@@ -216,7 +222,9 @@ class DeviceCube:
         rows_per_tile = int(max(1, max_t_bytes // (8 * nz * max(1, int(nx)))))
         if rows_per_tile >= ny:
             return self._trace_block(geom_kind, gx, gy, ny, nx, los_kind, los, ht, zref, max_segment_length, out_wet, out_hydro,
-                                     reduce_max, reduce_sum, peers_fn(0, ny) if peers_fn else None)
+                                     reduce_max, reduce_sum, peers_fn(0, ny) if peers_fn else None, exchange)
+        # (the row-tiled walk reduces through the host hooks even when a device exchange is attached: its first pass visits every
+        # tile before any plan can be made; the exchange only closes the step with its barrier)
         tiles = [(r0, min(ny, r0 + rows_per_tile)) for r0 in range(0, ny, rows_per_tile)]
 
         def block(r0, r1):
@@ -234,6 +242,8 @@ class DeviceCube:
         maxlen, counts = _global_plan(maxlen, counts, reduce_max, reduce_sum)
         info = TraceInfo(ht=float(ht))
         info.n_rays, info.n_nan_rays, info.n_layers = int(counts[0]), int(counts[1]), int(counts[3])
+        if counts[1] == counts[0]:
+            raise ValueError('geo2rdr did not converge. Check orbit coverage')  # delay.py:279-280, over the whole raster
         clamp = bool(counts[2] == counts[0])
         ow = out_wet.reshape(ny, nx) if hasattr(out_wet, 'reshape') else out_wet
         oh = out_hydro.reshape(ny, nx) if hasattr(out_hydro, 'reshape') else out_hydro
@@ -245,9 +255,9 @@ class DeviceCube:
                 nparts, oob = self.ray_integrate(maxlen, max_segment_length, clamp, ow[r0:r1], oh[r0:r1],
                                                  peers=peers_fn(r0, r1) if peers_fn else None)
                 oob_tot += oob
-            # K3 re-evaluates the first-sample predicate on its own heights (bitwise K0's for all but polar / projected-cube rays).
-            # A single process checks it for free; across ranks K0's globally reduced count stands -- one collective less per step
-            if reduce_sum is not None or bool(oob_tot[0] == counts[0]) == clamp:
+            # K3 re-evaluates the first-sample predicate on its own heights (bitwise K0's for all but polar / projected-cube rays)
+            below3 = oob_tot[:1] if reduce_sum is None else reduce_sum(oob_tot[:1])
+            if bool(below3[0] == counts[0]) == clamp:
                 break
             clamp = not clamp  # K0's hint and K3's own evaluation disagree on a knife edge: K3 rules
             info.reruns = 1
@@ -256,18 +266,132 @@ class DeviceCube:
         info.clamp_low_first = clamp
         info.oob_below, info.oob_above = int(oob_tot[1]), int(oob_tot[2])
         info.tiles = len(tiles)
+        if exchange is not None:
+            exchange.barrier()   # all rows of all ranks are in the maps
+        _check_clamp_coverage(info, max_segment_length)
         return info
 
+    # ------------------------------------------------------------------------------------ fused step (device-side plan)
+    def trace_begin(self, geom_kind, gx, gy, ny, nx, los_kind, los, ht, zref, flags=0):
+        """K0 (+ the cross-GPU publication of its K + 3 words when an exchange is attached); only enqueues."""
+        dev = is_device(gx) or is_device(los)
+        self._keep_geom = (gx, gy, los)  # device pointers must outlive the step
+        self._n_rays = int(ny) * int(nx)
+        self.h.call('rdr_trace_begin', geom_kind, ptr(gx), ptr(gy), int(ny), int(nx), los_kind, ptr(los), float(ht), float(zref),
+                    int(flags), _lib.MEM_DEVICE if dev else _lib.MEM_HOST)
+
+    def trace_finish(self, max_segment_length, out_wet, out_hydro, force_clamp=-1, mode=_lib.K3_AUTO, accumulate=False, peers=None):
+        """k_plan + K3 on the device plan; only enqueues.  ``peers`` as in :meth:`ray_integrate`."""
+        dev = is_device(out_wet)
+        if dev:
+            import torch
+            dt = _lib.F32 if out_wet.dtype == torch.float32 else _lib.F64
+        else:
+            dt = _lib.F32 if out_wet.dtype == np.float32 else _lib.F64
+        args = ('rdr_trace_finish', float(max_segment_length), int(force_clamp), int(mode), ptr(out_wet), ptr(out_hydro), dt,
+                int(bool(accumulate)), _lib.MEM_DEVICE if dev else _lib.MEM_HOST)
+        if peers is not None and len(peers[0]):
+            n = len(peers[0])
+            pw, ph = (C.c_void_p * n)(*[int(a) for a in peers[0]]), (C.c_void_p * n)(*[int(a) for a in peers[1]])
+            self.h.call('rdr_set_peer_outputs', n, pw, ph)
+            try:
+                self.h.call(*args)
+            finally:
+                self.h.call('rdr_set_peer_outputs', 0, None, None)
+        else:
+            self.h.call(*args)
+
+    def trace_result(self):
+        """Synchronise and read the step plan back: (maxlen[K], nparts[K], info[20]) -- see rdr_trace_result."""
+        nz = self.grid[2].size
+        maxlen, nparts, info = np.zeros(nz), np.zeros(nz, dtype=np.int64), np.zeros(20, dtype=np.int64)
+        self.h.call('rdr_trace_result', ptr(maxlen), ptr(nparts), ptr(info))
+        k = int(info[2])
+        return maxlen[:k].copy(), nparts[:k].copy(), info
+
+    def set_exchange(self, rank: int, world: int, bufs) -> None:
+        """Attach (world > 0) / detach the peer-mapped exchange buffers of the cross-GPU plan (rdr_set_exchange)."""
+        if world:
+            arr = (C.c_void_p * world)(*[int(a) for a in bufs])
+            self.h.call('rdr_set_exchange', int(rank), int(world), arr)
+        else:
+            self.h.call('rdr_set_exchange', 0, 0, None)
+
     def _trace_block(self, geom_kind, gx, gy, ny, nx, los_kind, los, ht, zref, max_segment_length, out_wet, out_hydro,
-                     reduce_max=None, reduce_sum=None, peers=None) -> TraceInfo:
+                     reduce_max=None, reduce_sum=None, peers=None, exchange=None) -> TraceInfo:
+        """One height of one row block as ONE fused step: K0 -> [exchange barrier] -> device plan -> K3, no host in between.
+
+        ``exchange``: an object with ``barrier()`` (signal-pad barrier on the kernels' stream; raider_b200.dist.SymmetricMaps)
+        whose buffers were attached with :meth:`set_exchange` -- the per-layer maxima and predicate counters of all ranks then meet
+        on the device.  Host hooks (``reduce_max`` / ``reduce_sum`` without an exchange: gloo, no P2P) take the unfused route.
+        """
+        if reduce_max is not None and exchange is None:
+            return self._trace_block_hosted(geom_kind, gx, gy, ny, nx, los_kind, los, ht, zref, max_segment_length, out_wet, out_hydro,
+                                            reduce_max, reduce_sum, peers)
+        info = TraceInfo(ht=float(ht))
+        flags, force_clamp, mode = 0, -1, _lib.K3_AUTO
+        for attempt in range(4):
+            self.trace_begin(geom_kind, gx, gy, ny, nx, los_kind, los, ht, zref, flags)
+            if exchange is not None:
+                exchange.barrier()       # every rank's K0 words have landed in every rank's slots (and the previous maps are free)
+            self.trace_finish(max_segment_length, out_wet, out_hydro, force_clamp=force_clamp, mode=mode, peers=peers)
+            if exchange is not None:
+                exchange.barrier()       # all rows of all ranks are in the maps; K3's cross-check counts have landed
+            maxlen, nparts, res = self.trace_result()
+            status, blocked = int(res[0]), int(res[1])
+            info.n_rays, info.n_nan_rays, info.n_layers = int(res[3]), int(res[4]), int(res[2])
+            if blocked & _lib.PLAN_ALL_NAN:
+                raise ValueError('geo2rdr did not converge. Check orbit coverage')  # delay.py:279-280, over the whole raster
+            if blocked & _lib.PLAN_ABSURD:
+                raise ValueError('a per-layer maximum ray length is NaN or absurd: nParts (delay.py:283) is undefined')
+            if blocked & _lib.PLAN_KNIFE_EDGE:
+                # nParts = ceil(max / S) + 1 hangs on the last bits of a maximum: redo the step with the exact (Bowring) K0
+                import logging
+                logging.getLogger('raider_b200').warning(
+                    'nParts knife edge: max ray length of layer %d is %.9f m = %.9f segments of %g m; redoing the step with the exact K0',
+                    int(res[11]), maxlen[int(res[11])], maxlen[int(res[11])] / max_segment_length, max_segment_length)
+                flags |= _lib.TRACE_EXACT_K0
+                info.knife_edge_redo = True
+                continue
+            if blocked & _lib.PLAN_SPAN_TOO_LONG:
+                mode = _lib.K3_FAST
+                continue
+            if status & _lib.PLAN_KNIFE_EDGE:
+                import logging
+                logging.getLogger('raider_b200').warning(
+                    'nParts knife edge persists with the exact K0: max ray length of layer %d is within 1e-6 segments of a multiple of %g m; '
+                    'the step count of that layer may differ from the reference by one', int(res[11]), max_segment_length)
+                info.knife_edge_layer = int(res[11])
+            clamp = bool(res[7])
+            # K3 re-evaluates the first-sample predicate on its own heights (bitwise K0's for all but polar / projected-cube rays);
+            # its global count rode the exchange.  On a knife edge K3 rules: redo with the clamp forced.
+            if bool(res[6] == res[3]) != clamp and force_clamp < 0:
+                force_clamp = int(not clamp)
+                info.reruns += 1
+                continue
+            break
+        info.maxlen, info.nparts = maxlen, nparts
+        info.samples_per_ray = int(nparts.sum())
+        info.clamp_low_first = bool(res[7])
+        info.oob_below, info.oob_above = int(res[8]), int(res[9])
+        info.k_split, info.n_spans = int(res[12]), int(res[13])
+        info.staged_passes, info.unstaged_passes = int(res[16]), int(res[17])
+        _check_clamp_coverage(info, max_segment_length)
+        return info
+
+    def _trace_block_hosted(self, geom_kind, gx, gy, ny, nx, los_kind, los, ht, zref, max_segment_length, out_wet, out_hydro,
+                            reduce_max=None, reduce_sum=None, peers=None) -> TraceInfo:
+        """The unfused route: K0, the reductions through host hooks (any torch.distributed backend), K3."""
         info = TraceInfo(ht=float(ht))
         maxlen, counts = self.ray_layers(geom_kind, gx, gy, ny, nx, los_kind, los, ht, zref)
         maxlen, counts = _global_plan(maxlen, counts, reduce_max, reduce_sum)
         info.n_rays, info.n_nan_rays, info.n_layers = int(counts[0]), int(counts[1]), int(counts[3])
+        if counts[1] == counts[0]:
+            raise ValueError('geo2rdr did not converge. Check orbit coverage')  # delay.py:279-280, over the whole raster
         clamp = bool(counts[2] == counts[0])
         nparts, oob = self.ray_integrate(maxlen, max_segment_length, clamp, out_wet, out_hydro, peers=peers)
-        # (across ranks K0's globally reduced count stands: see trace())
-        if reduce_sum is None and bool(oob[0] == counts[0]) != clamp:  # K0's hint and K3's own evaluation disagree on a knife edge: K3 rules
+        below3 = oob[:1] if reduce_sum is None else reduce_sum(oob[:1])   # K3's own evaluation of the predicate, summed over ranks
+        if bool(below3[0] == counts[0]) != clamp:  # K0's hint and K3's own evaluation disagree on a knife edge: K3 rules
             clamp = not clamp
             nparts, oob = self.ray_integrate(maxlen, max_segment_length, clamp, out_wet, out_hydro, peers=peers)
             info.reruns = 1
@@ -276,6 +400,20 @@ class DeviceCube:
         info.clamp_low_first = clamp
         info.oob_below, info.oob_above = int(oob[1]), int(oob[2])
         return info
+
+
+def _check_clamp_coverage(info: 'TraceInfo', max_segment_length: float) -> None:
+    """Only the first-sample lower clamp of delay.py:306-311 is applied on the device.  The other clamps (any later sample with ALL
+    pixels below min(z), any sample with ALL pixels above max(z)) cannot fire for valid inputs (zref <= max(z) - 1, top layer
+    - 0.01 m); should every ray nevertheless have left the model vertically, the device returned NaN where the reference clamps:
+    say so instead of returning it silently."""
+    n = max(info.n_rays, 1)
+    if info.oob_above >= n or (info.oob_below >= n and not info.clamp_low_first):
+        import logging
+        logging.getLogger('raider_b200').critical(
+            'every ray has samples outside the vertical range of the model (below: %d, above: %d of %d rays): the reference clamps such '
+            'samples to min(z) / max(z) when ALL pixels of a sample slot are outside (delay.py:306-311); the device path returns NaN',
+            info.oob_below, info.oob_above, info.n_rays)
 
 
 def _global_plan(maxlen, counts, reduce_max, reduce_sum):
