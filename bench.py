@@ -112,11 +112,32 @@ def global_config(n_gpus: int):
     return {'cube': cube, 'xpts': xpts, 'ypts': ypts, 'zref': float(zs[-1] - 1.0), 'max_segment_length': 225.0}
 
 
-def workload_config(world: int, cube: dict) -> dict:
-    """The `config` both arms print: BASELINE.json configs[1] (C2), 2000 x 2000 rays per GPU."""
+def c5_config(table=None):
+    """BASELINE configs[4]: NISAR-scale raster, 12000 x 20000 = 2.4e8 rays, GMAO-like cube 0.25 x 0.3125 deg, NZ = 72 (or the
+    145-node table), fixed 30 deg incidence, the reference's default 1000 m segments; STRONG scaling: the rows are split over the GPUs."""
+    from raider_b200 import synthetic as syn
+    return syn.config_c5(table=table)
+
+
+def workload_config(world: int, cube: dict, config: str = 'c2') -> dict:
+    """The `config` both arms print."""
+    if config == 'c5':
+        return {'workload': f'C5 NISAR-scale slant delay: 12000x20000 = 2.4e8 rays over {world} GPU(s) (strong scaling), fixed {INC} deg incidence, '
+                            f'heading {HEAD}, 0.0002 deg posting, cube {cube["y"].size}x{cube["x"].size}x{cube["z"].size} @0.25x0.3125 deg fp32, 1000 m max segment',
+                'rays_per_step': 12000 * 20000}
     return {'workload': f'C2 slant delay: {N_SIDE}x{N_SIDE} rays per GPU ({N_SIDE * world}x{N_SIDE} global), fixed {INC} deg incidence, heading {HEAD}, '
                         f'0.001 deg posting, cube {cube["y"].size}x{cube["x"].size}x37 @0.25 deg fp32, 225 m max segment',
             'rays_per_step': N_SIDE * world * N_SIDE}
+
+
+def kernel_source_hash() -> str:
+    """sha256 over the kernel sources + the header: profiles/k2_traffic.json is only trusted when it was captured from these."""
+    import hashlib
+    h = hashlib.sha256()
+    for p in sorted((ROOT / 'raider_b200' / 'csrc').glob('*')) + [ROOT / 'include' / 'raider_b200.h']:
+        h.update(p.name.encode())
+        h.update(p.read_bytes())
+    return h.hexdigest()[:16]
 
 
 def enu_const():
@@ -129,37 +150,47 @@ def enu_const():
 # ----------------------------------------------------------------------------------------------------------------
 def _cpu_block(args):
     """One worker: the oracle's _build_cube_ray on a row block with the global per-layer maxima injected."""
-    cube, xpts, ypts, zref, seg, maxlen = args
+    cube, xpts, ypts, zref, seg, maxlen = args[:6]
+    want_out = len(args) > 6 and args[6]
     os.environ.setdefault('OMP_NUM_THREADS', '1')
     from oracle import raytrace as rt
     crs = rt.GeographicCRS()
     t0 = time.perf_counter()
     out = rt.build_cube_ray(xpts, ypts, np.array([0.0]), rt.FixedIncidenceLOS(INC, HEAD), crs, crs, list(rt.get_interpolators(cube)),
                             MAX_SEGMENT_LENGTH=seg, MAX_TROPO_HEIGHT=zref, layer_maxlen=None if maxlen is None else [maxlen])
-    return time.perf_counter() - t0, float(out[0].sum() + out[1].sum())
+    dt = time.perf_counter() - t0
+    return (dt, out) if want_out else (dt, float(out[0].sum() + out[1].sum()))
 
 
-def cpu_global_maxlen(cfg):
-    """Per-layer maxima of the FULL raster, from its border pixels (the max of a smooth field sits on the border; exactness
-    is checked by the GPU run's own maxima in the `ours` arm -- here it only keeps samples/ray identical to the full job)."""
+def cpu_global_maxlen(cfg, interior_step: int = 20):
+    """The ORACLE'S OWN per-layer maxima of the full raster (delay.py:283) -- nothing borrowed from the GPU: losreader.build_ray's
+    restatement on the border pixels plus every `interior_step`-th row and column of the interior (the ray length is a smooth
+    function of position, its maximum sits on the border; the interior sample is the check of that).  Returns (maxima, border
+    maxima): the two must coincide."""
     from oracle import geodesy, raytrace as rt
     xp, yp = cfg['xpts'], cfg['ypts']
-    xx = np.concatenate([xp, xp, np.full(yp.size, xp[0]), np.full(yp.size, xp[-1])])
-    yy = np.concatenate([np.full(xp.size, yp[0]), np.full(xp.size, yp[-1]), yp, yp])
-    xx, yy = xx[None, :], yy[None, :]
-    xyz = np.stack(geodesy.lla2ecef(yy, xx, np.zeros_like(yy)), -1)
-    look = rt.FixedIncidenceLOS(INC, HEAD).getLookVectors(0.0, [xx, yy, 0 * yy], xyz, yy)
-    lens = rt.build_ray(cfg['cube']['z'], 0.0, xyz, look, cfg['zref'])[0]
-    return lens.max((1, 2))
+    bx = np.concatenate([xp, xp, np.full(yp.size, xp[0]), np.full(yp.size, xp[-1])])
+    by = np.concatenate([np.full(xp.size, yp[0]), np.full(xp.size, yp[-1]), yp, yp])
+    ix, iy = np.meshgrid(xp[::interior_step], yp[::interior_step])
+    los = rt.FixedIncidenceLOS(INC, HEAD)
+
+    def maxima(xx, yy):
+        xx, yy = xx.reshape(1, -1), yy.reshape(1, -1)
+        xyz = np.stack(geodesy.lla2ecef(yy, xx, np.zeros_like(yy)), -1)
+        look = los.getLookVectors(0.0, [xx, yy, 0 * yy], xyz, yy)
+        return rt.build_ray(cfg['cube']['z'], 0.0, xyz, look, cfg['zref'])[0].max((1, 2))
+    border, interior = maxima(bx, by), maxima(ix, iy)
+    return np.maximum(border, interior), border
 
 
-def cpu_baseline_single(cfg, maxlen, rows=100):
+def cpu_baseline_single(cfg, maxlen, rows=100, want_out=False):
     """cpu_baseline leg: 1 core, `rows` x 2000 rays from the middle of the raster."""
     mid = cfg['ypts'].size // 2
-    dt, _ = _cpu_block((cfg['cube'], cfg['xpts'], cfg['ypts'][mid:mid + rows], cfg['zref'], cfg['max_segment_length'], maxlen))
+    dt, out = _cpu_block((cfg['cube'], cfg['xpts'], cfg['ypts'][mid:mid + rows], cfg['zref'], cfg['max_segment_length'], maxlen, want_out))
     n = rows * cfg['xpts'].size
-    return {'value': n / dt, 'unit': UNIT, 'cores': 1, 'kind': 'port',
-            'sample': f'{rows}x{cfg["xpts"].size} rays (rows {mid}..{mid + rows - 1} of the C2 raster), global nParts injected, {dt:.1f} s'}
+    res = {'value': n / dt, 'unit': UNIT, 'cores': 1, 'kind': 'port',
+           'sample': f'{rows}x{cfg["xpts"].size} rays (rows {mid}..{mid + rows - 1} of the raster), nParts from the oracle\'s own full-raster maxima, {dt:.1f} s'}
+    return (res, out, slice(mid, mid + rows)) if want_out else res
 
 
 def run_reference(args):
@@ -170,7 +201,7 @@ def run_reference(args):
     import multiprocessing as mp
     cfg = global_config(1)
     cores = os.cpu_count() or 1
-    maxlen = cpu_global_maxlen(cfg)
+    maxlen, _ = cpu_global_maxlen(cfg)
     # calibrate: ~6 s per step so that (steps + warmup) stays within a few minutes
     t_probe, _ = _cpu_block((cfg['cube'], cfg['xpts'], cfg['ypts'][1000:1002], cfg['zref'], cfg['max_segment_length'], maxlen))
     budget = min(8.0, 150.0 / max(1, args.steps + args.warmup))
@@ -201,10 +232,52 @@ def run_reference(args):
 # ----------------------------------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------------------------------
+def _events(torch, stream, flush, fn, reps):
+    out = []
+    for _ in range(reps):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        fn()
+        b.record(stream)
+        torch.cuda.synchronize()
+        out.append(a.elapsed_time(b))
+    return float(np.mean(out))
+
+
+def run_variant(torch, stream, flush, name, cfg, enu, model_crs=None, reps=5):
+    """One more workload beside the headline, on one GPU: the fused step (K0 -> device plan -> K3) with CUDA events around the
+    whole step and around its two halves, and the difference to the PROJ-form integrator on the same rays."""
+    from raider_b200 import _lib
+    from raider_b200.engine import DeviceCube
+    cube = DeviceCube.from_dict(cfg['cube'], crs=model_crs)
+    cube.h.set_stream(stream.cuda_stream)
+    ny, nx = cfg['ypts'].size, cfg['xpts'].size
+    ow = torch.empty((ny, nx), dtype=torch.float64, device='cuda')
+    oh = torch.empty((ny, nx), dtype=torch.float64, device='cuda')
+    a = (_lib.GEOM_GRID, cfg['xpts'], cfg['ypts'], ny, nx, _lib.LOS_ENU_CONST, enu, 0.0, cfg['zref'])
+    S = cfg['max_segment_length']
+    for _ in range(3):
+        info = cube.trace(*a, S, ow, oh)
+    ms_step = _events(torch, stream, flush, lambda: cube.trace(*a, S, ow, oh), reps)
+    ms_k0 = _events(torch, stream, flush, lambda: cube.trace_begin(*a), reps)
+    cube.trace_begin(*a)
+    ms_k3 = _events(torch, stream, flush, lambda: cube.trace_finish(S, ow, oh), reps)
+    w = ow[::40].clone()
+    cube.trace_begin(*a)
+    cube.trace_finish(S, ow, oh, mode=_lib.K3_GENERAL)
+    torch.cuda.synchronize()
+    diff = float((ow[::40] - w).abs().max().item())
+    del cube, ow, oh
+    return {'workload': name, 'rays': ny * nx, 'rays_per_s': ny * nx / (ms_step * 1e-3), 'ms_per_step': ms_step, 'ms_k0': ms_k0, 'ms_k3': ms_k3,
+            'layers': info.n_layers, 'samples_per_ray': info.samples_per_ray, 'layers_in_thin_kernel': info.k_split,
+            'tma_staged_passes': [info.staged_passes, info.unstaged_passes], 'max_abs_diff_vs_proj_form_m': diff, 'nan': int(torch.isnan(w).sum().item())}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from raider_b200 import _lib
+    from raider_b200 import _lib, synthetic as syn
     from raider_b200.delay import _build_cube_ray
     from raider_b200.delayFcns import getInterpolators
     from raider_b200.dist import Comm, shard_rows
@@ -223,7 +296,14 @@ def run_ours(args):
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
         comm = Comm()
 
-    cfg = global_config(world)
+    c5 = args.config.startswith('c5')
+    if c5:
+        cfg = c5_config('ml145' if args.config == 'c5-ml145' else None)
+        metric = METRIC.replace('C2: 2000x2000 raster, 30deg incidence, NZ=37 cube, ~300 steps/ray',
+                                'C5: 12000x20000 raster, 30deg incidence, ' + ('145-node table' if args.config == 'c5-ml145' else 'NZ=72 cube') + ', 1000 m segments')
+    else:
+        cfg = global_config(world)
+        metric = METRIC
     ny_g, nx = cfg['ypts'].size, cfg['xpts'].size
     r0, r1 = shard_rows(ny_g, rank, world)
     ypts = np.ascontiguousarray(cfg['ypts'][r0:r1])
@@ -235,20 +315,18 @@ def run_ours(args):
 
     cube = DeviceCube.from_dict(cfg['cube'], device=local)
     cube.h.set_stream(stream.cuda_stream)
-    rmax = comm.reduce_max if comm else None
-    rsum = comm.reduce_sum if comm else None
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device='cuda')  # > 126 MB L2
     # N > 1: the full maps live in peer-mapped symmetric memory and K3 stores every ray into all GPUs' copies (the all-gather of
     # the output map fused into the integration kernel); NCCL all-gather only when symmetric memory cannot be set up
     sym = comm.symmetric_maps(1, ny_g, nx) if comm else None
     if sym is not None:
         out_w, out_h = sym.maps[0][0, r0:r1], sym.maps[1][0, r0:r1]
+        cube.set_exchange(rank, world, sym.xchg_ptrs)   # K0's maxima / counters meet on the device (k_publish -> barrier -> k_plan)
     else:
         out_w = torch.empty((ny, nx), dtype=torch.float64, device='cuda')
         out_h = torch.empty((ny, nx), dtype=torch.float64, device='cuda')
-
-    if sym is not None:
-        cube.set_exchange(rank, world, sym.xchg_ptrs)   # K0's maxima / counters meet on the device (k_publish -> barrier -> k_plan)
+    rmax = comm.reduce_max if (comm and sym is None) else None
+    rsum = comm.reduce_sum if (comm and sym is None) else None
 
     def step():
         if sym is not None:
@@ -297,28 +375,53 @@ def run_ours(args):
     value = n_global / (ms_per_step * 1e-3)
     checksum = float(fw.sum().item() + fh.sum().item())
     nan_count = int(torch.isnan(fw).sum().item())
-    fused_vs_allgather = None
+    fused_vs_allgather = sharded_vs_unsharded = None
     if sym is not None:
         # the maps K3 assembled by peer stores against an NCCL all-gather of the same row blocks (outside the timed region)
         fused_vs_allgather = max(float((comm.all_gather_rows(out_w.clone(), ny_g) - fw).abs().max().item()),
                                  float((comm.all_gather_rows(out_h.clone(), ny_g) - fh).abs().max().item()))
         fw, fh = fw.clone(), fh.clone()   # the e2e leg below reuses the symmetric buffers
+        # shard == whole: rank 0 retraces 64-row crops (one inside every rank's block) UNSHARDED -- one process, no exchange, the
+        # global per-layer maxima handed in -- and compares with the rows the ranks wrote into its maps
+        if rank == 0:
+            solo = DeviceCube.from_dict(cfg['cube'], device=local)
+            solo.h.set_stream(stream.cuda_stream)
+            cw = torch.empty((64, nx), dtype=torch.float64, device='cuda')
+            ch = torch.empty_like(cw)
+            sharded_vs_unsharded = 0.0
+            for q in range(world):
+                q0, q1 = shard_rows(ny_g, q, world)
+                c0 = q0 + max(0, (q1 - q0) // 2 - 32)
+                rows = np.ascontiguousarray(cfg['ypts'][c0:c0 + 64])
+                solo.ray_layers(_lib.GEOM_GRID, cfg['xpts'], rows, 64, nx, _lib.LOS_ENU_CONST, enu, 0.0, cfg['zref'])
+                npts, _ = solo.ray_integrate(info.maxlen, cfg['max_segment_length'], info.clamp_low_first, cw, ch)
+                assert np.array_equal(npts, info.nparts)
+                sharded_vs_unsharded = max(sharded_vs_unsharded, float((cw - fw[c0:c0 + 64]).abs().max().item()),
+                                           float((ch - fh[c0:c0 + 64]).abs().max().item()))
+            del solo, cw, ch
 
     # ---- e2e through the public API with host buffers ----------------------------------------------------------
     los = Raytracing(incidence=INC, heading=HEAD)
     cube_host = {k: (torch.from_numpy(np.ascontiguousarray(v)).pin_memory().numpy() if k in ('wet', 'hydro') else v)
                  for k, v in cfg['cube'].items()}
-    e2e_steps = max(3, min(args.steps, 10))
+    e2e_steps = max(3, min(args.steps, 10)) if not c5 else 3
+    host_block = os.environ.get('RDR_BENCH_E2E_HOSTBLOCK', '1') != '0'
 
     def e2e_step():
         ifs = getInterpolators(cube_host, device=local)                                   # cube + axes H2D
         if comm:
             from raider_b200.dist import build_cube_ray_sharded
             # every rank's rows go to its own page-locked host block AND into every GPU's full maps, from the same kernel
-            dev_maps, host_rows = build_cube_ray_sharded(cfg['xpts'], cfg['ypts'], np.array([0.0]), los, 4326, 4326, list(ifs), comm,
-                                                         MAX_SEGMENT_LENGTH=cfg['max_segment_length'], MAX_TROPO_HEIGHT=cfg['zref'],
-                                                         gather='device', host_block=True)
-            return host_rows, dev_maps
+            res = build_cube_ray_sharded(cfg['xpts'], cfg['ypts'], np.array([0.0]), los, 4326, 4326, list(ifs), comm,
+                                         MAX_SEGMENT_LENGTH=cfg['max_segment_length'], MAX_TROPO_HEIGHT=cfg['zref'],
+                                         gather='device', host_block=host_block)
+            if host_block:
+                return res[1], res[0]
+            rows = [_lib.pinned_empty((1, ny, nx)) for _ in range(2)]     # own rows: one device-to-host copy out of the full maps
+            for f in range(2):
+                torch.from_numpy(rows[f]).copy_(res[f][:, r0:r1], non_blocking=True)
+            torch.cuda.synchronize()
+            return rows, res
         return _build_cube_ray(cfg['xpts'], ypts, np.array([0.0]), los, 4326, 4326, list(ifs),   # axes H2D, delay maps D2H
                                MAX_SEGMENT_LENGTH=cfg['max_segment_length'], MAX_TROPO_HEIGHT=cfg['zref'])
 
@@ -342,6 +445,27 @@ def run_ours(args):
         e2e_dev_diff = max(float(np.abs(res[0][0][0] - fw[r0:r1].cpu().numpy()).max()), float((res[1][0][0] - fw).abs().max().item()))
     else:
         e2e_dev_diff = float(np.abs(res[0][0] - out_w.cpu().numpy()).max())
+    # the same through caller-supplied pageable outputArrs (what RAiDER.delay does when it passes outputArrs, delay.py:245-248,323)
+    e2e_pageable = None
+    if not comm and not c5:
+        outs = [np.zeros((1, ny, nx)), np.zeros((1, ny, nx))]
+
+        def e2e_pageable_step():
+            ifs = getInterpolators(cube_host, device=local)
+            outs[0][...] = 0.0
+            outs[1][...] = 0.0
+            _build_cube_ray(cfg['xpts'], ypts, np.array([0.0]), los, 4326, 4326, list(ifs), outputArrs=outs,
+                            MAX_SEGMENT_LENGTH=cfg['max_segment_length'], MAX_TROPO_HEIGHT=cfg['zref'])
+        e2e_pageable_step()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            e2e_pageable_step()
+        torch.cuda.synchronize()
+        tp = (time.perf_counter() - t0) / 3
+        e2e_pageable = {'value': n_global / tp, 'ms_per_step': 1e3 * tp,
+                        'api': '_build_cube_ray(..., outputArrs=<pageable np.zeros arrays>): in-place += on the host, zero-fill of the arrays included',
+                        'max_abs_diff_vs_device_path_m': float(np.abs(outs[0][0] - out_w.cpu().numpy()).max())}
 
     if rank != 0:
         clocks.__exit__()
@@ -349,150 +473,166 @@ def run_ours(args):
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the unfused trilinear-sample kernel K2 (rank 0, N = 1 semantics) ---------------------------
     peak, peak_src = measured_peak_gbs()
-    nslots = 48
-    maxlen, _ = cube.ray_layers(_lib.GEOM_GRID, cfg['xpts'], ypts, ny, nx, _lib.LOS_ENU_CONST, enu, 0.0, cfg['zref'])
-    if comm:
+    roofline = fused = cpu = variants = None
+    check = {'checksum': checksum, 'nan': nan_count, 'nparts_sum': int(info.samples_per_ray), 'fused_gather_vs_nccl_allgather_max_abs_diff_m': fused_vs_allgather,
+             'sharded_vs_unsharded_max_abs_diff_m': sharded_vs_unsharded, 'knife_edge_redo': bool(info.knife_edge_redo), 'clamp_reruns': int(info.reruns)}
+    if not c5:
+        # ---- roofline of the unfused trilinear-sample kernel K2 (rank 0, N = 1 semantics) ---------------------------
+        nslots = 48
+        solo = cube if not comm else DeviceCube.from_dict(cfg['cube'], device=local)
+        if comm:
+            solo.h.set_stream(stream.cuda_stream)
+        solo.ray_layers(_lib.GEOM_GRID, cfg['xpts'], ypts, ny, nx, _lib.LOS_ENU_CONST, enu, 0.0, cfg['zref'])
         maxlen = info.maxlen
-    pts = torch.empty((nslots, n_local, 3), dtype=torch.float64, device='cuda')
-    cube.ray_points(maxlen, cfg['max_segment_length'], slot0=100, nslots=nslots, out=pts)
-    npts = nslots * n_local
-    sw = torch.empty(npts, dtype=torch.float64, device='cuda')
-    sh = torch.empty(npts, dtype=torch.float64, device='cuda')
-    for _ in range(3):
-        cube.sample(pts.view(-1, 3), out=(sw, sh))
-    torch.cuda.synchronize()
-    k2 = []
-    for _ in range(10):
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(stream)
-        cube.sample(pts.view(-1, 3), out=(sw, sh))   # 10.2 GB of points + outputs per launch >> L2
-        b.record(stream)
+        pts = torch.empty((nslots, n_local, 3), dtype=torch.float64, device='cuda')
+        solo.ray_points(maxlen, cfg['max_segment_length'], slot0=100, nslots=nslots, out=pts)
+        npts = nslots * n_local
+        sw = torch.empty(npts, dtype=torch.float64, device='cuda')
+        sh = torch.empty(npts, dtype=torch.float64, device='cuda')
+        for _ in range(3):
+            solo.sample(pts.view(-1, 3), out=(sw, sh))
         torch.cuda.synchronize()
-        k2.append(a.elapsed_time(b))
-    k2_ms = float(np.mean(k2))
-    k2_bytes = npts * 40 + cube_bytes
-    k2_gbs = k2_bytes / (k2_ms * 1e-3) / 1e9
-    # DRAM traffic of that launch from the committed ncu --set full capture (dram__bytes_read.sum + dram__bytes_write.sum)
-    k2_traffic, k2_traffic_src = None, None
-    tp = ROOT / 'profiles' / 'k2_traffic.json'
-    if tp.exists():
-        try:
-            tj = json.loads(tp.read_text())
-            if int(tj['points_per_launch']) == npts:
-                k2_traffic, k2_traffic_src = float(tj['dram_bytes_read'] + tj['dram_bytes_write']), tj['source']
-        except Exception:
-            pass
-    # fp32-I/O tier of the same kernel (20 B/point)
-    pts32 = pts.to(torch.float32)
-    sw32 = torch.empty(npts, dtype=torch.float32, device='cuda')
-    sh32 = torch.empty(npts, dtype=torch.float32, device='cuda')
-    for _ in range(3):
-        cube.sample(pts32.view(-1, 3), out=(sw32, sh32))
-    torch.cuda.synchronize()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record(stream)
-    for _ in range(10):
-        cube.sample(pts32.view(-1, 3), out=(sw32, sh32))
-    b.record(stream)
-    torch.cuda.synchronize()
-    k2_32_gbs = (npts * 20 + cube_bytes) / (a.elapsed_time(b) / 10 * 1e-3) / 1e9
-    # CPU samplers beside K2: the installed scipy RGI the reference's delay path calls (delayFcns.py:55-56), 1
-    # thread, and the reference's own native RAiDER.interpolate.interpolate compiled from /root/reference (oracle/_ref), with
-    # its max_threads = 8 cap (module.cpp:81,293) -- both fields, on a bounded sample of the same points
-    cpu_sampler = None
-    if world == 1:
-        try:
-            from scipy.interpolate import RegularGridInterpolator as RGI
-            from oracle import build_ref
-            n_cpu = 2_000_000
-            hp = pts.view(-1, 3)[:: max(1, npts // n_cpu)][:n_cpu].cpu().numpy()
-            ys_, xs_, zs_ = (np.asarray(cfg['cube'][k], dtype=np.float64) for k in ('y', 'x', 'z'))
-            vals = [np.ascontiguousarray(cfg['cube'][k].transpose(1, 2, 0), dtype=np.float64) for k in ('wet', 'hydro')]
-            t0 = time.perf_counter()
-            ref_vals = [RGI((ys_, xs_, zs_), v, method='linear', bounds_error=False, fill_value=np.nan)(hp) for v in vals]
-            t_scipy = time.perf_counter() - t0
-            cpu_sampler = {'sample_points': int(hp.shape[0]), 'scipy_rgi_points_per_s': hp.shape[0] / t_scipy, 'scipy_threads': 1}
-            gw = torch.empty(hp.shape[0], dtype=torch.float64, device='cuda')
-            gh = torch.empty_like(gw)
-            cube.sample(torch.from_numpy(hp).cuda(), out=(gw, gh))
+        k2 = []
+        for _ in range(10):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            solo.sample(pts.view(-1, 3), out=(sw, sh))   # 10.2 GB of points + outputs per launch >> L2
+            b.record(stream)
             torch.cuda.synchronize()
-            cpu_sampler['k2_bit_identical_to_scipy_on_sample'] = bool(np.array_equal(gw.cpu().numpy(), ref_vals[0], equal_nan=True) and
-                                                                     np.array_equal(gh.cpu().numpy(), ref_vals[1], equal_nan=True))
-            if build_ref.available():
-                interp = build_ref.load('interpolate')
-                t0 = time.perf_counter()
-                nat = [interp.interpolate((ys_, xs_, zs_), v, hp, fill_value=np.nan, max_threads=8) for v in vals]
-                t_nat = time.perf_counter() - t0
-                cpu_sampler.update({'raider_interpolate_points_per_s': hp.shape[0] / t_nat, 'raider_interpolate_threads': 8,
-                                    'raider_interpolate_max_abs_diff_vs_scipy': float(np.nanmax(np.abs(nat[0] - ref_vals[0])))})
-        except Exception as e:  # the checker is optional equipment of the bench, never of the product
-            cpu_sampler = {'unavailable': repr(e)}
-    del pts, pts32, sw, sh, sw32, sh32
-
-    # ---- K3 alone (events around the integrate launch) for the fused accounts -----------------------------------
-    k3 = []
-    for _ in range(5):
+            k2.append(a.elapsed_time(b))
+        k2_ms = float(np.mean(k2))
+        k2_bytes = npts * 40 + cube_bytes
+        k2_gbs = k2_bytes / (k2_ms * 1e-3) / 1e9
+        # DRAM traffic of that launch from the committed ncu --set full capture (dram__bytes_read.sum + dram__bytes_write.sum); only
+        # trusted when the capture was taken from the kernel sources of this tree
+        k2_traffic, k2_traffic_src = None, None
+        tp = ROOT / 'profiles' / 'k2_traffic.json'
+        if tp.exists():
+            try:
+                tj = json.loads(tp.read_text())
+                if int(tj['points_per_launch']) == npts and tj.get('kernel_source_hash') == kernel_source_hash():
+                    k2_traffic, k2_traffic_src = float(tj['dram_bytes_read'] + tj['dram_bytes_write']), tj['source']
+                else:
+                    k2_traffic_src = 'profiles/k2_traffic.json was captured from other kernel sources / another launch size: not used'
+            except Exception:
+                pass
+        # fp32-I/O tier of the same kernel (20 B/point)
+        pts32 = pts.to(torch.float32)
+        sw32 = torch.empty(npts, dtype=torch.float32, device='cuda')
+        sh32 = torch.empty(npts, dtype=torch.float32, device='cuda')
+        for _ in range(3):
+            solo.sample(pts32.view(-1, 3), out=(sw32, sh32))
+        torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        flush.zero_()
         a.record(stream)
-        cube.ray_integrate(maxlen, cfg['max_segment_length'], False, out_w, out_h)
+        for _ in range(10):
+            solo.sample(pts32.view(-1, 3), out=(sw32, sh32))
         b.record(stream)
         torch.cuda.synchronize()
-        k3.append(a.elapsed_time(b))
-    k3_ms = float(np.mean(k3))
-    clocks.__exit__()
-    uniq = int(info.samples_per_ray - info.n_layers + 1)
-    fused = {
-        'kernel': 'k_ray_integrate_poly<double> (span cubics + layer quadrature; flagged rays: k_ray_integrate list pass)', 'ms': k3_ms,
-        'bound': 'fp64 issue, three-register DFMAs at 3 cycles (not HBM): see DESIGN.md section 4',
-        'algorithmic_bytes_per_ray': 16 + 8 * (info.n_layers + 1),
-        'hbm_gbs': n_local * (16 + 8 * (info.n_layers + 1)) / (k3_ms * 1e-3) / 1e9,
-        'equivalent_unfused_gbs': n_local * info.samples_per_ray * 40 / (k3_ms * 1e-3) / 1e9,
-        'samples_per_ray_reference': info.samples_per_ray, 'unique_samples_per_ray': uniq,
-        'samples_per_s': n_local * info.samples_per_ray / (k3_ms * 1e-3),
-    }
+        k2_32_gbs = (npts * 20 + cube_bytes) / (a.elapsed_time(b) / 10 * 1e-3) / 1e9
+        # CPU samplers beside K2: the installed scipy RGI the reference's delay path calls (delayFcns.py:55-56), 1
+        # thread, and the reference's own native RAiDER.interpolate.interpolate compiled from /root/reference (oracle/_ref), with
+        # its max_threads = 8 cap (module.cpp:81,293) -- both fields, on a bounded sample of the same points
+        cpu_sampler = None
+        if world == 1:
+            try:
+                from scipy.interpolate import RegularGridInterpolator as RGI
+                from oracle import build_ref
+                n_cpu = 2_000_000
+                hp = pts.view(-1, 3)[:: max(1, npts // n_cpu)][:n_cpu].cpu().numpy()
+                ys_, xs_, zs_ = (np.asarray(cfg['cube'][k], dtype=np.float64) for k in ('y', 'x', 'z'))
+                vals = [np.ascontiguousarray(cfg['cube'][k].transpose(1, 2, 0), dtype=np.float64) for k in ('wet', 'hydro')]
+                t0 = time.perf_counter()
+                ref_vals = [RGI((ys_, xs_, zs_), v, method='linear', bounds_error=False, fill_value=np.nan)(hp) for v in vals]
+                t_scipy = time.perf_counter() - t0
+                cpu_sampler = {'sample_points': int(hp.shape[0]), 'scipy_rgi_points_per_s': hp.shape[0] / t_scipy, 'scipy_threads': 1}
+                gw = torch.empty(hp.shape[0], dtype=torch.float64, device='cuda')
+                gh = torch.empty_like(gw)
+                solo.sample(torch.from_numpy(hp).cuda(), out=(gw, gh))
+                torch.cuda.synchronize()
+                cpu_sampler['k2_bit_identical_to_scipy_on_sample'] = bool(np.array_equal(gw.cpu().numpy(), ref_vals[0], equal_nan=True) and
+                                                                         np.array_equal(gh.cpu().numpy(), ref_vals[1], equal_nan=True))
+                if build_ref.available():
+                    interp = build_ref.load('interpolate')
+                    t0 = time.perf_counter()
+                    nat = [interp.interpolate((ys_, xs_, zs_), v, hp, fill_value=np.nan, max_threads=8) for v in vals]
+                    t_nat = time.perf_counter() - t0
+                    cpu_sampler.update({'raider_interpolate_points_per_s': hp.shape[0] / t_nat, 'raider_interpolate_threads': 8,
+                                        'raider_interpolate_max_abs_diff_vs_scipy': float(np.nanmax(np.abs(nat[0] - ref_vals[0])))})
+            except Exception as e:  # the checker is optional equipment of the bench, never of the product
+                cpu_sampler = {'unavailable': repr(e)}
+        del pts, pts32, sw, sh, sw32, sh32
+        roofline = {'kernel': 'k_sample_stream<double> (K2 trilinear_sample, unfused, TMA-bulk point stream)', 'bound': 'hbm', 'achieved': k2_gbs,
+                    'peak': peak, 'unit': 'GB/s', 'frac': k2_gbs / peak, 'traffic': k2_traffic, 'traffic_source': k2_traffic_src,
+                    'algorithmic_bytes_per_launch': k2_bytes, 'peak_source': peak_src, 'bytes_per_point': 40,
+                    'points_per_launch': npts, 'ms_per_launch': k2_ms, 'fp32_io_tier_gbs': k2_32_gbs, 'fp32_io_tier_frac': k2_32_gbs / peak,
+                    'fp32_tier_kernel': 'k_sample_stream_f32 (fp32 coordinates, arithmetic and values, 20 B/point; L1-bandwidth bound: 100 B/point through L1)',
+                    'points_per_s': npts / (k2_ms * 1e-3), 'cpu_samplers': cpu_sampler}
 
-    # ---- cpu_baseline (N = 1 only): the oracle port on a bounded sample, same inputs, global nParts from the GPU --
-    cpu = None
-    if world == 1:
-        cpu = cpu_baseline_single(cfg, info.maxlen)
-        # parity spot-check on the same sample while we are here
-        from oracle import raytrace as rt
-        crs = rt.GeographicCRS()
-        sl = slice(1000, 1004)
-        want = rt.build_cube_ray(cfg['xpts'], cfg['ypts'][sl], np.array([0.0]), rt.FixedIncidenceLOS(INC, HEAD), crs, crs,
-                                 list(rt.get_interpolators(cfg['cube'])), MAX_SEGMENT_LENGTH=cfg['max_segment_length'],
-                                 MAX_TROPO_HEIGHT=cfg['zref'], layer_maxlen=[info.maxlen])
-        got = out_w[sl].cpu().numpy()
-        cpu['max_abs_diff_vs_gpu_m'] = float(np.abs(got - want[0][0]).max())
+        # ---- the two halves of a step alone (events around K0 and around plan + K3) for the fused accounts -----------
+        targs = (_lib.GEOM_GRID, cfg['xpts'], ypts, ny, nx, _lib.LOS_ENU_CONST, enu, 0.0, cfg['zref'])
+        k0_ms = _events(torch, stream, flush, lambda: solo.trace_begin(*targs), 5)
+        solo.trace_begin(*targs)
+        tw, th = (out_w.clone(), out_h.clone()) if comm else (out_w, out_h)
+        k3_ms = _events(torch, stream, flush, lambda: solo.trace_finish(cfg['max_segment_length'], tw, th), 5)
+        uniq = int(info.samples_per_ray - info.n_layers + 1)
+        fused = {
+            'kernel': 'k_ray_integrate_poly<double> (span cubics + layer quadrature) [+ k_ray_integrate_thin for runs of <= 3-sample layers]; '
+                      'flagged rays: k_ray_integrate list pass; plan: k_plan on the device', 'ms': k3_ms, 'k0_ms': k0_ms,
+            'bound': 'fp64 issue, three-register DFMAs at 3 cycles (not HBM): see DESIGN.md section 4',
+            'algorithmic_bytes_per_ray': 16 + 8 * (info.n_layers + 1),
+            'hbm_gbs': n_local * (16 + 8 * (info.n_layers + 1)) / (k3_ms * 1e-3) / 1e9,
+            'equivalent_unfused_gbs': n_local * info.samples_per_ray * 40 / (k3_ms * 1e-3) / 1e9,
+            'samples_per_ray_reference': info.samples_per_ray, 'unique_samples_per_ray': uniq,
+            'samples_per_s': n_local * info.samples_per_ray / (k3_ms * 1e-3),
+        }
+
+        # ---- cpu_baseline (N = 1 only): the oracle port on a bounded sample of the same inputs.  nParts comes from the ORACLE'S OWN
+        # maxima of the full raster (border + interior sample of losreader.build_ray's restatement) -- nothing borrowed from the GPU
+        if world == 1:
+            own_max, border_max = cpu_global_maxlen(cfg)
+            own_np = np.ceil(own_max / cfg['max_segment_length']).astype(int) + 1
+            cpu, want, sl = cpu_baseline_single(cfg, own_max, rows=100, want_out=True)
+            got_w, got_h = out_w[sl].cpu().numpy(), out_h[sl].cpu().numpy()
+            cpu['max_abs_diff_vs_gpu_m'] = float(max(np.abs(got_w - want[0][0]).max(), np.abs(got_h - want[1][0]).max()))
+            cpu['rows_compared'] = 100
+            check.update({'nparts_equal_oracle_own_maxima': bool(np.array_equal(own_np, info.nparts)),
+                          'maxlen_max_abs_diff_vs_oracle_m': float(np.abs(own_max - info.maxlen).max()),
+                          'oracle_max_on_border': bool(np.array_equal(own_max, border_max))})
+
+            # ---- the production shapes beside the headline ("also run the 145-node table variant") -------
+            variants = {}
+            c145 = syn.config_c2(n=N_SIDE, table='ml145')
+            variants['ml145_1000m'] = run_variant(torch, stream, flush, 'C2 raster through the 145-node model-level table (models/model_levels.py:12 shape), 1000 m '
+                                                  'segments (the reference default): the production setting of ERA5 / GMAO / HRES cubes', c145, enu)
+            c3 = syn.config_c3(ny=N_SIDE, nx=N_SIDE, table='hrrr57')
+            variants['hrrr57_lcc'] = run_variant(torch, stream, flush, '2000x2000 rays over a 3 km spherical-Lambert cube (models/hrrr.py:255-260) with the 57-node '
+                                                 'table, 1000 m segments, fixed 30 deg incidence', c3, enu, model_crs=c3['crs'])
+    clocks.__exit__()
 
     line = {
-        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
-        'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': {**workload_config(world, cfg['cube']), 'samples_per_ray': info.samples_per_ray, 'layers': info.n_layers,
+        'metric': metric, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
+        'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'strong' if c5 else 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {**workload_config(world, cfg['cube'], 'c5' if c5 else 'c2'), 'samples_per_ray': info.samples_per_ray, 'layers': info.n_layers,
                    'l2': 'flushed with a 256 MB write between timed steps', 'parallelism': f'row-block x{world}' if world > 1 else 'single GPU',
-                   'collectives': ('one all-gather of K per-layer maxima + 3 counters per rank (max / sum taken locally); output maps reassembled on every GPU by ' +
-                                   ('peer stores from K3 over NVLink (symmetric memory) + 2 signal-pad barriers' if sym is not None
-                                    else 'all_gather_into_tensor (symmetric memory unavailable)')) if world > 1 else 'none'},
+                   'row_tiles_per_gpu': info.tiles, 'layers_in_thin_kernel': info.k_split,
+                   'collectives': ('no NCCL on the data path: K + 3 words per rank stored into every peer\'s exchange slots (symmetric memory), MAX / SUM taken by a one-CTA '
+                                   'kernel on every GPU, output maps reassembled on every GPU by peer stores from K3 over NVLink, 2 signal-pad barriers per step'
+                                   if sym is not None else 'all_gather_into_tensor (symmetric memory unavailable)') if world > 1 else 'none'},
         'clocks': clocks.summary(),
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'steps': e2e_steps,
                 'ms_per_step': 1e3 * t_e2e / e2e_steps,
                 'api': ('getInterpolators(host cube) + _build_cube_ray(host axes) -> host float64 maps' if world == 1 else
-                        'getInterpolators(host cube) + build_cube_ray_sharded(host axes, gather=device, host_block=True): every rank gets its own '
+                        'getInterpolators(host cube) + build_cube_ray_sharded(host axes, gather=device, host_block=' + str(host_block) + '): every rank gets its own '
                         'rows as host float64 arrays and the full maps in HBM; h2d/d2h bytes are per rank'),
-                'max_abs_diff_vs_device_path_m': e2e_dev_diff},
+                'max_abs_diff_vs_device_path_m': e2e_dev_diff, 'caller_supplied_pageable_outputs': e2e_pageable},
         'gpu_launches': int(launches),
-        'roofline': {'kernel': 'k_sample_stream<double> (K2 trilinear_sample, unfused, TMA-bulk point stream)', 'bound': 'hbm', 'achieved': k2_gbs,
-                     'peak': peak, 'unit': 'GB/s', 'frac': k2_gbs / peak, 'traffic': k2_traffic, 'traffic_source': k2_traffic_src,
-                     'algorithmic_bytes_per_launch': k2_bytes, 'peak_source': peak_src, 'bytes_per_point': 40,
-                     'points_per_launch': npts, 'ms_per_launch': k2_ms, 'fp32_io_tier_gbs': k2_32_gbs, 'fp32_io_tier_frac': k2_32_gbs / peak,
-                     'fp32_tier_kernel': 'k_sample_stream_f32 (fp32 coordinates, arithmetic and values, 20 B/point; L1-bandwidth bound: 100 B/point through L1)',
-                     'points_per_s': npts / (k2_ms * 1e-3), 'cpu_samplers': cpu_sampler},
+        'roofline': roofline,
         'fused': fused,
         'cpu_baseline': cpu,
-        'check': {'checksum': checksum, 'nan': nan_count, 'nparts_sum': int(info.samples_per_ray), 'fused_gather_vs_nccl_allgather_max_abs_diff_m': fused_vs_allgather},
+        'variants': variants,
+        'check': check,
     }
     print(json.dumps(line))
     if comm:
@@ -505,6 +645,9 @@ def main():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--config', default='c2', choices=['c2', 'c5', 'c5-ml145'],
+                    help='c2 (default): BASELINE configs[1], 2000x2000 rays per GPU, weak scaling; c5 / c5-ml145: BASELINE configs[4], 2.4e8 rays '
+                         'split over the GPUs (strong scaling), NZ = 72 or the 145-node table')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

@@ -70,7 +70,7 @@ for nm, cf in configs(sys.argv[1:] or ['c2', 'ml145']):
     torch.cuda.synchronize()
     wg, hg = ow.cpu().numpy(), oh.cpu().numpy()
     r = {'ms_step': t_step, 'ms_k0': t_k0, 'ms_k3': t_k3, 'rays_per_s': ny * nx / (t_step * 1e-3), 'layers': info.n_layers,
-         'samples_per_ray': info.samples_per_ray, 'k_split': info.k_split, 'n_spans': info.n_spans,
+         'samples_per_ray': info.samples_per_ray, 'k_split': info.k_split, 'n_spans': info.n_spans, 'staged': [info.staged_passes, info.unstaged_passes],
          'nparts_hist': np.bincount(info.nparts).tolist(), 'max_abs_diff_vs_general_m': float(max(np.abs(w - wg).max(), np.abs(h - hg).max())),
          'nan': int(np.isnan(w).sum()), 'fix_count': cube.h.last_fix_count, 'env': {k: v for k, v in os.environ.items() if k.startswith('RDR_')}}
     res[nm] = r

@@ -223,6 +223,7 @@ class Handle:
         ys, xs, zs = f64(ys), f64(xs), f64(zs)
         dev = is_device(wet)
         if not dev:
+            # float32 at the ABI (include/raider_b200.h); float64 callers go through DeviceCube, which splits hi + lo
             wet = np.ascontiguousarray(wet, dtype=np.float32)
             hydro = np.ascontiguousarray(hydro, dtype=np.float32)
         n = ys.size * xs.size * zs.size

@@ -975,7 +975,7 @@ __constant__ double c_septic_inv[8][8] = {
     {117649.0 / 92160.0, -117649.0 / 18432.0, 117649.0 / 10240.0, -117649.0 / 18432.0, -117649.0 / 18432.0, 117649.0 / 10240.0, -117649.0 / 18432.0, 117649.0 / 92160.0},
     {-117649.0 / 92160.0, 823543.0 / 92160.0, -823543.0 / 30720.0, 823543.0 / 18432.0, -823543.0 / 18432.0, 823543.0 / 30720.0, -823543.0 / 92160.0, 117649.0 / 92160.0},
 };
-constexpr double K0_MAX_RAY = 6.0e5;  // rays longer than this (incidence beyond ~82 deg through an 80 km model) take the exact form
+constexpr double K0_MAX_RAY = 3.0e5;  // rays longer than this (incidence beyond ~73 deg through an 80 km model) take the exact form: the error of a layer top in t is the height error over cos(incidence)
 
 struct Septic {
     double c[8];
@@ -1109,6 +1109,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_ray_layers(const RayGeom G, int
 // all-reduce of SURVEY 8(e), without NCCL and without the host.  The host reads the plan back after the step
 // (rdr_trace_result), when it synchronises for the results anyway.
 // ------------------------------------------------------------------------------------------------
+constexpr int THIN_TD = 8;   // along-ray distances in flight per thread in k_ray_integrate_thin (ring depth, power of two)
 constexpr int LERP_PAD = 8;  // records of padding behind the cell-record array (prefetch distance bound of k_ray_integrate_thin)
 constexpr int XCHG_STRIDE = MAX_LAYERS + 8;  // words per rank slot: maxima bits [K] | #NaN rays | #first sample below | #rays | K3's #first sample below
 // |maxlen / S - nearest integer| below which nParts is declared a knife edge: the default K0 reproduces the reference's maxima
@@ -1794,31 +1795,36 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_ray_integrate_poly(const FastCu
 // samples on the long scoreboard here (profiles/r01f ml145).  Sample positions, step counts and weights are the reference's.
 // Runs after k_ray_integrate_poly (which leaves the partial sums of layers [k_split, K) in `part`) and stores the results.
 // ------------------------------------------------------------------------------------------------
-// both fields of a cell record through a generic pointer (the record may sit in shared memory: staged columns)
-__device__ __forceinline__ void trilinear_cell_g(const LerpCell *q, double ty, double tx, double tz, double &vw, double &vh) {
-    const double4 q0 = q->q0, q1 = q->q1, q2 = q->q2, q3 = q->q3;
-    const double w0 = fma(tz, q0.z, q0.x), h0 = fma(tz, q0.w, q0.y);
-    const double w1 = fma(tz, q1.z, q1.x), h1 = fma(tz, q1.w, q1.y);
-    const double w2 = fma(tz, q2.z, q2.x), h2 = fma(tz, q2.w, q2.y);
-    const double w3 = fma(tz, q3.z, q3.x), h3 = fma(tz, q3.w, q3.y);
+// both fields of a cell record held in shared memory (staged columns), by shared-space address: 8 LDS.128
+__device__ __forceinline__ void trilinear_cell_s(uint32_t rec, double ty, double tx, double tz, double &vw, double &vh) {
+    double q[16];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(q[2 * i]), "=d"(q[2 * i + 1]) : "r"(rec + 16u * i));
+    // record layout (LerpCell): q0 = {w a0, h a0, w a1, h a1}, q1 = {a2, a3}, q2 = {a4, a5}, q3 = {a6, a7}
+    const double w0 = fma(tz, q[2], q[0]), h0 = fma(tz, q[3], q[1]);
+    const double w1 = fma(tz, q[6], q[4]), h1 = fma(tz, q[7], q[5]);
+    const double w2 = fma(tz, q[10], q[8]), h2 = fma(tz, q[11], q[9]);
+    const double w3 = fma(tz, q[14], q[12]), h3 = fma(tz, q[15], q[13]);
     vw = fma(ty, fma(tx, w3, w2), fma(tx, w1, w0));
     vh = fma(ty, fma(tx, h3, h2), fma(tx, h1, h0));
 }
 
-// STAGE: the north_star form -- the CTA's footprint of the cube is staged in shared memory by the TMA engine.  The 128 rays
-// of a CTA pass sit in 1-4 horizontal cells over the whole thin part (a 32 x 4 pixel tile is ~3 km wide, the rays drift
-// ~10 km below 20 km, a cell is ~25 km); the record columns of those cells -- contiguous in memory, z fastest -- are
-// copied with one cp.async.bulk each (UBLKCP) onto an mbarrier, `n_slots` columns at most (what fits beside MINB CTAs per
-// SM).  A sample then reads its record with 8 LDS.128 at ~30 cycles instead of 8 LDG.128 from L2 at ~600 under load
-// (profiles/r02a: 59 % of the stall samples of the unstaged kernel sit on the first use of those loads).  Rays whose cell is
-// not staged (footprint larger than the slots: km-scale grids) read the record from global memory as before.
+// STAGE: the north_star form -- the CTA's footprint of the cube is staged in shared memory by the TMA engine, span by span.
+// Within one span of the polynomial geometry (<= 12 km of ray) the 128 rays of a CTA pass (a 32 x 4 pixel tile, ~3 km wide)
+// drift a few km: they sit in 1-4 horizontal cells of a 0.25 deg cube, ~6 of a 3 km one.  The bounding box of those cells comes
+// for free from the span's end nodes (which the cubics need anyway); the record columns of the box, restricted to the z cells of
+// the span's layers -- contiguous in memory, z fastest -- are copied with one cp.async.bulk each (UBLKCP) onto an mbarrier, as
+// long as they fit the `rec_cap` records of shared memory left beside MINB CTAs per SM.  A sample then reads its record with
+// 8 LDS.128 at ~30 cycles instead of 8 LDG.128 from L2 at ~600 under load (profiles/r02a: 59 % of the stall samples of the
+// unstaged kernel sit on the first use of those loads).  Samples whose cell is not staged (box too large for the capacity, z cell
+// off the span's range) read the record from global memory as before.
 template <typename OUT, int BLOCK, int MINB, bool LCC, bool STAGE>
 __global__ void __launch_bounds__(BLOCK, MINB) k_ray_integrate_thin(const FastCube c, const RayGeom G, int64_t n_rays,
                                                               const double *__restrict__ t_in, const DevPlan *__restrict__ P,
                                                               const double *__restrict__ znodes, int nz, double zmin, OUT *__restrict__ out_wet,
                                                               OUT *__restrict__ out_hydro, int accumulate, const PeerOut peers,
                                                               unsigned long long *__restrict__ counters, int *__restrict__ fix_list, int tile_map,
-                                                              const double *__restrict__ part, int pf_cells, int pf_t, int n_slots,
+                                                              const double *__restrict__ part, int pf_cells, int pf_t, int rec_cap,
                                                               unsigned long long *__restrict__ stage_stats) {
     if (P->blocked) return;
     const int K = P->K, k_end = P->k_split, nspan = P->span_split;
@@ -1833,19 +1839,19 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_ray_integrate_thin(const FastCu
     const size_t stage_off = (((size_t)K * sizeof(LayerRec) + (2 * (size_t)nz - 1) * sizeof(double) + (size_t)K * sizeof(int)) + 127) / 128 * 128;
     uint64_t *s_bar = reinterpret_cast<uint64_t *>(fast_smem + stage_off);
     int *s_wbox = reinterpret_cast<int *>(fast_smem + stage_off + 16);            // [BLOCK / 32][4]
-    const LerpCell *s_cols = reinterpret_cast<const LerpCell *>(fast_smem + stage_off + 128);
+    // ring of along-ray distances: THIN_TD rows in flight per thread (cp.async), slot d of thread i at [d][i]
+    const uint32_t s_ring = smem_u32(fast_smem + stage_off + 128) + 8u * threadIdx.x;
+    LerpCell *s_cols = reinterpret_cast<LerpCell *>(fast_smem + stage_off + 128 + THIN_TD * BLOCK * sizeof(double));
+    const uint32_t s_cols_addr = smem_u32(s_cols);
     for (int i = threadIdx.x; i < k_end; i += BLOCK) s_layers[i] = P->layers[i];
     for (int i = threadIdx.x; i < nz; i += BLOCK) s_z[i] = znodes[i];
     for (int i = threadIdx.x; i < nz - 1; i += BLOCK) s_inv[i] = 1.0 / (znodes[i + 1] - znodes[i]);
     for (int i = threadIdx.x; i < nspan; i += BLOCK) s_span[i] = P->span_end[i];
-    // z cells the thin part can touch: its own layers' cells and one neighbour each way (layer tops sit mm .. m off their nodes)
-    const int iz_lo = max(P->layer_cell[0] - 1, 0), iz_hi = min(P->layer_cell[k_end - 1] + 1, c.nzc - 1), ncl = iz_hi - iz_lo + 1;
     if (STAGE && threadIdx.x == 0) mbar_init(s_bar, 1);
     __syncthreads();
     const ZTable T = {s_z, s_inv, nz};
     const double ky = RAD_TO_DEG * c.y_inv, kx = RAD_TO_DEG * c.x_inv;
     const int64_t n_pad = (n_rays + BLOCK - 1) / BLOCK * BLOCK;  // whole CTAs walk the loop together (barriers inside)
-    const int64_t pf_t_off = (int64_t)pf_t * n_rays;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned n_first_below = 0, phase = 0;
     unsigned long long n_staged = 0, n_unstaged = 0;
@@ -1866,70 +1872,42 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_ray_integrate_thin(const FastCu
         const double u6 = norm3(Vec3{F.uA, F.uB, F.uZ}) * 1.0e-6;  // |P_hi - P_lo| 1e-6 = |t_hi - t_lo| |u| 1e-6  (losreader.py:821, delay.py:315)
         bool bad = LCC ? false : !F.fast_ok;
         double acc_w = 0.0, acc_h = 0.0, vw, vh;
+        // the along-ray distances stream from HBM: a thin layer is ~200 cycles of work, a load from HBM takes 600 .. 900, so the
+        // rows k + 1 .. k + THIN_TD are kept in flight as asynchronous copies (LDGSTS) into a per-thread ring in shared memory --
+        // registers would have to be rotated by moves, and a move waits for its load
         const double *tp = t_in + rr;  // row k of the distances: bottom of layer k
         double t_a = __ldcs(tp), t_lo = t_a;
-        tp += n_rays;
-        double t_next = __ldcs(tp);
+#pragma unroll
+        for (int d = 0; d < THIN_TD; ++d) {
+            tp += n_rays;  // row d + 1
+            if (d + 1 <= K) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s_ring + (uint32_t)(d * BLOCK * 8)), "l"(tp) : "memory");
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+        uint32_t slot = 0;  // ring slot of row k + 1
         double tb_next = __ldcs(t_in + (int64_t)s_span[0] * n_rays + rr);
         RayNode n0 = node_eval<LCC>(c, F, R, t_a, bad);
-        // ---- footprint of this CTA pass: bounding box of the horizontal cells at the two ends of the thin part -> staged columns
-        int bx0 = 0, by0 = 0, nbx = 0, nby = 0;   // box origin and extent (cells); nbx = 0: nothing staged
-        if (STAGE) {
-            const RayNode ne = node_eval<LCC>(c, F, R, __ldcs(t_in + (int64_t)k_end * n_rays + rr), bad);
-            int ia, ib, ja, jb;
-            (void)cell_coord_clamped(n0.uy, c.ny, ia);
-            (void)cell_coord_clamped(ne.uy, c.ny, ib);
-            (void)cell_coord_clamped(n0.ux, c.nx, ja);
-            (void)cell_coord_clamped(ne.ux, c.nx, jb);
-            const int w_ylo = __reduce_min_sync(0xffffffffu, min(ia, ib)), w_yhi = __reduce_max_sync(0xffffffffu, max(ia, ib));
-            const int w_xlo = __reduce_min_sync(0xffffffffu, min(ja, jb)), w_xhi = __reduce_max_sync(0xffffffffu, max(ja, jb));
-            __syncthreads();  // the previous pass is done with the boxes and the columns
-            if (lane == 0) {
-                s_wbox[4 * warp] = w_ylo; s_wbox[4 * warp + 1] = w_yhi; s_wbox[4 * warp + 2] = w_xlo; s_wbox[4 * warp + 3] = w_xhi;
-            }
-            __syncthreads();
-            int ylo = s_wbox[0], yhi = s_wbox[1], xlo = s_wbox[2], xhi = s_wbox[3];
-#pragma unroll
-            for (int w = 1; w < BLOCK / 32; ++w) {
-                ylo = min(ylo, s_wbox[4 * w]); yhi = max(yhi, s_wbox[4 * w + 1]);
-                xlo = min(xlo, s_wbox[4 * w + 2]); xhi = max(xhi, s_wbox[4 * w + 3]);
-            }
-            const int ncols = (yhi - ylo + 1) * (xhi - xlo + 1);
-            if (ncols <= n_slots) {  // (CTA-uniform)
-                by0 = ylo; bx0 = xlo; nby = yhi - ylo + 1; nbx = xhi - xlo + 1;
-                const uint32_t col_bytes = (uint32_t)ncl * (uint32_t)sizeof(LerpCell);
-                if (threadIdx.x == 0) {
-                    mbar_expect_tx(s_bar, (uint32_t)ncols * col_bytes);
-                    for (int j = 0; j < ncols; ++j) {
-                        const int cy = by0 + j / nbx, cx = bx0 + j % nbx;
-                        tma_load_1d(const_cast<LerpCell *>(s_cols) + (size_t)j * ncl, c.cells + ((size_t)(cy * (c.nx - 1) + cx) * c.nzc + iz_lo), col_bytes, s_bar);
-                    }
-                }
-                mbar_wait(s_bar, phase);
-                phase ^= 1u;
-                n_staged += threadIdx.x == 0;
-            } else {
-                n_unstaged += threadIdx.x == 0;
-            }
-        }
         // very first sample of the ray (ff = 0 of the first layer); all pixels below min(z) -> clamp (delay.py:306-307)
         n_first_below += __popc(__ballot_sync(0xffffffffu, valid && (n0.h < zmin)));
         sample_cell(c, s_layers[0], T, n0.uy, n0.ux, clamp_low_first ? zmin : n0.h, vw, vh, bad);
-        // the horizontal cell the ray is in: index, floor values of the cell coordinates, record column (biased by -iz_lo when staged)
-        int iy, ix;
+        // the horizontal cell the ray is in: index, floor values of the cell coordinates, record column in global memory and -- when the
+        // cell is inside the staged box -- in shared memory (shared-space address of its record for z cell 0)
+        int iy, ix, bx0 = 0, by0 = 0, nbx = 0, nby = 0, lev0 = 0, nlev = 0;   // staged box: origin, extent (cells), first z cell, z cells
         double fy, fx;
         const LerpCell *col;
+        uint32_t col_s = 0;
+        bool in_smem = false;
         auto enter_cell = [&](double uy, double ux) {
             const double sy = __dadd_rd(uy, c_fast.floor_magic), sx = __dadd_rd(ux, c_fast.floor_magic);
             iy = min(max(__double2loint(sy), 0), c.ny - 2);
             ix = min(max(__double2loint(sx), 0), c.nx - 2);
             fy = sy - c_fast.floor_magic;
             fx = sx - c_fast.floor_magic;
-            const int cy = iy - by0, cx = ix - bx0;
-            if (STAGE && (unsigned)cy < (unsigned)nby && (unsigned)cx < (unsigned)nbx)
-                col = s_cols + ((cy * nbx + cx) * ncl - iz_lo);
-            else
-                col = c.cells + (unsigned)(iy * (c.nx - 1) + ix) * (unsigned)c.nzc;
+            col = c.cells + (unsigned)(iy * (c.nx - 1) + ix) * (unsigned)c.nzc;
+            if (STAGE) {
+                const int cy = iy - by0, cx = ix - bx0;
+                in_smem = ((unsigned)cy < (unsigned)nby) & ((unsigned)cx < (unsigned)nbx);
+                col_s = s_cols_addr + (uint32_t)(((cy * nbx + cx) * nlev - lev0) * (int)sizeof(LerpCell));
+            }
         };
         enter_cell(n0.uy, n0.ux);
         Cubic py, px, ph;
@@ -1947,13 +1925,15 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_ray_integrate_thin(const FastCu
             }
             int iz = L.iz;
             double tz = fma(h, L.inv_dz, L.neg_zlo_inv);
-            const LerpCell *rec = col + iz;
-            if (!(h >= L.h_lo && h < L.h_hi)) {  // (rare) not in the layer's own cell: whatever cell it is, straight from global memory
-                z_lookup(T, h, iz, tz, bad);
-                rec = c.cells + ((unsigned)(iy * (c.nx - 1) + ix) * (unsigned)c.nzc + (unsigned)iz);
+            const bool own_cell = (h >= L.h_lo) & (h < L.h_hi);
+            if (STAGE && in_smem && own_cell) {
+                trilinear_cell_s(col_s + (uint32_t)iz * (uint32_t)sizeof(LerpCell), ty, tx, tz, w_out, h_out);
+            } else {
+                if (!own_cell) z_lookup(T, h, iz, tz, bad);  // (rare) not in the layer's own cell
+                const LerpCell *rec = col + iz;
+                if (!STAGE && pf_cells) asm volatile("prefetch.global.L1 [%0];" ::"l"(rec + pf_cells));  // (the record array is padded at its end)
+                trilinear_cell(rec, ty, tx, tz, w_out, h_out);
             }
-            if (!STAGE && pf_cells) asm volatile("prefetch.global.L1 [%0];" ::"l"(rec + pf_cells));  // (the record array is padded at its end)
-            trilinear_cell_g(rec, ty, tx, tz, w_out, h_out);
         };
         int k = 0;
         for (int sp = 0; sp < nspan; ++sp) {
@@ -1965,16 +1945,62 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_ray_integrate_thin(const FastCu
             const RayNode n1 = node_eval<LCC>(c, F, R, fma(span, 1.0 / 3.0, t_a), bad);
             const RayNode n2 = node_eval<LCC>(c, F, R, fma(span, 2.0 / 3.0, t_a), bad);
             const RayNode n3 = node_eval<LCC>(c, F, R, t_b, bad);
+            if (STAGE) {
+                // ---- footprint of this span: bounding box of the horizontal cells at its two ends, over the CTA -> staged columns
+                int ia, ib, ja, jb;
+                (void)cell_coord_clamped(n0.uy, c.ny, ia);
+                (void)cell_coord_clamped(n3.uy, c.ny, ib);
+                (void)cell_coord_clamped(n0.ux, c.nx, ja);
+                (void)cell_coord_clamped(n3.ux, c.nx, jb);
+                const int w_ylo = __reduce_min_sync(0xffffffffu, min(ia, ib)), w_yhi = __reduce_max_sync(0xffffffffu, max(ia, ib));
+                const int w_xlo = __reduce_min_sync(0xffffffffu, min(ja, jb)), w_xhi = __reduce_max_sync(0xffffffffu, max(ja, jb));
+                __syncthreads();  // the CTA is done with the boxes and the columns of the previous span
+                if (lane == 0) {
+                    s_wbox[4 * warp] = w_ylo; s_wbox[4 * warp + 1] = w_yhi; s_wbox[4 * warp + 2] = w_xlo; s_wbox[4 * warp + 3] = w_xhi;
+                }
+                __syncthreads();
+                int ylo = s_wbox[0], yhi = s_wbox[1], xlo = s_wbox[2], xhi = s_wbox[3];
+#pragma unroll
+                for (int w = 1; w < BLOCK / 32; ++w) {
+                    ylo = min(ylo, s_wbox[4 * w]); yhi = max(yhi, s_wbox[4 * w + 1]);
+                    xlo = min(xlo, s_wbox[4 * w + 2]); xhi = max(xhi, s_wbox[4 * w + 3]);
+                }
+                // z cells of the span's layers and one neighbour each way (layer tops sit mm .. m off their nodes)
+                lev0 = max(s_layers[k].iz - 1, 0);
+                nlev = min(s_layers[k1 - 1].iz + 1, c.nzc - 1) - lev0 + 1;
+                const int ncols = (yhi - ylo + 1) * (xhi - xlo + 1);
+                if (ncols * nlev <= rec_cap) {  // (CTA-uniform)
+                    by0 = ylo; bx0 = xlo; nby = yhi - ylo + 1; nbx = xhi - xlo + 1;
+                    const uint32_t col_bytes = (uint32_t)nlev * (uint32_t)sizeof(LerpCell);
+                    if (threadIdx.x == 0) {
+                        mbar_expect_tx(s_bar, (uint32_t)ncols * col_bytes);
+                        for (int j = 0; j < ncols; ++j) {
+                            const int cy = by0 + j / nbx, cx = bx0 + j % nbx;
+                            tma_load_1d(s_cols + (size_t)j * nlev, c.cells + ((size_t)(cy * (c.nx - 1) + cx) * c.nzc + lev0), col_bytes, s_bar);
+                        }
+                    }
+                    mbar_wait(s_bar, phase);
+                    phase ^= 1u;
+                    n_staged += threadIdx.x == 0;
+                } else {
+                    nby = nbx = 0;
+                    n_unstaged += threadIdx.x == 0;
+                }
+                enter_cell(n0.uy, n0.ux);  // (the staging changed: refresh the column addresses of the cell the ray is in)
+            }
             py = cubic_through(n0.uy, n1.uy, n2.uy, n3.uy);
             px = cubic_through(n0.ux, n1.ux, n2.ux, n3.ux);
             ph = cubic_through(n0.h, n1.h, n2.h, n3.h);
             const double inv_span = rcp3(span);
             for (; k < k1; ++k) {
                 const LayerRec L = s_layers[k];
-                const double t_hi = t_next;
-                tp += n_rays;  // row k + 2
-                if (k + 2 <= K) t_next = __ldcs(tp);
-                if (pf_t && k + 2 + pf_t <= K) asm volatile("prefetch.global.L2 [%0];" ::"l"(tp + pf_t_off));
+                double t_hi;
+                asm volatile("cp.async.wait_group %0;" ::"n"(THIN_TD - 1) : "memory");  // row k + 1 has landed
+                asm volatile("ld.shared.f64 %0, [%1];" : "=d"(t_hi) : "r"(s_ring + slot * (uint32_t)(BLOCK * 8)) : "memory");
+                tp += n_rays;  // row k + 1 + THIN_TD goes into the slot just read
+                if (k + 1 + THIN_TD <= K) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s_ring + slot * (uint32_t)(BLOCK * 8)), "l"(tp) : "memory");
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                slot = (slot + 1) & (THIN_TD - 1);
                 const double dt = t_hi - t_lo;
                 const double wt_full = (fabs(dt) * u6) * L.step;  // delay.py:315
                 const double wt_half = 0.5 * wt_full;
@@ -2006,6 +2032,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_ray_integrate_thin(const FastCu
             t_a = t_b;
             n0 = n3;
         }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");  // (rows beyond the thin part that were still in flight)
         if (valid) {
             const double pw = k_end < K ? __ldcs(part + r) : 0.0;  // the layers above were summed by k_ray_integrate_poly
             if (k_end < K && __double_as_longlong(pw) == PART_FLAGGED) {
@@ -3195,7 +3222,7 @@ static int plan_enqueue(rdr_handle_t h, const unsigned long long *slots, int wor
     const char *span_env = getenv("RDR_K3_SPAN");
     const double span_max = span_env && atof(span_env) > 0 ? atof(span_env) : 12000.0;
     const char *thin_env = getenv("RDR_K3_THIN_MIN");  // fewest thin layers (<= 3 samples) that are worth the thin-layer kernel; 0: never
-    const int thin_min = thin_env ? atoi(thin_env) : 16;
+    const int thin_min = thin_env ? (atoi(thin_env) > 0 ? std::max(atoi(thin_env), 4) : 0) : 16;  // (the thin kernel preloads 4 rows of distances)
     unsigned long long *counters = h->d_red.as<unsigned long long>() + XCHG_STRIDE;
     const int *d_cell = reinterpret_cast<const int *>(h->d_plan.as<double>() + 2 * (size_t)K);
     const double *znodes = h->d_axes.as<double>() + h->ny + h->nx;
@@ -3321,17 +3348,16 @@ static int k3_enqueue(rdr_handle_t h, void *out_wet, void *out_hydro, int out_dt
                 const char *pfc_env = getenv("RDR_K3_THIN_PF"), *pft_env = getenv("RDR_K3_THIN_PFT"), *st_env = getenv("RDR_K3_THIN_STAGE");
                 const int pf_cells = pfc_env ? std::min(std::max(atoi(pfc_env), 0), LERP_PAD) : 0;
                 const int pf_t = pft_env ? std::max(atoi(pft_env), 0) : 6;
-                const int minb_t = tune_minb("RDR_K3_THIN_MINB", 3);
+                const int minb_t = tune_minb("RDR_K3_THIN_MINB", 4);
                 const int grid_t = grid_for(n, BLOCK, h->sm_count, 4 * minb_t);
-                // staged record columns (north_star: cube staged into shared memory via TMA): as many column slots of K + 2 records as
-                // fit beside minb_t CTAs per SM (227 KB per SM, 1 KB reserved per CTA)
-                const size_t base_t = (smem_p + 127) / 128 * 128 + 128;
-                const size_t col_bytes = ((size_t)K + 2) * sizeof(LerpCell);
+                // staged record columns (north_star: cube staged into shared memory via TMA): the records that fit beside minb_t CTAs per
+                // SM (227 KB per SM, 1 KB reserved per CTA), at most 48 KB worth
+                const size_t base_t = (smem_p + 127) / 128 * 128 + 128 + THIN_TD * BLOCK * sizeof(double);
                 const size_t budget = (size_t)227 * 1024 / minb_t - 1024;
-                int n_slots = budget > base_t ? (int)std::min<size_t>((budget - base_t) / col_bytes, 16) : 0;
-                if (st_env) n_slots = std::min(n_slots, std::max(atoi(st_env), 0));
-                const bool stage = n_slots > 0;
-                const size_t smem_t = stage ? base_t + (size_t)n_slots * col_bytes : smem_p;
+                int rec_cap = budget > base_t ? (int)std::min<size_t>((budget - base_t) / sizeof(LerpCell), 384) : 0;
+                if (st_env) rec_cap = std::min(rec_cap, std::max(atoi(st_env), 0));
+                const bool stage = rec_cap > 0;
+                const size_t smem_t = base_t + (size_t)rec_cap * sizeof(LerpCell);
                 unsigned long long *stage_stats = h->d_red.as<unsigned long long>() + XCHG_STRIDE + 4;
 #define RDR_LAUNCH_K3T(T, M, L, ST)                                                                                                        \
     do {                                                                                                                                    \
@@ -3340,7 +3366,7 @@ static int k3_enqueue(rdr_handle_t h, void *out_wet, void *out_hydro, int out_dt
         k_ray_integrate_thin<T, BLOCK, M, L, ST><<<grid_t, BLOCK, smem_t, h->stream>>>(fc, G, n, t_in, P, znodes, (int)h->nz, h->zs.front(), \
                                                                                     static_cast<T *>(dw), static_cast<T *>(dh), accumulate, \
                                                                                     peers, counters, h->d_fix.as<int>(), tile_thin, part,  \
-                                                                                    pf_cells, pf_t, n_slots, stage_stats);                 \
+                                                                                    pf_cells, pf_t, rec_cap, stage_stats);                 \
     } while (0)
 #define RDR_LAUNCH_K3T_S(T, M, L) \
     do { if (stage) RDR_LAUNCH_K3T(T, M, L, true); else RDR_LAUNCH_K3T(T, M, L, false); } while (0)

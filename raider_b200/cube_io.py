@@ -2,16 +2,16 @@
 
 On-disk contract (reference writer tools/RAiDER/models/weatherModel.py:659-724; readers tools/RAiDER/delay.py:66-78,
 tools/RAiDER/delayFcns.py:31-41): variables ``wet, hydro, wet_total, hydro_total`` with dims (z, y, x), coordinate
-variables ``x, y, z`` and a ``proj`` variable carrying ``crs_wkt``.  The reference writes NetCDF-4/HDF5 through
-xarray; neither xarray nor an HDF5 reader exists offline, so this module
+variables ``x, y, z`` and a ``proj`` variable carrying ``crs_wkt`` plus the CF grid-mapping attributes of the CRS.  The
+reference writes NetCDF-4 (= HDF5) through xarray; neither xarray nor an HDF5 library exists offline, so this module
 
+* reads the reference's **NetCDF-4 / HDF5** files with the dependency-free reader of :mod:`raider_b200.hdf5_lite`,
 * reads/writes the same variable layout as **NetCDF-3 classic** through ``scipy.io.netcdf_file`` (always available),
-* reads ``.npz`` archives with the same keys,
-* and, when ``xarray`` *is* importable (a real RAiDER environment), opens NetCDF-4 files through it.
+* reads ``.npz`` archives with the same keys.
 
-The CRS travels as a proj4 string attribute ``proj4`` on ``proj`` next to ``crs_wkt`` when we write; when reading a
-file produced by the reference (WKT only) the WKT is handed to pyproj if present, else EPSG:4326 is assumed unless the
-WKT names a Lambert conic (then pyproj is required and we say so).
+The CRS is taken from the CF grid-mapping attributes xarray / pyproj write next to ``crs_wkt`` (``grid_mapping_name`` =
+``latitude_longitude`` or ``lambert_conformal_conic`` with its parallels / origin / sphere radius), from a ``proj4`` attribute
+(what :func:`write_cube` writes), or -- when pyproj is importable -- from the WKT.
 """
 from __future__ import annotations
 
@@ -22,11 +22,29 @@ import numpy as np
 FIELDS = ('wet', 'hydro', 'wet_total', 'hydro_total')
 
 
+def _scalar(v):
+    return float(np.asarray(v).ravel()[0])
+
+
 def _crs_from_attrs(attrs: dict):
     from .crs import parse_crs
     if attrs.get('proj4'):
         v = attrs['proj4']
         return parse_crs(v.decode() if isinstance(v, bytes) else v)
+    gm = attrs.get('grid_mapping_name')
+    gm = gm.decode() if isinstance(gm, bytes) else gm
+    if gm == 'latitude_longitude':
+        return parse_crs(4326)
+    if gm == 'lambert_conformal_conic':
+        a = _scalar(attrs.get('semi_major_axis', attrs.get('earth_radius', 6378137.0)))
+        b = _scalar(attrs.get('semi_minor_axis', a))
+        sp = np.atleast_1d(np.asarray(attrs['standard_parallel'], dtype=np.float64))
+        d = dict(proj='lcc', lat_1=float(sp[0]), lat_2=float(sp[-1]), lat_0=_scalar(attrs['latitude_of_projection_origin']),
+                 lon_0=_scalar(attrs['longitude_of_central_meridian']), a=a, b=b, x_0=_scalar(attrs.get('false_easting', 0.0)),
+                 y_0=_scalar(attrs.get('false_northing', 0.0)))
+        return parse_crs(d)
+    if gm is not None:
+        raise NotImplementedError(f'weather-model grid mapping {gm!r} is not supported by the B200 delay path')
     wkt = attrs.get('crs_wkt')
     if wkt is None:
         return parse_crs(4326)  # delay.py:69-73: warn + assume WGS84
@@ -36,7 +54,7 @@ def _crs_from_attrs(attrs: dict):
         return parse_crs(pyproj.CRS.from_wkt(wkt))
     except ImportError:
         if 'Lambert' in wkt or 'PROJCRS' in wkt or 'PROJCS' in wkt:
-            raise NotImplementedError('projected weather-model CRS given as WKT needs pyproj to be parsed')
+            raise NotImplementedError('projected weather-model CRS given as WKT only needs pyproj to be parsed')
         return parse_crs(4326)
 
 
@@ -66,20 +84,28 @@ def load_cube(path_or_ds) -> dict:
     if magic[:3] == b'CDF':
         from scipy.io import netcdf_file
         with netcdf_file(str(path), 'r', mmap=False) as nc:
-            out = {k: np.array(nc.variables[k][:]) for k in ('x', 'y', 'z')}
+            def native(a):   # NetCDF-3 is big-endian on disk
+                a = np.array(a)
+                return a.astype(a.dtype.newbyteorder('='))
+            out = {k: native(nc.variables[k][:]) for k in ('x', 'y', 'z')}
             for k in FIELDS:
                 if k in nc.variables:
-                    out[k] = np.array(nc.variables[k][:])
+                    out[k] = native(nc.variables[k][:])
             attrs = dict(nc.variables['proj']._attributes) if 'proj' in nc.variables else {}
         out['crs'] = _crs_from_attrs(attrs)
         return out
-    try:
-        import xarray as xr
-    except ImportError as e:
-        raise ImportError(f'{path} is NetCDF-4/HDF5; reading it needs xarray (+h5netcdf/netCDF4), which is not installed. '
-                          'Convert it to NetCDF-3 classic or .npz, or install xarray.') from e
-    with xr.load_dataset(path) as ds:
-        return load_cube(ds)
+    if magic == b'\x89HDF':
+        # the reference's own format (weatherModel.py:659-724): NetCDF-4 = HDF5, read without any HDF5 library
+        from . import hdf5_lite
+        with hdf5_lite.File(path) as f:
+            out = {k: np.asarray(f[k].read(), dtype=np.float64) for k in ('x', 'y', 'z')}
+            for k in FIELDS:
+                if k in f:
+                    out[k] = f[k].read()
+            attrs = dict(f['proj'].attrs) if 'proj' in f else {}
+        out['crs'] = _crs_from_attrs(attrs)
+        return out
+    raise ValueError(f'{path}: not a NetCDF-3, NetCDF-4 / HDF5 or .npz weather-model cube')
 
 
 def write_cube(path, cube: dict, proj4: str = '+proj=longlat +datum=WGS84 +no_defs') -> Path:
@@ -96,8 +122,10 @@ def write_cube(path, cube: dict, proj4: str = '+proj=longlat +datum=WGS84 +no_de
             v[:] = np.asarray(cube[d], dtype=np.float64)
         for k in FIELDS:
             if k in cube:
-                v = nc.createVariable(k, 'f4', ('z', 'y', 'x'))
-                v[:] = np.asarray(cube[k], dtype=np.float32)
+                # wet / hydro float32, the zenith totals float64 -- the dtypes of the reference's files (weatherModel.py:398-403,617-619)
+                dt = ('f8', np.float64) if k.endswith('_total') else ('f4', np.float32)
+                v = nc.createVariable(k, dt[0], ('z', 'y', 'x'))
+                v[:] = np.asarray(cube[k], dtype=dt[1])
         p = nc.createVariable('proj', 'i4', ())
         p.data[()] = 0  # (netcdf_variable.assignValue indexes [:], which a 0-d array rejects)
         p.proj4 = proj4

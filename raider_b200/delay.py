@@ -96,23 +96,13 @@ def tropo_delay(
 def _interp_delay_cube(ds, pnts):
     """delay.py:116-121: ``getInterpolators(ds, 'ztd')`` then evaluate at the query points.
 
-    The delay cube is float64; the device cube stores float32 pairs, so it is staged as hi + lo float32 parts
-    (value == hi + lo to ~2^-48) and sampled twice -- linear interpolation is linear in the values.
+    The delay cube is float64; :class:`DeviceCube` stages float64 fields as hi + lo float32 parts (value == hi + lo to ~2^-48)
+    and samples both -- linear interpolation is linear in the values.
     """
     x, y, z = (np.asarray(ds.variables[k][:], dtype=np.float64) for k in ('x', 'y', 'z'))
-    out = [0.0, 0.0]
-    parts = []
-    for k in ('wet', 'hydro'):
-        v = np.asarray(ds.variables[k][:], dtype=np.float64)
-        hi = v.astype(np.float32)
-        lo = (v - hi.astype(np.float64)).astype(np.float32)
-        parts.append((hi, lo))
-    for part in (0, 1):
-        cube = DeviceCube(y, x, z, parts[0][part], parts[1][part], layout=_lib.LAYOUT_ZYX)
-        w, h = cube.sample(pnts)
-        out[0] = out[0] + w
-        out[1] = out[1] + h
-    return out[0], out[1]
+    cube = DeviceCube(y, x, z, np.asarray(ds.variables['wet'][:], dtype=np.float64), np.asarray(ds.variables['hydro'][:], dtype=np.float64),
+                      layout=_lib.LAYOUT_ZYX)
+    return cube.sample(pnts)
 
 
 def _get_delays_on_cube(datetime, weather_model_file, wm_proj, aoi, heights, los, crs, zref, nproc=1):

@@ -41,7 +41,7 @@ class DeviceInterpolator:
 def getInterpolators(wm_file: Union[dict, Path, str, DeviceCube], kind: str = 'pointwise', shared: bool = False, device=None):
     """Stage the cube of a processed weather model file and return (ifWet, ifHydro).
 
-    ``wm_file`` may be a path (NetCDF-3 classic, .npz, or NetCDF-4 when xarray is installed), an xarray Dataset, or a
+    ``wm_file`` may be a path (NetCDF-4 / HDF5 as the reference writes it, NetCDF-3 classic, .npz), an xarray Dataset, or a
     dict with keys x, y, z, wet, hydro[, wet_total, hydro_total] holding (z, y, x) arrays.  ``kind='total'`` selects
     the ``*_total`` fields (zenith path), ``kind='ztd'`` is the reference's point-mode re-interpolation of a *delay*
     cube (delay.py:116), which also reads ``wet``/``hydro``.  ``shared`` (a multiprocessing stub in the reference,
@@ -53,6 +53,8 @@ def getInterpolators(wm_file: Union[dict, Path, str, DeviceCube], kind: str = 'p
         ds = load_cube(wm_file)
         wet = np.asarray(ds['wet_total' if kind == 'total' else 'wet'])
         hydro = np.asarray(ds['hydro_total' if kind == 'total' else 'hydro'])
+        if kind == 'pointwise':   # the refractivity fields are float32 at rest (weatherModel.py:617-619)
+            wet, hydro = wet.astype(np.float32, copy=False), hydro.astype(np.float32, copy=False)
         if np.any(np.isnan(wet)) or np.any(np.isnan(hydro)):
             logger.critical('Weather model contains NaNs!')
         cube = DeviceCube(ds['y'], ds['x'], ds['z'], wet, hydro, layout=_lib.LAYOUT_ZYX, crs=ds.get('crs'), device=device)
@@ -67,5 +69,5 @@ def as_device_cube(interpolators, crs=None) -> DeviceCube:
     if isinstance(a, DeviceInterpolator) or isinstance(b, DeviceInterpolator):
         raise TypeError('interpolators must be the (ifWet, ifHydro) pair returned by one getInterpolators call')
     ys, xs, zs = (np.asarray(g) for g in a.grid)
-    return DeviceCube(ys, xs, zs, np.asarray(a.values, dtype=np.float32), np.asarray(b.values, dtype=np.float32),
-                      layout=_lib.LAYOUT_YXZ, crs=crs)
+    # (float64 values are staged as hi + lo float32 parts by DeviceCube: the zenith path stays at scipy's precision)
+    return DeviceCube(ys, xs, zs, np.asarray(a.values), np.asarray(b.values), layout=_lib.LAYOUT_YXZ, crs=crs)

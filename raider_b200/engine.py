@@ -47,6 +47,19 @@ class DeviceCube:
     def __init__(self, ys, xs, zs, wet, hydro, layout=_lib.LAYOUT_ZYX, crs=None, device: int | None = None) -> None:
         self.h = Handle(device)
         self.crs = parse_crs(crs)
+        # The staged fields are float32 (what the reference's files hold for wet / hydro, weatherModel.py:617-619).  Float64
+        # fields (wet_total / hydro_total are float64 in the reference's files, weatherModel.py:398-403; scipy RGIs built on
+        # float64 values) are staged as hi + lo float32 parts in two cubes -- value == hi + lo to ~2^-48 -- and sampled /
+        # integrated twice: interpolation and the trapezoid sum are linear in the values.
+        self.lo = None
+        if not is_device(wet) and np.asarray(wet).dtype == np.float64:
+            w64, h64 = np.asarray(wet, dtype=np.float64), np.asarray(hydro, dtype=np.float64)
+            wet, hydro = w64.astype(np.float32), h64.astype(np.float32)
+            with np.errstate(invalid='ignore'):
+                w_lo = np.where(np.isfinite(w64), w64 - wet.astype(np.float64), 0.0).astype(np.float32)
+                h_lo = np.where(np.isfinite(h64), h64 - hydro.astype(np.float64), 0.0).astype(np.float32)
+            if np.any(w_lo) or np.any(h_lo):
+                self.lo = DeviceCube(ys, xs, zs, w_lo, h_lo, layout=layout, crs=crs, device=device)
         self.h.set_cube(ys, xs, zs, wet, hydro, layout=layout, crs_kind=self.crs.kind, crs_params=self.crs.params())
         # ascending copies, as scipy exposes them through .grid (read at delay.py:239)
         self.grid = tuple(np.sort(f64(a)) for a in (ys, xs, zs))
@@ -82,6 +95,10 @@ class DeviceCube:
             if out is None:
                 out = (torch.empty(p.shape[:-1], dtype=p.dtype, device=p.device), torch.empty(p.shape[:-1], dtype=p.dtype, device=p.device))
             self.h.call('rdr_sample', ptr(p), n, ptr(out[0]), ptr(out[1]), dt, semantics, _lib.MEM_DEVICE)
+            if self.lo is not None:
+                lw, lh = self.lo.sample(pts, semantics)
+                out[0].add_(lw)
+                out[1].add_(lh)
             return out
         p = np.asarray(pts)
         if p.dtype != np.float32:
@@ -93,6 +110,10 @@ class DeviceCube:
         w = np.empty(p.shape[:-1], dtype=p.dtype)
         hy = np.empty(p.shape[:-1], dtype=p.dtype)
         self.h.call('rdr_sample', ptr(p), n, ptr(w), ptr(hy), _lib.F32 if p.dtype == np.float32 else _lib.F64, semantics, _lib.MEM_HOST)
+        if self.lo is not None:
+            lw, lh = self.lo.sample(p, semantics)
+            w += lw
+            hy += lh
         return w, hy
 
     def sample_grid(self, xpts, ypts, ht: float):
@@ -101,6 +122,10 @@ class DeviceCube:
         w = np.empty((ypts.size, xpts.size))
         hy = np.empty((ypts.size, xpts.size))
         self.h.call('rdr_sample_grid', ptr(xpts), xpts.size, ptr(ypts), ypts.size, float(ht), ptr(w), ptr(hy), _lib.MEM_HOST)
+        if self.lo is not None:
+            lw, lh = self.lo.sample_grid(xpts, ypts, ht)
+            w += lw
+            hy += lh
         return w, hy
 
     def sample_grid_levels(self, xpts, ypts, zpts):
@@ -109,6 +134,10 @@ class DeviceCube:
         w = np.empty((zpts.size, ypts.size, xpts.size))
         hy = np.empty((zpts.size, ypts.size, xpts.size))
         self.h.call('rdr_sample_grid_levels', ptr(xpts), xpts.size, ptr(ypts), ypts.size, ptr(zpts), zpts.size, ptr(w), ptr(hy), _lib.MEM_HOST)
+        if self.lo is not None:
+            lw, lh = self.lo.sample_grid_levels(xpts, ypts, zpts)
+            w += lw
+            hy += lh
         return w, hy
 
     # ------------------------------------------------------------------------------------ K0 + K3
@@ -216,6 +245,27 @@ class DeviceCube:
 
         ``peers_fn(r0, r1)`` -> ``(wet_ptrs, hydro_ptrs)`` for rows [r0, r1) of this call's block: see ``ray_integrate``.
         """
+        if self.lo is not None:
+            # float64 refractivity fields (the reference's files hold float32, weatherModel.py:617-619): integrate the hi and the lo
+            # parts and add -- the trapezoid sums are linear in the values; nParts and the predicates are geometry only
+            lo, self.lo = self.lo, None
+            try:
+                info = self.trace(geom_kind, gx, gy, ny, nx, los_kind, los, ht, zref, max_segment_length, out_wet, out_hydro,
+                                  reduce_max, reduce_sum, max_t_bytes, peers_fn, exchange)
+            finally:
+                self.lo = lo
+            if is_device(out_wet):
+                import torch
+                tw, th = torch.empty_like(out_wet), torch.empty_like(out_hydro)
+            else:
+                tw, th = _lib.pinned_empty(out_wet.shape, out_wet.dtype), _lib.pinned_empty(out_hydro.shape, out_hydro.dtype)
+            lo.trace(geom_kind, gx, gy, ny, nx, los_kind, los, ht, zref, max_segment_length, tw, th, reduce_max, reduce_sum, max_t_bytes,
+                     None, exchange)
+            out_wet += tw
+            out_hydro += th
+            if peers_fn is not None:
+                raise NotImplementedError('peer-mirrored outputs with float64 refractivity fields')
+            return info
         if max_t_bytes is None:
             max_t_bytes = float(os.environ.get('RAIDER_B200_T_BUDGET_GB', '64')) * 2**30
         nz = self.grid[2].size
