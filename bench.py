@@ -325,14 +325,16 @@ def run_ours(args):
     else:
         out_w = torch.empty((ny, nx), dtype=torch.float64, device='cuda')
         out_h = torch.empty((ny, nx), dtype=torch.float64, device='cuda')
-    rmax = comm.reduce_max if (comm and sym is None) else None
-    rsum = comm.reduce_sum if (comm and sym is None) else None
+    # host reduce hooks: the fallback when symmetric memory is unavailable, and the route of the row-tiled walk (rasters whose
+    # along-ray distances exceed the HBM budget per GPU); the fused step ignores them
+    rmax = comm.reduce_max if comm else None
+    rsum = comm.reduce_sum if comm else None
 
     def step():
         if sym is not None:
             # one fused step: K0 -> publish -> barrier -> device plan -> K3 (+ peer stores of its rows) -> barrier; no host in between
             info = cube.trace(_lib.GEOM_GRID, cfg['xpts'], ypts, ny, nx, _lib.LOS_ENU_CONST, enu, 0.0, cfg['zref'], cfg['max_segment_length'],
-                              out_w, out_h, peers_fn=lambda a, b: sym.peer_ptrs(0, r0 + a, r0 + b), exchange=sym)
+                              out_w, out_h, reduce_max=rmax, reduce_sum=rsum, peers_fn=lambda a, b: sym.peer_ptrs(0, r0 + a, r0 + b), exchange=sym)
             return info, sym.maps[0][0], sym.maps[1][0]
         info = cube.trace(_lib.GEOM_GRID, cfg['xpts'], ypts, ny, nx, _lib.LOS_ENU_CONST, enu, 0.0, cfg['zref'], cfg['max_segment_length'],
                           out_w, out_h, reduce_max=rmax, reduce_sum=rsum)

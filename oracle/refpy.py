@@ -260,6 +260,17 @@ def load():
     ns = types.SimpleNamespace()
     for name in ('constants', 'utilFcns', 'losreader', 'delayFcns', 'delay'):
         setattr(ns, name, importlib.import_module(f'RAiDER.{name}'))
+    # the inverse-time weights of the azimuth_time_grid interpolation (s1_azimuth_timing.py:337-399) are pure NumPy; the module's
+    # other imports (ASF search, orbit download) get empty stand-ins
+    for name, mod in {'asf_search': _module('asf_search'), 's1_orbits': _module('s1_orbits')}.items():
+        sys.modules.setdefault(name, mod)
+    shp = sys.modules['shapely.geometry']
+    if getattr(shp, '__raider_b200_standin__', False) and getattr(shp, 'Point', object) is object:
+        shp.Point = type('Point', (), {})
+    try:
+        ns.s1_azimuth_timing = importlib.import_module('RAiDER.s1_azimuth_timing')
+    except Exception:   # optional: only its weights function is used, by one test
+        ns.s1_azimuth_timing = None
     ns.CRS = CRS
     ns.Transformer = Transformer
     ns.dataset = dataset

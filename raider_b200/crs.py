@@ -91,9 +91,21 @@ class LambertConformalSphere:
 def _from_proj_dict(d: dict):
     proj = d.get('proj')
     if proj in ('longlat', 'latlong', 'lonlat'):
+        # only WGS-84 is geographic here: another datum / ellipsoid would need a datum shift the device geodesy does not do
+        datum, ellps = str(d.get('datum', 'WGS84')).upper(), str(d.get('ellps', 'WGS84')).upper()
+        if datum != 'WGS84' or ellps != 'WGS84' or 'towgs84' in d or 'nadgrids' in d:
+            raise NotImplementedError(f'geographic CRS on datum {d.get("datum", d.get("ellps"))!r}: only WGS-84 (EPSG:4326) is supported')
+        if 'a' in d or 'b' in d or 'rf' in d or 'R' in d:
+            a, rf = float(d.get('a', d.get('R', 6378137.0))), float(d.get('rf', 298.257223563 if 'R' not in d else 0.0))
+            if abs(a - 6378137.0) > 1e-6 or abs(rf - 298.257223563) > 1e-9:
+                raise NotImplementedError('geographic CRS on a non-WGS-84 ellipsoid is not supported')
         return Geographic()
     if proj == 'lcc':
-        a = float(d.get('a', d.get('R', 6378137.0)))
+        if not any(k in d for k in ('a', 'R')):
+            # PROJ's default ellipsoid is GRS80: an lcc without an explicit sphere is ellipsoidal
+            raise NotImplementedError('Lambert conformal conic without an explicit sphere (+R or +a == +b): PROJ would use the GRS80 ellipsoid, '
+                                      'only the spherical HRRR form is supported')
+        a = float(d.get('a', d.get('R')))
         b = float(d.get('b', a))
         if 'R' not in d and abs(a - b) > 1e-6 * a and 'rf' not in d:
             raise NotImplementedError('ellipsoidal Lambert conformal conic is not supported (only the spherical HRRR form)')

@@ -78,6 +78,34 @@ class DeviceCube:
         return cls(cube['y'], cube['x'], cube['z'], w, hy, layout=_lib.LAYOUT_ZYX, crs=crs if crs is not None else cube.get('crs'),
                    device=device)
 
+    @classmethod
+    def from_epochs(cls, cubes: list, weights: list, kind: str = 'pointwise', crs=None, device=None) -> 'DeviceCube':
+        """The temporal interpolation of cli/raider.py:792-833 at staging: ``sum_i w_i * cube_i`` per field.
+
+        Scalar weights ('center_time', cli/raider.py:877-888): float32 arithmetic on the device, exactly the reference's xarray
+        expression (python float x float32 array stays float32).  Per-voxel weight arrays ('azimuth_time_grid',
+        s1_azimuth_timing.py:337-399; float64, shape (z, y, x)): the reference's product is float64 -- formed here in float64 in its
+        order (0 + w_0 f_0 + w_1 f_1 + ...) and staged as hi + lo float32 parts, so sampling and ray tracing see the float64 blend."""
+        if len(cubes) != len(weights) or not cubes:
+            raise ValueError('one weight (scalar or (z, y, x) array) per epoch')
+        fw, fh = ('wet_total', 'hydro_total') if kind == 'total' else ('wet', 'hydro')
+        c0 = cubes[0]
+        crs = crs if crs is not None else c0.get('crs')
+        if all(np.ndim(w) == 0 for w in weights):
+            if len(cubes) != 2:
+                raise ValueError('scalar weights blend exactly two epochs (cli/raider.py:877-888)')
+            cube = cls(c0['y'], c0['x'], c0['z'], c0[fw], c0[fh], layout=_lib.LAYOUT_ZYX, crs=crs, device=device)
+            cube.blend(cubes[1][fw], cubes[1][fh], float(weights[0]), float(weights[1]))
+            return cube
+        shape = np.shape(c0[fw])
+        wet = hydro = 0
+        for c, w in zip(cubes, weights):
+            w = np.broadcast_to(np.asarray(w, dtype=np.float64), shape)
+            wet = wet + w * np.asarray(c[fw])
+            hydro = hydro + w * np.asarray(c[fh])
+        return cls(c0['y'], c0['x'], c0['z'], np.asarray(wet, dtype=np.float64), np.asarray(hydro, dtype=np.float64), layout=_lib.LAYOUT_ZYX,
+                   crs=crs, device=device)
+
     def blend(self, wet1, hydro1, w0: float, w1: float, layout=_lib.LAYOUT_ZYX) -> None:
         """Fused two-epoch temporal interpolation (cli/raider.py:817-819) at staging time."""
         self.h.blend_cube(wet1, hydro1, w0, w1, layout)

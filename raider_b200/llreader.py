@@ -30,8 +30,17 @@ class AOI:
         return self._output_spacing
 
     def set_output_xygrid(self, dst_crs=4326) -> None:
-        """llreader.py:173-191: xpts ascending, ypts descending, end points inclusive (EPSG:4326 only here)."""
+        """llreader.py:173-191: xpts ascending, ypts descending, end points inclusive.  A projected ``dst_crs`` gets the bounding
+        box transformed the reference's way (utilFcns.transform_bbox: an 11 x 11 mesh over the box, buffered by 100 m worth of
+        degrees, projected; the extremes of the projected mesh)."""
+        from .crs import Geographic, parse_crs
+        crs = parse_crs(dst_crs)
         S, N, W, E = self.bounds()
+        if not isinstance(crs, Geographic):
+            buffer = 100.0 / 1.0e5
+            X, Y = np.meshgrid(np.linspace(W - buffer, E + buffer, num=11), np.linspace(S - buffer, N + buffer, num=11))
+            xx, yy = crs.from_ll(X, Y)
+            S, N, W, E = np.nanmin(yy), np.nanmax(yy), np.nanmin(xx), np.nanmax(xx)
         sp = self.get_output_spacing(dst_crs)
         self.xpts = np.arange(W, E + sp, sp)
         self.ypts = np.arange(N, S - sp, -sp)

@@ -193,7 +193,7 @@ def test_reference_golden_hrrr_ztd_on_device(gpu):
     xs = np.linspace(px - 0.05, px + 0.05, 9)
     ys = np.linspace(py - 0.05, py + 0.05, 7)
     zs = np.array([0.0, 50.0, 100.0, 500.0, 1000.0])
-    want = rt.build_cube(xs, ys, zs, rt.LambertCRS(*[float(v) for v in fx['lcc']]), rt.GeographicCRS(), list(rt.get_interpolators(cube, 'total')))
+    want = rt.build_cube(xs, ys, zs, rt.LambertCRS(**dict(zip(('lat_1', 'lat_2', 'lat_0', 'lon_0', 'R', 'x_0', 'y_0'), (float(v) for v in fx['lcc'])))), rt.GeographicCRS(), list(rt.get_interpolators(cube, 'total')))
     got = _build_cube(xs, ys, zs, lcc, 4326, list(getInterpolators(cube, 'total')))
     assert np.abs(got[0] - want[0]).max() < 1e-12 and np.abs(got[1] - want[1]).max() < 1e-12
 
@@ -219,7 +219,7 @@ def test_ray_tracing_through_the_references_hrrr_cube(gpu):
     ifs = getInterpolators(cube)
     out = _build_cube_ray(xs, ys, zpts, Raytracing(incidence=25.0, heading=-168.0), lcc, 4326, list(ifs), MAX_TROPO_HEIGHT=zref)
     st = {}
-    want = rt.build_cube_ray(xs, ys, zpts, rt.FixedIncidenceLOS(25.0, -168.0), rt.LambertCRS(*[float(v) for v in fx['lcc']]), rt.GeographicCRS(),
+    want = rt.build_cube_ray(xs, ys, zpts, rt.FixedIncidenceLOS(25.0, -168.0), rt.LambertCRS(**dict(zip(('lat_1', 'lat_2', 'lat_0', 'lon_0', 'R', 'x_0', 'y_0'), (float(v) for v in fx['lcc'])))), rt.GeographicCRS(),
                              list(rt.get_interpolators(cube)), MAX_TROPO_HEIGHT=zref, stats=st)
     info = ifs[0].cube.last_info
     assert np.array_equal(info[0].nparts, st['nParts'][0]) and np.array_equal(info[1].nparts, st['nParts'][1])
