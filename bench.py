@@ -440,6 +440,23 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         t_e2e = float(t.item())
     e2e_value = n_global * e2e_steps / t_e2e
+    # What bounds e2e across ranks: all GPUs of the box push their row blocks into host memory at the same time.  Measured here:
+    # the plain device-to-host copy of this rank's two row blocks (2 x 8 B per ray, page-locked target) with every rank copying
+    # at once -- no kernels, no API around it.  e2e cannot beat ms_per_step (device) + this.
+    d2h_ms = None
+    if comm and not c5:
+        hb = [_lib.pinned_empty((ny, nx)) for _ in range(2)]
+        src = [out_w.clone(), out_h.clone()]
+        sync_all()
+        t0 = time.perf_counter()
+        for _ in range(5):
+            for f in range(2):
+                torch.from_numpy(hb[f]).copy_(src[f], non_blocking=True)
+            torch.cuda.synchronize()
+        td = torch.tensor([(time.perf_counter() - t0) / 5], dtype=torch.float64, device='cuda')
+        dist.all_reduce(td, op=dist.ReduceOp.MAX)
+        d2h_ms = 1e3 * float(td.item())
+        del hb, src
     cube_bytes = int(cfg['cube']['wet'].nbytes + cfg['cube']['hydro'].nbytes)
     h2d = cube_bytes + 8 * (cfg['xpts'].size + ny + cfg['cube']['x'].size + cfg['cube']['y'].size + cfg['cube']['z'].size)
     d2h = 2 * 8 * n_local
@@ -619,6 +636,8 @@ def run_ours(args):
         'config': {**workload_config(world, cfg['cube'], 'c5' if c5 else 'c2'), 'samples_per_ray': info.samples_per_ray, 'layers': info.n_layers,
                    'l2': 'flushed with a 256 MB write between timed steps', 'parallelism': f'row-block x{world}' if world > 1 else 'single GPU',
                    'row_tiles_per_gpu': info.tiles, 'layers_in_thin_kernel': info.k_split,
+                   'output_map_replication': ('NVLink-SHARP multicast: one multimem.st per value from K3' if (sym is not None and sym.mc_base) else
+                                              'one peer store per value and GPU from K3' if sym is not None else None),
                    'collectives': ('no NCCL on the data path: K + 3 words per rank stored into every peer\'s exchange slots (symmetric memory), MAX / SUM taken by a one-CTA '
                                    'kernel on every GPU, output maps reassembled on every GPU by peer stores from K3 over NVLink, 2 signal-pad barriers per step'
                                    if sym is not None else 'all_gather_into_tensor (symmetric memory unavailable)') if world > 1 else 'none'},
@@ -628,7 +647,9 @@ def run_ours(args):
                 'api': ('getInterpolators(host cube) + _build_cube_ray(host axes) -> host float64 maps' if world == 1 else
                         'getInterpolators(host cube) + build_cube_ray_sharded(host axes, gather=device, host_block=' + str(host_block) + '): every rank gets its own '
                         'rows as host float64 arrays and the full maps in HBM; h2d/d2h bytes are per rank'),
-                'max_abs_diff_vs_device_path_m': e2e_dev_diff, 'caller_supplied_pageable_outputs': e2e_pageable},
+                'max_abs_diff_vs_device_path_m': e2e_dev_diff, 'caller_supplied_pageable_outputs': e2e_pageable,
+                'concurrent_d2h_of_the_row_blocks_alone_ms': d2h_ms,
+                'concurrent_d2h_gbs_per_gpu': (d2h / (d2h_ms * 1e-3) / 1e9) if d2h_ms else None},
         'gpu_launches': int(launches),
         'roofline': roofline,
         'fused': fused,

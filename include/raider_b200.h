@@ -211,6 +211,10 @@ int64_t rdr_exchange_bytes(int world);
  * collective.  The caller orders the kernels of all ranks (barrier) before reading the maps.  n = 0 clears the list;
  * accumulate != 0 calls ignore it.  The reference has no parallel delay path (delay.py:178-185 raises for nproc > 1). */
 int rdr_set_peer_outputs(rdr_handle_t h, int n, void *const *wet, void *const *hydro);
+/* The same through NVLink-SHARP multicast: wet_mc / hydro_mc are the addresses of this rank's row block inside the MULTICAST mapping
+ * of the symmetric maps (torch symmetric memory `multicast_ptr`, cuMulticast*): the integration kernel issues ONE multimem.st per
+ * value and the NVSwitch replicates it into every GPU's copy (the local one included).  NULL, NULL detaches. */
+int rdr_set_multicast_outputs(rdr_handle_t h, void *wet_mc, void *hydro_mc);
 
 /* K1b -- north_star (a): generate the 3-D sample points along each ray of the last rdr_ray_layers call, in model
  * coordinates, i.e. the per-sub-step `pts` arrays of delay.py:292-298 (replaces the role of tools/bindings makePoints3D in

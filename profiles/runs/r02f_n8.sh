@@ -1,0 +1,11 @@
+set -x
+cd $GRAFT_REPO_ROOT
+mkdir -p gpurun_out
+nvidia-smi -L > gpurun_out/r02f_smi.txt
+N=${NGPU:-8}
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 profiles/dist_check.py > gpurun_out/r02f_dist_check_n$N.json 2> gpurun_out/r02f_dist_check_n$N.err
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/r02f_bench_n$N.json 2> gpurun_out/r02f_bench_n$N.err
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus $N --steps 5 --warmup 3 --config c5 > gpurun_out/r02f_bench_c5_n$N.json 2> gpurun_out/r02f_bench_c5_n$N.err
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29514 bench.py --gpus $N --steps 5 --warmup 3 --config c5-ml145 > gpurun_out/r02f_bench_c5ml145_n$N.json 2> gpurun_out/r02f_bench_c5ml145_n$N.err
+RDR_BENCH_E2E_HOSTBLOCK=0 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29515 bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/r02f_bench_n${N}_e2e_copy.json 2> gpurun_out/r02f_bench_n${N}_e2e_copy.err
+cat gpurun_out/r02f_dist_check_n$N.json; tail -3 gpurun_out/r02f_bench_n$N.err; tail -3 gpurun_out/r02f_bench_c5_n$N.err

@@ -55,6 +55,7 @@ SIGNATURES = {
     'rdr_ray_layers': (_int, [_vp, _int, _vp, _vp, _i64, _i64, _int, _vp, _f64, _f64, _vp, _vp, _int]),
     'rdr_ray_integrate': (_int, [_vp, _vp, _f64, _int, _vp, _vp, _int, _int, _vp, _vp, _int]),
     'rdr_set_peer_outputs': (_int, [_vp, _int, _vp, _vp]),
+    'rdr_set_multicast_outputs': (_int, [_vp, _vp, _vp]),
     'rdr_trace_begin': (_int, [_vp, _int, _vp, _vp, _i64, _i64, _int, _vp, _f64, _f64, _int, _int]),
     'rdr_trace_finish': (_int, [_vp, _f64, _int, _int, _vp, _vp, _int, _int, _int]),
     'rdr_trace_result': (_int, [_vp, _vp, _vp, _vp]),

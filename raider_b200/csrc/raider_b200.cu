@@ -190,6 +190,7 @@ struct PeerOut {
     void *wet[RDR_MAX_PEERS];
     void *hydro[RDR_MAX_PEERS];
     int n;
+    int multicast;  // wet[0] / hydro[0] are NVLink-SHARP multicast addresses: ONE multimem.st reaches every GPU of the group
 };
 
 }  // namespace
@@ -871,6 +872,17 @@ __device__ __forceinline__ void store_result(OUT *__restrict__ out_wet, OUT *__r
     }
     __stcs(out_wet + r, (OUT)acc_w);
     __stcs(out_hydro + r, (OUT)acc_h);
+    if (peers.multicast) {
+        // one store into the multicast mapping of the symmetric maps: the NVSwitch replicates it into every GPU's copy
+        if (sizeof(OUT) == 8) {
+            asm volatile("multimem.st.weak.global.f64 [%0], %1;" ::"l"(static_cast<OUT *>(peers.wet[0]) + r), "d"((double)acc_w) : "memory");
+            asm volatile("multimem.st.weak.global.f64 [%0], %1;" ::"l"(static_cast<OUT *>(peers.hydro[0]) + r), "d"((double)acc_h) : "memory");
+        } else {
+            asm volatile("multimem.st.weak.global.f32 [%0], %1;" ::"l"(static_cast<OUT *>(peers.wet[0]) + r), "f"((float)acc_w) : "memory");
+            asm volatile("multimem.st.weak.global.f32 [%0], %1;" ::"l"(static_cast<OUT *>(peers.hydro[0]) + r), "f"((float)acc_h) : "memory");
+        }
+        return;
+    }
     for (int p = 0; p < peers.n; ++p) {
         static_cast<OUT *>(peers.wet[p])[r] = (OUT)acc_w;
         static_cast<OUT *>(peers.hydro[p])[r] = (OUT)acc_h;
@@ -3272,7 +3284,7 @@ static int k3_enqueue(rdr_handle_t h, void *out_wet, void *out_hydro, int out_dt
     const DevPlan *P = h->d_devplan.as<DevPlan>();
     const double *t_in = h->d_t.as<double>();
     PeerOut peers = h->peers;
-    if (accumulate) peers.n = 0;  // += has no meaning across replicas: peers only mirror freshly written maps
+    if (accumulate) peers.n = peers.multicast = 0;  // += has no meaning across replicas: peers only mirror freshly written maps
     FastCube fc;
     const char *force_general = getenv("RDR_K3_GENERAL");
     // integrator: poly (default; geographic or Lambert cube with uniform horizontal axes), fast (per-sample Bowring; geographic
@@ -3649,11 +3661,22 @@ RDR_API int rdr_set_peer_outputs(rdr_handle_t h, int n, void *const *wet, void *
     CHECK_ARG(h, n >= 0 && n <= RDR_MAX_PEERS, "rdr_set_peer_outputs: at most 8 peer destinations");
     CHECK_ARG(h, n == 0 || (wet && hydro), "rdr_set_peer_outputs: NULL pointer list");
     h->peers.n = n;
+    h->peers.multicast = 0;
     for (int i = 0; i < n; ++i) {
         CHECK_ARG(h, wet[i] && hydro[i], "rdr_set_peer_outputs: NULL destination");
         h->peers.wet[i] = wet[i];
         h->peers.hydro[i] = hydro[i];
     }
+    return RDR_OK;
+}
+
+RDR_API int rdr_set_multicast_outputs(rdr_handle_t h, void *wet_mc, void *hydro_mc) {
+    CHECK_ARG(h, h != nullptr, "rdr_set_multicast_outputs: NULL handle");
+    CHECK_ARG(h, (wet_mc == nullptr) == (hydro_mc == nullptr), "rdr_set_multicast_outputs: both or neither");
+    h->peers.n = 0;
+    h->peers.multicast = wet_mc ? 1 : 0;
+    h->peers.wet[0] = wet_mc;
+    h->peers.hydro[0] = hydro_mc;
     return RDR_OK;
 }
 

@@ -137,6 +137,9 @@ class SymmetricMaps:
         self.base = [int(a) for a in self.hdl.buffer_ptrs]
         if len(self.base) != comm.world or self.base[comm.rank] != self.maps.data_ptr():
             raise RuntimeError('symmetric-memory rendezvous returned unexpected buffer pointers')
+        # NVLink-SHARP multicast mapping of the maps (0 when the fabric / driver offers none): one store reaches every GPU
+        import os
+        self.mc_base = 0 if os.environ.get('RAIDER_B200_NO_MULTICAST') else int(getattr(self.hdl, 'multicast_ptr', 0) or 0)
         # exchange slots of the device-side plan (rdr_set_exchange): 2 parities x world slots of K + 3 words per rank
         from . import _lib
         words = int(_lib.load().rdr_exchange_bytes(comm.world)) // 8
@@ -154,6 +157,9 @@ class SymmetricMaps:
 
     def peer_ptrs(self, hh: int, r0: int, r1: int, include_self: bool = False):
         """Addresses of rows [r0, r1) of height slice hh inside every other rank's maps (8-byte elements)."""
+        if getattr(self, 'mc_base', 0):
+            return ([self.mc_base + 8 * ((0 * self.nz + hh) * self.ny + r0) * self.nx], [self.mc_base + 8 * ((1 * self.nz + hh) * self.ny + r0) * self.nx],
+                    'multicast')
         wet, hydro = [], []
         for q, b in enumerate(self.base):
             if q == self.comm.rank and not include_self:

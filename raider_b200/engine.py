@@ -195,6 +195,12 @@ class DeviceCube:
         other GPUs (peer-mapped symmetric memory); the kernel mirrors every ray's results there as it finishes the ray
         (rdr_set_peer_outputs) -- the all-gather of the output map fused into the integration.
         """
+        if peers is not None and len(peers) == 3 and peers[2] == 'multicast':
+            self.h.call('rdr_set_multicast_outputs', int(peers[0][0]), int(peers[1][0]))
+            try:
+                return self.ray_integrate(maxlen, max_segment_length, clamp_low_first, out_wet, out_hydro, accumulate)
+            finally:
+                self.h.call('rdr_set_multicast_outputs', None, None)
         if peers is not None and len(peers[0]):
             n = len(peers[0])
             pw, ph = (C.c_void_p * n)(*[int(a) for a in peers[0]]), (C.c_void_p * n)(*[int(a) for a in peers[1]])
@@ -368,7 +374,14 @@ class DeviceCube:
             dt = _lib.F32 if out_wet.dtype == np.float32 else _lib.F64
         args = ('rdr_trace_finish', float(max_segment_length), int(force_clamp), int(mode), ptr(out_wet), ptr(out_hydro), dt,
                 int(bool(accumulate)), _lib.MEM_DEVICE if dev else _lib.MEM_HOST)
-        if peers is not None and len(peers[0]):
+        if peers is not None and len(peers) == 3 and peers[2] == 'multicast':
+            # ONE multicast destination: the NVSwitch replicates every store into all GPUs' maps (rdr_set_multicast_outputs)
+            self.h.call('rdr_set_multicast_outputs', int(peers[0][0]), int(peers[1][0]))
+            try:
+                self.h.call(*args)
+            finally:
+                self.h.call('rdr_set_multicast_outputs', None, None)
+        elif peers is not None and len(peers[0]):
             n = len(peers[0])
             pw, ph = (C.c_void_p * n)(*[int(a) for a in peers[0]]), (C.c_void_p * n)(*[int(a) for a in peers[1]])
             self.h.call('rdr_set_peer_outputs', n, pw, ph)

@@ -463,14 +463,71 @@ def test_full_size_properties(gpu):
     w2, h2 = np.empty((ny, nx)), np.empty((ny, nx))
     cube2.trace(_lib.GEOM_GRID, cfg['xpts'], cfg['ypts'], ny, nx, _lib.LOS_ENU_CONST, enu, 0.0, cfg['zref'], cfg['max_segment_length'], w2, h2)
     assert np.array_equal(w2, 2 * w) and np.array_equal(h2, 2 * h)
-    # oracle on a 40 x 40 crop with the global maxima injected: the crop must reproduce the device within 1e-6 m
+    # The oracle's OWN per-layer maxima of the full raster (nothing borrowed from the device): losreader.build_ray's restatement on
+    # the border pixels + every 20th row / column; the maximum of the smooth length field sits on the border, the interior
+    # sample checks that.  nParts must be the device's, bit for bit; the maxima agree to the 1e-8 m of K0's polynomial form.
     from oracle import raytrace as rt
+    own_max = _oracle_full_raster_maxima(cfg, rt.FixedIncidenceLOS(30.0, -168.0), rt.GeographicCRS())
+    own_np = np.ceil(own_max / cfg['max_segment_length']).astype(int) + 1
+    assert np.array_equal(own_np, info.nparts) and np.abs(own_max - info.maxlen).max() < 5e-8
+    # oracle on a 64 x 64 crop with ITS OWN full-raster maxima: the crop must reproduce the device within 1e-6 m
     crs = rt.GeographicCRS()
-    sl = slice(980, 1020)
+    sl = slice(968, 1032)
     want = rt.build_cube_ray(cfg['xpts'][sl], cfg['ypts'][sl], cfg['zpts'], rt.FixedIncidenceLOS(30.0, -168.0), crs, crs,
                              list(rt.get_interpolators(cfg['cube'])), MAX_SEGMENT_LENGTH=cfg['max_segment_length'],
-                             MAX_TROPO_HEIGHT=cfg['zref'], layer_maxlen=[info.maxlen])
+                             MAX_TROPO_HEIGHT=cfg['zref'], layer_maxlen=[own_max])
     assert np.abs(w[sl, sl] - want[0][0]).max() < TOL_F64_M and np.abs(h[sl, sl] - want[1][0]).max() < TOL_F64_M
+    assert np.abs(w[sl, sl] - want[0][0]).max() < 1e-9
+
+
+def _oracle_full_raster_maxima(cfg, los, pts_crs, model_zs=None, step=20, ht=0.0):
+    """Per-layer maxima of |P_hi - P_lo| over the full raster from the oracle alone: border + every `step`-th row / column."""
+    from oracle import geodesy, raytrace as rt
+    xp, yp = cfg['xpts'], cfg['ypts']
+    bx = np.concatenate([xp, xp, np.full(yp.size, xp[0]), np.full(yp.size, xp[-1])])
+    by = np.concatenate([np.full(xp.size, yp[0]), np.full(xp.size, yp[-1]), yp, yp])
+    ix, iy = np.meshgrid(xp[::step], yp[::step])
+    zs = cfg['cube']['z'] if model_zs is None else model_zs
+
+    def maxima(xx, yy):
+        xx, yy = xx.reshape(1, -1), yy.reshape(1, -1)
+        llh = [xx, yy, np.full(yy.shape, ht)]
+        xyz = np.stack(geodesy.lla2ecef(llh[1], llh[0], llh[2]), -1)
+        return rt.build_ray(zs, ht, xyz, los.getLookVectors(ht, llh, xyz, yy), cfg['zref'])[0].max((1, 2))
+    border, interior = maxima(bx, by), maxima(ix, iy)
+    assert np.all(interior <= border), 'the longest ray of a layer is not on the border of the raster'
+    return border
+
+
+def test_full_size_crops_c5_and_c3(gpu):
+    """64 x 64 crops out of FULL-SIZE C5 (2.4e8 rays, NZ = 72, row-tiled walk on one GPU) and C3 (8e7 rays over a 3 km Lambert cube,
+    fixed incidence) against the oracle run with its own full-raster maxima: step counts bit-exact, delays within 1e-6 m."""
+    from oracle import raytrace as rt
+    from raider_b200 import _lib, synthetic as syn
+    from raider_b200.engine import DeviceCube
+    enu = np.array([np.sin(np.radians(30)) * np.cos(np.radians(-78)), np.sin(np.radians(30)) * np.sin(np.radians(-78)), np.cos(np.radians(30))])
+    los = rt.FixedIncidenceLOS(30.0, -168.0)
+    for name, cfg, model_crs in (('c5', syn.config_c5(), None), ('c3', syn.config_c3(table='hrrr57'), 'lcc')):
+        ny, nx = cfg['ypts'].size, cfg['xpts'].size
+        cube = DeviceCube.from_dict(cfg['cube'])
+        import torch
+        w = torch.empty((ny, nx), dtype=torch.float64, device='cuda')
+        h = torch.empty((ny, nx), dtype=torch.float64, device='cuda')
+        info = cube.trace(_lib.GEOM_GRID, cfg['xpts'], cfg['ypts'], ny, nx, _lib.LOS_ENU_CONST, enu, 0.0, cfg['zref'], cfg['max_segment_length'], w, h)
+        torch.cuda.synchronize()
+        own_max = _oracle_full_raster_maxima(cfg, los, rt.GeographicCRS(), step=200)
+        own_np = np.ceil(own_max / cfg['max_segment_length']).astype(int) + 1
+        assert np.array_equal(own_np, info.nparts), name
+        assert np.abs(own_max - info.maxlen).max() < 5e-8, name
+        mcrs = rt.LambertCRS(**cfg['crs'].args) if model_crs else rt.GeographicCRS()
+        for r0, c0 in ((0, 0), (ny // 2 - 32, nx // 2 - 32), (ny - 64, nx - 64)):
+            rs, cs = slice(r0, r0 + 64), slice(c0, c0 + 64)
+            want = rt.build_cube_ray(cfg['xpts'][cs], cfg['ypts'][rs], cfg['zpts'], los, mcrs, rt.GeographicCRS(), list(rt.get_interpolators(cfg['cube'])),
+                                     MAX_SEGMENT_LENGTH=cfg['max_segment_length'], MAX_TROPO_HEIGHT=cfg['zref'], layer_maxlen=[own_max])
+            gw, gh = w[rs, cs].cpu().numpy(), h[rs, cs].cpu().numpy()
+            assert np.abs(gw - want[0][0]).max() < TOL_F64_M and np.abs(gh - want[1][0]).max() < TOL_F64_M, (name, r0, c0)
+            assert np.abs(gh - want[1][0]).max() < 1e-9, (name, r0, c0)
+        del cube, w, h
 
 
 def test_table_division_is_ieee_exact(gpu):
