@@ -20,9 +20,12 @@ Only ``tests/``, ``__graft_entry__.smoke()`` and the cpu-baseline / ``--impl ref
 ``bench.py`` may import this package, and only as the checker or the timed CPU baseline.  The
 product (``raider_b200``) never imports it and has no CPU fallback.
 
-Pin status (details in DESIGN.md): sampling, makePoints and interpolate* are pinned against the
-compiled reference natives and the reference's own vectors; the ray tracer is pinned by the
-reference's constant-refractivity identity (test/test_synthetic.py:217-274) and analytic
-checks; sub-micrometre parity with PROJ and isce3 look vectors is UNPINNED (neither library is
-available offline).
+Pin status (details in DESIGN.md section 7): sampling, makePoints and interpolate* are pinned bit for bit against the
+compiled reference natives and the reference's own vectors; the ray tracer (``oracle.raytrace``) is pinned BIT FOR BIT
+against the reference's own Python -- ``oracle.refpy`` imports RAiDER.delay / losreader / delayFcns / utilFcns unmodified
+from /root/reference under stand-ins for pyproj / xarray / rasterio / shapely, and tests/test_oracle_vs_reference_py.py
+compares every function; ``oracle.geodesy``'s spherical Lambert + ``build_cube`` reproduce the reference's own golden
+(test/test_HRRR_ztd.py:18) from the reference's real HDF5 cube to the 7 decimals the reference asserts.  What stays UNPINNED:
+PROJ's own rounding of the WGS-84 ``cart`` inverse below ~1e-9 m, and isce3's look vectors (``oracle.orbit``) -- neither
+library is available offline.
 """

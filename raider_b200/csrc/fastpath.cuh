@@ -253,10 +253,19 @@ __device__ __forceinline__ double cell_coord_clamped(double u, int n_nodes, int 
     return u - fl;
 }
 
-// per-ray constants of the sampler: the ground point's own cell coordinates and d(cell coordinate) / d(radian)
+// per-ray constants of the sampler: the ground point's own cell coordinates and d(cell coordinate) / d(radian);
+// for a Lambert cube: {uy0, ux0, ky, kx} = {sec phi_g, tan phi_g, rho_g, theta_g} of the ground point (node_eval<true>)
 struct RayCell {
     double uy0, ux0, ky, kx;
 };
+
+// R of a ray over a spherical-Lambert cube (PROJ lcc): rho_g = c tan(pi/4 + phi_g/2)^-n = c (cos phi_g / (1 + sin phi_g))^n,
+// theta_g = n (lam_g - lam_0) with the longitude difference wrapped into [-pi, pi]
+__device__ __forceinline__ RayCell ray_cell_lcc(const LccParams &P, double slat, double clat, double lon_deg) {
+    double lam = lon_deg * DEG_TO_RAD - P.lam0;
+    if (fabs(lam) > PI) lam -= 2.0 * PI * rint(lam / (2.0 * PI));
+    return RayCell{1.0 / clat, slat / clat, P.c * pow(clat / (1.0 + slat), P.n), lam * P.n};
+}
 
 // One sample of both fields at frame point (A, B, Z) of a ray: geodetic latitude / longitude / height, cell lookup, trilinear
 // value in lerp form.  Raises `bad` instead of handling any edge rule.
@@ -320,11 +329,40 @@ __device__ __forceinline__ RayNode node_eval(const FastCube &c, const RayFrame &
     const double A = fma(t, F.uA, F.A0), B = t * F.uB, Z = fma(t, F.uZ, F.Z0);
     RayNode n;
     if (LCC) {
-        double lon, lat;
-        ecef2lla(Vec3{A, B, Z}, lon, lat, n.h);
-        const double2 xy = lcc_forward(c.lcc, lon + F.lon0_deg, lat);
-        n.uy = fma(xy.y, c.y_inv, c.y_c0);
-        n.ux = fma(xy.x, c.x_inv, c.x_c0);
+        // Spherical Lambert forward (PROJ lcc, the HRRR grid) of a point a small angle (dphi, dlam) away from the ray's ground point,
+        // without pow / tan per node: with psi = ln tan(pi/4 + phi/2) the projection is rho = rho_g exp(-n (psi - psi_g)),
+        // theta = theta_g + n dlam, and psi - psi_g is the Taylor series of the integral of sec: its k-th derivative is
+        // sec(phi_g) p_k(tan phi_g), p_{k+1} = t p_k + (1 + t^2) p_k'.  Eight terms are exact to < 1e-8 m over the whole small-angle
+        // window (0.02 rad; profiles/lcc_series_accuracy.py), i.e. 4e-12 of a 3 km cell.  R = {sec phi_g, tan phi_g, rho_g, theta_g}.
+        const FrameBowring o = frame_bowring(A, B, Z);
+        n.h = frame_height(o);
+        const double slat = fma(o.y_phi, F.clat, -o.x_phi * F.slat) * o.rq;  // sin(phi - phi0)
+        const double slon = B * o.rp;                                        // sin(lam - lam0)
+        const double slat2 = slat * slat, slon2 = slon * slon;
+        bad |= !(slat2 <= c_fast.sin_window2) | !(slon2 <= c_fast.sin_window2);
+        const double d = asin_small(slat, slat2), dlam = asin_small(slon, slon2);
+        const double t = R.ux0, t2 = t * t;
+        const double c8 = t * fma(t2, fma(t2, fma(t2, 5040.0, 10920.0), 7266.0), 1385.0) * (1.0 / 40320.0);
+        const double c7 = fma(t2, fma(t2, fma(t2, 720.0, 1320.0), 662.0), 61.0) * (1.0 / 5040.0);
+        const double c6 = t * fma(t2, fma(t2, 120.0, 180.0), 61.0) * (1.0 / 720.0);
+        const double c5 = fma(t2, fma(t2, 24.0, 28.0), 5.0) * (1.0 / 120.0);
+        const double c4 = t * fma(t2, 6.0, 5.0) * (1.0 / 24.0);
+        const double c3 = fma(t2, 2.0, 1.0) * (1.0 / 6.0);
+        const double c2 = 0.5 * t;
+        double q = fma(d, c8, c7);
+        q = fma(d, q, c6);
+        q = fma(d, q, c5);
+        q = fma(d, q, c4);
+        q = fma(d, q, c3);
+        q = fma(d, q, c2);
+        q = fma(d, q, 1.0);
+        const double dpsi = (R.uy0 * d) * q;
+        const double rho = R.ky * exp(-c.lcc.n * dpsi);
+        double sn, cs;
+        sincos(fma(c.lcc.n, dlam, R.kx), &sn, &cs);
+        const double x = fma(c.lcc.R, rho * sn, c.lcc.x0), y = fma(c.lcc.R, c.lcc.rho0 - rho * cs, c.lcc.y0);
+        n.uy = fma(y, c.y_inv, c.y_c0);
+        n.ux = fma(x, c.x_inv, c.x_c0);
     } else {
         const FrameBowring o = frame_bowring(A, B, Z);
         n.h = frame_height(o);

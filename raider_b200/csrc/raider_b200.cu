@@ -1216,7 +1216,9 @@ __global__ void __launch_bounds__(256) k_plan(const unsigned long long *__restri
                 last_thin = k;
             }
         int k_split = 0;
-        if (thin_min > 0 && n_thin >= thin_min) {
+        if (thin_min < 0) {
+            k_split = K;  // unified mode: the staged kernel takes every layer (closed-form sums for the thick ones included)
+        } else if (thin_min > 0 && n_thin >= thin_min) {
             // cut where the thin layers stop dominating: the longest prefix in which >= 3/4 of the layers are thin
             int seen = 0;
             for (int k = 0; k <= last_thin; ++k) {
@@ -1542,9 +1544,9 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_ray_integrate_poly(const FastCu
         ray_latlon(G, rr, lat, lon);
         RayFrame F;
         frame_setup(lat, lon, G.ht, G.los_kind, G.los, rr, G.e, G.n, G.u, F);
-        const RayCell R = {fma(lat, c.y_inv, c.y_c0), fma(lon, c.x_inv, c.x_c0), ky, kx};
+        const RayCell R = LCC ? ray_cell_lcc(c.lcc, F.slat, F.clat, lon) : RayCell{fma(lat, c.y_inv, c.y_c0), fma(lon, c.x_inv, c.x_c0), ky, kx};
         const double unorm = norm3(Vec3{F.uA, F.uB, F.uZ});  // |P_hi - P_lo| = |t_hi - t_lo| |u|  (losreader.py:821)
-        bool bad = LCC ? false : !F.fast_ok;
+        bool bad = !F.fast_ok;   // (too close to the polar axis for the small-angle formulas: the PROJ-form kernel takes the ray)
         double acc_w = 0.0, acc_h = 0.0, vw, vh;
         double t_a = __ldcs(t_in + (int64_t)k0 * n_rays + rr), t_lo = t_a;
         // the along-ray distances stream from HBM: the top of the next layer and the end of the next span are requested one
@@ -1830,13 +1832,13 @@ __device__ __forceinline__ void trilinear_cell_s(uint32_t rec, double ty, double
 // 8 LDS.128 at ~30 cycles instead of 8 LDG.128 from L2 at ~600 under load (profiles/r02a: 59 % of the stall samples of the
 // unstaged kernel sit on the first use of those loads).  Samples whose cell is not staged (box too large for the capacity, z cell
 // off the span's range) read the record from global memory as before.
-template <typename OUT, int BLOCK, int MINB, bool LCC, bool STAGE>
+template <typename OUT, int BLOCK, int MINB, bool LCC, bool STAGE, bool QUAD>
 __global__ void __launch_bounds__(BLOCK, MINB) k_ray_integrate_thin(const FastCube c, const RayGeom G, int64_t n_rays,
                                                               const double *__restrict__ t_in, const DevPlan *__restrict__ P,
                                                               const double *__restrict__ znodes, int nz, double zmin, OUT *__restrict__ out_wet,
                                                               OUT *__restrict__ out_hydro, int accumulate, const PeerOut peers,
                                                               unsigned long long *__restrict__ counters, int *__restrict__ fix_list, int tile_map,
-                                                              const double *__restrict__ part, int pf_cells, int pf_t, int rec_cap,
+                                                              const double *__restrict__ part, int pf_cells, int quad, int rec_cap,
                                                               unsigned long long *__restrict__ stage_stats) {
     if (P->blocked) return;
     const int K = P->K, k_end = P->k_split, nspan = P->span_split;
@@ -1880,9 +1882,9 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_ray_integrate_thin(const FastCu
         ray_latlon(G, rr, lat, lon);
         RayFrame F;
         frame_setup(lat, lon, G.ht, G.los_kind, G.los, rr, G.e, G.n, G.u, F);
-        const RayCell R = {fma(lat, c.y_inv, c.y_c0), fma(lon, c.x_inv, c.x_c0), ky, kx};
+        const RayCell R = LCC ? ray_cell_lcc(c.lcc, F.slat, F.clat, lon) : RayCell{fma(lat, c.y_inv, c.y_c0), fma(lon, c.x_inv, c.x_c0), ky, kx};
         const double u6 = norm3(Vec3{F.uA, F.uB, F.uZ}) * 1.0e-6;  // |P_hi - P_lo| 1e-6 = |t_hi - t_lo| |u| 1e-6  (losreader.py:821, delay.py:315)
-        bool bad = LCC ? false : !F.fast_ok;
+        bool bad = !F.fast_ok;   // (too close to the polar axis for the small-angle formulas: the PROJ-form kernel takes the ray)
         double acc_w = 0.0, acc_h = 0.0, vw, vh;
         // the along-ray distances stream from HBM: a thin layer is ~200 cycles of work, a load from HBM takes 600 .. 900, so the
         // rows k + 1 .. k + THIN_TD are kept in flight as asynchronous copies (LDGSTS) into a per-thread ring in shared memory --
@@ -1922,6 +1924,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_ray_integrate_thin(const FastCu
             }
         };
         enter_cell(n0.uy, n0.ux);
+        // the last sample evaluated (the start of the next layer): height and fractions in the held horizontal cell
+        double last_h = clamp_low_first ? zmin : n0.h, last_ty = n0.uy - fy, last_tx = n0.ux - fx;
         Cubic py, px, ph;
         auto sample = [&](const LayerRec &L, double s, double &w_out, double &h_out) {
             const double s2 = s * s;  // Estrin, as in k_ray_integrate_poly (same rounding)
@@ -1938,6 +1942,9 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_ray_integrate_thin(const FastCu
             int iz = L.iz;
             double tz = fma(h, L.inv_dz, L.neg_zlo_inv);
             const bool own_cell = (h >= L.h_lo) & (h < L.h_hi);
+            last_h = h;
+            last_ty = ty;
+            last_tx = tx;
             if (STAGE && in_smem && own_cell) {
                 trilinear_cell_s(col_s + (uint32_t)iz * (uint32_t)sizeof(LerpCell), ty, tx, tz, w_out, h_out);
             } else {
@@ -2017,7 +2024,59 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_ray_integrate_thin(const FastCu
                 const double wt_full = (fabs(dt) * u6) * L.step;  // delay.py:315
                 const double wt_half = 0.5 * wt_full;
                 double ew, eh;
-                if (L.np == 2) {
+                bool layer_done = false;
+                if (STAGE && QUAD && quad && L.np >= 4 && in_smem) {
+                    // Layer quadrature exactly as in k_ray_integrate_poly (see there): the composite trapezoid sum of a layer whose
+                    // samples share one cube cell, in closed form from the values at its start, middle and end -- here with the
+                    // cell's record read from the staged column in shared memory instead of a register-held copy.
+                    const double s_lo = (t_lo - t_a) * inv_span, ds = dt * inv_span;
+                    const double sm = fma(0.5, ds, s_lo), se = s_lo + ds;
+                    const double sm2 = sm * sm, se2 = se * se;
+                    const double uym = fma(sm2, fma(sm, py.c3, py.c2), fma(sm, py.c1, py.c0)), uye = fma(se2, fma(se, py.c3, py.c2), fma(se, py.c1, py.c0));
+                    const double uxm = fma(sm2, fma(sm, px.c3, px.c2), fma(sm, px.c1, px.c0)), uxe = fma(se2, fma(se, px.c3, px.c2), fma(se, px.c1, px.c0));
+                    const double h_m = fma(sm2, fma(sm, ph.c3, ph.c2), fma(sm, ph.c1, ph.c0)), h_e = fma(se2, fma(se, ph.c3, ph.c2), fma(se, ph.c1, ph.c0));
+                    const double tym = uym - fy, txm = uxm - fx, tye = uye - fy, txe = uxe - fx;
+                    const unsigned hi_max = max(max((unsigned)__double2hiint(tym), (unsigned)__double2hiint(txm)),
+                                                max((unsigned)__double2hiint(tye), (unsigned)__double2hiint(txe)));
+                    const double z_hi = T.z[L.iz + 1];
+                    const bool top_cell = L.iz + 2 >= T.nz;  // nothing above: the end point must be inside (it is: zref < max(z))
+                    const bool one_cell = (hi_max < 0x3ff00000u) & (last_h >= L.z_lo - LAYER_QUAD_TOL) & (h_m >= L.z_lo) & (h_m < z_hi) &
+                                          (h_e >= L.z_lo) & (top_cell ? (h_e <= z_hi) : (h_e < z_hi + LAYER_QUAD_TOL));
+                    if (one_cell) {
+                        const uint32_t rec = col_s + (uint32_t)L.iz * (uint32_t)sizeof(LerpCell);
+                        double p0w = vw, p0h = vh, mw, mh, p1w, p1h;
+                        const double tz0 = fma(last_h, L.inv_dz, L.neg_zlo_inv), tzm = fma(h_m, L.inv_dz, L.neg_zlo_inv), tze = fma(h_e, L.inv_dz, L.neg_zlo_inv);
+                        if (last_h < L.z_lo) trilinear_cell_s(rec, last_ty, last_tx, tz0, p0w, p0h);  // start point below the cell
+                        trilinear_cell_s(rec, tym, txm, tzm, mw, mh);
+                        trilinear_cell_s(rec, tye, txe, tze, p1w, p1h);
+                        ew = p1w;
+                        eh = p1h;
+                        // the quartic term of the curved chord (see k_ray_integrate_poly): a7 (qy bx bz + by qx bz + by bx qz) kappa_n
+                        const double qy = 2.0 * ((last_ty + tye) - 2.0 * tym), by = (tye - last_ty) - qy;
+                        const double qx = 2.0 * ((last_tx + txe) - 2.0 * txm), bx = (txe - last_tx) - qx;
+                        const double qz = 2.0 * ((tz0 + tze) - 2.0 * tzm), bz = (tze - tz0) - qz;
+                        const double st2 = L.step * L.step;
+                        const double g4 = fma(qy, bx * bz, by * fma(qx, bz, bx * qz)) * fma(st2, fma(st2, -1.0 / 30.0, 1.0 / 24.0), -1.0 / 120.0);
+                        double a7w, a7h;
+                        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a7w), "=d"(a7h) : "r"(rec + 112u));  // q3.z, q3.w
+                        const double e4w = a7w * g4, e4h = a7h * g4;
+                        if (!top_cell && h_e >= z_hi)  // end point above the cell: its value in the cell it lies in (the next layer's; staged: lev0 .. + 1)
+                            trilinear_cell_s(rec + (uint32_t)sizeof(LerpCell), tye, txe, (h_e - z_hi) * T.inv[L.iz + 1], ew, eh);
+                        const double W = (fabs(dt) * u6), cn = st2 * (1.0 / 3.0), hn = 0.5 * L.step;
+                        double tw = fma(fma(-2.0, mw, p0w + p1w), cn, fma(fma(4.0, mw, p0w + p1w), 1.0 / 6.0, e4w));
+                        double th = fma(fma(-2.0, mh, p0h + p1h), cn, fma(fma(4.0, mh, p0h + p1h), 1.0 / 6.0, e4h));
+                        tw = fma((vw - p0w) + (ew - p1w), hn, tw);
+                        th = fma((vh - p0h) + (eh - p1h), hn, th);
+                        acc_w = fma(W, tw, acc_w);
+                        acc_h = fma(W, th, acc_h);
+                        last_h = h_e;
+                        last_ty = tye;
+                        last_tx = txe;
+                        layer_done = true;
+                    }
+                }
+                if (layer_done) {
+                } else if (L.np == 2) {
                     // one interval: 0.5 w (f(lo) + f(hi)); the sample at the layer top sits at t_hi
                     sample(L, (t_hi - t_a) * inv_span, ew, eh);
                     acc_w = fma(wt_half, vw + ew, acc_w);
@@ -3234,7 +3293,9 @@ static int plan_enqueue(rdr_handle_t h, const unsigned long long *slots, int wor
     const char *span_env = getenv("RDR_K3_SPAN");
     const double span_max = span_env && atof(span_env) > 0 ? atof(span_env) : 12000.0;
     const char *thin_env = getenv("RDR_K3_THIN_MIN");  // fewest thin layers (<= 3 samples) that are worth the thin-layer kernel; 0: never
-    const int thin_min = thin_env ? (atoi(thin_env) > 0 ? std::max(atoi(thin_env), 4) : 0) : 16;  // (the thin kernel preloads 4 rows of distances)
+    const char *uni_env = getenv("RDR_K3_UNIFIED");   // 1: every layer goes to the staged kernel (K >= 4 rows of distances are preloaded)
+    int thin_min = thin_env ? (atoi(thin_env) > 0 ? std::max(atoi(thin_env), 4) : 0) : 16;
+    if (uni_env && atoi(uni_env) != 0 && K >= 8) thin_min = -1;
     unsigned long long *counters = h->d_red.as<unsigned long long>() + XCHG_STRIDE;
     const int *d_cell = reinterpret_cast<const int *>(h->d_plan.as<double>() + 2 * (size_t)K);
     const double *znodes = h->d_axes.as<double>() + h->ny + h->nx;
@@ -3357,10 +3418,10 @@ static int k3_enqueue(rdr_handle_t h, void *out_wet, void *out_hydro, int out_dt
             CUDA_TRY(h, cudaGetLastError());
             if (h->thin_ok) {
                 // the thin-layer part of the plan (no-op when the plan has none); runs second and stores the results
-                const char *pfc_env = getenv("RDR_K3_THIN_PF"), *pft_env = getenv("RDR_K3_THIN_PFT"), *st_env = getenv("RDR_K3_THIN_STAGE");
+                const char *pfc_env = getenv("RDR_K3_THIN_PF"), *st_env = getenv("RDR_K3_THIN_STAGE");
                 const int pf_cells = pfc_env ? std::min(std::max(atoi(pfc_env), 0), LERP_PAD) : 0;
-                const int pf_t = pft_env ? std::max(atoi(pft_env), 0) : 6;
                 const int minb_t = tune_minb("RDR_K3_THIN_MINB", 4);
+                const int quad_t = !(quad_env && atoi(quad_env) == 0);
                 const int grid_t = grid_for(n, BLOCK, h->sm_count, 4 * minb_t);
                 // staged record columns (north_star: cube staged into shared memory via TMA): the records that fit beside minb_t CTAs per
                 // SM (227 KB per SM, 1 KB reserved per CTA), at most 48 KB worth
@@ -3371,27 +3432,30 @@ static int k3_enqueue(rdr_handle_t h, void *out_wet, void *out_hydro, int out_dt
                 const bool stage = rec_cap > 0;
                 const size_t smem_t = base_t + (size_t)rec_cap * sizeof(LerpCell);
                 unsigned long long *stage_stats = h->d_red.as<unsigned long long>() + XCHG_STRIDE + 4;
-#define RDR_LAUNCH_K3T(T, M, L, ST)                                                                                                        \
+#define RDR_LAUNCH_K3T(T, M, L, ST, Q)                                                                                                     \
     do {                                                                                                                                    \
-        CUDA_TRY(h, allow_smem(k_ray_integrate_thin<T, BLOCK, M, L, ST>, smem_t));                                                          \
-        if (ST) CUDA_TRY(h, cudaFuncSetAttribute(k_ray_integrate_thin<T, BLOCK, M, L, ST>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)); \
-        k_ray_integrate_thin<T, BLOCK, M, L, ST><<<grid_t, BLOCK, smem_t, h->stream>>>(fc, G, n, t_in, P, znodes, (int)h->nz, h->zs.front(), \
-                                                                                    static_cast<T *>(dw), static_cast<T *>(dh), accumulate, \
-                                                                                    peers, counters, h->d_fix.as<int>(), tile_thin, part,  \
-                                                                                    pf_cells, pf_t, rec_cap, stage_stats);                 \
+        CUDA_TRY(h, allow_smem(k_ray_integrate_thin<T, BLOCK, M, L, ST, Q>, smem_t));                                                       \
+        if (ST) CUDA_TRY(h, cudaFuncSetAttribute(k_ray_integrate_thin<T, BLOCK, M, L, ST, Q>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)); \
+        k_ray_integrate_thin<T, BLOCK, M, L, ST, Q><<<grid_t, BLOCK, smem_t, h->stream>>>(fc, G, n, t_in, P, znodes, (int)h->nz, h->zs.front(), \
+                                                                                       static_cast<T *>(dw), static_cast<T *>(dh), accumulate, \
+                                                                                       peers, counters, h->d_fix.as<int>(), tile_thin, part,  \
+                                                                                       pf_cells, quad_t, rec_cap, stage_stats);               \
     } while (0)
+    // QUAD (closed-form sums of thick layers inside the staged kernel) is only built for the unified mode (RDR_K3_UNIFIED=1), the A/B of
+    // "cell records in shared memory" against k_ray_integrate_poly's register-held record: it costs the thin-layer loop registers
 #define RDR_LAUNCH_K3T_S(T, M, L) \
-    do { if (stage) RDR_LAUNCH_K3T(T, M, L, true); else RDR_LAUNCH_K3T(T, M, L, false); } while (0)
+    do { if (stage) RDR_LAUNCH_K3T(T, M, L, true, false); else RDR_LAUNCH_K3T(T, M, L, false, false); } while (0)
 #define RDR_LAUNCH_K3T_M(T, L)                          \
     switch (minb_t) {                                   \
-        case 4: RDR_LAUNCH_K3T_S(T, 4, L); break;       \
+        case 3: RDR_LAUNCH_K3T_S(T, 3, L); break;       \
         case 5: RDR_LAUNCH_K3T_S(T, 5, L); break;       \
-        default: RDR_LAUNCH_K3T_S(T, 3, L); break;      \
+        default: if (unified && stage) RDR_LAUNCH_K3T(T, 4, L, true, true); else RDR_LAUNCH_K3T_S(T, 4, L); break; \
     }
+                const bool unified = getenv("RDR_K3_UNIFIED") && atoi(getenv("RDR_K3_UNIFIED")) != 0;
                 if (out_dtype == RDR_F64) {
                     if (lcc) { RDR_LAUNCH_K3T_M(double, true) } else { RDR_LAUNCH_K3T_M(double, false) }
                 } else {
-                    if (lcc) RDR_LAUNCH_K3T_S(float, 3, true); else RDR_LAUNCH_K3T_S(float, 3, false);
+                    if (lcc) RDR_LAUNCH_K3T_S(float, 4, true); else RDR_LAUNCH_K3T_S(float, 4, false);
                 }
 #undef RDR_LAUNCH_K3T_M
 #undef RDR_LAUNCH_K3T_S

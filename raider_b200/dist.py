@@ -137,9 +137,11 @@ class SymmetricMaps:
         self.base = [int(a) for a in self.hdl.buffer_ptrs]
         if len(self.base) != comm.world or self.base[comm.rank] != self.maps.data_ptr():
             raise RuntimeError('symmetric-memory rendezvous returned unexpected buffer pointers')
-        # NVLink-SHARP multicast mapping of the maps (0 when the fabric / driver offers none): one store reaches every GPU
+        # NVLink-SHARP multicast mapping of the maps (0 when the fabric / driver offers none): one multimem.st reaches every GPU.
+        # Opt-in (RAIDER_B200_MULTICAST=1): measured on 8 x B200 it is correct (maps == NCCL all-gather) but not faster than one
+        # plain peer store per GPU -- 3.82 vs 3.65 .. 3.87 ms per C2 step (profiles/r02g_*) -- so the proven path stays the default
         import os
-        self.mc_base = 0 if os.environ.get('RAIDER_B200_NO_MULTICAST') else int(getattr(self.hdl, 'multicast_ptr', 0) or 0)
+        self.mc_base = int(getattr(self.hdl, 'multicast_ptr', 0) or 0) if os.environ.get('RAIDER_B200_MULTICAST') == '1' else 0
         # exchange slots of the device-side plan (rdr_set_exchange): 2 parities x world slots of K + 3 words per rank
         from . import _lib
         words = int(_lib.load().rdr_exchange_bytes(comm.world)) // 8
