@@ -25,7 +25,9 @@ compiled reference natives and the reference's own vectors; the ray tracer (``or
 against the reference's own Python -- ``oracle.refpy`` imports RAiDER.delay / losreader / delayFcns / utilFcns unmodified
 from /root/reference under stand-ins for pyproj / xarray / rasterio / shapely, and tests/test_oracle_vs_reference_py.py
 compares every function; ``oracle.geodesy``'s spherical Lambert + ``build_cube`` reproduce the reference's own golden
-(test/test_HRRR_ztd.py:18) from the reference's real HDF5 cube to the 7 decimals the reference asserts.  What stays UNPINNED:
-PROJ's own rounding of the WGS-84 ``cart`` inverse below ~1e-9 m, and isce3's look vectors (``oracle.orbit``) -- neither
-library is available offline.
+(test/test_HRRR_ztd.py:18) from the reference's real HDF5 cube to the 7 decimals the reference asserts; ``oracle.orbit`` (isce3's
+Hermite interpolation + zero-Doppler solve) standing in for isce3 under the reference's own Raytracing class reproduces the
+reference's end-to-end ray-tracing golden (test/test_slant.py:99) to 5e-8 m.  What stays UNPINNED: PROJ's own rounding of the
+WGS-84 ``cart`` inverse below ~1e-9 m and isce3's rounding below ~2e-8 rad of look direction -- neither library is available
+offline.
 """

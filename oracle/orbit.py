@@ -19,11 +19,17 @@ The arithmetic lives in a third-party dependency that is absent from /root/refer
   else ``aztime -= f / f'`` with ``f = dr . v - fdop * |dr|``, ``f' = -v . v + (fdop / |dr| + dfdop/dr) (dr . v)``
   (``fdop = 0`` for the zero-Doppler LUT the reference passes); not converged after ``maxiter`` -> failure.
 
-PARITY UNPINNED against isce3 itself (not available offline).  Pinned instead by closed forms
-(tests/test_oracle_pins.py): a circular orbit (the construction of test/fake_raytracing:73-117) where zero-Doppler
-time and slant range are known analytically, Hermite interpolation reproducing its nodes and a degree-7 polynomial orbit
-exactly, and the zero-Doppler property ``(sat - target) . v_sat = 0`` on the reference's Sentinel-1 state vectors
-(test/orbit_files/S1_sv_file.txt = test/test_losreader.py:20-92).
+PIN STATUS.  isce3 itself is not available offline, so there is no bit-for-bit pin of these two routines.  They are pinned
+END TO END by the reference's own golden: ``test/test_slant.py:99`` (2.97711681 m: ``Raytracing`` on the Sentinel-1 precise-orbit
+file ``test/orbit_files/S1B_OPER_AUX_POEORB_...EOF`` through the reference's ERA-5 cube) is reproduced to 5e-8 m -- inside the 7
+decimals the reference asserts -- by the reference's own Python with THIS module standing in for isce3
+(tests/test_oracle_vs_reference_py.py::test_reference_goldens_of_test_slant_are_reproduced, and from the committed fixture in
+tests/test_oracle_pins.py).  A slant delay moves by about 2.5 m per radian of look direction at that geometry, so the golden
+bounds the look-vector error of this restatement at ~2e-8 rad (centimetres of sensor position).  Below that, parity with isce3's
+own rounding is unpinned.  Closed forms pin the pieces as well (tests/test_oracle_pins.py): a circular orbit (the construction of
+test/fake_raytracing:73-117) where zero-Doppler time and slant range are known analytically, Hermite interpolation reproducing
+its nodes and a degree-7 polynomial orbit exactly, and the zero-Doppler property ``(sat - target) . v_sat = 0`` on the reference's
+Sentinel-1 state vectors (test/orbit_files/S1_sv_file.txt = test/test_losreader.py:20-92).
 """
 from __future__ import annotations
 
@@ -118,6 +124,13 @@ def geo2rdr(target_xyz, orbit: Orbit, threshold: float = 1.0e-7, maxiter: int = 
     raise RuntimeError('geo2rdr failed to converge')
 
 
+def geo2rdr_llh(lon_rad: float, lat_rad: float, hgt: float, orbit: Orbit, threshold: float = 1.0e-7, maxiter: int = 30):
+    """``isce3.geometry.geo2rdr(llh, ellipsoid, orbit, ...)`` as losreader.py:240-250 calls it: the target is given as
+    (lon, lat) in RADIANS + height and converted to ECEF on the WGS84 ellipsoid (``Ellipsoid::lonLatToXyz``) before the solve."""
+    xyz = np.array(geodesy.lla2ecef(np.rad2deg(lat_rad), np.rad2deg(lon_rad), hgt), dtype=np.float64)
+    return geo2rdr(xyz, orbit, threshold=threshold, maxiter=maxiter)
+
+
 class OrbitLOS:
     """LOS provider with the duck type of losreader.py:219-255: ECEF unit vectors ground -> sensor from an orbit."""
 
@@ -127,15 +140,16 @@ class OrbitLOS:
     def getLookVectors(self, ht, llh, xyz, yy):
         yy = np.asarray(yy)
         los = np.full(yy.shape + (3,), np.nan)
+        lon_r, lat_r = np.deg2rad(llh[0]), np.deg2rad(llh[1])    # losreader.py:226-228
         for ii in range(yy.shape[0]):
             for jj in range(yy.shape[1]):
                 p = xyz[ii, jj, :]
-                if np.isnan(p).any() or np.isnan(llh[0][ii, jj]) or np.isnan(llh[1][ii, jj]):
+                if np.isnan(p).any() or np.isnan(lon_r[ii, jj]) or np.isnan(lat_r[ii, jj]) or np.isnan(ht):
                     continue
                 try:
-                    aztime, slant = geo2rdr(p, self.orbit)
+                    aztime, slant = geo2rdr_llh(lon_r[ii, jj], lat_r[ii, jj], ht, self.orbit)   # the solve sees llh ...
                     sat, _ = self.orbit.interpolate(aztime)
-                    los[ii, jj, :] = (sat - p) / slant
+                    los[ii, jj, :] = (sat - p) / slant                                         # ... the vector the caller's xyz
                 except RuntimeError:
                     pass
         return los
@@ -145,4 +159,13 @@ def look_vectors_points(lat, lon, hgt, orbit: Orbit):
     """Look vectors for flat point lists (lat, lon in degrees)."""
     lat, lon, hgt = (np.atleast_1d(np.asarray(a, dtype=np.float64)) for a in (lat, lon, hgt))
     xyz = np.stack(geodesy.lla2ecef(lat, lon, hgt), axis=-1)
-    return OrbitLOS(orbit).getLookVectors(0.0, [lon[None], lat[None], hgt[None]], xyz[None], lat[None])[0]
+    los = np.full(lat.shape + (3,), np.nan)
+    for i in range(lat.size):
+        if np.isnan(xyz[i]).any():
+            continue
+        try:
+            aztime, slant = geo2rdr(xyz[i], orbit)
+            los[i] = (orbit.interpolate(aztime)[0] - xyz[i]) / slant
+        except RuntimeError:
+            pass
+    return los

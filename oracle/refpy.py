@@ -114,6 +114,10 @@ class CRS:
     def to_wkt(self):
         return f'STANDIN[{self.kind},{sorted(self.params.items())}]'
 
+    @property
+    def axis_info(self):   # utilFcns.transform_bbox (utilFcns.py:598) reads axis_info[0].unit_name
+        return [types.SimpleNamespace(unit_name='degree' if self.kind == 'geographic' else 'metre')]
+
     def __eq__(self, other):
         if not isinstance(other, CRS):
             try:
@@ -201,6 +205,95 @@ def dataset(cube: dict) -> Dataset:
     return Dataset({k: np.asarray(v) for k, v in cube.items()})
 
 
+# ------------------------------------------------------------------------------------------------------------------
+# isce3 stand-in: the six names losreader.py uses (losreader.py:24,193-198,240-251,593-598,656-686,751-767), backed by
+# the restatement of isce3's published algorithms in oracle/orbit.py.  With it the reference's own Raytracing /
+# Conventional classes, get_orbit and state_to_los run unmodified; what that pins is the CALL STRUCTURE around isce3.
+# isce3's arithmetic itself is pinned only through the reference's end-to-end golden (test/test_slant.py:99), which
+# tests/test_oracle_vs_reference_py.py reproduces with this stand-in.
+# ------------------------------------------------------------------------------------------------------------------
+class _IsceDateTime:
+    def __init__(self, t):
+        self.t = t.t if isinstance(t, _IsceDateTime) else t
+
+    def _key(self):
+        return self.t
+
+    def __eq__(self, other):
+        return isinstance(other, _IsceDateTime) and self.t == other.t
+
+    def __lt__(self, other):
+        return self.t < other.t
+
+    def __hash__(self):
+        return hash(self.t)
+
+
+class _IsceStateVector:
+    def __init__(self, datetime, position, velocity):
+        self.datetime = _IsceDateTime(datetime)
+        self.position = np.asarray(position, dtype=np.float64)
+        self.velocity = np.asarray(velocity, dtype=np.float64)
+
+
+class _IsceOrbit:
+    """isce3.core.Orbit: the reference epoch is the first state vector's time; times are seconds since it."""
+
+    def __init__(self, svs):
+        from . import orbit as _orbit
+        self.reference_epoch = svs[0].datetime
+        t = np.array([(sv.datetime.t - self.reference_epoch.t).total_seconds() for sv in svs], dtype=np.float64)
+        if np.any(np.diff(t) <= 0):
+            raise ValueError('isce3.core.Orbit needs uniformly spaced, increasing state vectors')
+        self._o = _orbit.Orbit(t, np.stack([sv.position for sv in svs]), np.stack([sv.velocity for sv in svs]))
+
+    @property
+    def time(self):
+        return self._o.t
+
+    @property
+    def position(self):
+        return self._o.pos
+
+    @property
+    def velocity(self):
+        return self._o.vel
+
+    def interpolate(self, t):
+        pos, vel = self._o.interpolate(float(t))
+        if np.isnan(pos).any():
+            raise ValueError('orbit interpolation outside the state vectors')  # OrbitInterpBorderMode::Error (default)
+        return pos, vel
+
+
+class _IsceEllipsoid:
+    a, e2 = geodesy.WGS84_A, geodesy.WGS84_ES
+
+    @staticmethod
+    def n_vector(lon, lat):
+        return np.array([np.cos(lat) * np.cos(lon), np.cos(lat) * np.sin(lon), np.sin(lat)])
+
+
+def _isce_geo2rdr(llh, ellipsoid, orbit, doppler, wavelength, side, threshold=1.0e-8, maxiter=50, delta_range=10.0):
+    from . import orbit as _orbit
+    lon, lat, h = (float(v) for v in llh)
+    return _orbit.geo2rdr_llh(lon, lat, h, orbit._o, threshold=threshold, maxiter=maxiter)
+
+
+def _isce_modules():
+    look = types.SimpleNamespace(Right='right', Left='left')
+    core = _module('isce3.ext.isce3.core', Orbit=_IsceOrbit, StateVector=_IsceStateVector, DateTime=_IsceDateTime,
+                   Ellipsoid=_IsceEllipsoid, LUT2d=type('LUT2d', (), {}), LookSide=look)
+    geometry = _module('isce3.ext.isce3.geometry', geo2rdr=_isce_geo2rdr)
+    inner = _module('isce3.ext.isce3', core=core, geometry=geometry)
+    ext = _module('isce3.ext', isce3=inner)
+    top = _module('isce3', ext=ext, core=core, geometry=geometry)
+    for m in (top, ext, inner):
+        m.__path__ = []
+    return {'isce3': top, 'isce3.ext': ext, 'isce3.ext.isce3': inner, 'isce3.ext.isce3.core': core,
+            'isce3.ext.isce3.geometry': geometry}
+
+
 def _module(name: str, **attrs) -> types.ModuleType:
     m = types.ModuleType(name)
     m.__dict__.update(attrs)
@@ -231,6 +324,7 @@ def load():
         'shapely': _module('shapely'),
         'shapely.geometry': _module('shapely.geometry', Polygon=object, Point=object, box=None),
     }
+    installs.update(_isce_modules())
     installs['rasterio.crs'] = installs['rasterio'].crs
     installs['rasterio.transform'] = installs['rasterio'].transform
     installs['rasterio'].__path__ = []

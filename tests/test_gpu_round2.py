@@ -198,6 +198,34 @@ def test_reference_golden_hrrr_ztd_on_device(gpu):
     assert np.abs(got[0] - want[0]).max() < 1e-12 and np.abs(got[1] - want[1]).max() < 1e-12
 
 
+def test_reference_goldens_of_test_slant_on_device(gpu):
+    """test/test_slant.py:49 (2.333865144 m) and :99 (2.97711681 m) through the CUDA path, on the reference's own ERA-5 cube (145
+    z-nodes, real refractivity), the AOI grid the reference builds (90 x 90 x 4 heights) and a Sentinel-1 precise orbit: LOS solved
+    on the device (geo2rdr), K0, K3.  The whole cubes are compared with what the REFERENCE'S OWN PYTHON produced in the build
+    container (tests/golden/make_golden_era5_slant.py; fixture tests/golden/era5_slant_ref.npz), tolerance 1e-6 m."""
+    import datetime as dt
+    from pathlib import Path
+    from raider_b200.delay import _build_cube, _build_cube_ray
+    from raider_b200.delayFcns import getInterpolators
+    from raider_b200.losreader import Raytracing
+    gold = Path(__file__).resolve().parent / 'golden'
+    fx = np.load(gold / 'era5_slant_ref.npz')
+    cube = {k: fx[k] for k in ('x', 'y', 'z', 'wet', 'hydro', 'wet_total', 'hydro_total')}
+    iy, ix = fx['gold_index']
+    zw, zh = _build_cube(fx['xpts'], fx['ypts'], fx['zpts'], 4326, 4326, list(getInterpolators(cube, 'total')))
+    np.testing.assert_almost_equal(float(fx['gold_std']), (zw + zh)[0, iy, ix])           # 7 decimals, as the reference asserts
+    assert np.abs(zw - fx['ref_ztd_wet']).max() < 1e-12 and np.abs(zh - fx['ref_ztd_hydro']).max() < 1e-12
+    los = Raytracing(filename=str(gold / 'orbit_S1B_20200130_sv.txt'), time=dt.datetime.fromisoformat(str(fx['time'])))
+    assert los.getSensorDirection() == 'desc'
+    ifs = getInterpolators(cube)
+    rw, rh = _build_cube_ray(fx['xpts'], fx['ypts'], fx['zpts'], los, 4326, 4326, list(ifs), MAX_TROPO_HEIGHT=float(fx['zref']))
+    np.testing.assert_almost_equal(float(fx['gold_ray']), (rw + rh)[0, iy, ix])
+    assert not np.isnan(rw).any() and not np.isnan(rh).any()
+    assert np.abs(rw - fx['ref_ray_wet']).max() < TOL_F64_M and np.abs(rh - fx['ref_ray_hydro']).max() < TOL_F64_M
+    info = ifs[0].cube.last_info
+    assert len(info) == 4 and all(i.n_layers > 100 for i in info)      # the 145-node production table
+
+
 def test_ray_tracing_through_the_references_hrrr_cube(gpu):
     """Slant delays through the REAL refractivity fields of the reference's HRRR cube (3 km Lambert grid, the 57-node table of
     models/model_levels.py:517 as the file holds it) against the oracle: real data, real level table, projected model CRS."""

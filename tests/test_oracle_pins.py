@@ -331,6 +331,33 @@ def test_orbit_los_on_reference_state_vectors():
 
 
 # ---------------------------------------------------------------------------------------- weather-model processing (f4)
+def test_oracle_reproduces_the_references_test_slant_goldens_from_the_fixture():
+    """test/test_slant.py:49 (2.333865144 m) and :99 (2.97711681 m): the oracle alone (oracle.orbit's isce3 restatement +
+    oracle.raytrace) on the committed fixture -- the reference's ERA-5 cube, the AOI grid the reference builds, the state vectors
+    its get_sv keeps -- to the 7 decimals the reference asserts, and bitwise equal to the cubes the reference's own Python gave
+    in the build container (tests/golden/make_golden_era5_slant.py).  This is what pins oracle/orbit.py on the GPU box."""
+    from pathlib import Path
+    from oracle import orbit as ob
+    from raider_b200.losreader import read_txt_file
+    gold = Path(__file__).resolve().parent / 'golden'
+    fx = np.load(gold / 'era5_slant_ref.npz')
+    cube = {k: fx[k] for k in ('x', 'y', 'z', 'wet', 'hydro', 'wet_total', 'hydro_total')}
+    iy, ix = fx['gold_index']
+    crs = rt.GeographicCRS()
+    zw, zh = rt.build_cube(fx['xpts'], fx['ypts'], fx['zpts'], crs, crs, list(rt.get_interpolators(cube, 'total')))
+    np.testing.assert_almost_equal(float(fx['gold_std']), (zw + zh)[0, iy, ix])
+    assert np.array_equal(zw, fx['ref_ztd_wet']) and np.array_equal(zh, fx['ref_ztd_hydro'])
+    sv = read_txt_file(str(gold / 'orbit_S1B_20200130_sv.txt'))
+    t = np.array([(v - sv[0][0]).total_seconds() for v in sv[0]])
+    orbit = ob.Orbit(t, np.stack(sv[1:4], -1), np.stack(sv[4:7], -1))
+    st = {}
+    pw, ph = rt.build_cube_ray(fx['xpts'], fx['ypts'], fx['zpts'][:1], ob.OrbitLOS(orbit), crs, crs, list(rt.get_interpolators(cube)),
+                               MAX_TROPO_HEIGHT=float(fx['zref']), stats=st)
+    np.testing.assert_almost_equal(float(fx['gold_ray']), (pw + ph)[0, iy, ix])
+    assert np.array_equal(pw[0], fx['ref_ray_wet'][0]) and np.array_equal(ph[0], fx['ref_ray_hydro'][0])
+    assert st['nParts'][0].size == 137          # the 145-node production table (models/model_levels.py:12) above 0 m, real data
+
+
 def test_uniform_in_z_small_known_answer():
     """test/test_weather_model.py:178-211, value for value."""
     from oracle import weather as ow

@@ -313,3 +313,41 @@ def test_los_contract_matches_reference_classes(ref):
     c.setPoints(lats, lons, hts)
     d = rng.uniform(1, 3, size=(4, 5))
     assert same(c(d), d / ref.losreader.inc_hd_to_enu(np.float64(30.0), np.float64(0.0))[..., -1])
+
+
+# ------------------------------------------------------------------- the reference's end-to-end goldens of the slant path
+def test_reference_goldens_of_test_slant_are_reproduced(ref):
+    """test/test_slant.py:49 (2.333865144 m, projected LOS on a cube = zenith totals) and :99 (2.97711681 m, Raytracing through a
+    Sentinel-1 precise-orbit file) on the reference's own ERA-5 cube, to the 7 decimals the reference asserts: reference AOI
+    grid + reference Raytracing / get_orbit / _build_cube_ray, with the NetCDF-4 file read by raider_b200.hdf5_lite and isce3
+    replaced by oracle/orbit.py's restatement -- THE pin of that restatement.  The port (oracle.raytrace + oracle.orbit.OrbitLOS)
+    is bitwise equal to the reference run, and the committed fixture (tests/golden/era5_slant_ref.npz) holds exactly these
+    arrays.  One height only here (8100 Newton solves in pure Python); make_golden_era5_slant.py ran all four."""
+    import sys
+    from pathlib import Path
+    from oracle import orbit as ob
+    sys.path.insert(0, str(Path(__file__).resolve().parent / 'golden'))
+    import make_golden_era5_slant as mk
+    fx = np.load(Path(__file__).resolve().parent / 'golden' / 'era5_slant_ref.npz')
+    _, cube, aoi = mk.reference_setup()
+    assert np.array_equal(aoi.xpts, fx['xpts']) and np.array_equal(aoi.ypts, fx['ypts'])
+    for k in ('x', 'y', 'z', 'wet', 'hydro', 'wet_total', 'hydro_total'):
+        assert same(cube[k], fx[k])
+    iy, ix = mk.gold_index(aoi)
+    assert (iy, ix) == tuple(fx['gold_index'])
+    zw, zh = mk.reference_ztd(ref, cube, aoi, fx['zpts'])
+    np.testing.assert_almost_equal(mk.GOLD_STD, (zw + zh)[0, iy, ix])
+    assert same(zw, fx['ref_ztd_wet']) and same(zh, fx['ref_ztd_hydro'])
+    z0 = fx['zpts'][:1]
+    (rw, rh), los, toa = mk.reference_ray(ref, cube, aoi, z0)
+    np.testing.assert_almost_equal(mk.GOLD_RAY, (rw + rh)[0, iy, ix])
+    assert toa == float(fx['zref']) and same(rw[0], fx['ref_ray_wet'][0]) and same(rh[0], fx['ref_ray_hydro'][0])
+    o = los._orbit
+    crs = rt.GeographicCRS()
+    pw, ph = rt.build_cube_ray(aoi.xpts, aoi.ypts, z0, ob.OrbitLOS(ob.Orbit(o.time, o.position, o.velocity)), crs, crs,
+                               list(rt.get_interpolators(cube)), MAX_TROPO_HEIGHT=toa)
+    assert same(pw, rw) and same(ph, rh)
+    # the state vectors of the fixture's text file are the ones get_sv kept
+    from raider_b200.losreader import read_txt_file
+    sv = read_txt_file(str(Path(__file__).resolve().parent / 'golden' / 'orbit_S1B_20200130_sv.txt'))
+    assert np.array_equal(np.stack(sv[1:4], -1), o.position) and np.array_equal(np.stack(sv[4:7], -1), o.velocity)
