@@ -1010,8 +1010,34 @@ __device__ __forceinline__ double septic_top_of_atmosphere(const Septic &S, doub
     return t;
 }
 
+// The layer tops as ONE polynomial in the level height.  What the reference stores for a layer top is not the root of h(t) = z but
+// the third iterate of its fixed-slope Newton scheme started at t = z (losreader.py:720-733 with factor = the first layer's cos
+// factor): T(z) = g_z(g_z(g_z(z))), g_z(t) = t + (z - h(t)) / factor.  For one ray that is a smooth function of z alone (h(t) is
+// the septic above, the factor is fixed once the first layer is done), and the degree-7 interpolant through its values at the
+// eight Chebyshev nodes of [top of layer 1, top of layer K - 1] misses it by <= 1.6e-8 m up to 70 deg incidence through the
+// 80 km of the 145-node tables (<= 1e-8 m up to 60 deg; profiles/k0_tfit_accuracy.py) -- the size of the rounding noise of the
+// PROJ-form height that the septic itself carries.  A layer top is then 7 DFMA (two layers interleaved: no dependent chain
+// between them) instead of three dependent Horner evaluations (30 DFMA): per ray 8 x 30 for the nodes + 56 for the coefficients
+// + 7 K, i.e. 1270 instead of 4170 DFMA on the 145-node tables.  The first layer (ten iterations at factor 1, which defines the
+// factor) is evaluated as before.  Layer x positions are ray independent: s_x[k], computed once per CTA.
+__constant__ double c_tfit_u[8] = {  // (x_j + 1) / 2, x_j = cos(pi (2 j + 1) / 16)
+    0.9903926402016152, 0.9157348061512726, 0.7777851165098011, 0.5975451610080641,
+    0.40245483899193585, 0.22221488349019886, 0.08426519384872738, 0.009607359798384785};
+__constant__ double c_tfit_inv[8][8] = {  // inverse Vandermonde matrix of the Chebyshev nodes (monomials in x), 50-digit arithmetic rounded once
+    {-0.02486404592245725, 0.08352232973991236, -0.18707572033318612, 0.628417436515731, 0.628417436515731, -0.18707572033318612, 0.08352232973991236, -0.02486404592245725},
+    {-0.025351161379823003, 0.10045145186799834, -0.3367274004519704, 3.2211615113525687, -3.2211615113525687, 0.3367274004519704, -0.10045145186799834, 0.025351161379823003},
+    {0.7698016495254523, -2.5519026177451503, 5.380329742491341, -3.5982287742716426, -3.5982287742716426, 5.380329742491341, -2.5519026177451503, 0.7698016495254523},
+    {0.7848829554303298, -3.069147182274407, 9.684337681751762, -18.443912220177555, 18.443912220177555, -9.684337681751762, 3.069147182274407, -0.7848829554303298},
+    {-3.1779876260079822, 9.672340827762346, -12.500767952508536, 6.006414750754172, 6.006414750754172, -12.500767952508536, 9.672340827762346, -3.1779876260079822},
+    {-3.2402480843731825, 11.632825402935941, -22.500787856406752, 30.787866300500635, -30.787866300500635, 22.500787856406752, -11.632825402935941, 3.2402480843731825},
+    {3.0614674589207183, -7.391036260090294, 7.391036260090294, -3.0614674589207183, -3.0614674589207183, 7.391036260090294, -7.391036260090294, 3.0614674589207183},
+    {3.1214451522580524, -8.889123728313635, 13.303513796840724, -15.692564486451687, 15.692564486451687, -13.303513796840724, 8.889123728313635, -3.1214451522580524},
+};
+constexpr int K0_TFIT_MIN = 16;  // fewest layers for which the fit pays (8 node solves = 8 layers' worth of iterations)
+
 // returns false (nothing stored or counted) when a ray of the warp is too long for the polynomial: the caller redoes the warp exactly.
-// s_plan: low[K] | high[K] in shared memory.
+// s_plan: low[K] | high[K] | x[K] (fit coordinate of the layer tops, TFIT only) in shared memory.
+template <bool TFIT>
 __device__ __forceinline__ bool ray_layers_septic(const RayFrame &F, double ht, int K, const double *__restrict__ s_plan,
                                                   double *__restrict__ t_out, int64_t n_rays, int64_t r, bool valid, int lane, double zmin,
                                                   unsigned long long *smax, bool &any_nan) {
@@ -1055,18 +1081,62 @@ __device__ __forceinline__ bool ray_layers_septic(const RayFrame &F, double ht, 
     }
     double *tp = t_out + r;
     if (valid) __stcs(tp, t_lo);
-    for (int k = 0;;) {
+    // top of layer k at distance t_top, the layer's chord length: store, NaN flag, warp maximum
+    auto emit = [&](int k, double t_top, double length) {
         tp += n_rays;
-        if (valid) __stcs(tp, t_hi);
-        const bool isn = !(len == len);
+        if (valid) __stcs(tp, t_top);
+        const bool isn = !(length == length);
         any_nan |= isn;
-        const unsigned long long bits = (valid && !isn) ? (unsigned long long)__double_as_longlong(len) : 0ull;
+        const unsigned long long bits = (valid && !isn) ? (unsigned long long)__double_as_longlong(length) : 0ull;
         const unsigned long long m = warp_max_bits(bits);
         if (lane == 0 && m > smax[k]) atomicMax(&smax[k], m);
-        if (++k == K) break;
-        t_lo = t_hi;
-        t_hi = septic_top_of_atmosphere<3>(S, s_plan[K + k], rcosf);
-        len = fabs(t_hi - t_lo) * unorm;
+    };
+    emit(0, t_hi, len);
+    if (TFIT) {
+        double c[8];
+        {
+            const double zA = s_plan[K + 1], dz = s_plan[2 * K - 1] - zA;
+            double T[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) T[j] = septic_top_of_atmosphere<3>(S, fma(c_tfit_u[j], dz, zA), rcosf);  // eight independent chains
+#pragma unroll
+            for (int j = 1; j < 8; ++j) T[j] -= T[0];  // (row sums of the inverse: 1 for k = 0, 0 above -- the constant goes back into c0)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                double a = c_tfit_inv[k][1] * T[1];
+#pragma unroll
+                for (int j = 2; j < 8; ++j) a = fma(c_tfit_inv[k][j], T[j], a);
+                c[k] = a;
+            }
+            c[0] += T[0];
+        }
+        const double *s_x = s_plan + 2 * K;
+        int k = 1;
+        for (; k + 1 < K; k += 2) {  // two layers at a time: independent Horner chains
+            const double x0 = s_x[k], x1 = s_x[k + 1];
+            double r0 = fma(x0, c[7], c[6]), r1 = fma(x1, c[7], c[6]);
+#pragma unroll
+            for (int i = 5; i >= 0; --i) {
+                r0 = fma(x0, r0, c[i]);
+                r1 = fma(x1, r1, c[i]);
+            }
+            emit(k, r0, fabs(r0 - t_hi) * unorm);
+            emit(k + 1, r1, fabs(r1 - r0) * unorm);
+            t_hi = r1;
+        }
+        if (k < K) {
+            const double x0 = s_x[k];
+            double r0 = fma(x0, c[7], c[6]);
+#pragma unroll
+            for (int i = 5; i >= 0; --i) r0 = fma(x0, r0, c[i]);
+            emit(k, r0, fabs(r0 - t_hi) * unorm);
+        }
+    } else {
+        for (int k = 1; k < K; ++k) {
+            t_lo = t_hi;
+            t_hi = septic_top_of_atmosphere<3>(S, s_plan[K + k], rcosf);
+            emit(k, t_hi, fabs(t_hi - t_lo) * unorm);
+        }
     }
     return true;
 }
@@ -1075,10 +1145,15 @@ template <int BLOCK, int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB) k_ray_layers(const RayGeom G, int64_t n_rays, int K, const double *__restrict__ plan,
                                                       double *__restrict__ t_out, unsigned long long *__restrict__ red, double zmin,
                                                       int use_poly) {
-    extern __shared__ unsigned long long smax[];  // [K + 2] maxima / counters | low[K] | high[K]
+    extern __shared__ unsigned long long smax[];  // [K + 2] maxima / counters | low[K] | high[K] | x[K]
     double *s_plan = reinterpret_cast<double *>(smax + K + 2);
+    const bool tfit = use_poly == 2 && K >= K0_TFIT_MIN;
     for (int i = threadIdx.x; i < K + 2; i += BLOCK) smax[i] = 0ull;
     for (int i = threadIdx.x; i < 2 * K; i += BLOCK) s_plan[i] = plan[i];
+    if (tfit) {  // fit coordinate of every layer top: x = 2 (z - zA) / (zB - zA) - 1 on [top of layer 1, top of layer K - 1]
+        const double zA = plan[K + 1], two_inv = 2.0 / (plan[2 * K - 1] - zA);
+        for (int i = threadIdx.x; i < K; i += BLOCK) s_plan[2 * K + i] = fma(plan[K + i] - zA, two_inv, -1.0);
+    }
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const int64_t n_pad = (n_rays + 31) / 32 * 32;
@@ -1093,8 +1168,10 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_ray_layers(const RayGeom G, int
         // the branch is taken per warp (all lanes vote): the ballots / REDUX inside need the full warp
         if (__all_sync(0xffffffffu, F.fast_ok)) {
             // (a warp with a ray too long for the polynomial bails out of that form before storing or counting anything)
-            if (!use_poly || !ray_layers_septic(F, G.ht, K, s_plan, t_out, n_rays, r, valid, lane, zmin, smax, any_nan))
-                ray_layers_one<false>(F, K, plan, t_out, n_rays, r, valid, lane, zmin, smax, any_nan);
+            const bool done = !use_poly ? false
+                              : tfit    ? ray_layers_septic<true>(F, G.ht, K, s_plan, t_out, n_rays, r, valid, lane, zmin, smax, any_nan)
+                                        : ray_layers_septic<false>(F, G.ht, K, s_plan, t_out, n_rays, r, valid, lane, zmin, smax, any_nan);
+            if (!done) ray_layers_one<false>(F, K, plan, t_out, n_rays, r, valid, lane, zmin, smax, any_nan);
         } else {
             ray_layers_one<true>(F, K, plan, t_out, n_rays, r, valid, lane, zmin, smax, any_nan);
         }
@@ -3266,9 +3343,11 @@ static int k0_enqueue(rdr_handle_t h, int geom_kind, const double *gx, const dou
     constexpr int BLOCK = 128;
     const int minb = tune_minb("RDR_K0_MINB", 6);
     const int grid = grid_for(n, BLOCK, h->sm_count, 4 * minb);
-    const size_t smem = (K + 2) * sizeof(unsigned long long) + 2 * (size_t)K * sizeof(double);
-    const char *k0_env = getenv("RDR_K0_MODE");  // cubic (default) | exact: Newton iterates on the span cubics of h(t) or on Bowring heights
-    const int use_cubic = !exact_k0 && !(k0_env && !strcmp(k0_env, "exact"));
+    const size_t smem = (K + 2) * sizeof(unsigned long long) + 3 * (size_t)K * sizeof(double);
+    // RDR_K0_MODE: poly (default: septic h(t) + the layer tops as a polynomial in z) | iter (septic h(t), three iterates per layer) |
+    // exact (the reference's iterates on Bowring heights)
+    const char *k0_env = getenv("RDR_K0_MODE");
+    const int use_cubic = (exact_k0 || (k0_env && !strcmp(k0_env, "exact"))) ? 0 : (k0_env && !strcmp(k0_env, "iter")) ? 1 : 2;
     h->k0_was_cubic = use_cubic != 0;
 #define RDR_LAUNCH_K0(M)                                                                                                              \
     k_ray_layers<BLOCK, M><<<grid, BLOCK, smem, h->stream>>>(make_geom(h), n, K, h->d_plan.as<double>(), h->d_t.as<double>(),          \
