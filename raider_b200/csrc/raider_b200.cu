@@ -1227,8 +1227,8 @@ struct DevPlan {
 
 __global__ void __launch_bounds__(256) k_plan(const unsigned long long *__restrict__ slots, int world, int stride, int K,
                                               const int *__restrict__ layer_cell, const double *__restrict__ zs, int nz, double max_seg,
-                                              double span_max, int thin_min, int force_clamp, int block_mask, DevPlan *__restrict__ P,
-                                              unsigned long long *__restrict__ k3_counters) {
+                                              double span_max, int thin_min, int thin_absorb, int force_clamp, int block_mask,
+                                              DevPlan *__restrict__ P, unsigned long long *__restrict__ k3_counters) {
     __shared__ int s_status, s_knife;
     __shared__ int s_np[MAX_LAYERS];
     __shared__ double s_len[MAX_LAYERS];
@@ -1303,6 +1303,14 @@ __global__ void __launch_bounds__(256) k_plan(const unsigned long long *__restri
                 if (s_np[k] <= 3 && 4 * seen >= 3 * (k + 1)) k_split = k + 1;
             }
             if (k_split < thin_min) k_split = 0;
+            // a short thick tail (the top of the 145-node tables: 15 layers of 4 .. 7 samples) is cheaper sample by sample in the
+            // thin-layer kernel than as a second pass of every ray through the quadrature kernel (per-ray set-up, partial sums
+            // through HBM): absorb it when it holds at most `thin_absorb` samples beyond its layer tops
+            if (k_split > 0 && k_split < K) {
+                int extra = 0;
+                for (int k = k_split; k < K; ++k) extra += s_np[k] - 1;
+                if (extra <= thin_absorb) k_split = K;
+            }
         }
         // spans of the polynomial integrators: whole layers, greedy, <= span_max metres of the longest ray, cut at k_split
         int nspan = 0, span_split = 0;
@@ -1319,8 +1327,8 @@ __global__ void __launch_bounds__(256) k_plan(const unsigned long long *__restri
         P->span_end[nspan++] = K;
         longest = fmax(longest, acc);
         if (k_split == K) span_split = nspan;
-        // a single layer longer than 4 spans would stretch the cubic's error bound (T^4) by > 256
-        if (longest > 4.0 * span_max) st |= RDR_PLAN_SPAN_TOO_LONG;
+        // a single layer longer than 2 spans (48 km at the default) would stretch the cubic's error bound (T^4) by > 16
+        if (longest > 2.0 * span_max) st |= RDR_PLAN_SPAN_TOO_LONG;
         P->status = st;
         P->blocked = st & block_mask;
         P->K = K;
@@ -1901,7 +1909,7 @@ __device__ __forceinline__ void trilinear_cell_s(uint32_t rec, double ty, double
 }
 
 // STAGE: the north_star form -- the CTA's footprint of the cube is staged in shared memory by the TMA engine, span by span.
-// Within one span of the polynomial geometry (<= 12 km of ray) the 128 rays of a CTA pass (a 32 x 4 pixel tile, ~3 km wide)
+// Within one span of the polynomial geometry (<= 24 km of ray) the 128 rays of a CTA pass (a 32 x 4 pixel tile, ~3 km wide)
 // drift a few km: they sit in 1-4 horizontal cells of a 0.25 deg cube, ~6 of a 3 km one.  The bounding box of those cells comes
 // for free from the span's end nodes (which the cubics need anyway); the record columns of the box, restricted to the z cells of
 // the span's layers -- contiguous in memory, z fastest -- are copied with one cp.async.bulk each (UBLKCP) onto an mbarrier, as
@@ -3370,16 +3378,18 @@ static int plan_enqueue(rdr_handle_t h, const unsigned long long *slots, int wor
     const int K = h->n_layers;
     CUDA_TRY(h, h->d_devplan.reserve(sizeof(DevPlan)));
     const char *span_env = getenv("RDR_K3_SPAN");
-    const double span_max = span_env && atof(span_env) > 0 ? atof(span_env) : 12000.0;
+    const double span_max = span_env && atof(span_env) > 0 ? atof(span_env) : 24000.0;
     const char *thin_env = getenv("RDR_K3_THIN_MIN");  // fewest thin layers (<= 3 samples) that are worth the thin-layer kernel; 0: never
     const char *uni_env = getenv("RDR_K3_UNIFIED");   // 1: every layer goes to the staged kernel (K >= 4 rows of distances are preloaded)
     int thin_min = thin_env ? (atoi(thin_env) > 0 ? std::max(atoi(thin_env), 4) : 0) : 16;
+    const char *absorb_env = getenv("RDR_K3_THIN_ABSORB");  // most samples of a thick tail that the thin-layer kernel takes over
+    const int thin_absorb = absorb_env ? std::max(atoi(absorb_env), 0) : 128;
     if (uni_env && atoi(uni_env) != 0 && K >= 8) thin_min = -1;
     unsigned long long *counters = h->d_red.as<unsigned long long>() + XCHG_STRIDE;
     const int *d_cell = reinterpret_cast<const int *>(h->d_plan.as<double>() + 2 * (size_t)K);
     const double *znodes = h->d_axes.as<double>() + h->ny + h->nx;
     k_plan<<<1, 256, 0, h->stream>>>(slots, world, XCHG_STRIDE, K, d_cell, znodes, (int)h->nz, max_segment_length, span_max,
-                                     h->thin_ok ? thin_min : 0, force_clamp, block_mask, h->d_devplan.as<DevPlan>(), counters);
+                                     h->thin_ok ? thin_min : 0, thin_absorb, force_clamp, block_mask, h->d_devplan.as<DevPlan>(), counters);
     h->launches++;
     CUDA_TRY(h, cudaGetLastError());
     h->last_max_seg = max_segment_length;
@@ -3637,7 +3647,7 @@ RDR_API int rdr_ray_integrate(rdr_handle_t h, const double *maxlen, double max_s
     std::vector<unsigned long long> slot(K + 3, 0ull);
     double acc = 0.0, longest = 0.0;
     const char *span_env = getenv("RDR_K3_SPAN");
-    const double span_max = span_env && atof(span_env) > 0 ? atof(span_env) : 12000.0;
+    const double span_max = span_env && atof(span_env) > 0 ? atof(span_env) : 24000.0;
     for (int k = 0; k < K; ++k) {
         const double q = ceil(maxlen[k] / max_segment_length);
         CHECK_ARG(h, q == q && q < 1e7 && maxlen[k] >= 0, "rdr_ray_integrate: per-layer max length is NaN or absurd");
@@ -3658,8 +3668,8 @@ RDR_API int rdr_ray_integrate(rdr_handle_t h, const double *maxlen, double max_s
     int rc;
     if ((rc = plan_enqueue(h, d_slot, 1, max_segment_length, clamp_low_first ? 1 : 0, RDR_PLAN_ABSURD))) return rc;
     bool staged = false;
-    // a single layer longer than 4 spans would stretch the cubic's error bound (T^4) by > 256: leave those calls to `fast`
-    if ((rc = k3_enqueue(h, out_wet, out_hydro, out_dtype, accumulate, mem, longest <= 4.0 * span_max ? 0 : 1, &staged))) return rc;
+    // a single layer longer than 2 spans would stretch the cubic's error bound (T^4) by > 16: leave those calls to `fast`
+    if ((rc = k3_enqueue(h, out_wet, out_hydro, out_dtype, accumulate, mem, longest <= 2.0 * span_max ? 0 : 1, &staged))) return rc;
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));  // `slot` goes out of scope; host outputs are complete on return
     if (oob_out || mem == RDR_MEM_HOST) {
         unsigned long long cnt[4] = {0, 0, 0, 0};
