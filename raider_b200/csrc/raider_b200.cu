@@ -938,7 +938,7 @@ __device__ __forceinline__ void ray_latlon(const RayGeom &G, int64_t r, double &
 
 template <bool EXACT>
 __device__ __forceinline__ void ray_layers_one(const RayFrame &F, int K, const double *__restrict__ plan, double *__restrict__ t_out, int64_t n_rays,
-                                               int64_t r, bool valid, int lane, double zmin, unsigned long long *smax, bool &any_nan) {
+                                               int64_t r, bool valid, int lane, double zmin, unsigned long long *srow, bool &any_nan) {
     double Alo, Blo, Zlo, Ahi = 0.0, Bhi = 0.0, Zhi = 0.0, rcosf = 1.0, t;
     for (int k = 0; k < K; ++k) {
         const double a = __ldg(plan + k), b = __ldg(plan + K + k);
@@ -950,7 +950,7 @@ __device__ __forceinline__ void ray_layers_one(const RayFrame &F, int K, const d
             const double A1 = fma(t, F.uA, F.A0), B1 = t * F.uB, Z1 = fma(t, F.uZ, F.Z0);
             const double h0 = EXACT ? ecef2height(Vec3{A1, B1, Z1}) : frame_height(A1, B1, Z1);
             const unsigned below = __ballot_sync(0xffffffffu, valid && (h0 < zmin));
-            if (lane == 0 && below) atomicAdd(&smax[K + 1], (unsigned long long)__popc(below));
+            if (lane == 0 && below) srow[K + 1] += (unsigned long long)__popc(below);
             frame_top_of_atmosphere<10, EXACT>(F, b, 1.0, Ahi, Bhi, Zhi, t);
         } else {
             Alo = Ahi; Blo = Bhi; Zlo = Zhi;
@@ -963,7 +963,7 @@ __device__ __forceinline__ void ray_layers_one(const RayFrame &F, int K, const d
         any_nan |= isn;
         const unsigned long long bits = (valid && !isn) ? (unsigned long long)__double_as_longlong(len) : 0ull;
         const unsigned long long m = warp_max_bits(bits);
-        if (lane == 0 && m > smax[k]) atomicMax(&smax[k], m);
+        if (lane == 0 && m > srow[k]) srow[k] = m;
     }
 }
 
@@ -1039,8 +1039,8 @@ constexpr int K0_TFIT_MIN = 16;  // fewest layers for which the fit pays (8 node
 // s_plan: low[K] | high[K] | x[K] (fit coordinate of the layer tops, TFIT only) in shared memory.
 template <bool TFIT>
 __device__ __forceinline__ bool ray_layers_septic(const RayFrame &F, double ht, int K, const double *__restrict__ s_plan,
-                                                  double *__restrict__ t_out, int64_t n_rays, int64_t r, bool valid, int lane, double zmin,
-                                                  unsigned long long *smax, bool &any_nan) {
+                                                  double *__restrict__ t_out, int64_t n_rays, int64_t rr, bool valid, int lane, double zmin,
+                                                  unsigned long long *srow, bool &any_nan) {
     const double unorm = norm3(Vec3{F.uA, F.uB, F.uZ});
     // length of the whole ray from the incidence at the ground point: cos = look . ellipsoid normal (curvature only shortens it)
     const double cos0 = fma(F.uA, F.clat, F.uZ * F.slat) / unorm;
@@ -1077,19 +1077,24 @@ __device__ __forceinline__ bool ray_layers_septic(const RayFrame &F, double ht, 
         // will reconstruct (K3 re-evaluates the predicate itself and has the last word)
         const double h0 = frame_height(fma(t_lo, F.uA, F.A0), t_lo * F.uB, fma(t_lo, F.uZ, F.Z0));
         const unsigned below = __ballot_sync(0xffffffffu, valid && (h0 < zmin));
-        if (lane == 0 && below) atomicAdd(&smax[K + 1], (unsigned long long)__popc(below));
+        if (lane == 0 && below) srow[K + 1] += (unsigned long long)__popc(below);
     }
-    double *tp = t_out + r;
-    if (valid) __stcs(tp, t_lo);
-    // top of layer k at distance t_top, the layer's chord length: store, NaN flag, warp maximum
+    // The lanes past the end of the raster (last warp only) carry a copy of the last ray (rr = n_rays - 1): they compute and store
+    // the same values to the same addresses and cannot change a maximum, so the layer loop needs no `valid` predicate.
+    double *tp = t_out + rr;
+    __stcs(tp, t_lo);
+    // top of layer k at distance t_top, the layer's chord length: store, NaN flag, warp maximum (this warp's row: no atomics)
     auto emit = [&](int k, double t_top, double length) {
         tp += n_rays;
-        if (valid) __stcs(tp, t_top);
-        const bool isn = !(length == length);
+        __stcs(tp, t_top);
+        const unsigned hi = (unsigned)__double2hiint(length), lo = (unsigned)__double2loint(length);
+        const bool isn = hi > 0x7ff00000u || (hi == 0x7ff00000u && lo != 0u);  // length >= 0 (fabs): NaN by its bit pattern
         any_nan |= isn;
-        const unsigned long long bits = (valid && !isn) ? (unsigned long long)__double_as_longlong(length) : 0ull;
-        const unsigned long long m = warp_max_bits(bits);
-        if (lane == 0 && m > smax[k]) atomicMax(&smax[k], m);
+        const unsigned h1 = isn ? 0u : hi;
+        const unsigned mhi = __reduce_max_sync(0xffffffffu, h1);
+        const unsigned mlo = __reduce_max_sync(0xffffffffu, h1 == mhi ? lo : 0u);
+        const unsigned long long m = ((unsigned long long)mhi << 32) | mlo, cur = srow[k];
+        if (lane == 0 && m > cur) srow[k] = m;
     };
     emit(0, t_hi, len);
     if (TFIT) {
@@ -1145,10 +1150,11 @@ template <int BLOCK, int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB) k_ray_layers(const RayGeom G, int64_t n_rays, int K, const double *__restrict__ plan,
                                                       double *__restrict__ t_out, unsigned long long *__restrict__ red, double zmin,
                                                       int use_poly) {
-    extern __shared__ unsigned long long smax[];  // [K + 2] maxima / counters | low[K] | high[K] | x[K]
-    double *s_plan = reinterpret_cast<double *>(smax + K + 2);
+    extern __shared__ unsigned long long smax[];  // [BLOCK / 32][K + 2] maxima / counters per warp | low[K] | high[K] | x[K]
+    constexpr int NW = BLOCK / 32;
+    double *s_plan = reinterpret_cast<double *>(smax + NW * (K + 2));
     const bool tfit = use_poly == 2 && K >= K0_TFIT_MIN;
-    for (int i = threadIdx.x; i < K + 2; i += BLOCK) smax[i] = 0ull;
+    for (int i = threadIdx.x; i < NW * (K + 2); i += BLOCK) smax[i] = 0ull;
     for (int i = threadIdx.x; i < 2 * K; i += BLOCK) s_plan[i] = plan[i];
     if (tfit) {  // fit coordinate of every layer top: x = 2 (z - zA) / (zB - zA) - 1 on [top of layer 1, top of layer K - 1]
         const double zA = plan[K + 1], two_inv = 2.0 / (plan[2 * K - 1] - zA);
@@ -1156,6 +1162,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_ray_layers(const RayGeom G, int
     }
     __syncthreads();
     const int lane = threadIdx.x & 31;
+    unsigned long long *srow = smax + (threadIdx.x >> 5) * (K + 2);  // this warp's maxima / counters (lane 0 writes: no atomics)
     const int64_t n_pad = (n_rays + 31) / 32 * 32;
     for (int64_t r = blockIdx.x * (int64_t)BLOCK + threadIdx.x; r < n_pad; r += (int64_t)gridDim.x * BLOCK) {
         const bool valid = r < n_rays;
@@ -1169,18 +1176,22 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_ray_layers(const RayGeom G, int
         if (__all_sync(0xffffffffu, F.fast_ok)) {
             // (a warp with a ray too long for the polynomial bails out of that form before storing or counting anything)
             const bool done = !use_poly ? false
-                              : tfit    ? ray_layers_septic<true>(F, G.ht, K, s_plan, t_out, n_rays, r, valid, lane, zmin, smax, any_nan)
-                                        : ray_layers_septic<false>(F, G.ht, K, s_plan, t_out, n_rays, r, valid, lane, zmin, smax, any_nan);
-            if (!done) ray_layers_one<false>(F, K, plan, t_out, n_rays, r, valid, lane, zmin, smax, any_nan);
+                              : tfit    ? ray_layers_septic<true>(F, G.ht, K, s_plan, t_out, n_rays, rr, valid, lane, zmin, srow, any_nan)
+                                        : ray_layers_septic<false>(F, G.ht, K, s_plan, t_out, n_rays, rr, valid, lane, zmin, srow, any_nan);
+            if (!done) ray_layers_one<false>(F, K, plan, t_out, n_rays, r, valid, lane, zmin, srow, any_nan);
         } else {
-            ray_layers_one<true>(F, K, plan, t_out, n_rays, r, valid, lane, zmin, smax, any_nan);
+            ray_layers_one<true>(F, K, plan, t_out, n_rays, r, valid, lane, zmin, srow, any_nan);
         }
         const unsigned nn = __ballot_sync(0xffffffffu, valid && any_nan);
-        if (lane == 0 && nn) atomicAdd(&smax[K], (unsigned long long)__popc(nn));
+        if (lane == 0 && nn) srow[K] += (unsigned long long)__popc(nn);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < K + 2; i += BLOCK) {
-        const unsigned long long v = smax[i];
+        unsigned long long v = smax[i];
+        for (int w = 1; w < NW; ++w) {
+            const unsigned long long u = smax[w * (K + 2) + i];
+            v = i < K ? max(v, u) : v + u;
+        }
         if (v) {
             if (i < K) atomicMax(red + i, v); else atomicAdd(red + i, v);
         }
@@ -3351,7 +3362,7 @@ static int k0_enqueue(rdr_handle_t h, int geom_kind, const double *gx, const dou
     constexpr int BLOCK = 128;
     const int minb = tune_minb("RDR_K0_MINB", 6);
     const int grid = grid_for(n, BLOCK, h->sm_count, 4 * minb);
-    const size_t smem = (K + 2) * sizeof(unsigned long long) + 3 * (size_t)K * sizeof(double);
+    const size_t smem = (BLOCK / 32) * (size_t)(K + 2) * sizeof(unsigned long long) + 3 * (size_t)K * sizeof(double);
     // RDR_K0_MODE: poly (default: septic h(t) + the layer tops as a polynomial in z) | iter (septic h(t), three iterates per layer) |
     // exact (the reference's iterates on Bowring heights)
     const char *k0_env = getenv("RDR_K0_MODE");
