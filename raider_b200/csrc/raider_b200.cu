@@ -1083,6 +1083,7 @@ __device__ __forceinline__ bool ray_layers_septic(const RayFrame &F, double ht, 
     // the same values to the same addresses and cannot change a maximum, so the layer loop needs no `valid` predicate.
     double *tp = t_out + rr;
     __stcs(tp, t_lo);
+    const uint32_t srow_s = smem_u32(srow);
     // top of layer k at distance t_top, the layer's chord length: store, NaN flag, warp maximum (this warp's row: no atomics)
     auto emit = [&](int k, double t_top, double length) {
         tp += n_rays;
@@ -1093,8 +1094,20 @@ __device__ __forceinline__ bool ray_layers_septic(const RayFrame &F, double ht, 
         const unsigned h1 = isn ? 0u : hi;
         const unsigned mhi = __reduce_max_sync(0xffffffffu, h1);
         const unsigned mlo = __reduce_max_sync(0xffffffffu, h1 == mhi ? lo : 0u);
-        const unsigned long long m = ((unsigned long long)mhi << 32) | mlo, cur = srow[k];
-        if (lane == 0 && m > cur) srow[k] = m;
+        const unsigned long long m = ((unsigned long long)mhi << 32) | mlo;
+        // lane 0 alone reads and updates the warp's row, by predicate (no branch).  Letting every lane read the row (a broadcast whose
+        // value only lane 0 uses) is 9 % faster for K0, but it is a read / write pair between lanes without a barrier in between,
+        // which racecheck reports; this form is clean (profiles/r02w_racecheck.txt: 0 hazards).
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            ".reg .u64 cur;\n"
+            "setp.eq.u32 p, %2, 0;\n"
+            "@p ld.shared.u64 cur, [%0];\n"
+            "@p setp.gt.u64 p, %1, cur;\n"
+            "@p st.shared.u64 [%0], %1;\n"
+            "}\n" ::"r"(srow_s + 8u * (unsigned)k),
+            "l"(m), "r"(lane));
     };
     emit(0, t_hi, len);
     if (TFIT) {
