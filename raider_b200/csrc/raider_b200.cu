@@ -3397,12 +3397,30 @@ static int k0_enqueue(rdr_handle_t h, int geom_kind, const double *gx, const dou
     return RDR_OK;
 }
 
+// Default span length of the polynomial integrators [m of the longest ray].  24 km keeps the delays within 3e-10 m of the PROJ-form
+// arithmetic and costs the fewest span set-ups (profiles/runs/r02p_span.sh); on km-scale grids (HRRR: 3 km cells) the footprint
+// of a 24 km span no longer fits the staged-record capacity of the thin-layer kernel (10 columns x 42 z cells), and 12 km is
+// faster (K3 2.06 vs 2.31 ms on the 57-node Lambert variant of bench.py).  RDR_K3_SPAN overrides.
+static double default_span_max(rdr_handle_t h) {
+    const char *span_env = getenv("RDR_K3_SPAN");
+    if (span_env && atof(span_env) > 0) return atof(span_env);
+    const double dy = (h->ys.back() - h->ys.front()) / (double)std::max<size_t>(h->ys.size() - 1, 1);
+    const double dx = (h->xs.back() - h->xs.front()) / (double)std::max<size_t>(h->xs.size() - 1, 1);
+    double cell_m;
+    if (h->crs_kind == RDR_CRS_LCC_SPHERE) {
+        cell_m = std::min(fabs(dy), fabs(dx));
+    } else {
+        const double mid = 0.5 * (h->ys.back() + h->ys.front()) * (M_PI / 180.0);
+        cell_m = std::min(fabs(dy), fabs(dx) * std::max(cos(mid), 0.05)) * 111.0e3;
+    }
+    return cell_m < 8000.0 ? 12000.0 : 24000.0;
+}
+
 // ---- k_plan: MAX / SUM over the slots, nParts, layer records, spans, predicates -> the device plan ------------------------------
 static int plan_enqueue(rdr_handle_t h, const unsigned long long *slots, int world, double max_segment_length, int force_clamp, int block_mask) {
     const int K = h->n_layers;
     CUDA_TRY(h, h->d_devplan.reserve(sizeof(DevPlan)));
-    const char *span_env = getenv("RDR_K3_SPAN");
-    const double span_max = span_env && atof(span_env) > 0 ? atof(span_env) : 24000.0;
+    const double span_max = default_span_max(h);
     const char *thin_env = getenv("RDR_K3_THIN_MIN");  // fewest thin layers (<= 3 samples) that are worth the thin-layer kernel; 0: never
     const char *uni_env = getenv("RDR_K3_UNIFIED");   // 1: every layer goes to the staged kernel (K >= 4 rows of distances are preloaded)
     int thin_min = thin_env ? (atoi(thin_env) > 0 ? std::max(atoi(thin_env), 4) : 0) : 16;
@@ -3670,8 +3688,7 @@ RDR_API int rdr_ray_integrate(rdr_handle_t h, const double *maxlen, double max_s
     // restates it for its caller; the kernels take it from the device plan (k_plan), which gets the caller's maxima as its slot
     std::vector<unsigned long long> slot(K + 3, 0ull);
     double acc = 0.0, longest = 0.0;
-    const char *span_env = getenv("RDR_K3_SPAN");
-    const double span_max = span_env && atof(span_env) > 0 ? atof(span_env) : 24000.0;
+    const double span_max = default_span_max(h);
     for (int k = 0; k < K; ++k) {
         const double q = ceil(maxlen[k] / max_segment_length);
         CHECK_ARG(h, q == q && q < 1e7 && maxlen[k] >= 0, "rdr_ray_integrate: per-layer max length is NaN or absurd");
