@@ -171,7 +171,8 @@ enum {
 /* flags of rdr_trace_begin */
 enum {
     RDR_TRACE_EXACT_K0 = 1,      /* Newton iterates of getTopOfAtmosphere (losreader.py:720-733) on PROJ-form (Bowring) heights instead of
-                                    on span cubics of h(t): layer maxima to ~1e-9 m of the reference's instead of ~1e-8 m */
+                                    on the per-ray polynomials of K0 (h(t) as a septic, the layer tops as a degree-7 polynomial in z): layer maxima to
+                                    ~1e-9 m of the reference's instead of ~1e-8 m */
     RDR_TRACE_NO_KNIFE_GUARD = 2 /* integrate even on an nParts knife edge (tuning runs) */
 };
 /* The same three stages as rdr_ray_layers / rdr_ray_integrate, but nothing returns to the host in between: K0's per-layer maxima
@@ -190,7 +191,7 @@ enum {
  *   maxlen_out[n_layers], nparts_out[n_layers]  global maxima and the integer step counts used (may be NULL)
  *   info_out[20] = {status, blocked, n_layers, n_rays, n_nan_rays, K0's #first samples below min(z), K3's own count of the same,
  *                   clamp used, #samples below min(z), #samples above max(z), #rays redone in PROJ form, knife-edge layer or -1,
- *                   k_split (layers handled by the thin-layer kernel), n_spans, K0 ran on span cubics, K3 ran the polynomial form,
+ *                   k_split (layers handled by the thin-layer kernel), n_spans, K0 ran its polynomial form, K3 ran the polynomial form,
  *                   #CTA passes of the thin-layer kernel with TMA-staged record columns, #passes without, 0, 0};
  *                   counts 3..6 are global (all ranks), 8..10 and 16..17 this rank's.  blocked != 0: nothing was integrated. */
 int rdr_trace_begin(rdr_handle_t h, int geom_kind, const double *gx, const double *gy, int64_t ny, int64_t nx, int los_kind,

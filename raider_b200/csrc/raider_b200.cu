@@ -1,9 +1,13 @@
 // libraider_b200.so -- hand-written sm_100a kernels + C ABI for the RAiDER slant/zenith delay hot path.
 // See include/raider_b200.h for the boundary and DESIGN.md for the kernel inventory:
-//   K0 k_ray_layers          build_ray/getTopOfAtmosphere over a raster (Newton iterates on span cubics of h(t)) + global
+//   K0 k_ray_layers          build_ray/getTopOfAtmosphere over a raster (h(t) as one septic per ray, the layer tops as one polynomial in z) + global
 //                            per-layer max length
 //   K3 k_ray_integrate_poly  the production integrator: span cubics of the cube coordinates, closed-form layer sums, register-held
 //                            cell record; also stores the results into the other GPUs' maps (rdr_set_peer_outputs)
+//      k_ray_integrate_thin  runs of layers with <= 3 samples (the 145-node production tables): cell records staged in shared memory
+//                            per span by TMA bulk copies, along-ray distances through a cp.async ring
+//      k_plan / k_publish    the step plan (nParts, layer records, spans, predicates) built on the device from K0's maxima -- of
+//                            all ranks, exchanged through peer-mapped symmetric memory -- between K0 and K3: no host round trip
 //      k_ray_integrate_fast  per-sample Bowring form (tests / comparisons);  k_ray_integrate  PROJ-form per sample (flagged rays, any CRS)
 //   K2 k_sample_stream*      unfused trilinear sampler (points streamed from HBM through a TMA-bulk ring) -- the HBM-roofline kernel;
 //                            k_sample_stream_f32 its fp32 tier
@@ -246,7 +250,7 @@ struct rdr_handle_s {
     DevBuf d_devplan; // DevPlan: the step plan k_plan builds on the device
     DevBuf d_part;    // double [2][n_rays]: partial sums the quadrature kernel hands to the thin-layer kernel
     bool thin_ok = true;        // the record array carries the prefetch padding (always, kept for clarity)
-    bool k0_was_cubic = true;   // last K0 ran on span cubics (default) rather than on Bowring heights
+    bool k0_was_cubic = true;   // last K0 ran in its polynomial form (default) rather than on Bowring heights
     bool last_k3_poly = false;
     int trace_flags = 0;
     double last_max_seg = 0;
@@ -1226,7 +1230,7 @@ constexpr int THIN_TD = 8;   // along-ray distances in flight per thread in k_ra
 constexpr int LERP_PAD = 8;  // records of padding behind the cell-record array (prefetch distance bound of k_ray_integrate_thin)
 constexpr int XCHG_STRIDE = MAX_LAYERS + 8;  // words per rank slot: maxima bits [K] | #NaN rays | #first sample below | #rays | K3's #first sample below
 // |maxlen / S - nearest integer| below which nParts is declared a knife edge: the default K0 reproduces the reference's maxima
-// to ~1e-8 m (span cubics of h(t)), the exact form to ~1e-9 m; 1e-6 of a segment is 1 mm at the default 1000 m
+// to ~1e-8 m (polynomials of h(t) and of the layer tops), the exact form to ~1e-9 m; 1e-6 of a segment is 1 mm at the default 1000 m
 constexpr double KNIFE_EPS = 1.0e-6;
 
 // written into `part` by the quadrature kernel for a ray it put on the fix list (a NaN no arithmetic produces)
