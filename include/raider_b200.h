@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define RDR_ABI_VERSION 2
+#define RDR_ABI_VERSION 3
 
 typedef struct rdr_handle_s *rdr_handle_t;
 
@@ -139,7 +139,8 @@ int rdr_ray_plan(rdr_handle_t h, double ht, double zref, int64_t *n_layers, doub
  * ray runs the 10-then-3 Newton schedule for every contributing layer, keeps the along-ray distance of each layer
  * top in handle scratch, and reduces max_over_raster(ray_length[k]) (delay.py:283) with warp shuffles + atomics.
  *   maxlen_out[n_layers]  host, this call's (this GPU's) per-layer maxima  -> all-reduce(MAX) across GPUs
- *   counts_out[4]         host: {n_rays, n_rays_with_nan_length, n_first_sample_below_zmin, n_layers}
+ *   counts_out[5]         host: {n_rays, n_rays_with_nan_length, n_first_sample_below_zmin, n_layers, n_last_sample_above_zmax}
+ *                         (ABI 3: five entries; the last one feeds the upper `.all()` clamp of delay.py:310-311)
  */
 int rdr_ray_layers(rdr_handle_t h, int geom_kind, const double *gx, const double *gy, int64_t ny, int64_t nx,
                    int los_kind, const double *los, double ht, double zref,
@@ -149,12 +150,15 @@ int rdr_ray_layers(rdr_handle_t h, int geom_kind, const double *gx, const double
  * rdr_ray_layers call: nParts from the (globally reduced) maxlen, sub-step points, ECEF -> model CRS, trilinear
  * wet+hydro sample, trapezoid weights, fp64 accumulation in layer-then-step order.
  *   maxlen[n_layers]      host: global per-layer maxima (delay.py:283)
- *   clamp_low_first       1 if *all* pixels of the very first sample are below min(z) globally (delay.py:306-307)
+ *   clamp                 bit 0: *all* pixels of the very first sample are below min(z) globally (delay.py:306-307: the sample is
+ *                         taken at min(z)); bit 1 (ABI 3): all pixels of the very last sample -- the top of the top layer -- are above
+ *                         max(z) globally (delay.py:310-311: taken at max(z); happens at the default zref = top - 1 m from ~58 deg
+ *                         incidence on, where the three Newton iterates of losreader.py:720-733 overshoot by more than that metre)
  *   out_wet/out_hydro     [n_rays] f64 (or f32 when out_dtype == RDR_F32); accumulate != 0 -> out += (delay.py:245-248,323)
  *   nparts_out[n_layers]  host, optional: the integer step counts used (bit-exact contract)
  *   oob_out[2]            host, optional: {samples below min(z), samples above max(z)} that became NaN
  */
-int rdr_ray_integrate(rdr_handle_t h, const double *maxlen, double max_segment_length, int clamp_low_first,
+int rdr_ray_integrate(rdr_handle_t h, const double *maxlen, double max_segment_length, int clamp,
                       void *out_wet, void *out_hydro, int out_dtype, int accumulate,
                       int64_t *nparts_out, int64_t *oob_out, int mem);
 
@@ -181,19 +185,24 @@ enum {
  * device memory.  rdr_trace_begin and rdr_trace_finish only enqueue work on the handle's stream (device-resident or page-locked
  * outputs are complete once the stream reaches that point; other host outputs once rdr_trace_result returns).
  *
- * Across GPUs (rdr_set_exchange): rdr_trace_begin also stores this rank's K + 3 words into its slot of every peer's exchange
+ * Across GPUs (rdr_set_exchange): rdr_trace_begin also stores this rank's K + 5 words into its slot of every peer's exchange
  * buffer; the caller puts ONE barrier on the stream (all ranks' rdr_trace_begin work done) before rdr_trace_finish, whose plan
  * kernel takes MAX / SUM over the slots -- the all-reduce of SURVEY 8(e) without NCCL or the host -- and a second barrier after it
  * (which also publishes the delay maps written through rdr_set_peer_outputs).
- *   force_clamp   -1: the plan decides the clamp of delay.py:306-307 from K0's global count; 0 / 1: forced (redo after a cross-check miss)
+ *   force_clamp   -1: the plan decides both `.all()` clamps (delay.py:306-307 first sample below min(z), :310-311 last sample above
+ *                 max(z)) from K0's global counts; >= 0: bit 0 = the lower clamp's value (redo after a cross-check miss), bit 1 / bit 2 =
+ *                 upper clamp forced on / off (neither: from the count)
  *   mode          0: polynomial integrators (quadrature + thin-layer kernels); 1: per-sample Bowring form; 2: PROJ-form for every sample
  * rdr_trace_result synchronises the stream and reports the step:
  *   maxlen_out[n_layers], nparts_out[n_layers]  global maxima and the integer step counts used (may be NULL)
  *   info_out[20] = {status, blocked, n_layers, n_rays, n_nan_rays, K0's #first samples below min(z), K3's own count of the same,
  *                   clamp used, #samples below min(z), #samples above max(z), #rays redone in PROJ form, knife-edge layer or -1,
  *                   k_split (layers handled by the thin-layer kernel), n_spans, K0 ran its polynomial form, K3 ran the polynomial form,
- *                   #CTA passes of the thin-layer kernel with TMA-staged record columns, #passes without, 0, 0};
- *                   counts 3..6 are global (all ranks), 8..10 and 16..17 this rank's.  blocked != 0: nothing was integrated. */
+ *                   #CTA passes of the thin-layer kernel with TMA-staged record columns, #passes without,
+ *                   K0's #last samples above max(z), upper clamp used};
+ *                   counts 3..6 and 18 are global (all ranks), 8..10 and 16..17 this rank's.  blocked != 0: nothing was integrated.
+ *                   Rays whose last sample lies above max(z) are integrated by the PROJ-form kernel (list mode), which applies the
+ *                   upper clamp; the polynomial kernels hand them over. */
 int rdr_trace_begin(rdr_handle_t h, int geom_kind, const double *gx, const double *gy, int64_t ny, int64_t nx, int los_kind,
                     const double *los, double ht, double zref, int flags, int mem);
 int rdr_trace_finish(rdr_handle_t h, double max_segment_length, int force_clamp, int mode, void *out_wet, void *out_hydro,

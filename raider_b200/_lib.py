@@ -27,7 +27,7 @@ SEM_SCIPY, SEM_RAIDER_FILL, SEM_RAIDER_CLAMP = 0, 1, 2
 PLAN_ABSURD, PLAN_ALL_NAN, PLAN_KNIFE_EDGE, PLAN_SPAN_TOO_LONG = 1, 2, 4, 8
 TRACE_EXACT_K0, TRACE_NO_KNIFE_GUARD = 1, 2
 K3_AUTO, K3_FAST, K3_GENERAL = 0, 1, 2
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 _i64, _f64, _int, _vp = C.c_int64, C.c_double, C.c_int, C.c_void_p
 _pd = C.POINTER(C.c_double)

@@ -942,7 +942,8 @@ __device__ __forceinline__ void ray_latlon(const RayGeom &G, int64_t r, double &
 
 template <bool EXACT>
 __device__ __forceinline__ void ray_layers_one(const RayFrame &F, int K, const double *__restrict__ plan, double *__restrict__ t_out, int64_t n_rays,
-                                               int64_t r, bool valid, int lane, double zmin, unsigned long long *srow, bool &any_nan) {
+                                               int64_t r, bool valid, int lane, double zmin, double zmax, unsigned long long *srow,
+                                               bool &any_nan) {
     double Alo, Blo, Zlo, Ahi = 0.0, Bhi = 0.0, Zhi = 0.0, rcosf = 1.0, t;
     for (int k = 0; k < K; ++k) {
         const double a = __ldg(plan + k), b = __ldg(plan + K + k);
@@ -969,6 +970,10 @@ __device__ __forceinline__ void ray_layers_one(const RayFrame &F, int K, const d
         const unsigned long long m = warp_max_bits(bits);
         if (lane == 0 && m > srow[k]) srow[k] = m;
     }
+    // hint for the whole-raster upper clamp (delay.py:310-311): height of the very last sample (the top of the top layer)
+    const double hK = EXACT ? ecef2height(Vec3{Ahi, Bhi, Zhi}) : frame_height(Ahi, Bhi, Zhi);
+    const unsigned above = __ballot_sync(0xffffffffu, valid && (hK > zmax));
+    if (lane == 0 && above) srow[K + 2] += (unsigned long long)__popc(above);
 }
 
 // K0 with the height along the ray as ONE polynomial.  h(t) along a straight ray is so smooth (k-th derivative ~ r^(1-k)) that the
@@ -1044,7 +1049,7 @@ constexpr int K0_TFIT_MIN = 16;  // fewest layers for which the fit pays (8 node
 template <bool TFIT>
 __device__ __forceinline__ bool ray_layers_septic(const RayFrame &F, double ht, int K, const double *__restrict__ s_plan,
                                                   double *__restrict__ t_out, int64_t n_rays, int64_t rr, bool valid, int lane, double zmin,
-                                                  unsigned long long *srow, bool &any_nan) {
+                                                  double zmax, unsigned long long *srow, bool &any_nan) {
     const double unorm = norm3(Vec3{F.uA, F.uB, F.uZ});
     // length of the whole ray from the incidence at the ground point: cos = look . ellipsoid normal (curvature only shortens it)
     const double cos0 = fma(F.uA, F.clat, F.uZ * F.slat) / unorm;
@@ -1152,6 +1157,7 @@ __device__ __forceinline__ bool ray_layers_septic(const RayFrame &F, double ht, 
 #pragma unroll
             for (int i = 5; i >= 0; --i) r0 = fma(x0, r0, c[i]);
             emit(k, r0, fabs(r0 - t_hi) * unorm);
+            t_hi = r0;
         }
     } else {
         for (int k = 1; k < K; ++k) {
@@ -1160,18 +1166,26 @@ __device__ __forceinline__ bool ray_layers_septic(const RayFrame &F, double ht, 
             emit(k, t_hi, fabs(t_hi - t_lo) * unorm);
         }
     }
+    {
+        // hint for the whole-raster upper clamp (delay.py:310-311): height of the very last sample (the top of the top layer),
+        // evaluated exactly on the point K3 will reconstruct.  With zref at its default (1 m below the model top) the reference's
+        // three iterates overshoot the top by more than that metre from ~58 deg incidence on (80 km tables).
+        const double hK = frame_height(fma(t_hi, F.uA, F.A0), t_hi * F.uB, fma(t_hi, F.uZ, F.Z0));
+        const unsigned above = __ballot_sync(0xffffffffu, valid && (hK > zmax));
+        if (lane == 0 && above) srow[K + 2] += (unsigned long long)__popc(above);
+    }
     return true;
 }
 
 template <int BLOCK, int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB) k_ray_layers(const RayGeom G, int64_t n_rays, int K, const double *__restrict__ plan,
                                                       double *__restrict__ t_out, unsigned long long *__restrict__ red, double zmin,
-                                                      int use_poly) {
-    extern __shared__ unsigned long long smax[];  // [BLOCK / 32][K + 2] maxima / counters per warp | low[K] | high[K] | x[K]
+                                                      double zmax, int use_poly) {
+    extern __shared__ unsigned long long smax[];  // [BLOCK / 32][K + 3] maxima / counters (#NaN, #first below, #last above) per warp | low[K] | high[K] | x[K]
     constexpr int NW = BLOCK / 32;
-    double *s_plan = reinterpret_cast<double *>(smax + NW * (K + 2));
+    double *s_plan = reinterpret_cast<double *>(smax + NW * (K + 3));
     const bool tfit = use_poly == 2 && K >= K0_TFIT_MIN;
-    for (int i = threadIdx.x; i < NW * (K + 2); i += BLOCK) smax[i] = 0ull;
+    for (int i = threadIdx.x; i < NW * (K + 3); i += BLOCK) smax[i] = 0ull;
     for (int i = threadIdx.x; i < 2 * K; i += BLOCK) s_plan[i] = plan[i];
     if (tfit) {  // fit coordinate of every layer top: x = 2 (z - zA) / (zB - zA) - 1 on [top of layer 1, top of layer K - 1]
         const double zA = plan[K + 1], two_inv = 2.0 / (plan[2 * K - 1] - zA);
@@ -1179,7 +1193,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_ray_layers(const RayGeom G, int
     }
     __syncthreads();
     const int lane = threadIdx.x & 31;
-    unsigned long long *srow = smax + (threadIdx.x >> 5) * (K + 2);  // this warp's maxima / counters (lane 0 writes: no atomics)
+    unsigned long long *srow = smax + (threadIdx.x >> 5) * (K + 3);  // this warp's maxima / counters (lane 0 writes: no atomics)
     const int64_t n_pad = (n_rays + 31) / 32 * 32;
     for (int64_t r = blockIdx.x * (int64_t)BLOCK + threadIdx.x; r < n_pad; r += (int64_t)gridDim.x * BLOCK) {
         const bool valid = r < n_rays;
@@ -1193,24 +1207,25 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_ray_layers(const RayGeom G, int
         if (__all_sync(0xffffffffu, F.fast_ok)) {
             // (a warp with a ray too long for the polynomial bails out of that form before storing or counting anything)
             const bool done = !use_poly ? false
-                              : tfit    ? ray_layers_septic<true>(F, G.ht, K, s_plan, t_out, n_rays, rr, valid, lane, zmin, srow, any_nan)
-                                        : ray_layers_septic<false>(F, G.ht, K, s_plan, t_out, n_rays, rr, valid, lane, zmin, srow, any_nan);
-            if (!done) ray_layers_one<false>(F, K, plan, t_out, n_rays, r, valid, lane, zmin, srow, any_nan);
+                              : tfit    ? ray_layers_septic<true>(F, G.ht, K, s_plan, t_out, n_rays, rr, valid, lane, zmin, zmax, srow, any_nan)
+                                        : ray_layers_septic<false>(F, G.ht, K, s_plan, t_out, n_rays, rr, valid, lane, zmin, zmax, srow, any_nan);
+            if (!done) ray_layers_one<false>(F, K, plan, t_out, n_rays, r, valid, lane, zmin, zmax, srow, any_nan);
         } else {
-            ray_layers_one<true>(F, K, plan, t_out, n_rays, r, valid, lane, zmin, srow, any_nan);
+            ray_layers_one<true>(F, K, plan, t_out, n_rays, r, valid, lane, zmin, zmax, srow, any_nan);
         }
         const unsigned nn = __ballot_sync(0xffffffffu, valid && any_nan);
         if (lane == 0 && nn) srow[K] += (unsigned long long)__popc(nn);
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < K + 2; i += BLOCK) {
+    for (int i = threadIdx.x; i < K + 3; i += BLOCK) {
         unsigned long long v = smax[i];
         for (int w = 1; w < NW; ++w) {
-            const unsigned long long u = smax[w * (K + 2) + i];
+            const unsigned long long u = smax[w * (K + 3) + i];
             v = i < K ? max(v, u) : v + u;
         }
         if (v) {
-            if (i < K) atomicMax(red + i, v); else atomicAdd(red + i, v);
+            // red: maxima [K] | #NaN rays | #first sample below | (#rays) | (K3's #first below) | #last sample above
+            if (i < K) atomicMax(red + i, v); else atomicAdd(red + (i == K + 2 ? K + 4 : i), v);
         }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) red[K + 2] = (unsigned long long)n_rays;  // the slot carries the call's ray count (k_plan)
@@ -1228,7 +1243,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_ray_layers(const RayGeom G, int
 // ------------------------------------------------------------------------------------------------
 constexpr int THIN_TD = 8;   // along-ray distances in flight per thread in k_ray_integrate_thin (ring depth, power of two)
 constexpr int LERP_PAD = 8;  // records of padding behind the cell-record array (prefetch distance bound of k_ray_integrate_thin)
-constexpr int XCHG_STRIDE = MAX_LAYERS + 8;  // words per rank slot: maxima bits [K] | #NaN rays | #first sample below | #rays | K3's #first sample below
+constexpr int XCHG_STRIDE = MAX_LAYERS + 8;  // words per rank slot: maxima bits [K] | #NaN rays | #first sample below | #rays | K3's #first sample below | #last sample above
 // |maxlen / S - nearest integer| below which nParts is declared a knife edge: the default K0 reproduces the reference's maxima
 // to ~1e-8 m (polynomials of h(t) and of the layer tops), the exact form to ~1e-9 m; 1e-6 of a segment is 1 mm at the default 1000 m
 constexpr double KNIFE_EPS = 1.0e-6;
@@ -1243,8 +1258,9 @@ struct DevPlan {
     int k_split;          // layers [0, k_split): thin-layer kernel, [k_split, K): quadrature kernel
     int span_split;       // spans  [0, span_split) belong to the thin part
     int clamp_low_first;  // delay.py:306-307 decided from K0's global count
+    int clamp_high_last;  // delay.py:310-311 for the very last sample (top of the top layer), decided from K0's global count
     int knife_layer;      // a layer whose maxlen / S is within KNIFE_EPS of an integer (-1: none)
-    long long n_rays, n_nan, n_below;  // global counters
+    long long n_rays, n_nan, n_below, n_above;  // global counters
     double longest_span;
     double maxlen[MAX_LAYERS];
     int nparts[MAX_LAYERS];
@@ -1305,10 +1321,11 @@ __global__ void __launch_bounds__(256) k_plan(const unsigned long long *__restri
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        long long n_nan = 0, n_below = 0, n_rays = 0;
+        long long n_nan = 0, n_below = 0, n_rays = 0, n_above = 0;
         for (int q = 0; q < world; ++q) {
             n_nan += (long long)slots[(size_t)q * stride + K];
             n_below += (long long)slots[(size_t)q * stride + K + 1];
+            n_above += (long long)slots[(size_t)q * stride + K + 4];
             n_rays += (long long)slots[(size_t)q * stride + K + 2];
         }
         int st = s_status;
@@ -1363,11 +1380,15 @@ __global__ void __launch_bounds__(256) k_plan(const unsigned long long *__restri
         P->nspan = nspan;
         P->k_split = k_split;
         P->span_split = span_split;
-        P->clamp_low_first = force_clamp >= 0 ? force_clamp : (n_below == n_rays);
+        // force_clamp < 0: both predicates from K0's global counts; otherwise bit 0 = the lower clamp's value, bit 1 = upper clamp forced on,
+        // bit 2 = upper clamp forced off (neither: from the count)
+        P->clamp_low_first = force_clamp >= 0 ? (force_clamp & 1) : (n_below == n_rays);
+        P->clamp_high_last = (force_clamp >= 0 && (force_clamp & 2)) ? 1 : (force_clamp >= 0 && (force_clamp & 4)) ? 0 : (n_above == n_rays);
         P->knife_layer = s_knife;
         P->n_rays = n_rays;
         P->n_nan = n_nan;
         P->n_below = n_below;
+        P->n_above = n_above;
         P->longest_span = longest;
     }
 }
@@ -1399,7 +1420,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_ray_integrate(const CubeView c,
     if (n_items == 0 || P->blocked) return;
     const int *__restrict__ nparts = P->nparts;
     const int *__restrict__ layer_cell = P->layer_cell;
-    const int clamp_low_first = P->clamp_low_first;
+    const int clamp_low_first = P->clamp_low_first, clamp_high_last = P->clamp_high_last;
     const int64_t n_pad = (n_items + 31) / 32 * 32;
     unsigned n_below = 0, n_above = 0, n_first_below = 0;
     for (int64_t idx = blockIdx.x * (int64_t)BLOCK + threadIdx.x; idx < n_pad; idx += (int64_t)gridDim.x * BLOCK) {
@@ -1468,6 +1489,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_ray_integrate(const CubeView c,
                 ecef2lla_fast2(pa, pb, R, lon[0], lat[0], hh[0], lon[1], lat[1], hh[1]);
                 to_model(lon[0], lat[0], X[0], Y[0]);
                 to_model(lon[1], lat[1], X[1], Y[1]);
+                if (clamp_high_last && k == K - 1 && j + 1 == np - 1) hh[1] = zmax;  // all pixels above max(z): delay.py:310-311
                 count_oob(hh[0]);
                 count_oob(hh[1]);
                 sample_scipy_pair_hinted(c, Y, X, hh, iy, ix, iz, sw, sh);
@@ -1484,6 +1506,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_ray_integrate(const CubeView c,
                 double lon, lat, h, X, Y;
                 ecef2lla_fast(p, R, lon, lat, h);
                 to_model(lon, lat, X, Y);
+                if (clamp_high_last && k == K - 1) h = zmax;  // all pixels above max(z): delay.py:310-311
                 count_oob(h);
                 sample_scipy<GUESS_HINT, GUESS_HINT>(c, Y, X, h, iy, ix, iz, vw, vh);
                 acc_w = __dadd_rn(acc_w, __dmul_rn(wt_half, vw));
@@ -3379,7 +3402,7 @@ static int k0_enqueue(rdr_handle_t h, int geom_kind, const double *gx, const dou
     constexpr int BLOCK = 128;
     const int minb = tune_minb("RDR_K0_MINB", 6);
     const int grid = grid_for(n, BLOCK, h->sm_count, 4 * minb);
-    const size_t smem = (BLOCK / 32) * (size_t)(K + 2) * sizeof(unsigned long long) + 3 * (size_t)K * sizeof(double);
+    const size_t smem = (BLOCK / 32) * (size_t)(K + 3) * sizeof(unsigned long long) + 3 * (size_t)K * sizeof(double);
     // RDR_K0_MODE: poly (default: septic h(t) + the layer tops as a polynomial in z) | iter (septic h(t), three iterates per layer) |
     // exact (the reference's iterates on Bowring heights)
     const char *k0_env = getenv("RDR_K0_MODE");
@@ -3387,7 +3410,7 @@ static int k0_enqueue(rdr_handle_t h, int geom_kind, const double *gx, const dou
     h->k0_was_cubic = use_cubic != 0;
 #define RDR_LAUNCH_K0(M)                                                                                                              \
     k_ray_layers<BLOCK, M><<<grid, BLOCK, smem, h->stream>>>(make_geom(h), n, K, h->d_plan.as<double>(), h->d_t.as<double>(),          \
-                                                            h->d_red.as<unsigned long long>(), h->zs.front(), use_cubic)
+                                                            h->d_red.as<unsigned long long>(), h->zs.front(), h->zs.back(), use_cubic)
     switch (minb) {
         case 4: RDR_LAUNCH_K0(4); break;
         case 5: RDR_LAUNCH_K0(5); break;
@@ -3659,13 +3682,13 @@ RDR_API int rdr_ray_layers(rdr_handle_t h, int geom_kind, const double *gx, cons
     CHECK_ARG(h, h != nullptr, "rdr_ray_layers: NULL handle");
     ScopedDevice sd(h->device);
     if (counts_out) {
-        counts_out[0] = ny * nx; counts_out[1] = 0; counts_out[2] = 0; counts_out[3] = 0;
+        counts_out[0] = ny * nx; counts_out[1] = 0; counts_out[2] = 0; counts_out[3] = 0; counts_out[4] = 0;
     }
     int rc = k0_enqueue(h, geom_kind, gx, gy, ny, nx, los_kind, los, ht, zref, 0, mem, "rdr_ray_layers");
     if (rc) return rc;
     const int K = h->n_layers;
-    std::vector<unsigned long long> red(K + 2);
-    CUDA_TRY(h, cudaMemcpyAsync(red.data(), h->d_red.p, (K + 2) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+    std::vector<unsigned long long> red(K + 5);
+    CUDA_TRY(h, cudaMemcpyAsync(red.data(), h->d_red.p, (K + 5) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     if (maxlen_out)
         for (int k = 0; k < K; ++k) memcpy(&maxlen_out[k], &red[k], sizeof(double));
@@ -3673,13 +3696,14 @@ RDR_API int rdr_ray_layers(rdr_handle_t h, int geom_kind, const double *gx, cons
         counts_out[1] = (int64_t)red[K];
         counts_out[2] = (int64_t)red[K + 1];
         counts_out[3] = K;
+        counts_out[4] = (int64_t)red[K + 4];
     }
     // (every ray of THIS call being NaN is not an error here: the reference's np.isnan(ray_lengths).all() (delay.py:279) is over the
     // whole raster, a call may be one row tile or one rank's block -- the caller decides on the summed counts)
     return RDR_OK;
 }
 
-RDR_API int rdr_ray_integrate(rdr_handle_t h, const double *maxlen, double max_segment_length, int clamp_low_first, void *out_wet,
+RDR_API int rdr_ray_integrate(rdr_handle_t h, const double *maxlen, double max_segment_length, int clamp, void *out_wet,
                               void *out_hydro, int out_dtype, int accumulate, int64_t *nparts_out, int64_t *oob_out, int mem) {
     CHECK_ARG(h, h != nullptr, "rdr_ray_integrate: NULL handle");
     if (!h->has_cube || !h->has_rays) return fail(h, RDR_ERR_STATE, "rdr_ray_integrate: call rdr_ray_layers first");
@@ -3711,7 +3735,8 @@ RDR_API int rdr_ray_integrate(rdr_handle_t h, const double *maxlen, double max_s
     unsigned long long *d_slot = h->d_red.as<unsigned long long>();
     CUDA_TRY(h, cudaMemcpyAsync(d_slot, slot.data(), slot.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, h->stream));
     int rc;
-    if ((rc = plan_enqueue(h, d_slot, 1, max_segment_length, clamp_low_first ? 1 : 0, RDR_PLAN_ABSURD))) return rc;
+    // clamp: bit 0 = the first sample is below min(z) on every pixel of the raster, bit 1 = the last sample is above max(z) on every pixel
+    if ((rc = plan_enqueue(h, d_slot, 1, max_segment_length, (clamp & 1) | ((clamp & 2) ? 2 : 4), RDR_PLAN_ABSURD))) return rc;
     bool staged = false;
     // a single layer longer than 2 spans would stretch the cubic's error bound (T^4) by > 16: leave those calls to `fast`
     if ((rc = k3_enqueue(h, out_wet, out_hydro, out_dtype, accumulate, mem, longest <= 2.0 * span_max ? 0 : 1, &staged))) return rc;
@@ -3766,7 +3791,7 @@ RDR_API int rdr_trace_begin(rdr_handle_t h, int geom_kind, const double *gx, con
     h->trace_flags = flags;
     if (h->xchg_world > 0) {
         h->xchg_parity ^= 1;
-        return publish(h, h->d_red.as<unsigned long long>(), h->n_layers + 3, 0);
+        return publish(h, h->d_red.as<unsigned long long>(), h->n_layers + 5, 0);
     }
     return RDR_OK;
 }
@@ -3848,8 +3873,8 @@ RDR_API int rdr_trace_result(rdr_handle_t h, double *maxlen_out, int64_t *nparts
         info_out[15] = h->last_k3_poly ? 1 : 0;
         info_out[16] = (int64_t)cnt[4];     // CTA passes of the thin-layer kernel whose record columns were staged in shared memory
         info_out[17] = (int64_t)cnt[5];     // ... and those that read the records from global memory (footprint larger than the slots)
-        info_out[18] = 0;
-        info_out[19] = 0;
+        info_out[18] = P->n_above;          // K0's global count of last samples above max(z)
+        info_out[19] = P->clamp_high_last;
     }
     return RDR_OK;
 }

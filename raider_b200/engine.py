@@ -26,7 +26,8 @@ class TraceInfo:
     maxlen: np.ndarray | None = None      # global per-layer max ray length (delay.py:283)
     nparts: np.ndarray | None = None      # int steps per layer
     samples_per_ray: int = 0              # sum(nParts): samples the reference evaluates per ray
-    clamp_low_first: bool = False         # delay.py:306-307 fired
+    clamp_low_first: bool = False         # delay.py:306-307 fired (first sample below min(z) on every pixel)
+    clamp_high_last: bool = False         # delay.py:310-311 fired (last sample above max(z) on every pixel)
     reruns: int = 0
     oob_below: int = 0
     oob_above: int = 0
@@ -177,10 +178,11 @@ class DeviceCube:
         return lo[: n.value].copy(), hi[: n.value].copy()
 
     def ray_layers(self, geom_kind, gx, gy, ny, nx, los_kind, los, ht, zref):
-        """K0.  Returns (maxlen[K], counts[4]) for this device's rays; raises NoLayersError when K == 0."""
+        """K0.  Returns (maxlen[K], counts[5] = {rays, NaN rays, first samples below min(z), K, last samples above max(z)}) for this
+        device's rays; raises NoLayersError when K == 0."""
         nz = self.grid[2].size
         maxlen = np.zeros(nz)
-        counts = np.zeros(4, dtype=np.int64)
+        counts = np.zeros(5, dtype=np.int64)
         dev = is_device(gx) or is_device(los)
         self._keep_geom = (gx, gy, los)  # device pointers must outlive rdr_ray_integrate
         self._n_rays = int(ny) * int(nx)
@@ -218,7 +220,8 @@ class DeviceCube:
             dt = _lib.F32 if out_wet.dtype == torch.float32 else _lib.F64
         else:
             dt = _lib.F32 if out_wet.dtype == np.float32 else _lib.F64
-        self.h.call('rdr_ray_integrate', ptr(maxlen), float(max_segment_length), int(bool(clamp_low_first)), ptr(out_wet), ptr(out_hydro),
+        # (clamp_low_first: bool, or the two-bit flag word of the ABI -- bit 0 lower clamp of the first sample, bit 1 upper clamp of the last)
+        self.h.call('rdr_ray_integrate', ptr(maxlen), float(max_segment_length), int(clamp_low_first) & 3, ptr(out_wet), ptr(out_hydro),
                     dt, int(bool(accumulate)), ptr(nparts), ptr(oob), _lib.MEM_DEVICE if dev else _lib.MEM_HOST)
         return nparts, oob
 
@@ -322,13 +325,16 @@ class DeviceCube:
             bx, by, bl = block(r0, r1)
             m, c = self.ray_layers(geom_kind, bx, by, r1 - r0, nx, los_kind, bl, ht, zref)
             maxlen = m if maxlen is None else np.maximum(maxlen, m)
-            counts = c.copy() if counts is None else np.concatenate([counts[:3] + c[:3], c[3:]])
+            if counts is None:
+                counts = c.copy()
+            else:
+                counts[_SUMMED] += c[_SUMMED]
         maxlen, counts = _global_plan(maxlen, counts, reduce_max, reduce_sum)
         info = TraceInfo(ht=float(ht))
         info.n_rays, info.n_nan_rays, info.n_layers = int(counts[0]), int(counts[1]), int(counts[3])
         if counts[1] == counts[0]:
             raise ValueError('geo2rdr did not converge. Check orbit coverage')  # delay.py:279-280, over the whole raster
-        clamp = bool(counts[2] == counts[0])
+        clamp = _clamp_flags(counts)
         ow = out_wet.reshape(ny, nx) if hasattr(out_wet, 'reshape') else out_wet
         oh = out_hydro.reshape(ny, nx) if hasattr(out_hydro, 'reshape') else out_hydro
         for attempt in range(2):
@@ -341,13 +347,13 @@ class DeviceCube:
                 oob_tot += oob
             # K3 re-evaluates the first-sample predicate on its own heights (bitwise K0's for all but polar / projected-cube rays)
             below3 = oob_tot[:1] if reduce_sum is None else reduce_sum(oob_tot[:1])
-            if bool(below3[0] == counts[0]) == clamp:
+            if bool(below3[0] == counts[0]) == bool(clamp & 1):
                 break
-            clamp = not clamp  # K0's hint and K3's own evaluation disagree on a knife edge: K3 rules
+            clamp ^= 1  # K0's hint and K3's own evaluation disagree on a knife edge: K3 rules
             info.reruns = 1
         info.maxlen, info.nparts = maxlen, nparts
         info.samples_per_ray = int(nparts.sum())
-        info.clamp_low_first = clamp
+        info.clamp_low_first, info.clamp_high_last = bool(clamp & 1), bool(clamp & 2)
         info.oob_below, info.oob_above = int(oob_tot[1]), int(oob_tot[2])
         info.tiles = len(tiles)
         if exchange is not None:
@@ -463,7 +469,7 @@ class DeviceCube:
             break
         info.maxlen, info.nparts = maxlen, nparts
         info.samples_per_ray = int(nparts.sum())
-        info.clamp_low_first = bool(res[7])
+        info.clamp_low_first, info.clamp_high_last = bool(res[7]), bool(res[19])
         info.oob_below, info.oob_above = int(res[8]), int(res[9])
         info.k_split, info.n_spans = int(res[12]), int(res[13])
         info.staged_passes, info.unstaged_passes = int(res[16]), int(res[17])
@@ -479,25 +485,25 @@ class DeviceCube:
         info.n_rays, info.n_nan_rays, info.n_layers = int(counts[0]), int(counts[1]), int(counts[3])
         if counts[1] == counts[0]:
             raise ValueError('geo2rdr did not converge. Check orbit coverage')  # delay.py:279-280, over the whole raster
-        clamp = bool(counts[2] == counts[0])
+        clamp = _clamp_flags(counts)
         nparts, oob = self.ray_integrate(maxlen, max_segment_length, clamp, out_wet, out_hydro, peers=peers)
         below3 = oob[:1] if reduce_sum is None else reduce_sum(oob[:1])   # K3's own evaluation of the predicate, summed over ranks
-        if bool(below3[0] == counts[0]) != clamp:  # K0's hint and K3's own evaluation disagree on a knife edge: K3 rules
-            clamp = not clamp
+        if bool(below3[0] == counts[0]) != bool(clamp & 1):  # K0's hint and K3's own evaluation disagree on a knife edge: K3 rules
+            clamp ^= 1
             nparts, oob = self.ray_integrate(maxlen, max_segment_length, clamp, out_wet, out_hydro, peers=peers)
             info.reruns = 1
         info.maxlen, info.nparts = maxlen, nparts
         info.samples_per_ray = int(nparts.sum())
-        info.clamp_low_first = clamp
+        info.clamp_low_first, info.clamp_high_last = bool(clamp & 1), bool(clamp & 2)
         info.oob_below, info.oob_above = int(oob[1]), int(oob[2])
         return info
 
 
 def _check_clamp_coverage(info: 'TraceInfo', max_segment_length: float) -> None:
-    """Only the first-sample lower clamp of delay.py:306-311 is applied on the device.  The other clamps (any later sample with ALL
-    pixels below min(z), any sample with ALL pixels above max(z)) cannot fire for valid inputs (zref <= max(z) - 1, top layer
-    - 0.01 m); should every ray nevertheless have left the model vertically, the device returned NaN where the reference clamps:
-    say so instead of returning it silently."""
+    """Two of the `.all()` clamps of delay.py:306-311 are applied on the device: the first sample of a ray (all pixels below min(z))
+    and the last one (all pixels above max(z): the default zref = top - 1 m with rays steeper than ~58 deg).  The others (an interior
+    sample slot with ALL pixels outside the vertical range) cannot fire for valid inputs; should every ray nevertheless have left the
+    model vertically at such a slot, the device returned NaN where the reference clamps: say so instead of returning it silently."""
     n = max(info.n_rays, 1)
     if info.oob_above >= n or (info.oob_below >= n and not info.clamp_low_first):
         import logging
@@ -514,10 +520,21 @@ def _global_plan(maxlen, counts, reduce_max, reduce_sum):
         return maxlen, counts
     pair = getattr(getattr(reduce_max, '__self__', None), 'reduce_pair', None)
     if pair is not None:
-        m, c3 = pair(maxlen, counts[:3])
+        m, c4 = pair(maxlen, counts[_SUMMED])
     else:
-        m, c3 = reduce_max(maxlen), reduce_sum(counts[:3])
-    return m, np.concatenate([c3, counts[3:]])
+        m, c4 = reduce_max(maxlen), reduce_sum(counts[_SUMMED])
+    out = counts.copy()
+    out[_SUMMED] = c4
+    return m, out
+
+
+_SUMMED = [0, 1, 2, 4]   # of the counts of rdr_ray_layers: rays, NaN rays, first samples below min(z), [3 = K], last samples above max(z)
+
+
+def _clamp_flags(counts) -> int:
+    """The two whole-raster `.all()` predicates of delay.py:306-311 from K0's global counts: bit 0 = every pixel's first sample lies
+    below min(z), bit 1 = every pixel's last sample lies above max(z)."""
+    return int(counts[2] == counts[0]) | (int(counts[4] == counts[0]) << 1)
 
 
 def los_device_spec(los, ny: int, nx: int):

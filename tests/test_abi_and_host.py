@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol(lib):
     raw = C.CDLL(str(_lib.LIB_PATH))
     for name in declared:
         assert hasattr(raw, name), f'{name} is declared in the header but not exported by the .so'
-    assert lib.rdr_abi_version() == 2
+    assert lib.rdr_abi_version() == 3
 
 
 def test_no_extra_exports(lib):

@@ -70,8 +70,9 @@ def _worker(rank, world, port, q):
         # both reductions of a step in one collective (what engine._global_plan uses when the hooks come from a Comm)
         from raider_b200.engine import _global_plan
         pm, pc = comm.reduce_pair(np.array([float(rank), 5.0 - rank, 2.5]), np.array([rank + 1, 10, 0]))
-        gm, gc = _global_plan(np.array([float(rank), 5.0 - rank, 2.5]), np.array([rank + 1, 10, 0, 33], dtype=np.int64), comm.reduce_max, comm.reduce_sum)
-        pair_ok = pm.tolist() == [1.0, 5.0, 2.5] and pc.tolist() == [3, 20, 0] and gm.tolist() == pm.tolist() and gc.tolist() == [3, 20, 0, 33]
+        # counts of rdr_ray_layers: {rays, NaN rays, first samples below min(z), K, last samples above max(z)}: all but K are summed
+        gm, gc = _global_plan(np.array([float(rank), 5.0 - rank, 2.5]), np.array([rank + 1, 10, 0, 33, rank + 1], dtype=np.int64), comm.reduce_max, comm.reduce_sum)
+        pair_ok = pm.tolist() == [1.0, 5.0, 2.5] and pc.tolist() == [3, 20, 0] and gm.tolist() == pm.tolist() and gc.tolist() == [3, 20, 0, 33, 3]
         q.put((rank, bool(np.array_equal(out[0], full[0]) and np.array_equal(out[1], full[1])), out[0].shape,
                bool(np.array_equal(naive[0], full[0][:, r0:r1])), gathered[:, 0].tolist(),
                comm.reduce_max(np.array([float(rank), 5.0 - rank])).tolist(), comm.reduce_sum(np.array([rank + 1, 10])).tolist(), pair_ok))

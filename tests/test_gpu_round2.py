@@ -82,6 +82,43 @@ def test_thin_layer_kernel_staged_vs_unstaged_vs_quadrature(gpu, monkeypatch):
     assert np.abs(w - wq).max() < 1e-10 and np.abs(h - hq).max() < 1e-10
 
 
+@pytest.mark.parametrize('inc', [20.0, 45.0, 65.0])
+def test_k0_layer_top_polynomial_on_the_references_145_node_table(gpu, monkeypatch, inc):
+    """K0's three forms on the reference's own 145-node table (80 km, from the committed ERA-5 fixture): `poly` (default: h(t) as a
+    septic, the layer tops as one degree-7 polynomial in z), `iter` (septic, three iterates per layer) and `exact` (the reference's
+    iterates on PROJ-form heights).  Layer maxima within 1e-7 m of each other (measured 2e-8), nParts identical and equal to the
+    oracle's from its own maxima, delays within the contract of each other and of the oracle."""
+    from pathlib import Path
+    from oracle import raytrace as rt
+    from raider_b200 import synthetic as syn
+    from raider_b200.engine import DeviceCube
+    zs = np.load(Path(__file__).resolve().parent / 'golden' / 'era5_slant_ref.npz')['z']
+    n = 24
+    xp, yp = syn.raster(33.5, -117.8, n, n, 0.02)
+    xs, ys = syn.cube_axes_around(xp, yp, pad_deg=2.5 if inc > 60 else 1.2)
+    cube_d = syn.make_cube(ys, xs, zs, totals=False)
+    cfg = {'cube': cube_d, 'xpts': xp, 'ypts': yp, 'zpts': np.array([0.0]), 'zref': float(zs[-1] - 1), 'max_segment_length': 1000.0}
+    cube = DeviceCube.from_dict(cube_d)
+    res = {}
+    for mode in ('poly', 'iter', 'exact'):
+        monkeypatch.setenv('RDR_K0_MODE', mode)
+        res[mode] = _trace(cube, cfg, _enu(inc, -168.0))
+    monkeypatch.delenv('RDR_K0_MODE')
+    st = {}
+    crs = rt.GeographicCRS()
+    want = rt.build_cube_ray(xp, yp, cfg['zpts'], rt.FixedIncidenceLOS(inc, -168.0), crs, crs, list(rt.get_interpolators(cube_d)),
+                             MAX_TROPO_HEIGHT=cfg['zref'], stats=st)
+    assert not np.isnan(want[0]).any() and st['nParts'][0].size == 137
+    # from ~58 deg on, the three iterates of losreader.py:720-733 overshoot the default zref (1 m below the 80 km top) by more than
+    # that metre on EVERY pixel: the reference takes the last sample at max(z) (delay.py:310-311), and so does the device
+    assert all(info.clamp_high_last == (inc > 60.0) for _, _, info in res.values())
+    for mode, (w, h, info) in res.items():
+        assert np.array_equal(info.nparts, st['nParts'][0]), mode
+        assert np.abs(info.maxlen - res['exact'][2].maxlen).max() < 1e-7, mode
+        assert np.abs(w - want[0][0]).max() < TOL_F64_M and np.abs(h - want[1][0]).max() < TOL_F64_M, mode
+        assert np.abs(h - res['exact'][1]).max() < 1e-9, mode
+
+
 def test_thin_layer_kernel_on_a_km_scale_grid(gpu):
     """A 3-km Lambert cube (C3 shape, 57-node table): the rays cross a horizontal cell every layer or two, the staged footprint is
     several columns wide; against the oracle."""
@@ -270,3 +307,48 @@ def test_caller_supplied_output_arrays_accumulate(gpu):
     assert _build_cube_ray(cfg['xpts'], cfg['ypts'], cfg['zpts'], los, 4326, 4326, list(ifs), outputArrs=mine, MAX_SEGMENT_LENGTH=225.0,
                            MAX_TROPO_HEIGHT=cfg['zref']) is None
     assert np.array_equal(mine[0], seed[0] + fresh[0]) and np.array_equal(mine[1], seed[1] + fresh[1])
+
+
+def test_upper_clamp_of_the_last_sample(gpu):
+    """delay.py:310-311: when the top of the top layer lies above max(z) on EVERY pixel (steep rays, zref at its default of 1 m below
+    the model top) the reference samples it at max(z).  K0 counts it, the plan decides it globally, the PROJ-form kernel applies it
+    (the polynomial kernels hand such rays over); the hosted two-call form and the fused step agree; a raster where only SOME pixels
+    overshoot gets NaN on those, like the reference (the `.all()` is false)."""
+    from pathlib import Path
+    from oracle import raytrace as rt
+    from raider_b200 import _lib, synthetic as syn
+    from raider_b200.engine import DeviceCube
+    zs = np.load(Path(__file__).resolve().parent / 'golden' / 'era5_slant_ref.npz')['z']
+    n = 16
+    xp, yp = syn.raster(33.5, -117.8, n, n, 0.02)
+    xs, ys = syn.cube_axes_around(xp, yp, pad_deg=3.0)
+    cube_d = syn.make_cube(ys, xs, zs, totals=False)
+    cfg = {'cube': cube_d, 'xpts': xp, 'ypts': yp, 'zpts': np.array([0.0]), 'zref': float(zs[-1] - 1), 'max_segment_length': 1000.0}
+    cube = DeviceCube.from_dict(cube_d)
+    crs = rt.GeographicCRS()
+    ifs = list(rt.get_interpolators(cube_d))
+    # (a) every pixel overshoots
+    want = rt.build_cube_ray(xp, yp, cfg['zpts'], rt.FixedIncidenceLOS(66.0, -168.0), crs, crs, ifs, MAX_TROPO_HEIGHT=cfg['zref'])
+    assert not np.isnan(want[0]).any()
+    w, h, info = _trace(cube, cfg, _enu(66.0, -168.0))
+    assert info.clamp_high_last and not info.clamp_low_first and info.oob_above == 0
+    assert np.abs(w - want[0][0]).max() < TOL_F64_M and np.abs(h - want[1][0]).max() < TOL_F64_M
+    assert np.abs(h - want[1][0]).max() < 1e-9
+    # the two-call (hosted) form decides the same from counts_out[4] (identity hooks stand in for a one-rank reduction), also in row tiles
+    w2, h2, info2 = _trace(cube, cfg, _enu(66.0, -168.0), reduce_max=lambda a: a, reduce_sum=lambda a: a)
+    assert info2.clamp_high_last and np.array_equal(w2, w) and np.array_equal(h2, h)
+    w3, h3, info3 = _trace(cube, cfg, _enu(66.0, -168.0), max_t_bytes=8 * zs.size * n * 5)
+    assert info3.tiles > 1 and info3.clamp_high_last and np.array_equal(w3, w) and np.array_equal(h3, h)
+    # (b) an explicit LOS array: half the raster at 66 deg, half at 30 deg -> the predicate is false, the steep half is NaN (reference too)
+    from oracle import geodesy
+    inc = np.where(np.arange(n)[None, :] < n // 2, 66.0, 30.0) * np.ones((n, 1))
+    xx, yy = np.meshgrid(xp, yp)
+    enu = geodesy.inc_hd_to_enu(inc, np.full_like(inc, -168.0))
+    look = geodesy.enu2ecef(enu[..., 0], enu[..., 1], enu[..., 2], yy, xx, np.zeros_like(yy))
+    want = rt.build_cube_ray(xp, yp, cfg['zpts'], rt.ArrayLOS(look), crs, crs, ifs, MAX_TROPO_HEIGHT=cfg['zref'])
+    ww, hh = _lib.pinned_empty((n, n)), _lib.pinned_empty((n, n))
+    info = cube.trace(_lib.GEOM_GRID, xp, yp, n, n, _lib.LOS_ARRAY, np.ascontiguousarray(look.reshape(-1, 3)), 0.0, cfg['zref'], 1000.0, ww, hh)
+    assert not info.clamp_high_last
+    assert np.isnan(want[0][0][:, : n // 2]).all() and not np.isnan(want[0][0][:, n // 2:]).any()
+    assert np.array_equal(np.isnan(np.array(ww)), np.isnan(want[0][0]))
+    assert np.nanmax(np.abs(np.array(hh) - want[1][0])) < TOL_F64_M
