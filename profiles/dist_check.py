@@ -7,7 +7,9 @@ barrier); rank 0 also traces the WHOLE raster alone (no exchange) and compares b
   a  C2-shaped raster, two output heights, the last one at the model top (that slice is skipped by the reference: zeros);
   b  the 145-node table (thin-layer kernel + quadrature kernel across ranks);
   c  a raster whose first rank's block has no look vectors at all (NaN): no rank may raise or hang, those rows come out NaN;
-  d  the public API: build_cube_ray_sharded with host row blocks + device maps.
+  d  the public API: build_cube_ray_sharded with host row blocks + device maps;
+  e  66 deg incidence through the reference's 145-node table (80 km) at the default zref: every ray's last sample lies above max(z),
+     the upper `.all()` clamp of delay.py:310-311 is decided over ALL ranks (its count rides the exchange slots); no NaN, bitwise equal.
 Prints one JSON line on rank 0.
 """
 import json
@@ -53,7 +55,8 @@ def case(name, cfg, los, zpts, **kw):
                    max_abs_diff=float(np.nanmax(np.abs(np.asarray(full[0]) - want[0]))) if np.isfinite(want[0]).any() else 0.0,
                    nparts_equal=all(same(a.nparts, b.nparts) for a, b in zip(info, winfo) if not a.skipped),
                    maxlen_equal=all(same(a.maxlen, b.maxlen) for a, b in zip(info, winfo) if not a.skipped),
-                   skipped=[bool(a.skipped) for a in info], k_split=[int(a.k_split) for a in info])
+                   skipped=[bool(a.skipped) for a in info], k_split=[int(a.k_split) for a in info],
+                   clamp_high_last=[bool(a.clamp_high_last) for a in info])
     res[name] = out
 
 
@@ -107,6 +110,13 @@ r0, r1 = shard_rows(96, rank, world)
 ok = torch.tensor([int(same(host_rows[0][0], dev_maps[0][0, r0:r1].cpu().numpy()) and same(host_rows[1][0], dev_maps[1][0, r0:r1].cpu().numpy()))], device='cuda')
 dist.all_reduce(ok, op=dist.ReduceOp.MIN)
 res['d_host_rows_equal_device_maps_on_every_rank'] = bool(ok.item())
+
+# e: the upper clamp of the last sample, decided globally
+zs = np.load(Path(__file__).resolve().parents[1] / 'tests' / 'golden' / 'era5_slant_ref.npz')['z']
+xp, yp = syn.raster(33.5, -117.8, 64, 64, 0.02)
+xs, ys = syn.cube_axes_around(xp, yp, pad_deg=3.0)
+cfg = {'cube': syn.make_cube(ys, xs, zs, totals=False), 'xpts': xp, 'ypts': yp, 'zref': float(zs[-1] - 1), 'max_segment_length': 1000.0}
+case('e_upper_clamp_66deg', cfg, Raytracing(incidence=66.0, heading=-168.0), np.array([0.0]))
 
 if rank == 0:
     print(json.dumps(res))
