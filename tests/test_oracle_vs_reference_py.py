@@ -204,6 +204,20 @@ def test_build_cube_ray_edge_rules_bitwise(ref):
     cfg['zpts'] = np.array([float(cfg['cube']['z'][0])])
     o_ref, o_port = _both(ref, cfg, rt.FixedIncidenceLOS(30.0, -168.0))
     assert same(o_ref[0], o_port[0]) and same(o_ref[1], o_port[1])
+    # (3b) the upper clamp (delay.py:310-311): at the default zref (1 m below the model top) the third Newton iterate overshoots the
+    # top of an 80 km table by more than that metre from ~58 deg incidence on -- on every pixel, so the last sample is taken at max(z)
+    from pathlib import Path
+    zs = np.load(Path(__file__).resolve().parent / 'golden' / 'era5_slant_ref.npz')['z']
+    xp, yp = syn.raster(33.5, -117.8, 5, 5, 0.02)
+    xs, ys = syn.cube_axes_around(xp, yp, pad_deg=3.0)
+    cfg = {'cube': syn.make_cube(ys, xs, zs, totals=False), 'xpts': xp, 'ypts': yp, 'zpts': np.array([0.0]), 'zref': float(zs[-1] - 1),
+           'max_segment_length': 1000.0}
+    o_ref, o_port = _both(ref, cfg, rt.FixedIncidenceLOS(66.0, -168.0))
+    assert same(o_ref[0], o_port[0]) and same(o_ref[1], o_port[1]) and np.isfinite(o_ref[0]).all()
+    g = np.stack(geodesy.lla2ecef(yp[0], xp[0], 0.0))
+    u = np.asarray(rt.FixedIncidenceLOS(66.0, -168.0).getLookVectors(0.0, [xp[:1, None], yp[:1, None], np.zeros((1, 1))], None, None))[0, 0]
+    top = ref.losreader.build_ray(zs, 0.0, g[None, None, :], u[None, None, :], cfg['zref'])[2][-1][0, 0]
+    assert geodesy.ecef2height(top[0], top[1], top[2]) > zs[-1] + 1.0      # (the overshoot itself, on the reference's own build_ray)
     # (4) query raster given in the Lambert system of the cube (pts_crs != 4326: delay.py:262-265)
     name, cfgf, los, lcc = next(c for c in _golden_cases() if c[0] == 'f')
     cx, cy = lcc.lcc.forward(-98.0, 36.0)
