@@ -1,4 +1,4 @@
-"""Generate tests/golden/era5_slant_ref.npz + orbit_S1B_20200130_sv.txt -- run HERE (CPU container), never on the GPU box.
+"""Generate tests/golden/era5_slant_ref.npz + orbit_S1B_20200130_sv.txt + era5_gnss_ref.npz -- run HERE (CPU container), never on the GPU box.
 
     python tests/golden/make_golden_era5_slant.py
 
@@ -99,5 +99,42 @@ def main() -> None:
     print('std', (zw + zh)[0, iy, ix], 'ray', (rw + rh)[0, iy, ix], 'written', OUT / 'era5_slant_ref.npz')
 
 
+STATIONS = REFERENCE / 'test' / 'scenario_6' / 'stations.csv'
+GOLD_GNSS = ('TORP', 2.34514)                 # test/test_intersect.py:104 (4 decimals)
+
+
+def reference_station_ztd():
+    """test/test_intersect.py::test_gnss_intersect on the same ERA-5 file: a station AOI (llreader.StationFile) is answered by a ZTD
+    cube on the AOI's own grid at the model's z levels (delay.py:78-96, 147-160) that is then interpolated at the stations
+    (delay.py:104-121).  All of it is the reference's own Python (pandas reads the CSV)."""
+    from oracle import refpy
+    from raider_b200.cube_io import load_cube
+    ref = refpy.load()
+    llreader = importlib.import_module('RAiDER.llreader')
+    cube = load_cube(WM)
+    aoi = llreader.StationFile(str(STATIONS), cube_spacing_in_m=2000.0)
+    aoi.add_buffer(0.25)
+    aoi.set_output_xygrid(4326)
+    crs = ref.CRS(4326)
+    zpts = cube['z']                                                  # height_levels = wm_levels (delay.py:80-84)
+    zw, zh = ref.delay._build_cube(aoi.xpts, aoi.ypts, zpts, crs, crs, ref.delayFcns.getInterpolators(ref.dataset(cube), 'total'))
+    lats, lons = aoi.readLL()
+    hgts = aoi.readZ()
+    pnts = ref.delay.transformPoints(lats, lons, hgts, crs, crs)
+    if_w, if_h = ref.delayFcns.getInterpolators(ref.dataset(dict(x=aoi.xpts, y=aoi.ypts, z=zpts, wet=zw, hydro=zh)), 'ztd')
+    return aoi, (lats, lons, hgts), (zw, zh), (if_w(pnts), if_h(pnts))
+
+
+def main_stations() -> None:
+    import pandas as pd
+    aoi, (lats, lons, hgts), _, (wd, hd) = reference_station_ztd()
+    ids = list(pd.read_csv(STATIONS)['ID'])
+    np.testing.assert_almost_equal((wd + hd)[ids.index(GOLD_GNSS[0])], GOLD_GNSS[1], decimal=4)
+    np.savez_compressed(OUT / 'era5_gnss_ref.npz', xpts=aoi.xpts, ypts=aoi.ypts, lats=lats, lons=lons, hgts=hgts, ref_wet=wd, ref_hydro=hd,
+                        gold_index=np.int64(ids.index(GOLD_GNSS[0])), gold_total=np.float64(GOLD_GNSS[1]))
+    print('stations', dict(zip(ids, wd + hd)), 'written', OUT / 'era5_gnss_ref.npz')
+
+
 if __name__ == '__main__':
     main()
+    main_stations()

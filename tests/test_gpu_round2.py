@@ -352,3 +352,22 @@ def test_upper_clamp_of_the_last_sample(gpu):
     assert np.isnan(want[0][0][:, : n // 2]).all() and not np.isnan(want[0][0][:, n // 2:]).any()
     assert np.array_equal(np.isnan(np.array(ww)), np.isnan(want[0][0]))
     assert np.nanmax(np.abs(np.array(hh) - want[1][0])) < TOL_F64_M
+
+
+def test_reference_golden_of_test_gnss_intersect_on_device(gpu):
+    """test/test_intersect.py:104 (TORP 2.34514 m total zenith delay, 4 decimals) through the product's tropo_delay in station (point)
+    mode: ZTD cube on the reference's AOI grid at the model's 145 z levels (device, float64 totals as hi + lo), then the cube
+    re-interpolated at the stations (device).  Against the values the reference's own Python produced (tests/golden/era5_gnss_ref.npz)."""
+    import datetime as dt
+    from pathlib import Path
+    from raider_b200.delay import tropo_delay
+    from raider_b200.llreader import Points
+    from raider_b200.losreader import Zenith
+    gold = Path(__file__).resolve().parent / 'golden'
+    fx, cx = np.load(gold / 'era5_gnss_ref.npz'), np.load(gold / 'era5_slant_ref.npz')
+    cube = {k: cx[k] for k in ('x', 'y', 'z', 'wet', 'hydro', 'wet_total', 'hydro_total')}
+    aoi = Points(fx['lats'], fx['lons'], fx['hgts'])
+    aoi.xpts, aoi.ypts = fx['xpts'], fx['ypts']          # the grid the reference's StationFile AOI builds (cli/raider.py:257-260)
+    wet, hydro = tropo_delay(dt.datetime(2020, 1, 30, 13, 52, 45), cube, aoi, Zenith())
+    np.testing.assert_almost_equal((wet + hydro)[int(fx['gold_index'])], float(fx['gold_total']), decimal=4)
+    assert np.abs(wet - fx['ref_wet']).max() < 1e-11 and np.abs(hydro - fx['ref_hydro']).max() < 1e-11

@@ -365,3 +365,29 @@ def test_reference_goldens_of_test_slant_are_reproduced(ref):
     from raider_b200.losreader import read_txt_file
     sv = read_txt_file(str(Path(__file__).resolve().parent / 'golden' / 'orbit_S1B_20200130_sv.txt'))
     assert np.array_equal(np.stack(sv[1:4], -1), o.position) and np.array_equal(np.stack(sv[4:7], -1), o.velocity)
+
+
+def test_reference_golden_of_test_gnss_intersect_is_reproduced(ref):
+    """test/test_intersect.py:104 (TORP 2.34514 m, 4 decimals): the station (point) mode of tropo_delay on the reference's ERA-5 file --
+    llreader.StationFile (pandas) -> ZTD cube on the AOI grid at the model's 145 z levels -> getInterpolators(ds, 'ztd') at the stations
+    (delay.py:78-121) -- run with the reference's own Python; the oracle (build_cube + the installed scipy) gives the same numbers, and
+    the committed fixture (tests/golden/era5_gnss_ref.npz) holds them for the GPU box."""
+    import sys
+    from pathlib import Path
+    from scipy.interpolate import RegularGridInterpolator as RGI
+    sys.path.insert(0, str(Path(__file__).resolve().parent / 'golden'))
+    import make_golden_era5_slant as mk
+    from raider_b200.cube_io import load_cube
+    fx = np.load(Path(__file__).resolve().parent / 'golden' / 'era5_gnss_ref.npz')
+    aoi, (lats, lons, hgts), (zw, zh), (wd, hd) = mk.reference_station_ztd()
+    np.testing.assert_almost_equal((wd + hd)[int(fx['gold_index'])], float(fx['gold_total']), decimal=4)
+    assert same(aoi.xpts, fx['xpts']) and same(aoi.ypts, fx['ypts']) and same(wd, fx['ref_wet']) and same(hd, fx['ref_hydro'])
+    assert same(lats, fx['lats']) and same(lons, fx['lons']) and same(hgts, fx['hgts'])
+    cube = load_cube(mk.WM)
+    crs = rt.GeographicCRS()
+    pw, ph = rt.build_cube(aoi.xpts, aoi.ypts, cube['z'], crs, crs, list(rt.get_interpolators(cube, 'total')))
+    assert same(pw, zw) and same(ph, zh)
+    pts = np.stack([lats, lons, hgts], axis=-1)
+    grid = (aoi.ypts, aoi.xpts, cube['z'])
+    assert same(RGI(grid, pw.transpose(1, 2, 0), fill_value=np.nan, bounds_error=False)(pts), wd)
+    assert same(RGI(grid, ph.transpose(1, 2, 0), fill_value=np.nan, bounds_error=False)(pts), hd)
