@@ -1,6 +1,6 @@
 """How well ONE degree-7 polynomial per ray reproduces the PROJ-form geodetic height h(t) along the ray (K0, k_ray_layers).
 
-CPU / NumPy only (run anywhere): emulates the construction of raider_b200.cu::ray_layers_septic -- eight exact heights at
+CPU / NumPy only (run anywhere): emulates the construction of k0_layers.cuh::ray_layers_septic -- eight exact heights at
 t = i L / 7, coefficients through the exactly inverted Vandermonde matrix applied to the differences from the ground height,
 Horner evaluation -- in double precision, and compares with the exact height (oracle.geodesy.ecef2height, PROJ's `cart`
 inverse) at 4001 points of every ray.  Also prints the same for the piecewise forms the first round used (cubic / 6 km).

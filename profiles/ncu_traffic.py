@@ -29,4 +29,4 @@ npts = int(sys.argv[2])
 print(json.dumps({'kernel': name, 'points_per_launch': npts, 'dram_bytes_read': rd, 'dram_bytes_write': wr, 'algorithmic_bytes': npts * 40,
                   'kernel_source_hash': kernel_source_hash(),
                   'source': 'ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --clock-control none over `python bench.py`: the largest '
-                            'k_sample_stream<double> launch (192 M points); profiles/runs/r02ad_final.sh'}, indent=1))
+                            'k_sample_stream<double> launch (192 M points); profiles/runs/r02ai_split.sh'}, indent=1))

@@ -13,7 +13,7 @@ PKG_DIR = Path(__file__).resolve().parent
 CSRC = PKG_DIR / 'csrc'
 OUT = PKG_DIR / 'libraider_b200.so'
 SOURCES = [CSRC / 'raider_b200.cu']
-HEADERS = [CSRC / 'geodesy.cuh', CSRC / 'sampler.cuh', CSRC / 'fastpath.cuh', PKG_DIR.parent / 'include' / 'raider_b200.h']
+HEADERS = sorted(CSRC.glob('*.cuh')) + [PKG_DIR.parent / 'include' / 'raider_b200.h']   # every fragment of the translation unit is a dependency
 
 NVCC_FLAGS = [
     '-gencode', 'arch=compute_100a,code=sm_100a',
